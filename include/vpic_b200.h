@@ -1,0 +1,176 @@
+/* vpic_b200.h -- the drop-in boundary, part 2: entry points.
+ *
+ * libvpic_b200.so exports two layers, both plain C ABI (pointers and sizes only):
+ *
+ *  (A) REFERENCE-NAMED ENTRY POINTS with the reference's exact prototypes
+ *      (advance_p, sort_p, load_interpolator, ... and the field-advance vtables).
+ *      These are what gets linked INSTEAD of the reference's translation units
+ *      (INTEGRATION.md shows the link line).  Pointers are whatever
+ *      the caller has: plain host memory is staged host->device->host around the
+ *      kernel; memory that came from vpb_malloc_managed()/util_malloc_aligned()
+ *      or vpb_dev_alloc() is used in place.
+ *
+ *  (B) vpb_* DEVICE-RESIDENT ENTRY POINTS: same operations on device pointers,
+ *      enqueued on the library's stream without host synchronisation, for callers
+ *      that keep the whole state in HBM between steps (bench.py `value`, the
+ *      step driver vpb_sim_*).
+ *
+ * Error behaviour mirrors the reference (util_base.h:213-219): invalid arguments
+ * print "Error at file(line): msg" to stderr and exit(1); recoverable conditions
+ * print a warning and continue.  There is NO CPU fallback: every entry point
+ * fails loudly if no CUDA device is usable.
+ */
+#ifndef VPIC_B200_H
+#define VPIC_B200_H
+
+#include "vpic_b200_abi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------- */
+/* (A) Reference-named entry points.  Compiled with the reference's own names  */
+/* unless VPB_NO_REFERENCE_NAMES is defined by the includer (tests that also   */
+/* include reference headers).                                                 */
+/* ------------------------------------------------------------------------- */
+#ifndef VPB_NO_REFERENCE_NAMES
+
+/* src/species_advance/standard/spa.h:57-65 (advance_p.cxx:399-472).
+ * Returns the number of movers left in pm[] (particles that hit something
+ * move_p cannot resolve locally), in increasing particle-index order. */
+int advance_p(vpb_particle_t *p0, int np, const float q_m, vpb_particle_mover_t *pm, int max_nm,
+              vpb_accumulator_t *a0, const vpb_interpolator_t *f0, const vpb_grid_t *g);
+
+/* spa.h:43-47 (move_p.c:20-136): finish one mover; 0 = done, 1 = still in use. */
+int move_p(vpb_particle_t *p0, vpb_particle_mover_t *m, vpb_accumulator_t *a0, const vpb_grid_t *g);
+
+/* spa.h:23-25 (sort_p.c:16-102): counting sort by voxel; fills sp->partition. */
+void sort_p(vpb_species_t *sp, const vpb_grid_t *g);
+
+/* spa.h:72-91 (center_p.cxx:155, uncenter_p.cxx:155) */
+void center_p(vpb_particle_t *p0, int np, const float q_m, const vpb_interpolator_t *f0, const vpb_grid_t *g);
+void uncenter_p(vpb_particle_t *p0, int np, const float q_m, const vpb_interpolator_t *f0, const vpb_grid_t *g);
+
+/* spa.h:99-104 (energy_p.cxx:124-157) */
+double energy_p(const vpb_particle_t *p0, int np, float q_m, const vpb_interpolator_t *f0, const vpb_grid_t *g);
+
+/* spa.h:108-112 (rho_p.c:23-79) */
+void accumulate_rho_p(vpb_field_t *f, const vpb_particle_t *p0, int np, const vpb_grid_t *g);
+
+/* spa.h:29-32 (boundary_p.c:9-71) */
+void accumulate_rhob(vpb_field_t *f0, const vpb_particle_t *p, const vpb_grid_t *g);
+
+/* spa.h:34-41 (boundary_p.c:77-505).  rng is the reference's mt_rng_t*, only
+ * forwarded to custom boundary handlers (none are implemented on the device). */
+void boundary_p(vpb_species_t *sp_list, vpb_field_t *f0, vpb_accumulator_t *a0, const vpb_grid_t *g, void *rng);
+
+/* src/sf_interface/sf_interface.h:83-163 */
+vpb_interpolator_t *new_interpolator(vpb_grid_t *g);
+void delete_interpolator(vpb_interpolator_t *fi);
+vpb_accumulator_t *new_accumulators(vpb_grid_t *g);
+void delete_accumulators(vpb_accumulator_t *a);
+void load_interpolator(vpb_interpolator_t *fi, const vpb_field_t *f, const vpb_grid_t *g);
+void clear_accumulators(vpb_accumulator_t *a, const vpb_grid_t *g);
+void reduce_accumulators(vpb_accumulator_t *a, const vpb_grid_t *g);
+void unload_accumulator(vpb_field_t *f, const vpb_accumulator_t *a, const vpb_grid_t *g);
+
+/* src/field_advance/field_advance.h:318-345: the vtables decks name through the
+ * standard_field_advance / vacuum_field_advance macros. */
+extern vpb_field_advance_methods_t _standard_field_advance[1];
+extern vpb_field_advance_methods_t _vacuum_field_advance[1];
+extern vpb_field_advance_methods_t _standard_v4_field_advance[1];
+extern vpb_field_advance_methods_t _vacuum_v4_field_advance[1];
+
+/* src/util/util_base.h:261-280 (util.c:46-91): the reference's single allocation
+ * choke-point.  Substituting it puts every large array in CUDA managed memory,
+ * so kernels run on deck-visible pointers in place. */
+void util_malloc_aligned(const char *err_fmt, const char *file, int line, const char *name,
+                         void *mem_ref, size_t n, size_t a);
+void util_free_aligned(void *mem_ref);
+
+#endif /* VPB_NO_REFERENCE_NAMES */
+
+/* ------------------------------------------------------------------------- */
+/* (B) Device-resident layer                                                   */
+/* ------------------------------------------------------------------------- */
+
+/* Bind this process to a CUDA device (one process per GPU) and create the
+ * library stream.  Idempotent.  Returns 0, or exits loudly if no device. */
+int vpb_init(int device_ordinal);
+void vpb_shutdown(void);
+int vpb_device_sm_count(void);
+
+void *vpb_dev_alloc(size_t bytes);           /* cudaMalloc, zero-filled */
+void vpb_dev_free(void *d);
+void *vpb_malloc_managed(size_t bytes);      /* cudaMallocManaged, zero-filled, preferred location = device */
+void *vpb_host_alloc_pinned(size_t bytes);
+void vpb_host_free_pinned(void *h);
+void vpb_h2d(void *d, const void *h, size_t bytes);   /* async on the library stream */
+void vpb_d2h(void *h, const void *d, size_t bytes);
+void vpb_d2d(void *dst, const void *src, size_t bytes);
+void vpb_memset(void *d, int byte, size_t bytes);
+void vpb_sync(void);
+void *vpb_stream(void);                      /* cudaStream_t of the library stream */
+
+/* Stream-ordered stopwatch on the library stream (CUDA events). */
+void vpb_timer_start(int slot);
+void vpb_timer_stop(int slot);
+float vpb_timer_ms(int slot);                /* synchronises on the stop event */
+
+/* Count of kernel launches made by this library since the last reset. */
+long vpb_launch_count(int reset);
+
+/* Tuning knobs (kernel variants measured in profiles/): name -> int. */
+void vpb_set_tuning(const char *name, int value);
+int vpb_get_tuning(const char *name);
+
+/* A domain is the immutable device mirror of a grid_t (scalars, bc[27], the
+ * neighbor table compressed to int32 local ids / particle-bc codes). */
+typedef struct vpb_domain vpb_domain_t;
+vpb_domain_t *vpb_domain_create(const vpb_grid_t *g, int rank, int nproc);
+void vpb_domain_destroy(vpb_domain_t *dom);
+long vpb_domain_nvoxel(const vpb_domain_t *dom);
+
+/* advance_p on device arrays.  d_nm (device int, may be NULL) receives the number
+ * of movers written to d_pm; the call does not synchronise.  Movers are emitted
+ * in increasing particle index (boundary_p.c:168-176 relies on that). */
+void vpb_advance_p(vpb_domain_t *dom, vpb_particle_t *d_p, int np, float q_m, vpb_particle_mover_t *d_pm,
+                   int max_nm, vpb_accumulator_t *d_a, const vpb_interpolator_t *d_f, int *d_nm);
+void vpb_center_p(vpb_domain_t *dom, vpb_particle_t *d_p, int np, float q_m, const vpb_interpolator_t *d_f);
+void vpb_uncenter_p(vpb_domain_t *dom, vpb_particle_t *d_p, int np, float q_m, const vpb_interpolator_t *d_f);
+/* d_en: device double[1], receives sum(q*w/(sqrt(1+w)+1)) before the c^2/q_m scale (energy_p.cxx:46) */
+void vpb_energy_p(vpb_domain_t *dom, const vpb_particle_t *d_p, int np, float q_m, const vpb_interpolator_t *d_f, double *d_en);
+void vpb_accumulate_rho_p(vpb_domain_t *dom, vpb_field_t *d_f, const vpb_particle_t *d_p, int np);
+
+/* Stable counting sort by voxel: d_out receives the sorted particles, d_partition
+ * (int[nvoxel+1]) the first particle of each voxel (sort_p.c:54-59,74). */
+void vpb_sort_p(vpb_domain_t *dom, const vpb_particle_t *d_in, vpb_particle_t *d_out, int np, int *d_partition);
+
+void vpb_load_interpolator(vpb_domain_t *dom, vpb_interpolator_t *d_fi, const vpb_field_t *d_f);
+void vpb_clear_accumulators(vpb_domain_t *dom, vpb_accumulator_t *d_a);
+void vpb_unload_accumulator(vpb_domain_t *dom, vpb_field_t *d_f, const vpb_accumulator_t *d_a);
+
+/* Field solve on device arrays; `vacuum` selects vfa_advance_e (vacuum/vfa_advance_e.c:7-9). */
+void vpb_advance_b(vpb_domain_t *dom, vpb_field_t *d_f, float frac);
+void vpb_advance_e(vpb_domain_t *dom, vpb_field_t *d_f, const vpb_material_coefficient_t *d_m, int n_mat, int vacuum);
+void vpb_clear_jf(vpb_domain_t *dom, vpb_field_t *d_f);
+void vpb_clear_rhof(vpb_domain_t *dom, vpb_field_t *d_f);
+void vpb_synchronize_jf(vpb_domain_t *dom, vpb_field_t *d_f);
+void vpb_synchronize_rho(vpb_domain_t *dom, vpb_field_t *d_f);
+/* d_en6: device double[6] = ex,ey,ez,cbx,cby,cbz energies of this rank (energy_f.c:93-179) */
+void vpb_energy_f(vpb_domain_t *dom, const vpb_field_t *d_f, const vpb_material_coefficient_t *d_m, int n_mat, double *d_en6);
+void vpb_compute_div_e_err(vpb_domain_t *dom, vpb_field_t *d_f, const vpb_material_coefficient_t *d_m, int n_mat);
+void vpb_compute_rms_div_e_err(vpb_domain_t *dom, const vpb_field_t *d_f, double *d_out);
+void vpb_clean_div_e(vpb_domain_t *dom, vpb_field_t *d_f, const vpb_material_coefficient_t *d_m, int n_mat);
+void vpb_compute_div_b_err(vpb_domain_t *dom, vpb_field_t *d_f);
+void vpb_compute_rms_div_b_err(vpb_domain_t *dom, const vpb_field_t *d_f, double *d_out);
+void vpb_clean_div_b(vpb_domain_t *dom, vpb_field_t *d_f);
+void vpb_compute_rhob(vpb_domain_t *dom, vpb_field_t *d_f, const vpb_material_coefficient_t *d_m, int n_mat);
+void vpb_compute_curl_b(vpb_domain_t *dom, vpb_field_t *d_f, const vpb_material_coefficient_t *d_m, int n_mat);
+void vpb_synchronize_tang_e_norm_b(vpb_domain_t *dom, vpb_field_t *d_f, double *d_err);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPIC_B200_H */

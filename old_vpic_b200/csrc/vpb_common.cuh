@@ -1,0 +1,110 @@
+// vpb_common.cuh -- shared device/host helpers for libvpic_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include "../../include/vpic_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libvpic_b200 is written for sm_100a (B200) only"
+#endif
+
+// Reference error conventions (src/util/util_base.h:201-219): ERROR prints and
+// exits, WARNING prints and continues.
+#define VPB_ERROR(...)                                                         \
+  do {                                                                         \
+    fprintf(stderr, "Error at %s(%i):\n\t", __FILE__, __LINE__);               \
+    fprintf(stderr, __VA_ARGS__);                                              \
+    fprintf(stderr, "\n");                                                     \
+    fflush(stderr);                                                            \
+    exit(1);                                                                   \
+  } while (0)
+#define VPB_WARNING(...)                                                       \
+  do {                                                                         \
+    fprintf(stderr, "Warning at %s(%i):\n\t", __FILE__, __LINE__);             \
+    fprintf(stderr, __VA_ARGS__);                                              \
+    fprintf(stderr, "\n");                                                     \
+    fflush(stderr);                                                            \
+  } while (0)
+#define VPB_CUDA(call)                                                         \
+  do {                                                                         \
+    cudaError_t _e = (call);                                                   \
+    if (_e != cudaSuccess)                                                     \
+      VPB_ERROR("CUDA failure %s: %s (no CPU fallback exists)", #call, cudaGetErrorString(_e)); \
+  } while (0)
+
+namespace vpb {
+
+// Device mirror of the parts of grid_t the kernels read (grid.h:112-167).
+struct DomainDev {
+  int nx, ny, nz;        // interior cells
+  int sx, sy, sz;        // nx+2, ny+2, nz+2
+  int sxy;               // sx*sy
+  int nv;                // sx*sy*sz voxels including ghosts
+  float dt, cvac, eps0, damp;
+  float dx, dy, dz, rdx, rdy, rdz;
+  int bc[27];
+  int rank, nproc;
+  // neighbor table compressed to int32 (grid.h:145-150): >=0 local voxel index,
+  // -1 reflect_particles, any other negative value = "move_p cannot resolve"
+  // (absorb / custom handler / voxel owned by another rank).
+  const int32_t *nbr;
+  // original 64-bit table, only read by migration (boundary_p.c:304-309)
+  const int64_t *nbr64;
+  int64_t rangel, rangeh;
+};
+
+struct Context {
+  int device = -1;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_start[16] = {}, ev_stop[16] = {};
+  long launches = 0;
+  // scratch owned by the context (grown on demand)
+  void *scratch = nullptr;
+  size_t scratch_bytes = 0;
+  int *h_pinned_i = nullptr;       // 64 pinned ints for small read-backs
+  double *h_pinned_d = nullptr;    // 64 pinned doubles
+};
+
+Context &ctx();                       // exits loudly if no device
+void *scratch(size_t bytes);          // stream-ordered scratch of at least `bytes`
+int tuning(const char *name, int dflt);
+
+inline void count_launch(int n = 1) { ctx().launches += n; }
+
+}  // namespace vpb
+
+struct vpb_domain {
+  vpb::DomainDev d;       // by-value kernel argument
+  int32_t *nbr = nullptr;  // device allocations owned by the domain
+  int64_t *nbr64 = nullptr;
+  const vpb_grid_t *host_grid = nullptr;
+};
+
+// ---------------------------------------------------------------------------
+// Device helpers
+// ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+namespace vpb {
+
+__device__ __forceinline__ float4 ldg4(const void *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ float2 ldg2(const void *p) { return __ldg(reinterpret_cast<const float2 *>(p)); }
+
+// Vector reduction to global memory: one REDG.E.ADD.F32x4 (sm_90+), 16-B aligned.
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add(float *addr, float a) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace vpb
+#endif

@@ -1,0 +1,210 @@
+// vpb_context.cu -- process/device context, memory plumbing and the device
+// mirror of grid_t.  One process drives one GPU (one rank per GPU).
+#include <map>
+#include <string>
+#include <string.h>
+#include <vector>
+#include "vpb_common.cuh"
+
+namespace vpb {
+
+static Context g_ctx;
+static bool g_ready = false;
+static std::map<std::string, int> g_tuning;
+
+Context &ctx() {
+  if (!g_ready) vpb_init(-1);
+  return g_ctx;
+}
+
+void *scratch(size_t bytes) {
+  Context &c = ctx();
+  if (bytes > c.scratch_bytes) {
+    // Stream-ordered: earlier kernels may still be reading the old block.
+    if (c.scratch) VPB_CUDA(cudaFreeAsync(c.scratch, c.stream));
+    size_t want = bytes + (bytes >> 2) + 4096;
+    VPB_CUDA(cudaMallocAsync(&c.scratch, want, c.stream));
+    c.scratch_bytes = want;
+  }
+  return c.scratch;
+}
+
+int tuning(const char *name, int dflt) {
+  auto it = g_tuning.find(name);
+  if (it != g_tuning.end()) return it->second;
+  std::string env = std::string("VPB_") + name;
+  for (auto &ch : env) ch = (ch == '.') ? '_' : (char)toupper(ch);
+  const char *e = getenv(env.c_str());
+  int v = e ? atoi(e) : dflt;
+  g_tuning[name] = v;
+  return v;
+}
+
+}  // namespace vpb
+
+using namespace vpb;
+
+extern "C" {
+
+int vpb_init(int device_ordinal) {
+  if (g_ready) {
+    if (device_ordinal >= 0 && device_ordinal != g_ctx.device)
+      VPB_ERROR("vpb_init(%d) after the process was bound to device %d", device_ordinal, g_ctx.device);
+    return 0;
+  }
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0)
+    VPB_ERROR("no CUDA device is usable (%s); libvpic_b200 has no CPU fallback", cudaGetErrorString(e));
+  if (device_ordinal < 0) {
+    const char *lr = getenv("LOCAL_RANK");
+    device_ordinal = lr ? atoi(lr) % n : 0;
+  }
+  if (device_ordinal >= n) VPB_ERROR("device %d requested, %d present", device_ordinal, n);
+  VPB_CUDA(cudaSetDevice(device_ordinal));
+  cudaDeviceProp prop;
+  VPB_CUDA(cudaGetDeviceProperties(&prop, device_ordinal));
+  if (prop.major < 10)
+    VPB_ERROR("device %d is sm_%d%d; libvpic_b200 is built for sm_100a only", device_ordinal, prop.major, prop.minor);
+  g_ctx.device = device_ordinal;
+  g_ctx.sm_count = prop.multiProcessorCount;
+  VPB_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 16; i++) {
+    VPB_CUDA(cudaEventCreate(&g_ctx.ev_start[i]));
+    VPB_CUDA(cudaEventCreate(&g_ctx.ev_stop[i]));
+  }
+  VPB_CUDA(cudaMallocHost(&g_ctx.h_pinned_i, 64 * sizeof(int)));
+  VPB_CUDA(cudaMallocHost(&g_ctx.h_pinned_d, 64 * sizeof(double)));
+  // keep freed stream-ordered blocks in the pool instead of returning them to the OS
+  cudaMemPool_t pool;
+  VPB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device_ordinal));
+  uint64_t thresh = UINT64_MAX;
+  VPB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+  g_ready = true;
+  return 0;
+}
+
+void vpb_shutdown(void) {
+  if (!g_ready) return;
+  cudaStreamSynchronize(g_ctx.stream);
+  if (g_ctx.scratch) cudaFreeAsync(g_ctx.scratch, g_ctx.stream);
+  cudaStreamSynchronize(g_ctx.stream);
+  for (int i = 0; i < 16; i++) { cudaEventDestroy(g_ctx.ev_start[i]); cudaEventDestroy(g_ctx.ev_stop[i]); }
+  cudaFreeHost(g_ctx.h_pinned_i);
+  cudaFreeHost(g_ctx.h_pinned_d);
+  cudaStreamDestroy(g_ctx.stream);
+  g_ctx = Context();
+  g_ready = false;
+}
+
+int vpb_device_sm_count(void) { return ctx().sm_count; }
+
+void *vpb_dev_alloc(size_t bytes) {
+  void *d = nullptr;
+  if (bytes == 0) bytes = 16;
+  VPB_CUDA(cudaMalloc(&d, bytes));
+  VPB_CUDA(cudaMemsetAsync(d, 0, bytes, ctx().stream));
+  return d;
+}
+void vpb_dev_free(void *d) {
+  if (!d) return;
+  VPB_CUDA(cudaStreamSynchronize(ctx().stream));
+  VPB_CUDA(cudaFree(d));
+}
+void *vpb_malloc_managed(size_t bytes) {
+  void *d = nullptr;
+  if (bytes == 0) bytes = 16;
+  VPB_CUDA(cudaMallocManaged(&d, bytes));
+  VPB_CUDA(cudaMemAdvise(d, bytes, cudaMemAdviseSetPreferredLocation, ctx().device));
+  VPB_CUDA(cudaMemsetAsync(d, 0, bytes, ctx().stream));
+  VPB_CUDA(cudaStreamSynchronize(ctx().stream));
+  return d;
+}
+void *vpb_host_alloc_pinned(size_t bytes) {
+  void *h = nullptr;
+  ctx();
+  VPB_CUDA(cudaMallocHost(&h, bytes ? bytes : 16));
+  return h;
+}
+void vpb_host_free_pinned(void *h) { if (h) VPB_CUDA(cudaFreeHost(h)); }
+void vpb_h2d(void *d, const void *h, size_t bytes) { VPB_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx().stream)); }
+void vpb_d2h(void *h, const void *d, size_t bytes) { VPB_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx().stream)); }
+void vpb_d2d(void *dst, const void *src, size_t bytes) { VPB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx().stream)); }
+void vpb_memset(void *d, int byte, size_t bytes) { VPB_CUDA(cudaMemsetAsync(d, byte, bytes, ctx().stream)); }
+void vpb_sync(void) { VPB_CUDA(cudaStreamSynchronize(ctx().stream)); }
+void *vpb_stream(void) { return (void *)ctx().stream; }
+
+void vpb_timer_start(int s) { VPB_CUDA(cudaEventRecord(ctx().ev_start[s & 15], ctx().stream)); }
+void vpb_timer_stop(int s) { VPB_CUDA(cudaEventRecord(ctx().ev_stop[s & 15], ctx().stream)); }
+float vpb_timer_ms(int s) {
+  float ms = 0;
+  VPB_CUDA(cudaEventSynchronize(ctx().ev_stop[s & 15]));
+  VPB_CUDA(cudaEventElapsedTime(&ms, ctx().ev_start[s & 15], ctx().ev_stop[s & 15]));
+  return ms;
+}
+
+long vpb_launch_count(int reset) {
+  long n = ctx().launches;
+  if (reset) ctx().launches = 0;
+  return n;
+}
+
+void vpb_set_tuning(const char *name, int value) { g_tuning[name] = value; }
+int vpb_get_tuning(const char *name) { return tuning(name, 0); }
+
+// ---------------------------------------------------------------------------
+// Domain: device mirror of grid_t
+// ---------------------------------------------------------------------------
+vpb_domain_t *vpb_domain_create(const vpb_grid_t *g, int rank, int nproc) {
+  if (!g) VPB_ERROR("Bad grid");
+  if (g->nx < 1 || g->ny < 1 || g->nz < 1) VPB_ERROR("Bad local grid size");
+  Context &c = ctx();
+  vpb_domain *dom = new vpb_domain();
+  DomainDev &d = dom->d;
+  d.nx = g->nx; d.ny = g->ny; d.nz = g->nz;
+  d.sx = g->nx + 2; d.sy = g->ny + 2; d.sz = g->nz + 2;
+  d.sxy = d.sx * d.sy;
+  long nv = (long)d.sxy * d.sz;
+  // the reference's own limit (grid.h:132-135): 6*voxel must fit an int
+  if (6 * nv > 0x7fffffffL) VPB_ERROR("local domain of %ld voxels exceeds the 2^31/6 voxel limit of grid_t", nv);
+  d.nv = (int)nv;
+  d.dt = g->dt; d.cvac = g->cvac; d.eps0 = g->eps0; d.damp = g->damp;
+  d.dx = g->dx; d.dy = g->dy; d.dz = g->dz;
+  d.rdx = g->rdx; d.rdy = g->rdy; d.rdz = g->rdz;
+  for (int i = 0; i < 27; i++) d.bc[i] = g->bc[i];
+  d.rank = rank; d.nproc = nproc;
+  d.rangel = g->rangel; d.rangeh = g->rangeh;
+  dom->host_grid = g;
+  if (g->neighbor) {
+    // compress: local ids to int32, everything else to a negative code
+    std::vector<int32_t> nb((size_t)6 * nv);
+    for (size_t k = 0; k < nb.size(); k++) {
+      int64_t n = g->neighbor[k];
+      if (n >= g->rangel && n <= g->rangeh) nb[k] = (int32_t)(n - g->rangel);
+      else if (n == vpb_reflect_particles) nb[k] = -1;
+      else if (n == vpb_absorb_particles) nb[k] = -2;
+      else if (n < 0) nb[k] = (n > -0x40000000L) ? (int32_t)n : -3;  // custom handler code
+      else nb[k] = INT32_MIN;                                        // owned by another rank
+    }
+    VPB_CUDA(cudaMalloc(&dom->nbr, nb.size() * sizeof(int32_t)));
+    VPB_CUDA(cudaMemcpyAsync(dom->nbr, nb.data(), nb.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c.stream));
+    VPB_CUDA(cudaMalloc(&dom->nbr64, nb.size() * sizeof(int64_t)));
+    VPB_CUDA(cudaMemcpyAsync(dom->nbr64, g->neighbor, nb.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c.stream));
+    VPB_CUDA(cudaStreamSynchronize(c.stream));
+  }
+  d.nbr = dom->nbr;
+  d.nbr64 = dom->nbr64;
+  return dom;
+}
+
+void vpb_domain_destroy(vpb_domain_t *dom) {
+  if (!dom) return;
+  VPB_CUDA(cudaStreamSynchronize(ctx().stream));
+  if (dom->nbr) cudaFree(dom->nbr);
+  if (dom->nbr64) cudaFree(dom->nbr64);
+  delete dom;
+}
+
+long vpb_domain_nvoxel(const vpb_domain_t *dom) { return dom ? dom->d.nv : 0; }
+
+}  // extern "C"

@@ -1,0 +1,132 @@
+// vpb_sf.cu -- species<->field coupling kernels (K5, K6, K10):
+//   load_interpolator   src/sf_interface/load_interpolator.cxx:12-144
+//   clear_accumulators  src/sf_interface/clear_accumulators.c:27-49
+//   unload_accumulator  src/sf_interface/unload_accumulator.cxx:12-67
+// Each voxel is one thread; x is the fastest thread index so the 80-byte field_t
+// / interpolator_t records of a warp are contiguous.  All three are pure
+// streaming stencils: expression order follows the reference's scalar code and
+// the file is built with -fmad=false, so results are bit-identical.
+#include "vpb_common.cuh"
+
+namespace vpb {
+
+// One thread per interior voxel (1..nx, 1..ny, 1..nz).  The first 32 bytes of a
+// field_t are {ex,ey,ez,div_e_err | cbx,cby,cbz,div_b_err}: two 128-bit loads.
+__global__ void __launch_bounds__(256) load_interpolator_kernel(vpb_interpolator_t *__restrict__ fi,
+                                                                const vpb_field_t *__restrict__ f, const DomainDev g) {
+  const int x = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = 1 + blockIdx.y;
+  const int z = 1 + blockIdx.z;
+  if (x > g.nx) return;
+  const size_t v = (size_t)x + (size_t)g.sx * ((size_t)y + (size_t)g.sy * z);
+  const float4 *f4 = reinterpret_cast<const float4 *>(f);  // 5 float4 per field_t
+  const size_t s0 = 5 * v, sX = 5, sY = 5 * (size_t)g.sx, sZ = 5 * (size_t)g.sxy;
+  const float4 e0 = __ldg(f4 + s0), b0 = __ldg(f4 + s0 + 1);
+  const float4 ex_ = __ldg(f4 + s0 + sX), bx_ = __ldg(f4 + s0 + sX + 1);
+  const float4 ey_ = __ldg(f4 + s0 + sY), by_ = __ldg(f4 + s0 + sY + 1);
+  const float4 ez_ = __ldg(f4 + s0 + sZ), bz_ = __ldg(f4 + s0 + sZ + 1);
+  const float4 eyz = __ldg(f4 + s0 + sY + sZ);
+  const float4 ezx = __ldg(f4 + s0 + sZ + sX);
+  const float4 exy = __ldg(f4 + s0 + sX + sY);
+  const float fourth = 0.25f, half = 0.5f;
+  float w0, w1, w2, w3;
+  float4 o0, o1, o2, o3;
+  float2 o4;
+  // ex: w0=f0 w1=fy w2=fz w3=fyz
+  w0 = e0.x; w1 = ey_.x; w2 = ez_.x; w3 = eyz.x;
+  o0.x = fourth * ((w3 + w0) + (w1 + w2));
+  o0.y = fourth * ((w3 - w0) + (w1 - w2));
+  o0.z = fourth * ((w3 - w0) - (w1 - w2));
+  o0.w = fourth * ((w3 + w0) - (w1 + w2));
+  // ey: w0=f0 w1=fz w2=fx w3=fzx
+  w0 = e0.y; w1 = ez_.y; w2 = ex_.y; w3 = ezx.y;
+  o1.x = fourth * ((w3 + w0) + (w1 + w2));
+  o1.y = fourth * ((w3 - w0) + (w1 - w2));
+  o1.z = fourth * ((w3 - w0) - (w1 - w2));
+  o1.w = fourth * ((w3 + w0) - (w1 + w2));
+  // ez: w0=f0 w1=fx w2=fy w3=fxy
+  w0 = e0.z; w1 = ex_.z; w2 = ey_.z; w3 = exy.z;
+  o2.x = fourth * ((w3 + w0) + (w1 + w2));
+  o2.y = fourth * ((w3 - w0) + (w1 - w2));
+  o2.z = fourth * ((w3 - w0) - (w1 - w2));
+  o2.w = fourth * ((w3 + w0) - (w1 + w2));
+  w0 = b0.x; w1 = bx_.x;
+  o3.x = half * (w1 + w0); o3.y = half * (w1 - w0);
+  w0 = b0.y; w1 = by_.y;
+  o3.z = half * (w1 + w0); o3.w = half * (w1 - w0);
+  w0 = b0.z; w1 = bz_.z;
+  o4.x = half * (w1 + w0); o4.y = half * (w1 - w0);
+  float4 *o = reinterpret_cast<float4 *>(fi + v);
+  o[0] = o0; o[1] = o1; o[2] = o2; o[3] = o3;
+  *reinterpret_cast<float2 *>(o + 4) = o4;   // _pad[2] is left untouched, like the reference
+}
+
+// One thread per voxel of (1..nx+1, 1..ny+1, 1..nz+1); jf += c*(4 quadrants).
+__global__ void __launch_bounds__(256) unload_accumulator_kernel(vpb_field_t *__restrict__ f, const float4 *__restrict__ a,
+                                                                 const DomainDev g, float cx, float cy, float cz) {
+  const int x = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = 1 + blockIdx.y;
+  const int z = 1 + blockIdx.z;
+  if (x > g.nx + 1) return;
+  const size_t v = (size_t)x + (size_t)g.sx * ((size_t)y + (size_t)g.sy * z);
+  const size_t sX = 1, sY = g.sx, sZ = g.sxy;
+  // accumulator_t = 3 float4: jx[4], jy[4], jz[4]
+  const float4 a0x = __ldg(a + 3 * v), a0y = __ldg(a + 3 * v + 1), a0z = __ldg(a + 3 * v + 2);
+  const float4 axy_ = __ldg(a + 3 * (v - sX) + 1), axz_ = __ldg(a + 3 * (v - sX) + 2);  // ax: jy, jz
+  const float4 ayx_ = __ldg(a + 3 * (v - sY)), ayz_ = __ldg(a + 3 * (v - sY) + 2);      // ay: jx, jz
+  const float4 azx_ = __ldg(a + 3 * (v - sZ)), azy_ = __ldg(a + 3 * (v - sZ) + 1);      // az: jx, jy
+  const float4 ayz_x = __ldg(a + 3 * (v - sY - sZ));         // ayz: jx
+  const float4 azx_y = __ldg(a + 3 * (v - sZ - sX) + 1);     // azx: jy
+  const float4 axy_z = __ldg(a + 3 * (v - sX - sY) + 2);     // axy: jz
+  float4 *jf = reinterpret_cast<float4 *>(f + v) + 3;        // jfx,jfy,jfz,rhof
+  float4 j = *jf;
+  j.x += cx * (a0x.x + ayx_.y + azx_.z + ayz_x.w);
+  j.y += cy * (a0y.x + azy_.y + axy_.z + azx_y.w);
+  j.z += cz * (a0z.x + axz_.y + ayz_.z + axy_z.w);
+  *jf = j;
+}
+
+}  // namespace vpb
+
+using namespace vpb;
+
+extern "C" {
+
+void vpb_load_interpolator(vpb_domain_t *dom, vpb_interpolator_t *d_fi, const vpb_field_t *d_f) {
+  if (!d_fi) VPB_ERROR("Bad interpolator");
+  if (!d_f) VPB_ERROR("Bad field");
+  if (!dom) VPB_ERROR("Bad grid");
+  const DomainDev &g = dom->d;
+  const int tb = g.nx >= 256 ? 256 : (g.nx >= 128 ? 128 : (g.nx >= 64 ? 64 : 32));
+  dim3 grid((g.nx + tb - 1) / tb, g.ny, g.nz);
+  load_interpolator_kernel<<<grid, tb, 0, ctx().stream>>>(d_fi, d_f, g);
+  count_launch();
+  VPB_CUDA(cudaGetLastError());
+}
+
+void vpb_clear_accumulators(vpb_domain_t *dom, vpb_accumulator_t *d_a) {
+  if (!d_a) VPB_ERROR("Bad accumulator");
+  if (!dom) VPB_ERROR("Bad grid");
+  // one replica on the device (no per-pipeline copies): clear_accumulators.c:27-49
+  VPB_CUDA(cudaMemsetAsync(d_a, 0, (size_t)dom->d.nv * sizeof(vpb_accumulator_t), ctx().stream));
+  count_launch();
+}
+
+void vpb_unload_accumulator(vpb_domain_t *dom, vpb_field_t *d_f, const vpb_accumulator_t *d_a) {
+  if (!d_f) VPB_ERROR("Bad field");
+  if (!d_a) VPB_ERROR("Bad accumulator");
+  if (!dom) VPB_ERROR("Bad grid");
+  const DomainDev &g = dom->d;
+  // same expressions and types as unload_accumulator.cxx:29-31 (double until the store)
+  const float cx = (float)(0.25 * g.rdy * g.rdz / g.dt);
+  const float cy = (float)(0.25 * g.rdz * g.rdx / g.dt);
+  const float cz = (float)(0.25 * g.rdx * g.rdy / g.dt);
+  const int n = g.nx + 1;
+  const int tb = n >= 256 ? 256 : (n >= 128 ? 128 : (n >= 64 ? 64 : 32));
+  dim3 grid((n + tb - 1) / tb, g.ny + 1, g.nz + 1);
+  unload_accumulator_kernel<<<grid, tb, 0, ctx().stream>>>(d_f, reinterpret_cast<const float4 *>(d_a), g, cx, cy, cz);
+  count_launch();
+  VPB_CUDA(cudaGetLastError());
+}
+
+}  // extern "C"
