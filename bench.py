@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- particle-advances/s of the PIC hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (config.workload): BASELINE.json configs[3], "thermal plasma weak scaling,
+256^3 cells and 64 ppc per species per GPU", periodic, dt = 0.95 Courant, vth = 0.1 c,
+sort every 20 steps; synthetic particles generated on the device.  One step = one full
+time step of vpic_simulation::advance() (src/vpic/advance.cxx:13-244) for this deck:
+clear_accumulators, sort_p when due, advance_p for both species, clear_jf,
+unload_accumulator, synchronize_jf, advance_b/advance_e/advance_b, load_interpolator.
+`value` = particles advanced per second of that whole step, all state resident in HBM.
+
+JSON keys beyond the base contract: roofline (advance_p kernel, algorithmic bytes
+64+176/ppc per particle), cpu_baseline (the reference's own V4/SSE
+pthreads advance_p, oracle/_ref, on this host's cores, bounded sample), e2e (advance_p
+through the reference-named C ABI entry point with HOST buffers), breakdown.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+VTH = 0.1
+SORT_INTERVAL = 20
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cells", type=int, default=256, help="cells per axis per GPU")
+    ap.add_argument("--ppc", type=int, default=64, help="particles per cell per species")
+    ap.add_argument("--e2e-particles", type=int, default=64 * 1024 * 1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------
+# clocks: sampled with nvidia-smi DURING the timed region
+# ----------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own advance_p on host cores
+# ----------------------------------------------------------------------------
+def cpu_reference_rate(cells, ppc, steps, warmup):
+    """particle advances/s of clear_accumulators + advance_p(e,i) + reduce_accumulators
+    (the reference's p_time bucket, advance.cxx:38-74) with the V4/SSE pthreads library."""
+    from oracle import loader
+    from old_vpic_b200 import abi
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    cores = os.cpu_count() or 1
+    tpp = max(1, min(cores, 16))                      # MAX_PIPELINE = 16 (pipelines.h:6)
+    kind = "reference"
+    if loader.ref_available("sse"):
+        L = loader.ref("sse", tpp=tpp)
+        g = helpers.RefGrid(L, (cells, cells, cells), "periodic")
+        adv = L.advance_p
+        clear = lambda a: L.clear_accumulators(a, g.ref())
+        reduce_ = lambda a: L.reduce_accumulators(a, g.ref())
+        nrep = 1 + L.refh_n_pipeline()
+    else:                                              # reference not built here: scalar port, 1 core
+        kind, tpp = "port", 1
+        O = loader.oracle()
+        g = helpers.host_grid((cells, cells, cells))
+        adv = O.orc_advance_p
+        clear = lambda a: O.orc_clear_accumulators(a, g.ref())
+        reduce_ = lambda a: None
+        nrep = 1
+    rng = np.random.default_rng(7)
+    np_ = cells ** 3 * ppc
+    stride = (g.nv + 1) // 2 * 2
+    acc = abi.aligned_zeros(nrep * stride, abi.accumulator_dtype)
+    fi = abi.aligned_zeros(g.nv, abi.interpolator_dtype)
+    species = []
+    for q, q_m in ((-1.0, -1.0), (1.0, 1.0)):
+        p = abi.aligned_zeros(np_, abi.particle_dtype)
+        p["i"] = np.repeat(helpers.interior_voxels(g), ppc)
+        for k in ("dx", "dy", "dz"):
+            p[k] = rng.uniform(-1, 1, np_).astype(np.float32)
+        for k in ("ux", "uy", "uz"):
+            p[k] = (VTH * rng.standard_normal(np_)).astype(np.float32)
+        p["q"] = q
+        species.append((p, q_m, abi.aligned_zeros(max(2 * np_ // 25, 16), abi.mover_dtype)))
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        clear(abi.ptr(acc))
+        for p, q_m, pm in species:
+            adv(abi.ptr(p), np_, q_m, abi.ptr(pm), len(pm), abi.ptr(acc), abi.ptr(fi), g.ref())
+        reduce_(abi.ptr(acc))
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return {"value": 2 * np_ / sec, "unit": "particle-advances/s", "cores": tpp, "kind": kind,
+            "sample": "thermal %d^3 cells x %d ppc x 2 species (%d particles), %d steps of clear_accumulators+advance_p+"
+                      "reduce_accumulators" % (cells, ppc, 2 * np_, steps), "ms_per_step": 1e3 * sec}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    warm = 1
+    r = cpu_reference_rate(64, args.ppc, steps, warm)
+    line = {"metric": "particle-advances/s (push+deposit)", "value": r["value"], "unit": "particle-advances/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": workload_config(args), "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": "BASELINE configs[3]: thermal e-/p+ plasma weak scaling, %d^3 cells and %d ppc per species per GPU, "
+                        "periodic, dt=0.95 Courant, vth=%.1fc, sort every %d steps" % (args.cells, args.ppc, VTH, SORT_INTERVAL),
+            "cells_per_gpu": [args.cells] * 3, "ppc_per_species": args.ppc, "species": 2,
+            "l2_policy": "inputs (>=100 GB of particles per GPU) are far larger than the 126 MB L2; no flush needed",
+            "decomposition": "1 rank per GPU"}
+
+
+# ----------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from old_vpic_b200 import abi, lib
+    from old_vpic_b200 import grid as helpers
+    from old_vpic_b200.sim import Simulation
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node %d" % args.gpus)
+    L = lib.load()
+    L.vpb_init(local)
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_uint8 * 128)()
+            L.vpb_comm_unique_id(buf)
+            uid = torch.tensor(list(buf), dtype=torch.uint8)
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        ub = (C.c_uint8 * 128)(*uid.cpu().tolist())
+        L.vpb_comm_init(rank, world, ub)
+
+    n = args.cells
+    topo = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
+    g = helpers.make_grid((n * topo[0], n * topo[1], n * topo[2]), "periodic", topo=topo, rank=rank)
+    sim = Simulation(g, n_mat=1, L=L)
+    np_ = n ** 3 * args.ppc
+    max_np = int(np_ * (1.0 if world == 1 else 1.02)) + 1024
+    for name, q_m, q, seed in (("electron", -1.0, -1.0, 7 + rank), ("ion", 1.0, 1.0, 1007 + rank)):
+        sp = sim.define_species(name, q_m, max_np, sort_interval=SORT_INTERVAL)
+        sim.load_thermal(sp, args.ppc, VTH, q, seed, tag0=rank * (1 << 40))
+    L.vpb_sync()
+
+    def barrier():
+        L.vpb_sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        sim.advance()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    L.vpb_prof_enable(1)
+    L.vpb_launch_count(1)
+    L.vpb_timer_start(0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sim.advance()
+    L.vpb_timer_stop(0)
+    ms = L.vpb_timer_ms(0)
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = L.vpb_launch_count(1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+
+    prof = {}
+    names = ["advance_p", "sort_p", "advance_b", "advance_e", "load_interpolator", "unload_accumulator", "other"]
+    for cls, nm in enumerate(names):
+        tot, cnt = C.c_double(0), C.c_int(0)
+        L.vpb_prof_collect(cls, C.byref(tot), C.byref(cnt), 0)
+        prof[nm] = (tot.value, cnt.value)
+    L.vpb_prof_collect(0, None, None, 1)
+    L.vpb_prof_enable(0)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+        return
+    total_particles = 2 * np_ * world
+    value = total_particles * args.steps / (ms_max * 1e-3)
+    peak, peak_src = measured_peak()
+    adv_ms, adv_n = prof["advance_p"]
+    bytes_alg = 64.0 + 176.0 / args.ppc
+    per_launch_particles = np_
+    achieved = bytes_alg * per_launch_particles / (adv_ms / max(adv_n, 1) * 1e-3) / 1e9 if adv_n else None
+    cells = n ** 3
+    line = {
+        "metric": "particle-advances/s (push+deposit)", "value": value, "unit": "particle-advances/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (device-generated thermal load)",
+        "config": workload_config(args), "clocks": clocks, "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": None, "kernel": "advance_p_kernel",
+                     "algorithmic_bytes_per_particle": bytes_alg, "particles_per_launch": per_launch_particles,
+                     "avg_launch_ms": adv_ms / max(adv_n, 1), "peak_source": peak_src,
+                     "layout_imposed_bytes_per_particle": 96.0 + 176.0 / args.ppc,
+                     "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None},
+        "breakdown_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
+        "advance_p_only_particle_advances_per_s": (2 * np_ * args.steps / (adv_ms * 1e-3)) if adv_ms else None,
+        "field_cell_updates_per_s": {"advance_b": (2 * cells * args.steps / (prof["advance_b"][0] * 1e-3)) if prof["advance_b"][0] else None,
+                                     "advance_e": (cells * args.steps / (prof["advance_e"][0] * 1e-3)) if prof["advance_e"][0] else None},
+        "host_wall_ms_per_step": 1e3 * wall / args.steps,
+    }
+    if not args.no_e2e:
+        line["e2e"] = e2e_measure(L, args, abi, helpers)
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = {k: v for k, v in cpu_reference_rate(64, args.ppc, 3, 1).items() if k != "ms_per_step"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+
+
+def e2e_measure(L, args, abi, helpers):
+    """advance_p through the reference-named entry point with pinned HOST arrays: every call copies the
+    particles, interpolator and accumulators host->device, runs the kernel, and copies particles, movers
+    and accumulators back (vpb_dropin.cu).  Bounded to --e2e-particles per species."""
+    n = 128
+    ppc = max(1, min(args.ppc, args.e2e_particles // n ** 3))
+    g = helpers.make_grid((n, n, n))
+    np_ = n ** 3 * ppc
+
+    def pinned(count, dtype):
+        dtype = np.dtype(dtype)
+        addr = L.vpb_host_alloc_pinned(count * dtype.itemsize)
+        a = np.ctypeslib.as_array(C.cast(addr, C.POINTER(C.c_uint8)), shape=(count * dtype.itemsize,)).view(dtype)
+        a.view(np.uint8)[:] = 0
+        return a
+
+    rng = np.random.default_rng(3)
+    p = pinned(np_, abi.particle_dtype)
+    p["i"] = np.repeat(helpers.interior_voxels(g), ppc)
+    for k in ("dx", "dy", "dz"):
+        p[k] = rng.uniform(-1, 1, np_).astype(np.float32)
+    for k in ("ux", "uy", "uz"):
+        p[k] = (VTH * rng.standard_normal(np_)).astype(np.float32)
+    p["q"] = -1.0
+    max_nm = max(2 * np_ // 25, 16)
+    pm = pinned(max_nm, abi.mover_dtype)
+    acc = pinned(g.nv, abi.accumulator_dtype)
+    fi = pinned(g.nv, abi.interpolator_dtype)
+    sz = (C.c_size_t * 2)()
+    for _ in range(2):
+        L.advance_p(abi.ptr(p), np_, -1.0, abi.ptr(pm), max_nm, abi.ptr(acc), abi.ptr(fi), g.ref())
+    L.vpb_staging_bytes(C.byref(sz, 0), C.byref(sz, 8))
+    reps = 3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        L.advance_p(abi.ptr(p), np_, -1.0, abi.ptr(pm), max_nm, abi.ptr(acc), abi.ptr(fi), g.ref())
+    sec = (time.perf_counter() - t0) / reps
+    L.vpb_staging_bytes(C.byref(sz, 0), C.byref(sz, 8))
+    return {"value": np_ / sec, "unit": "particle-advances/s", "h2d_bytes_per_step": int(sz[0] // reps),
+            "d2h_bytes_per_step": int(sz[1] // reps),
+            "sample": "advance_p() C-ABI call, pinned host arrays, %d^3 cells x %d ppc = %d particles per call" % (n, ppc, np_),
+            "ms_per_call": 1e3 * sec}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

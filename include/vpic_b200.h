@@ -95,6 +95,8 @@ void util_free_aligned(void *mem_ref);
 /* (B) Device-resident layer                                                   */
 /* ------------------------------------------------------------------------- */
 
+typedef struct vpb_domain vpb_domain_t;
+
 /* Bind this process to a CUDA device (one process per GPU) and create the
  * library stream.  Idempotent.  Returns 0, or exits loudly if no device. */
 int vpb_init(int device_ordinal);
@@ -118,8 +120,33 @@ void vpb_timer_start(int slot);
 void vpb_timer_stop(int slot);
 float vpb_timer_ms(int slot);                /* synchronises on the stop event */
 
+/* Per-kernel-class timing with CUDA events on the library stream (off by default).
+ * Classes: 0 advance_p, 1 sort_p, 2 advance_b, 3 advance_e, 4 load_interpolator,
+ * 5 unload_accumulator, 6 other. */
+void vpb_prof_enable(int on);
+void vpb_prof_collect(int cls, double *total_ms, int *count, int reset);
+
 /* Count of kernel launches made by this library since the last reset. */
 long vpb_launch_count(int reset);
+
+/* Multi-GPU: one rank per GPU, NCCL over NVLink.  Rank 0 creates the 128-byte id,
+ * the launcher distributes it (torch.distributed broadcast, MPI_Bcast, a file),
+ * every rank calls vpb_comm_init.  Replaces mp_init/new_mp (util/mp/mp.h:14-40). */
+void vpb_comm_unique_id(void *out128);
+void vpb_comm_init(int rank, int nproc, const void *uid128);
+void vpb_comm_finalize(void);
+int vpb_comm_rank(void);
+int vpb_comm_nproc(void);
+void vpb_comm_allsum_d(double *d_buf, int n);   /* mp_allsum_d on device doubles, in place */
+
+/* Bookkeeping the reference keeps implicitly behind its mp handle / structors. */
+void vpb_set_world(int nproc);                                   /* ranks in the job, for bc[] "is a rank" tests */
+void vpb_register_material_coefficients(const vpb_material_coefficient_t *m, int n_mat);
+void vpb_grid_changed(const vpb_grid_t *g);                      /* drop the cached device mirror of g */
+vpb_domain_t *vpb_domain_of_grid(const vpb_grid_t *g);           /* cached mirror used by layer (A) */
+void vpb_staging_release(void);                                  /* free layer (A)'s cached device buffers */
+void vpb_staging_bytes(size_t *h2d, size_t *d2h);                /* bytes staged since the last call */
+vpb_field_advance_methods_t *vpb_field_advance_table(int which); /* 0 std, 1 vacuum, 2 std_v4, 3 vacuum_v4 */
 
 /* Tuning knobs (kernel variants measured in profiles/): name -> int. */
 void vpb_set_tuning(const char *name, int value);
@@ -127,7 +154,6 @@ int vpb_get_tuning(const char *name);
 
 /* A domain is the immutable device mirror of a grid_t (scalars, bc[27], the
  * neighbor table compressed to int32 local ids / particle-bc codes). */
-typedef struct vpb_domain vpb_domain_t;
 vpb_domain_t *vpb_domain_create(const vpb_grid_t *g, int rank, int nproc);
 void vpb_domain_destroy(vpb_domain_t *dom);
 long vpb_domain_nvoxel(const vpb_domain_t *dom);
@@ -142,6 +168,12 @@ void vpb_uncenter_p(vpb_domain_t *dom, vpb_particle_t *d_p, int np, float q_m, c
 /* d_en: device double[1], receives sum(q*w/(sqrt(1+w)+1)) before the c^2/q_m scale (energy_p.cxx:46) */
 void vpb_energy_p(vpb_domain_t *dom, const vpb_particle_t *d_p, int np, float q_m, const vpb_interpolator_t *d_f, double *d_en);
 void vpb_accumulate_rho_p(vpb_domain_t *dom, vpb_field_t *d_f, const vpb_particle_t *d_p, int np);
+
+/* Synthetic load for benchmarks / large property tests: ppc particles in every interior
+ * voxel (born voxel-sorted), uniform in the cell, Maxwellian momenta of width vth. */
+void vpb_load_thermal(vpb_domain_t *dom, vpb_particle_t *d_p, int ppc, float vth, float q,
+                      unsigned long long seed, long tag0);
+void vpb_copy_positions(vpb_particle_t *d_dst, const vpb_particle_t *d_src, long np);
 
 /* Stable counting sort by voxel: d_out receives the sorted particles, d_partition
  * (int[nvoxel+1]) the first particle of each voxel (sort_p.c:54-59,74). */

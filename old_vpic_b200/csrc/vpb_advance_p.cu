@@ -375,10 +375,13 @@ extern "C" void vpb_advance_p(vpb_domain_t *dom, vpb_particle_t *d_p, int np, fl
   const int per_sm = tuning("advance_p.ctas_per_sm", 6);
   int grid = c.sm_count * per_sm;
   if (grid > A.ntiles) grid = A.ntiles;
-  if (tuning("advance_p.deposit", 1) == 0)
-    advance_p_kernel<0><<<grid, kTile, 0, c.stream>>>(A);
-  else
-    advance_p_kernel<1><<<grid, kTile, 0, c.stream>>>(A);
+  {
+    ProfScope prof(0);
+    if (tuning("advance_p.deposit", 1) == 0)
+      advance_p_kernel<0><<<grid, kTile, 0, c.stream>>>(A);
+    else
+      advance_p_kernel<1><<<grid, kTile, 0, c.stream>>>(A);
+  }
   const int tb = 256, tg = (A.ntiles + tb - 1) / tb;
   extract_tile_counts_kernel<<<tg, tb, 0, c.stream>>>(A.tile_info, tile_cnt, A.ntiles);
   exclusive_scan_i32(tile_cnt, tile_off, A.ntiles, scan_tmp, c.stream);

@@ -1,0 +1,127 @@
+// vpb_comm.cu -- NCCL transport (see vpb_comm.cuh).  libnccl is resolved at run
+// time with dlopen so that the library also loads in processes that never go
+// multi-GPU; the unique id is created here and distributed by the launcher
+// (bench.py broadcasts it with torch.distributed, INTEGRATION.md shows the MPI
+// equivalent).
+#include <dlfcn.h>
+#include <string.h>
+#include "vpb_comm.cuh"
+
+namespace vpb {
+
+typedef void *nccl_comm_t;
+struct nccl_uid { char internal[128]; };
+enum { NCCL_INT8 = 0, NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
+
+struct Nccl {
+  void *h = nullptr;
+  int (*GetUniqueId)(nccl_uid *) = nullptr;
+  int (*CommInitRank)(nccl_comm_t *, int, nccl_uid, int) = nullptr;
+  int (*CommDestroy)(nccl_comm_t) = nullptr;
+  int (*Send)(const void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  int (*Recv)(void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+
+static Nccl g_nccl;
+static nccl_comm_t g_comm = nullptr;
+static int g_rank = 0, g_nproc = 1;
+
+static void load_nccl() {
+  if (g_nccl.h) return;
+  const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+  for (int i = 0; names[i] && !g_nccl.h; i++) g_nccl.h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+  if (!g_nccl.h) VPB_ERROR("cannot dlopen libnccl.so.2 (%s); multi-GPU runs need NCCL", dlerror());
+#define SYM(field, name)                                                   \
+  *(void **)(&g_nccl.field) = dlsym(g_nccl.h, name);                       \
+  if (!g_nccl.field) VPB_ERROR("libnccl lacks %s", name)
+  SYM(GetUniqueId, "ncclGetUniqueId");
+  SYM(CommInitRank, "ncclCommInitRank");
+  SYM(CommDestroy, "ncclCommDestroy");
+  SYM(Send, "ncclSend");
+  SYM(Recv, "ncclRecv");
+  SYM(GroupStart, "ncclGroupStart");
+  SYM(GroupEnd, "ncclGroupEnd");
+  SYM(AllReduce, "ncclAllReduce");
+  SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+}
+
+#define VPB_NCCL(call)                                                                      \
+  do {                                                                                      \
+    int _r = (call);                                                                        \
+    if (_r != 0) VPB_ERROR("NCCL failure %s: %s", #call, g_nccl.GetErrorString(_r));        \
+  } while (0)
+
+int comm_rank() { return g_rank; }
+int comm_nproc() { return g_nproc; }
+bool comm_is_multi() { return g_comm != nullptr; }
+
+void comm_exchange(const Xfer *x, int n) {
+  cudaStream_t st = ctx().stream;
+  bool any_remote = false;
+  for (int i = 0; i < n; i++)
+    if ((x[i].send_peer >= 0 && x[i].send_peer != g_rank) || (x[i].recv_peer >= 0 && x[i].recv_peer != g_rank)) any_remote = true;
+  if (any_remote && !g_comm) VPB_ERROR("face shared with another rank but vpb_comm_init was not called");
+  if (any_remote) VPB_NCCL(g_nccl.GroupStart());
+  for (int i = 0; i < n; i++)
+    if (x[i].send_peer >= 0 && x[i].send_peer != g_rank)
+      VPB_NCCL(g_nccl.Send(x[i].send, x[i].send_bytes, NCCL_INT8, x[i].send_peer, g_comm, st));
+  for (int i = 0; i < n; i++)
+    if (x[i].recv_peer >= 0 && x[i].recv_peer != g_rank)
+      VPB_NCCL(g_nccl.Recv(x[i].recv, x[i].recv_bytes, NCCL_INT8, x[i].recv_peer, g_comm, st));
+  if (any_remote) VPB_NCCL(g_nccl.GroupEnd());
+}
+
+void comm_allsum_d(double *d_buf, int n) {
+  if (!g_comm || g_nproc == 1) return;
+  VPB_NCCL(g_nccl.AllReduce(d_buf, d_buf, (size_t)n, NCCL_FLOAT64, NCCL_SUM, g_comm, ctx().stream));
+}
+
+}  // namespace vpb
+
+using namespace vpb;
+
+extern "C" {
+
+// 128-byte NCCL unique id, created on one rank and handed to all the others by the launcher
+void vpb_comm_unique_id(void *out128) {
+  load_nccl();
+  nccl_uid id;
+  VPB_NCCL(g_nccl.GetUniqueId(&id));
+  memcpy(out128, &id, sizeof(id));
+}
+
+void vpb_comm_init(int rank, int nproc, const void *uid128) {
+  if (g_comm) VPB_ERROR("vpb_comm_init called twice");
+  if (nproc < 1 || rank < 0 || rank >= nproc) VPB_ERROR("Bad rank/nproc");
+  ctx();
+  g_rank = rank;
+  g_nproc = nproc;
+  if (nproc == 1) return;
+  load_nccl();
+  nccl_uid id;
+  memcpy(&id, uid128, sizeof(id));
+  VPB_NCCL(g_nccl.CommInitRank(&g_comm, nproc, id, rank));
+}
+
+void vpb_comm_finalize(void) {
+  if (g_comm) {
+    cudaStreamSynchronize(ctx().stream);
+    g_nccl.CommDestroy(g_comm);
+    g_comm = nullptr;
+  }
+  g_rank = 0;
+  g_nproc = 1;
+}
+
+int vpb_comm_rank(void) { return g_rank; }
+int vpb_comm_nproc(void) { return g_nproc; }
+
+// in-place sum over ranks of n device doubles (mp_allsum_d)
+void vpb_comm_allsum_d(double *d_buf, int n) { comm_allsum_d(d_buf, n); }
+
+}  // extern "C"

@@ -1,0 +1,29 @@
+// vpb_comm.cuh -- rank-to-rank transport for the face messages and the particle
+// migration: NCCL send/recv over NVLink, one rank per GPU.  Replaces the
+// reference's MPI layer for this path (src/util/mp/dmp/mp_dmp.c:225-295 and the
+// port helpers of src/grid/grid_comm.c).  A face shared with the rank itself
+// (periodic along an axis with one rank) is a device copy, not a message.
+#pragma once
+#include "vpb_common.cuh"
+
+namespace vpb {
+
+struct Xfer {
+  const void *send; size_t send_bytes; int send_peer;   // send_peer < 0: nothing to send
+  void *recv; size_t recv_bytes; int recv_peer;          // recv_peer < 0: nothing to receive
+};
+
+int comm_rank();
+int comm_nproc();
+bool comm_is_multi();
+
+// Posts every send and receive of `x[0..n)` as one NCCL group on the library
+// stream.  Messages between the same pair of ranks are matched in posting order,
+// so callers list sends by face 0..5 and receives by face 3,4,5,0,1,2 (a message
+// sent through face F arrives through the peer's face (F+3)%6).
+void comm_exchange(const Xfer *x, int n);
+
+// sum over ranks, in place, of n doubles on the device (mp_allsum_d, mp_dmp.c:299-311)
+void comm_allsum_d(double *d_buf, int n);
+
+}  // namespace vpb

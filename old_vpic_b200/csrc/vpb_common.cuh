@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include "../../include/vpic_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -74,6 +75,17 @@ int tuning(const char *name, int dflt);
 
 inline void count_launch(int n = 1) { ctx().launches += n; }
 
+// Optional per-kernel timing (CUDA events on the library stream around selected
+// launches); off unless vpb_prof_enable(1).  Classes: 0 advance_p, 1 sort_p,
+// 2 advance_b, 3 advance_e, 4 load_interpolator, 5 unload_accumulator, 6 other.
+void prof_begin(int cls);
+void prof_end(int cls);
+struct ProfScope {
+  int cls;
+  explicit ProfScope(int c) : cls(c) { prof_begin(c); }
+  ~ProfScope() { prof_end(cls); }
+};
+
 }  // namespace vpb
 
 struct vpb_domain {
@@ -81,6 +93,10 @@ struct vpb_domain {
   int32_t *nbr = nullptr;  // device allocations owned by the domain
   int64_t *nbr64 = nullptr;
   const vpb_grid_t *host_grid = nullptr;
+  // per-face message buffers (vpb_faces.cu), sized for the largest message kind
+  float *face_send[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  float *face_recv[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t face_cap[6] = {0, 0, 0, 0, 0, 0};
 };
 
 // ---------------------------------------------------------------------------

@@ -40,9 +40,52 @@ int tuning(const char *name, int dflt) {
   return v;
 }
 
+struct ProfRec { cudaEvent_t a, b; int cls; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;       // pool of event pairs
+static size_t g_prof_used = 0;
+
+void prof_begin(int cls) {
+  if (!g_prof_on) return;
+  if (g_prof_used == g_prof.size()) {
+    ProfRec r;
+    VPB_CUDA(cudaEventCreate(&r.a));
+    VPB_CUDA(cudaEventCreate(&r.b));
+    g_prof.push_back(r);
+  }
+  g_prof[g_prof_used].cls = cls;
+  VPB_CUDA(cudaEventRecord(g_prof[g_prof_used].a, ctx().stream));
+}
+void prof_end(int cls) {
+  if (!g_prof_on) return;
+  (void)cls;
+  VPB_CUDA(cudaEventRecord(g_prof[g_prof_used].b, ctx().stream));
+  g_prof_used++;
+}
+
 }  // namespace vpb
 
 using namespace vpb;
+
+extern "C" void vpb_prof_enable(int on) { g_prof_on = on != 0; g_prof_used = 0; }
+
+// Sum of the recorded durations of one kernel class since the last collect of
+// ANY class with reset!=0; synchronises the stream.
+extern "C" void vpb_prof_collect(int cls, double *total_ms, int *count, int reset) {
+  VPB_CUDA(cudaStreamSynchronize(ctx().stream));
+  double t = 0;
+  int n = 0;
+  for (size_t i = 0; i < g_prof_used; i++)
+    if (g_prof[i].cls == cls) {
+      float ms = 0;
+      VPB_CUDA(cudaEventElapsedTime(&ms, g_prof[i].a, g_prof[i].b));
+      t += ms;
+      n++;
+    }
+  if (total_ms) *total_ms = t;
+  if (count) *count = n;
+  if (reset) g_prof_used = 0;
+}
 
 extern "C" {
 
@@ -202,6 +245,10 @@ void vpb_domain_destroy(vpb_domain_t *dom) {
   VPB_CUDA(cudaStreamSynchronize(ctx().stream));
   if (dom->nbr) cudaFree(dom->nbr);
   if (dom->nbr64) cudaFree(dom->nbr64);
+  for (int f = 0; f < 6; f++) {
+    if (dom->face_send[f]) cudaFree(dom->face_send[f]);
+    if (dom->face_recv[f]) cudaFree(dom->face_recv[f]);
+  }
   delete dom;
 }
 

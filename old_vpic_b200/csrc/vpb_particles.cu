@@ -1,0 +1,248 @@
+// vpb_particles.cu -- particle-side kernels besides the push:
+//   center_p / uncenter_p   src/species_advance/standard/center_p.cxx:5-70, uncenter_p.cxx:5-72
+//   energy_p                energy_p.cxx:5-48,124-157
+//   accumulate_rho_p        rho_p.c:23-79
+//   sort_p                  sort_p.c:16-77 (stable counting sort + partition[])
+// Arithmetic follows the reference's scalar flavour (built with -fmad=false).
+#include "vpb_common.cuh"
+#include "vpb_scan.cuh"
+
+namespace vpb {
+
+struct Gather {
+  float hax, hay, haz, cbx, cby, cbz;
+};
+
+// advance_p.cxx:73-83: half E kick and B at the particle from the 18 coefficients
+__device__ __forceinline__ Gather gather_fields(const vpb_interpolator_t *__restrict__ f0, int ii, float qdt_2mc, float dx,
+                                                float dy, float dz) {
+  const char *fp = reinterpret_cast<const char *>(f0 + ii);
+  const float4 fe_x = ldg4(fp), fe_y = ldg4(fp + 16), fe_z = ldg4(fp + 32), fb_0 = ldg4(fp + 48);
+  const float2 fb_1 = ldg2(fp + 64);
+  Gather g;
+  g.hax = qdt_2mc * ((fe_x.x + dy * fe_x.y) + dz * (fe_x.z + dy * fe_x.w));
+  g.hay = qdt_2mc * ((fe_y.x + dz * fe_y.y) + dx * (fe_y.z + dz * fe_y.w));
+  g.haz = qdt_2mc * ((fe_z.x + dx * fe_z.y) + dy * (fe_z.z + dx * fe_z.w));
+  g.cbx = fb_0.x + dx * fb_0.y;
+  g.cby = fb_0.z + dy * fb_0.w;
+  g.cbz = fb_1.x + dz * fb_1.y;
+  return g;
+}
+
+// advance_p.cxx:90-102 with rotation constant k (qdt_2mc, or +-qdt_4mc for the half rotations)
+__device__ __forceinline__ void boris_rotate(float &ux, float &uy, float &uz, const Gather &g, float k) {
+  const float one = 1.f, one_third = (float)(1. / 3.), two_fifteenths = (float)(2. / 15.);
+  float v0 = k / sqrtf(one + (ux * ux + (uy * uy + uz * uz)));
+  float v1 = g.cbx * g.cbx + (g.cby * g.cby + g.cbz * g.cbz);
+  float v2 = (v0 * v0) * v1;
+  const float v3 = v0 * (one + v2 * (one_third + v2 * two_fifteenths));
+  float v4 = v3 / (one + v1 * (v3 * v3));
+  v4 += v4;
+  v0 = ux + v3 * (uy * g.cbz - uz * g.cby);
+  v1 = uy + v3 * (uz * g.cbx - ux * g.cbz);
+  v2 = uz + v3 * (ux * g.cby - uy * g.cbx);
+  ux += v4 * (v1 * g.cbz - v2 * g.cby);
+  uy += v4 * (v2 * g.cbx - v0 * g.cbz);
+  uz += v4 * (v0 * g.cby - v1 * g.cbx);
+}
+
+// MODE 0: center_p (half kick then half rotate); MODE 1: uncenter_p (constants
+// negated, half rotate then half kick).
+template <int MODE>
+__global__ void __launch_bounds__(256) center_kernel(vpb_particle_t *__restrict__ p, int np, float qdt_2mc, float qdt_4mc,
+                                                     const vpb_interpolator_t *__restrict__ f0) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x) {
+    float4 *pp = reinterpret_cast<float4 *>(p + k);
+    const float4 r0 = pp[0];
+    float4 r1 = pp[1];
+    const Gather g = gather_fields(f0, __float_as_int(r0.w), qdt_2mc, r0.x, r0.y, r0.z);
+    if (MODE == 0) { r1.x += g.hax; r1.y += g.hay; r1.z += g.haz; }
+    boris_rotate(r1.x, r1.y, r1.z, g, qdt_4mc);
+    if (MODE == 1) { r1.x += g.hax; r1.y += g.hay; r1.z += g.haz; }
+    pp[1] = r1;
+  }
+}
+
+__global__ void __launch_bounds__(256) energy_p_kernel(const vpb_particle_t *__restrict__ p, int np, float qdt_2mc,
+                                                       const vpb_interpolator_t *__restrict__ f0, double *__restrict__ out) {
+  __shared__ double ws[8];
+  double en = 0;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x) {
+    const float4 *pp = reinterpret_cast<const float4 *>(p + k);
+    const float4 r0 = __ldg(pp), r1 = __ldg(pp + 1);
+    const Gather g = gather_fields(f0, __float_as_int(r0.w), qdt_2mc, r0.x, r0.y, r0.z);
+    float v0 = r1.x + g.hax, v1 = r1.y + g.hay, v2 = r1.z + g.haz;   // energy_p.cxx:37-43
+    v0 = v0 * v0 + v1 * v1 + v2 * v2;
+    v0 /= sqrtf(1.f + v0) + 1.f;
+    en += (double)v0 * (double)r1.w;
+  }
+  en = warp_sum(en);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = en;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int j = 0; j < 8; j++) t += ws[j];
+    atomicAdd(out, t);
+  }
+}
+
+// rho_p.c:43-78: trilinear deposit of q/8V onto the 8 nodes of the particle's voxel
+__global__ void __launch_bounds__(256) rho_p_kernel(vpb_field_t *__restrict__ f, const vpb_particle_t *__restrict__ p, int np,
+                                                    float r8V, int sx, int sxy) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x) {
+    const float4 *pp = reinterpret_cast<const float4 *>(p + k);
+    const float4 r0 = __ldg(pp), r1 = __ldg(pp + 1);
+    float t, w0, w1, w2, w3, w4, w5, w6, w7;
+    t = r0.x; w0 = r8V * r1.w; t *= w0; w1 = w0 + t; w0 -= t;
+    t = r0.y; w3 = 1 + t; w2 = w0 * w3; w3 *= w1; t = 1 - t; w0 *= t; w1 *= t;
+    t = r0.z; w7 = 1 + t; w4 = w0 * w7; w5 = w1 * w7; w6 = w2 * w7; w7 *= w3;
+    t = 1 - t; w0 *= t; w1 *= t; w2 *= t; w3 *= t;
+    float *rho = &f[__float_as_int(r0.w)].rhof;
+    const size_t X = 20, Y = 20 * (size_t)sx, Z = 20 * (size_t)sxy;   // field_t = 20 floats
+    red_add(rho, w0); red_add(rho + X, w1); red_add(rho + Y, w2); red_add(rho + X + Y, w3);
+    red_add(rho + Z, w4); red_add(rho + Z + X, w5); red_add(rho + Z + Y, w6); red_add(rho + Z + Y + X, w7);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// sort_p: stable counting sort.  (1) histogram of voxel keys, (2) exclusive scan
+// = partition[], (3) claim a slot per particle with an atomic cursor (order
+// within a voxel arbitrary) recording only the SOURCE INDEX, (4) one warp per
+// voxel re-ranks its segment by source index (which makes the permutation equal
+// to the reference's stable scatter, sort_p.c:74), (5) gather the 48-byte
+// records through the permutation with 128-bit accesses.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sort_hist_kernel(const vpb_particle_t *__restrict__ p, int np, int *__restrict__ count) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x)
+    atomicAdd(count + __ldg(&p[k].i), 1);
+}
+
+__global__ void __launch_bounds__(256) sort_claim_kernel(const vpb_particle_t *__restrict__ p, int np, int *__restrict__ cursor,
+                                                         int *__restrict__ perm) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x)
+    perm[atomicAdd(cursor + __ldg(&p[k].i), 1)] = k;
+}
+
+__global__ void __launch_bounds__(256) sort_rank_kernel(const int *__restrict__ partition, int nv, const int *__restrict__ perm,
+                                                        int *__restrict__ perm_sorted) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int v = blockIdx.x * wpb + (threadIdx.x >> 5); v < nv; v += gridDim.x * wpb) {
+    const int b = partition[v], n = partition[v + 1] - b;
+    if (n <= 0) continue;
+    if (n <= 32) {
+      const int mine = lane < n ? perm[b + lane] : 0x7fffffff;
+      int r = 0;
+      for (int j = 0; j < n; j++) r += (__shfl_sync(0xffffffffu, mine, j) < mine);
+      if (lane < n) perm_sorted[b + r] = mine;
+    } else {
+      for (int i = lane; i < n; i += 32) {
+        const int mine = perm[b + i];
+        int r = 0;
+        for (int j = 0; j < n; j++) r += (perm[b + j] < mine);
+        perm_sorted[b + r] = mine;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) sort_gather_kernel(const vpb_particle_t *__restrict__ in, vpb_particle_t *__restrict__ out,
+                                                          int np, const int *__restrict__ perm) {
+  // three 16-byte pieces per particle; consecutive threads take consecutive pieces of the output
+  const long n3 = 3L * np;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < n3; t += (long)gridDim.x * blockDim.x) {
+    const int k = (int)(t / 3), piece = (int)(t - 3L * k);
+    reinterpret_cast<float4 *>(out)[t] = __ldg(reinterpret_cast<const float4 *>(in + perm[k]) + piece);
+  }
+}
+
+}  // namespace vpb
+
+using namespace vpb;
+
+static int grid_for(long n, int tb) {
+  long b = (n + tb - 1) / tb;
+  const long cap = (long)ctx().sm_count * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+extern "C" {
+
+void vpb_center_p(vpb_domain_t *dom, vpb_particle_t *d_p, int np, float q_m, const vpb_interpolator_t *d_f) {
+  if (np < 0) VPB_ERROR("Bad number of particles");
+  if (!d_f) VPB_ERROR("Bad interpolator");
+  if (!dom) VPB_ERROR("Bad grid");
+  if (np == 0) return;
+  const float qdt_2mc = (float)(0.5 * q_m * dom->d.dt / dom->d.cvac);   // center_p.cxx:171
+  const float qdt_4mc = (float)(0.5 * qdt_2mc);                         // center_p.cxx:15
+  center_kernel<0><<<grid_for(np, 256), 256, 0, ctx().stream>>>(d_p, np, qdt_2mc, qdt_4mc, d_f);
+  count_launch();
+  VPB_CUDA(cudaGetLastError());
+}
+
+void vpb_uncenter_p(vpb_domain_t *dom, vpb_particle_t *d_p, int np, float q_m, const vpb_interpolator_t *d_f) {
+  if (np < 0) VPB_ERROR("Bad number of particles");
+  if (!d_f) VPB_ERROR("Bad interpolator");
+  if (!dom) VPB_ERROR("Bad grid");
+  if (np == 0) return;
+  const float fwd = (float)(0.5 * q_m * dom->d.dt / dom->d.cvac);       // uncenter_p.cxx:171
+  const float qdt_2mc = -fwd;                                           // uncenter_p.cxx:14
+  const float qdt_4mc = (float)(-0.5 * fwd);                            // uncenter_p.cxx:15
+  center_kernel<1><<<grid_for(np, 256), 256, 0, ctx().stream>>>(d_p, np, qdt_2mc, qdt_4mc, d_f);
+  count_launch();
+  VPB_CUDA(cudaGetLastError());
+}
+
+void vpb_energy_p(vpb_domain_t *dom, const vpb_particle_t *d_p, int np, float q_m, const vpb_interpolator_t *d_f, double *d_en) {
+  if (np < 0) VPB_ERROR("Bad number of particles");
+  if (!d_f) VPB_ERROR("Bad interpolator");
+  if (!dom) VPB_ERROR("Bad grid");
+  VPB_CUDA(cudaMemsetAsync(d_en, 0, sizeof(double), ctx().stream));
+  if (np == 0) return;
+  const float qdt_2mc = (float)(0.5 * q_m * dom->d.dt / dom->d.cvac);
+  energy_p_kernel<<<grid_for(np, 256), 256, 0, ctx().stream>>>(d_p, np, qdt_2mc, d_f, d_en);
+  count_launch();
+  VPB_CUDA(cudaGetLastError());
+}
+
+void vpb_accumulate_rho_p(vpb_domain_t *dom, vpb_field_t *d_f, const vpb_particle_t *d_p, int np) {
+  if (!d_f) VPB_ERROR("Bad field");
+  if (!d_p) VPB_ERROR("Bad particle array");
+  if (np < 0) VPB_ERROR("Bad number of particles");
+  if (!dom) VPB_ERROR("Bad grid");
+  if (np == 0) return;
+  const DomainDev &g = dom->d;
+  const float r8V = (float)(0.125 * g.rdx * g.rdy * g.rdz);             // rho_p.c:37
+  rho_p_kernel<<<grid_for(np, 256), 256, 0, ctx().stream>>>(d_f, d_p, np, r8V, g.sx, g.sxy);
+  count_launch();
+  VPB_CUDA(cudaGetLastError());
+}
+
+void vpb_sort_p(vpb_domain_t *dom, const vpb_particle_t *d_in, vpb_particle_t *d_out, int np, int *d_partition) {
+  if (!dom) VPB_ERROR("Bad grid");
+  if (!d_partition) VPB_ERROR("Bad partition");
+  if (np < 0) VPB_ERROR("Bad number of particles");
+  Context &c = ctx();
+  ProfScope prof(1);
+  const int nv = dom->d.nv, nv1 = nv + 1;
+  // scratch: cursor[nv1] | perm[np] | perm_sorted[np] | scan scratch
+  auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t off_perm = al((size_t)nv1 * 4), off_perm2 = off_perm + al((size_t)np * 4 + 4),
+               off_scan = off_perm2 + al((size_t)np * 4 + 4);
+  char *s = (char *)scratch(off_scan + scan_scratch_bytes(nv1));
+  int *cursor = (int *)s, *perm = (int *)(s + off_perm), *perm2 = (int *)(s + off_perm2);
+  VPB_CUDA(cudaMemsetAsync(cursor, 0, (size_t)nv1 * 4, c.stream));
+  if (np > 0) sort_hist_kernel<<<grid_for(np, 256), 256, 0, c.stream>>>(d_in, np, cursor);
+  exclusive_scan_i32(cursor, d_partition, nv1, s + off_scan, c.stream);   // partition[nv] = np (sort_p.c:54-59)
+  count_launch(1 + scan_launches(nv1));
+  if (np == 0) return;
+  if (!d_in || !d_out) VPB_ERROR("Bad particle array");
+  VPB_CUDA(cudaMemcpyAsync(cursor, d_partition, (size_t)nv1 * 4, cudaMemcpyDeviceToDevice, c.stream));
+  sort_claim_kernel<<<grid_for(np, 256), 256, 0, c.stream>>>(d_in, np, cursor, perm);
+  sort_rank_kernel<<<grid_for((long)nv * 32, 256), 256, 0, c.stream>>>(d_partition, nv, perm, perm2);
+  sort_gather_kernel<<<grid_for(3L * np, 256), 256, 0, c.stream>>>(d_in, d_out, np, perm2);
+  count_launch(4);
+  VPB_CUDA(cudaGetLastError());
+}
+
+}  // extern "C"

@@ -99,6 +99,7 @@ void vpb_load_interpolator(vpb_domain_t *dom, vpb_interpolator_t *d_fi, const vp
   const DomainDev &g = dom->d;
   const int tb = g.nx >= 256 ? 256 : (g.nx >= 128 ? 128 : (g.nx >= 64 ? 64 : 32));
   dim3 grid((g.nx + tb - 1) / tb, g.ny, g.nz);
+  ProfScope prof(4);
   load_interpolator_kernel<<<grid, tb, 0, ctx().stream>>>(d_fi, d_f, g);
   count_launch();
   VPB_CUDA(cudaGetLastError());
@@ -124,6 +125,7 @@ void vpb_unload_accumulator(vpb_domain_t *dom, vpb_field_t *d_f, const vpb_accum
   const int n = g.nx + 1;
   const int tb = n >= 256 ? 256 : (n >= 128 ? 128 : (n >= 64 ? 64 : 32));
   dim3 grid((n + tb - 1) / tb, g.ny + 1, g.nz + 1);
+  ProfScope prof(5);
   unload_accumulator_kernel<<<grid, tb, 0, ctx().stream>>>(d_f, reinterpret_cast<const float4 *>(d_a), g, cx, cy, cz);
   count_launch();
   VPB_CUDA(cudaGetLastError());

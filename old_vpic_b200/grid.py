@@ -212,3 +212,37 @@ def partition_metal_box(g, gx0, gy0, gz0, gx1, gy1, gz1, gnx, gny, gnz, gpx, gpy
     for b in _outer_faces(g, (gnx, gny, gnz), (gpx, gpy, gpz)):
         g.set_fbc(b, abi.PEC_FIELDS)
         g.set_pbc(b, abi.REFLECT_PARTICLES)
+
+
+def courant_dt(dx, dy, dz, cvac=1.0, frac=0.95):
+    """dt = frac * courant_length / c, the decks' usual choice (vpic.hxx courant_length helper)."""
+    inv = sum(1.0 / (d * d) for d in (dx, dy, dz) if d > 0)
+    return frac / (cvac * np.sqrt(inv))
+
+
+def make_grid(n, kind="periodic", topo=(1, 1, 1), rank=0, L=None, dt=None, damp=0.0, pbc=abi.ABSORB_PARTICLES):
+    """One rank's grid_t for a global box of n=(gnx,gny,gnz) cells (cell size 1 unless L is given),
+    cvac=eps0=1 and dt=0.95 Courant unless given."""
+    nx, ny, nz = n
+    L = L or (float(nx), float(ny), float(nz))
+    g = Grid(rank=rank, nproc=topo[0] * topo[1] * topo[2])
+    args = (g, 0.0, 0.0, 0.0, L[0], L[1], L[2], nx, ny, nz, topo[0], topo[1], topo[2])
+    if kind == "periodic":
+        partition_periodic_box(*args)
+    elif kind == "metal":
+        partition_metal_box(*args)
+    elif kind == "absorbing":
+        partition_absorbing_box(*args, pbc)
+    else:
+        raise ValueError(kind)
+    s = g.struct
+    dims = [d for d, m in ((s.dx, nx), (s.dy, ny), (s.dz, nz)) if m > 1] or [s.dx]
+    g.set_units(dt if dt is not None else courant_dt(*(dims + [0, 0])[:3]), 1.0, 1.0, damp)
+    return g
+
+
+def interior_voxels(g):
+    """Local voxel index of every interior cell, x fastest."""
+    nx, ny, nz = g.n
+    z, y, x = np.meshgrid(np.arange(1, nz + 1), np.arange(1, ny + 1), np.arange(1, nx + 1), indexing="ij")
+    return (x + (nx + 2) * (y + (ny + 2) * z)).reshape(-1).astype(np.int32)

@@ -1,0 +1,175 @@
+"""Device-resident time-step driver: the call order of vpic_simulation::advance()
+(src/vpic/advance.cxx:13-244) issued against layer (B) of libvpic_b200.so, with
+every array resident in HBM between steps.  Host Python only sequences the calls
+(about 15 per step); nothing in the loop touches particle or field data on the
+host.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi, lib
+
+
+class DevArray:
+    """A typed device allocation owned by the library (cudaMalloc)."""
+
+    def __init__(self, L, n, dtype):
+        self.L, self.n, self.dtype = L, int(n), np.dtype(dtype)
+        self.nbytes = self.n * self.dtype.itemsize
+        self.ptr = L.vpb_dev_alloc(max(self.nbytes, 16))
+
+    def upload(self, host):
+        host = np.ascontiguousarray(host, dtype=self.dtype)
+        assert host.nbytes <= self.nbytes
+        self.L.vpb_h2d(self.ptr, host.ctypes.data, host.nbytes)
+        self.L.vpb_sync()
+
+    def download(self, n=None):
+        n = self.n if n is None else int(n)
+        out = abi.aligned_empty(n, self.dtype)
+        if n:
+            self.L.vpb_d2h(out.ctypes.data, self.ptr, n * self.dtype.itemsize)
+        self.L.vpb_sync()
+        return out
+
+    def free(self):
+        if self.ptr:
+            self.L.vpb_dev_free(self.ptr)
+            self.ptr = None
+
+
+class Species:
+    def __init__(self, L, name, q_m, max_np, max_nm, sort_interval, sp_id):
+        self.name, self.q_m, self.id = name, float(q_m), sp_id
+        self.max_np, self.max_nm, self.sort_interval = int(max_np), int(max_nm), int(sort_interval)
+        self.np = 0
+        self.p = DevArray(L, max_np, abi.particle_dtype)
+        self.pm = DevArray(L, max_nm, abi.mover_dtype)
+        self.nm = DevArray(L, 4, np.int32)
+
+
+class Simulation:
+    """One rank's share of a PIC run on one GPU."""
+
+    def __init__(self, grid, n_mat=1, vacuum=False, L=None):
+        self.L = L or lib.load()
+        self.L.vpb_init(-1)
+        self.grid = grid
+        self.dom = self.L.vpb_domain_create(grid.ref(), grid.rank, grid.nproc)
+        self.nv = grid.nv
+        self.vacuum = vacuum
+        self.f = DevArray(self.L, self.nv, abi.field_dtype)
+        self.fi = DevArray(self.L, self.nv, abi.interpolator_dtype)
+        self.a = DevArray(self.L, self.nv + 1, abi.accumulator_dtype)
+        self.m_host = None
+        self.m = None
+        self.n_mat = n_mat
+        if not vacuum:
+            from_vac = abi.aligned_zeros(n_mat, abi.material_coefficient_dtype)
+            for k in ("decayx", "drivex", "decayy", "drivey", "decayz", "drivez", "rmux", "rmuy", "rmuz", "nonconductive",
+                      "epsx", "epsy", "epsz"):
+                from_vac[k] = 1.0
+            self.m = DevArray(self.L, n_mat, abi.material_coefficient_dtype)
+            self.m.upload(from_vac)
+        self.species = []
+        self.sort_tmp = None
+        self.partition = DevArray(self.L, self.nv + 1, np.int32)
+        self.step = 0
+        self.clean_div_e_interval = 0
+        self.clean_div_b_interval = 0
+        self.scalars = DevArray(self.L, 16, np.float64)
+
+    @property
+    def m_ptr(self):
+        return None if self.m is None else self.m.ptr
+
+    def define_species(self, name, q_m, max_np, max_nm=None, sort_interval=20):
+        max_nm = max_nm if max_nm is not None else max(2 * max_np // 25, 16)   # vpic.hxx:416-420
+        sp = Species(self.L, name, q_m, max_np, max_nm, sort_interval, len(self.species))
+        self.species.append(sp)
+        return sp
+
+    def load_thermal(self, sp, ppc, vth, q, seed, tag0=0):
+        nx, ny, nz = self.grid.n
+        sp.np = ppc * nx * ny * nz
+        assert sp.np <= sp.max_np
+        self.L.vpb_load_thermal(self.dom, sp.p.ptr, ppc, vth, q, seed, tag0)
+
+    # -- pieces of advance.cxx ------------------------------------------------
+    def sort(self, sp):
+        L = self.L
+        if self.sort_tmp is None or self.sort_tmp.n < sp.max_np:
+            if self.sort_tmp is not None:
+                self.sort_tmp.free()
+            self.sort_tmp = DevArray(L, sp.max_np, abi.particle_dtype)
+        L.vpb_sort_p(self.dom, sp.p.ptr, self.sort_tmp.ptr, sp.np, self.partition.ptr)
+        sp.p, self.sort_tmp = self.sort_tmp, sp.p     # out-of-place: swap (sort_p.c:76-77)
+
+    def advance_fields(self):
+        L, dom, f = self.L, self.dom, self.f.ptr
+        L.vpb_advance_b(dom, f, 0.5)                                    # advance.cxx:129
+        L.vpb_advance_e(dom, f, self.m_ptr, self.n_mat, int(self.vacuum))   # :133
+        L.vpb_advance_b(dom, f, 0.5)                                    # :147
+
+    def advance(self):
+        L, dom = self.L, self.dom
+        if self.species:
+            L.vpb_clear_accumulators(dom, self.a.ptr)                   # advance.cxx:38
+        for sp in self.species:                                         # :43-51
+            if sp.sort_interval > 0 and self.step % sp.sort_interval == 0:
+                self.sort(sp)
+        for sp in self.species:                                         # :70-73
+            L.vpb_advance_p(dom, sp.p.ptr, sp.np, sp.q_m, sp.pm.ptr, sp.max_nm, self.a.ptr, self.fi.ptr, sp.nm.ptr)
+        # reduce_accumulators (:74) is a no-op with one replica; boundary_p (:94-96): see Simulation.migrate
+        self.migrate()
+        L.vpb_clear_jf(dom, self.f.ptr)                                 # :109
+        if self.species:
+            L.vpb_unload_accumulator(dom, self.f.ptr, self.a.ptr)       # :110
+        L.vpb_synchronize_jf(dom, self.f.ptr)                           # :112
+        self.advance_fields()
+        if self.clean_div_e_interval and self.step % self.clean_div_e_interval == 0:
+            self.clean_div_e()
+        if self.clean_div_b_interval and self.step % self.clean_div_b_interval == 0:
+            self.clean_div_b()
+        if self.species:
+            L.vpb_load_interpolator(dom, self.fi.ptr, self.f.ptr)       # :214
+        self.step += 1
+
+    def migrate(self):
+        """boundary_p (advance.cxx:94-96).  Filled in by the multi-GPU driver; on a single periodic or
+        reflecting rank advance_p leaves no movers."""
+        return
+
+    def clean_div_e(self):                                               # advance.cxx:151-173
+        L, dom, f = self.L, self.dom, self.f.ptr
+        L.vpb_clear_rhof(dom, f)
+        for sp in self.species:
+            L.vpb_accumulate_rho_p(dom, f, sp.p.ptr, sp.np)
+        L.vpb_synchronize_rho(dom, f)
+        for _ in range(2):
+            L.vpb_compute_div_e_err(dom, f, self.m_ptr, self.n_mat)
+            L.vpb_clean_div_e(dom, f, self.m_ptr, self.n_mat)
+
+    def clean_div_b(self):                                               # advance.cxx:177-195
+        L, dom, f = self.L, self.dom, self.f.ptr
+        for _ in range(2):
+            L.vpb_compute_div_b_err(dom, f)
+            L.vpb_clean_div_b(dom, f)
+
+    def energies(self):
+        """dump_energies (src/vpic/dump.cxx:37-78): 6 field energies then one kinetic energy per species."""
+        L, dom = self.L, self.dom
+        s = self.scalars
+        L.vpb_energy_f(dom, self.f.ptr, self.m_ptr, self.n_mat, s.ptr)
+        L.vpb_comm_allsum_d(s.ptr, 6)
+        g = self.grid.struct
+        out = list(s.download(6) * (0.5 * g.eps0 * g.dx * g.dy * g.dz))
+        for sp in self.species:
+            L.vpb_energy_p(dom, sp.p.ptr, sp.np, sp.q_m, self.fi.ptr, s.ptr)
+            L.vpb_comm_allsum_d(s.ptr, 1)
+            out.append(float(s.download(1)[0]) * g.cvac * g.cvac / sp.q_m)
+        return out
+
+    def mover_counts(self):
+        return [int(sp.nm.download(1)[0]) for sp in self.species]

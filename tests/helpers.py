@@ -18,30 +18,9 @@ from oracle import loader  # noqa: E402
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
-def courant_dt(dx, dy, dz, cvac=1.0, frac=0.95):
-    """dt = 0.95 * courant_length / c, as the decks do (deck_wrapper / vpic.hxx courant_length)."""
-    inv = sum(1.0 / (d * d) for d in (dx, dy, dz) if d > 0)
-    return frac / (cvac * np.sqrt(inv))
-
-
-def host_grid(n, kind="periodic", topo=(1, 1, 1), rank=0, L=None, dt=None, damp=0.0, pbc=abi.ABSORB_PARTICLES):
-    """grid_t built by the host mirror (no reference needed)."""
-    nx, ny, nz = n
-    L = L or (float(nx), float(ny), float(nz))
-    g = hostgrid.Grid(rank=rank, nproc=topo[0] * topo[1] * topo[2])
-    args = (g, 0.0, 0.0, 0.0, L[0], L[1], L[2], nx, ny, nz, topo[0], topo[1], topo[2])
-    if kind == "periodic":
-        hostgrid.partition_periodic_box(*args)
-    elif kind == "metal":
-        hostgrid.partition_metal_box(*args)
-    elif kind == "absorbing":
-        hostgrid.partition_absorbing_box(*args, pbc)
-    else:
-        raise ValueError(kind)
-    s = g.struct
-    dims = [d for d, m in ((s.dx, nx), (s.dy, ny), (s.dz, nz)) if m > 1] or [s.dx]
-    g.set_units(dt if dt is not None else courant_dt(*(dims + [0, 0])[:3]), 1.0, 1.0, damp)
-    return g
+courant_dt = hostgrid.courant_dt
+host_grid = hostgrid.make_grid
+interior_voxels = hostgrid.interior_voxels
 
 
 class RefGrid:
@@ -91,12 +70,6 @@ class RefGrid:
 def gptr(g):
     """void* of a grid_t for ctypes calls, whichever kind of grid object it is."""
     return g.ref()
-
-
-def interior_voxels(g):
-    nx, ny, nz = g.n
-    z, y, x = np.meshgrid(np.arange(1, nz + 1), np.arange(1, ny + 1), np.arange(1, nx + 1), indexing="ij")
-    return (x + (nx + 2) * (y + (ny + 2) * z)).reshape(-1).astype(np.int32)
 
 
 def random_particles(rng, g, np_, vth=0.1, sort=True, q=-1.0, edge_frac=0.0):

@@ -1,0 +1,178 @@
+"""GPU parity: particle-side kernels through the reference-named C ABI entry points
+(libvpic_b200.so) against the CPU oracle on identical seeded inputs.
+
+Bar (north_star): every integer -- voxel indices, mover counts and indices -- and,
+because the kernels follow the reference's scalar arithmetic without FMA, every
+particle float is BIT-EXACT.  Accumulators are float sums whose ORDER differs
+(atomics): tolerance 2e-5 of the largest accumulator entry, the same class of
+difference the reference shows between -tpp settings.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import (abi, assert_bits_equal, host_grid, max_rel, random_fields, random_interpolator,
+                     random_particles)
+from old_vpic_b200.abi import ptr
+
+pytestmark = pytest.mark.gpu
+
+ACC_TOL = 2e-5
+
+
+def acc_floats(a):
+    return np.ascontiguousarray(a).view(np.float32).reshape(-1, 12)
+
+
+@pytest.mark.parametrize("deposit", [1, 0])
+@pytest.mark.parametrize("kind", ["periodic", "metal", "absorbing"])
+@pytest.mark.parametrize("n,np_,sort", [((6, 5, 4), 5000, True), ((8, 1, 6), 7001, False), ((1, 1, 16), 300, True),
+                                        ((16, 16, 16), 16 * 16 * 16 * 40, True)])
+def test_advance_p(vpb, orc, deposit, kind, n, np_, sort):
+    g = host_grid(n, kind)
+    rng = np.random.default_rng(21)
+    p = random_particles(rng, g, np_, vth=0.6, sort=sort, edge_frac=0.02)
+    fi = random_interpolator(rng, g, amp=0.3)
+    q_m, max_nm = -1.0, np_
+    vpb.vpb_set_tuning(b"advance_p.deposit", deposit)
+    p_o, p_g = p.copy(), p.copy()
+    a_o = abi.aligned_zeros(g.nv, abi.accumulator_dtype)
+    a_g = a_o.copy()
+    pm_o = abi.aligned_zeros(max_nm, abi.mover_dtype)
+    pm_g = pm_o.copy()
+    nm_o = orc.orc_advance_p(ptr(p_o), np_, q_m, ptr(pm_o), max_nm, ptr(a_o), ptr(fi), g.ref())
+    nm_g = vpb.advance_p(ptr(p_g), np_, q_m, ptr(pm_g), max_nm, ptr(a_g), ptr(fi), g.ref())
+    assert nm_g == nm_o
+    if kind == "absorbing":
+        assert nm_o > 0
+    assert_bits_equal(p_g, p_o, "particles")
+    assert_bits_equal(pm_g[:nm_g], pm_o[:nm_o], "movers (ordered by particle index)")
+    assert (p_o["i"] != p["i"]).sum() > 0
+    assert max_rel(acc_floats(a_g), acc_floats(a_o)) < ACC_TOL
+    # charge conservation property, independent of the oracle: every accumulator entry that the oracle
+    # left untouched must be untouched on the GPU too
+    untouched = ~np.any(acc_floats(a_o) != 0, axis=1)
+    assert not np.any(acc_floats(a_g)[untouched] != 0)
+
+
+def test_advance_p_empty_and_tail(vpb, orc):
+    g = host_grid((4, 4, 4))
+    rng = np.random.default_rng(1)
+    fi = random_interpolator(rng, g)
+    a = abi.aligned_zeros(g.nv, abi.accumulator_dtype)
+    pm = abi.aligned_zeros(8, abi.mover_dtype)
+    p = random_particles(rng, g, 1)
+    assert vpb.advance_p(ptr(p), 0, -1.0, ptr(pm), 8, ptr(a), ptr(fi), g.ref()) == 0
+    assert not np.any(acc_floats(a))
+    for np_ in (1, 31, 255, 256, 257):
+        p = random_particles(rng, g, np_, vth=0.3)
+        p_o, p_g = p.copy(), p.copy()
+        a_o, a_g = a.copy(), a.copy()
+        orc.orc_advance_p(ptr(p_o), np_, 1.0, ptr(pm), 8, ptr(a_o), ptr(fi), g.ref())
+        vpb.advance_p(ptr(p_g), np_, 1.0, ptr(pm), 8, ptr(a_g), ptr(fi), g.ref())
+        assert_bits_equal(p_g, p_o, "np=%d" % np_)
+        assert max_rel(acc_floats(a_g), acc_floats(a_o)) < ACC_TOL
+
+
+def test_advance_p_managed_memory_in_place(vpb, orc):
+    """Arrays from vpb_malloc_managed are used in place (the util_malloc_aligned integration mode)."""
+    g = host_grid((6, 6, 6))
+    rng = np.random.default_rng(2)
+    np_ = 4000
+    p = random_particles(rng, g, np_, vth=0.5)
+    fi = random_interpolator(rng, g, amp=0.2)
+
+    def managed(arr):
+        addr = vpb.vpb_malloc_managed(arr.nbytes)
+        view = np.ctypeslib.as_array(C.cast(addr, C.POINTER(C.c_uint8)), shape=(arr.nbytes,)).view(arr.dtype)
+        view[:] = arr
+        return view
+
+    p_m, fi_m = managed(p), managed(fi)
+    a_m = managed(abi.aligned_zeros(g.nv, abi.accumulator_dtype))
+    pm_m = managed(abi.aligned_zeros(np_, abi.mover_dtype))
+    sz = (C.c_size_t * 2)()
+    vpb.vpb_staging_bytes(C.byref(sz, 0), C.byref(sz, 8))
+    nm = vpb.advance_p(ptr(p_m), np_, -1.0, ptr(pm_m), np_, ptr(a_m), ptr(fi_m), g.ref())
+    vpb.vpb_staging_bytes(C.byref(sz, 0), C.byref(sz, 8))
+    assert sz[0] == 0 and sz[1] == 0, "managed arrays must not be staged"
+    p_o = p.copy()
+    a_o = abi.aligned_zeros(g.nv, abi.accumulator_dtype)
+    pm_o = abi.aligned_zeros(np_, abi.mover_dtype)
+    assert nm == orc.orc_advance_p(ptr(p_o), np_, -1.0, ptr(pm_o), np_, ptr(a_o), ptr(fi), g.ref())
+    assert_bits_equal(p_m, p_o, "particles (managed)")
+    assert max_rel(acc_floats(a_m), acc_floats(a_o)) < ACC_TOL
+
+
+@pytest.mark.parametrize("which", ["center_p", "uncenter_p"])
+def test_center_uncenter(vpb, orc, which):
+    g = host_grid((6, 5, 4))
+    rng = np.random.default_rng(3)
+    p = random_particles(rng, g, 3333, vth=0.4)
+    fi = random_interpolator(rng, g, amp=0.3)
+    p_o, p_g = p.copy(), p.copy()
+    getattr(orc, "orc_" + which)(ptr(p_o), len(p), 0.7, ptr(fi), g.ref())
+    getattr(vpb, which)(ptr(p_g), len(p), 0.7, ptr(fi), g.ref())
+    assert_bits_equal(p_g, p_o, which)
+
+
+def test_center_then_uncenter_round_trip(vpb):
+    """Size-independent property: uncenter_p inverts center_p to rounding."""
+    g = host_grid((8, 8, 8))
+    rng = np.random.default_rng(4)
+    p = random_particles(rng, g, 20000, vth=0.4)
+    fi = random_interpolator(rng, g, amp=0.2)
+    q = p.copy()
+    vpb.center_p(ptr(q), len(q), -1.0, ptr(fi), g.ref())
+    vpb.uncenter_p(ptr(q), len(q), -1.0, ptr(fi), g.ref())
+    for k in ("ux", "uy", "uz"):
+        assert np.max(np.abs(q[k] - p[k])) < 5e-6
+
+
+def test_energy_p(vpb, orc):
+    g = host_grid((6, 5, 4))
+    rng = np.random.default_rng(5)
+    p = random_particles(rng, g, 10001, vth=0.4)
+    fi = random_interpolator(rng, g, amp=0.3)
+    e_o = orc.orc_energy_p(ptr(p), len(p), -1.0, ptr(fi), g.ref())
+    e_g = vpb.energy_p(ptr(p), len(p), -1.0, ptr(fi), g.ref())
+    assert e_g == pytest.approx(e_o, rel=1e-12)   # fp64 accumulation, different order
+
+
+def test_accumulate_rho_p(vpb, orc):
+    g = host_grid((6, 5, 4), "metal")
+    rng = np.random.default_rng(6)
+    p = random_particles(rng, g, 4000)
+    f = random_fields(rng, g)
+    f_o, f_g = f.copy(), f.copy()
+    orc.orc_accumulate_rho_p(ptr(f_o), ptr(p), len(p), g.ref())
+    vpb.accumulate_rho_p(ptr(f_g), ptr(p), len(p), g.ref())
+    for k in abi.field_dtype.names:
+        if k != "rhof":
+            assert np.array_equal(f_g[k].view(np.uint8), f_o[k].view(np.uint8)), k
+    assert max_rel(f_g["rhof"], f_o["rhof"]) < ACC_TOL
+
+
+@pytest.mark.parametrize("n,np_", [((6, 5, 4), 3000), ((16, 16, 16), 150000), ((3, 3, 3), 5000), ((4, 4, 4), 0)])
+def test_sort_p(vpb, orc, n, np_):
+    """Stable counting sort: bit-exact against the reference's out-of-place sort (sort_p.c:61-77)."""
+    g = host_grid(n)
+    rng = np.random.default_rng(7)
+    p = random_particles(rng, g, max(np_, 1), sort=False)
+    sp = abi.SpeciesStruct()
+    sp.np, sp.max_np, sp.p = np_, max(np_, 1), p.ctypes.data
+    sp.sort_interval, sp.sort_out_of_place = 20, 1
+    part_g = np.full(g.nv + 1, -1, np.int32)
+    sp.partition = part_g.ctypes.data
+    p_in = p.copy()
+    vpb.sort_p(C.byref(sp), g.ref())
+    if np_ == 0:
+        return
+    p_o = abi.aligned_zeros(np_, abi.particle_dtype)
+    part_o = np.zeros(g.nv + 1, np.int32)
+    orc.orc_sort_p(ptr(p_in), ptr(p_o), np_, ptr(part_o), g.ref())
+    assert np.array_equal(part_g, part_o)
+    assert_bits_equal(p[:np_], p_o, "sorted particles (tags included)")
+    assert np.all(np.diff(p["i"][:np_]) >= 0)
+    assert part_g[-1] == np_
