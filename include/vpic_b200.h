@@ -163,6 +163,7 @@ long vpb_domain_nvoxel(const vpb_domain_t *dom);
  * in increasing particle index (boundary_p.c:168-176 relies on that). */
 void vpb_advance_p(vpb_domain_t *dom, vpb_particle_t *d_p, int np, float q_m, vpb_particle_mover_t *d_pm,
                    int max_nm, vpb_accumulator_t *d_a, const vpb_interpolator_t *d_f, int *d_nm);
+int vpb_advance_p_ignored(void);   /* movers the last vpb_advance_p dropped because pm[] was full (synchronises) */
 void vpb_center_p(vpb_domain_t *dom, vpb_particle_t *d_p, int np, float q_m, const vpb_interpolator_t *d_f);
 void vpb_uncenter_p(vpb_domain_t *dom, vpb_particle_t *d_p, int np, float q_m, const vpb_interpolator_t *d_f);
 /* d_en: device double[1], receives sum(q*w/(sqrt(1+w)+1)) before the c^2/q_m scale (energy_p.cxx:46) */
@@ -174,6 +175,24 @@ void vpb_accumulate_rho_p(vpb_domain_t *dom, vpb_field_t *d_f, const vpb_particl
 void vpb_load_thermal(vpb_domain_t *dom, vpb_particle_t *d_p, int ppc, float vth, float q,
                       unsigned long long seed, long tag0);
 void vpb_copy_positions(vpb_particle_t *d_dst, const vpb_particle_t *d_src, long np);
+
+/* One species' device arrays as boundary_p needs them (the device-side part of species_t). */
+typedef struct vpb_species_state {
+  vpb_particle_t *p;
+  vpb_particle_mover_t *pm;
+  int np, max_np;
+  int nm, max_nm;     /* nm movers in pm[], ascending particle index (as advance_p leaves them) */
+  int id, _pad;       /* species_t.id, carried in particle_injector_t.sp_id */
+} vpb_species_state_t;
+
+/* One round of boundary_p (boundary_p.c:77-505) for n_sp<=7 species: absorb / migrate the movers,
+ * back-fill, exchange with the face neighbours over NCCL, inject and finish the arrivals.  np and nm
+ * of every species are updated; the call synchronises.  advance.cxx:94-96 calls it 3 times a step. */
+void vpb_boundary_p(vpb_domain_t *dom, vpb_species_state_t *sp, int n_sp, vpb_field_t *d_f, vpb_accumulator_t *d_a);
+
+/* single mover / single particle, for the reference's host-side callers (inject_particle, handlers) */
+void vpb_move_p_one(vpb_domain_t *dom, vpb_particle_t *d_p, vpb_particle_mover_t *d_pm, vpb_accumulator_t *d_a, int *d_result);
+void vpb_accumulate_rhob_one(vpb_domain_t *dom, vpb_field_t *d_f, const vpb_particle_t *d_particle);
 
 /* Stable counting sort by voxel: d_out receives the sorted particles, d_partition
  * (int[nvoxel+1]) the first particle of each voxel (sort_p.c:54-59,74). */

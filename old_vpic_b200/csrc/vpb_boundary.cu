@@ -1,0 +1,465 @@
+// vpb_boundary.cu -- K4: boundary_p, the particle-migration step
+// (src/species_advance/standard/boundary_p.c:9-71,77-505) on device arrays, with
+// NCCL send/recv over NVLink in place of the reference's MPI ports.
+//
+// One call = one round of the reference's boundary_p for all species of a rank:
+//   1. every mover left by advance_p (or by a previous round's injection) sits on
+//      a domain face.  classify: absorbing face -> accumulate_rhob and drop; face
+//      shared with another rank -> becomes a 48-byte particle_injector_t (the
+//      reference's wire record, normal coordinate sign-flipped, voxel index
+//      rebased to the receiver) in that face's send buffer; anything else ->
+//      absorbed with a warning, as the reference does (boundary_p.c:312-315).
+//      Send order per face is the reference's: species in list order, movers in
+//      decreasing particle index (boundary_p.c:194-201).
+//   2. the removed particles' slots are back-filled from the tail of the array.
+//   3. per-face counts, then payloads, are exchanged (one NCCL group each).
+//   4. received particles are appended in the reference's order (faces as the
+//      reference's receive loop visits them, each buffer back to front,
+//      boundary_p.c:457-497), finish their move with move_p, and those that hit
+//      yet another face become the movers of the next round.
+// Difference from the reference, documented in DESIGN.md: the serial back-fill
+// loop (r[0] = p0[--np]) makes the final ORDER of the surviving particles depend
+// on the serial visiting order; here the k-th highest hole takes the k-th highest
+// tail survivor.  The multiset of particles per species is identical.
+#include <vector>
+#include "vpb_comm.cuh"
+#include "vpb_move_p.cuh"
+
+namespace vpb {
+
+constexpr int kBins = 8;          // 0..6 real bins, 7 = "none"
+constexpr int kRankThreads = 1024;
+
+// Stable multi-bin ranking by ONE block: rank[k] = base[code] + number of earlier
+// elements (in visiting order) with the same code.  reverse!=0 visits k = n-1..0.
+// base[] (device, 7 ints) is read at entry and updated at exit, so consecutive
+// calls continue the numbering (species after species).
+__global__ void __launch_bounds__(kRankThreads) rank_bins_kernel(const unsigned char *__restrict__ code, int n, int reverse,
+                                                                 int *__restrict__ rank, int *__restrict__ base_io) {
+  __shared__ int base[kBins];
+  __shared__ int wcnt[kRankThreads / 32][kBins];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid < kBins) base[tid] = tid < 7 ? base_io[tid] : 0;
+  __syncthreads();
+  for (int r0 = 0; r0 < n; r0 += kRankThreads) {
+    const int r = r0 + tid;
+    const int k = reverse ? n - 1 - r : r;
+    const int c = r < n ? code[k] : 7;
+    int mine = 0;
+#pragma unroll
+    for (int b = 0; b < 7; b++) {
+      const unsigned m = __ballot_sync(0xffffffffu, c == b);
+      if (lane == 0) wcnt[w][b] = __popc(m);
+      if (c == b) mine = __popc(m & ((1u << lane) - 1u));
+    }
+    __syncthreads();
+    if (c < 7) {
+      int before = 0;
+      for (int j = 0; j < w; j++) before += wcnt[j][c];
+      rank[k] = base[c] + before + mine;
+    }
+    __syncthreads();
+    if (tid < 7) {
+      int t = 0;
+      for (int j = 0; j < kRankThreads / 32; j++) t += wcnt[j][tid];
+      base[tid] += t;
+    }
+    __syncthreads();
+  }
+  if (tid < 7) base_io[tid] = base[tid];
+}
+
+// boundary_p.c:9-71 on the device: trilinear deposit of a removed particle's charge to rhob,
+// surface nodes weighted twice
+__device__ void accumulate_rhob_dev(vpb_field_t *__restrict__ f, float dx, float dy, float dz, int vi, float q, const DomainDev &g) {
+  float w0 = (float)(0.125 * q * g.rdx * g.rdy * g.rdz), w1, w2, w3, w4, w5, w6, w7, t;
+  t = dx; t *= w0; w1 = w0 + t; w0 -= t;
+  t = dy; w3 = 1 + t; w2 = w0 * w3; w3 *= w1; t = 1 - t; w0 *= t; w1 *= t;
+  t = dz; w7 = 1 + t; w4 = w0 * w7; w5 = w1 * w7; w6 = w2 * w7; w7 *= w3;
+  t = 1 - t; w0 *= t; w1 *= t; w2 *= t; w3 *= t;
+  int i = vi, j = i / g.sx;
+  i -= j * g.sx;
+  const int k = j / g.sy;
+  j -= k * g.sy;
+  if (i == 1) { w0 += w0; w2 += w2; w4 += w4; w6 += w6; }
+  if (i == g.nx) { w1 += w1; w3 += w3; w5 += w5; w7 += w7; }
+  if (j == 1) { w0 += w0; w1 += w1; w4 += w4; w5 += w5; }
+  if (j == g.ny) { w2 += w2; w3 += w3; w6 += w6; w7 += w7; }
+  if (k == 1) { w0 += w0; w1 += w1; w2 += w2; w3 += w3; }
+  if (k == g.nz) { w4 += w4; w5 += w5; w6 += w6; w7 += w7; }
+  float *rhob = &f[vi].rhob;
+  const size_t X = 20, Y = 20 * (size_t)g.sx, Z = 20 * (size_t)g.sxy;
+  red_add(rhob, w0); red_add(rhob + X, w1); red_add(rhob + Y, w2); red_add(rhob + X + Y, w3);
+  red_add(rhob + Z, w4); red_add(rhob + Z + X, w5); red_add(rhob + Z + Y, w6); red_add(rhob + Z + Y + X, w7);
+}
+
+struct FaceInfo {
+  int64_t rbase[6];    // range[] of the rank across each face (0 if not shared remotely)
+  int64_t rangem;      // range[nproc]
+};
+
+// boundary_p.c:203-316: which face did mover k end on, and what happens there.
+// code: 0..5 = send through that face, 6 = removed locally (absorbed).
+__global__ void __launch_bounds__(256) classify_kernel(const vpb_particle_t *__restrict__ p, const vpb_particle_mover_t *__restrict__ pm,
+                                                       int nm, unsigned char *__restrict__ code, vpb_field_t *__restrict__ f,
+                                                       const DomainDev g, const FaceInfo fi, int *__restrict__ n_unknown) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nm) return;
+  const int pi = pm[k].i;
+  const float4 r0 = reinterpret_cast<const float4 *>(p + pi)[0];
+  const float4 r1 = reinterpret_cast<const float4 *>(p + pi)[1];
+  const int vi = __float_as_int(r0.w);
+  const float pos[3] = {r0.x, r0.y, r0.z}, u[3] = {r1.x, r1.y, r1.z};
+  int c = -1;
+  bool unknown = true;
+#pragma unroll
+  for (int face = 0; face < 6 && c < 0; face++) {
+    const int ax = face % 3;
+    const bool hit = face < 3 ? (pos[ax] == -1.f && u[ax] < 0) : (pos[ax] == 1.f && u[ax] > 0);
+    if (!hit) continue;
+    const int64_t nn = g.nbr64[6 * (size_t)vi + face];
+    if (nn == vpb_absorb_particles) { c = 6; unknown = false; }
+    else if ((nn >= 0 && nn < g.rangel) || (nn > g.rangeh && nn <= fi.rangem)) { c = face; unknown = false; }
+    // custom handlers (nn <= -3) are host callbacks in the reference: not available here -> falls through
+  }
+  if (c < 0) c = 6;
+  if (c == 6) {
+    accumulate_rhob_dev(f, r0.x, r0.y, r0.z, vi, r1.w, g);
+    if (unknown) atomicAdd(n_unknown, 1);
+  }
+  code[k] = (unsigned char)c;
+}
+
+// write the injector records of one species (boundary_p.c:250-263)
+__global__ void __launch_bounds__(256) pack_injectors_kernel(const vpb_particle_t *__restrict__ p, const vpb_particle_mover_t *__restrict__ pm,
+                                                             int nm, const unsigned char *__restrict__ code, const int *__restrict__ rank,
+                                                             int sp_id, const DomainDev g, const FaceInfo fi, float4 *const *__restrict__ sendbuf) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nm) return;
+  const int face = code[k];
+  if (face >= 6) return;
+  const float4 m = reinterpret_cast<const float4 *>(pm)[k];
+  const int pi = __float_as_int(m.w);
+  float4 r0 = reinterpret_cast<const float4 *>(p + pi)[0];
+  const float4 r1 = reinterpret_cast<const float4 *>(p + pi)[1];
+  const int ax = face % 3;
+  if (ax == 0) r0.x = -r0.x; else if (ax == 1) r0.y = -r0.y; else r0.z = -r0.z;
+  const int64_t nn = g.nbr64[6 * (size_t)__float_as_int(r0.w) + face];
+  r0.w = __int_as_float((int)(nn - fi.rbase[face]));
+  float4 *o = sendbuf[face] + 3 * (size_t)rank[k];
+  o[0] = r0;
+  o[1] = r1;
+  o[2] = make_float4(m.x, m.y, m.z, __int_as_float(sp_id));
+}
+
+// removal: tailflag[j]=1 if particle np'+j is a mover; *nh = number of movers below np'
+__global__ void __launch_bounds__(256) mark_tail_kernel(const vpb_particle_mover_t *__restrict__ pm, int nm, int np_new,
+                                                        unsigned char *__restrict__ tail_code, int *__restrict__ nh) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nm) return;
+  const int i = pm[k].i;
+  if (i >= np_new) tail_code[i - np_new] = 7;   // 7 = not ranked
+  const int inext = (k + 1 < nm) ? pm[k + 1].i : 0x7fffffff;
+  if (i < np_new && inext >= np_new) *nh = k + 1;
+}
+
+// survivor j of the tail (rank r among survivors, counted from the top) fills hole pm[nh-1-r]
+__global__ void __launch_bounds__(256) backfill_kernel(vpb_particle_t *__restrict__ p, const vpb_particle_mover_t *__restrict__ pm,
+                                                       int nm, int np_new, const unsigned char *__restrict__ tail_code,
+                                                       const int *__restrict__ rank, const int *__restrict__ nh) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;   // 3 float4 per particle
+  const int j = (int)(t / 3), piece = (int)(t - 3L * j);
+  if (j >= nm || tail_code[j] != 0) return;
+  const int hole = pm[*nh - 1 - rank[j]].i;
+  reinterpret_cast<float4 *>(p + hole)[piece] = reinterpret_cast<const float4 *>(p + np_new + j)[piece];
+}
+
+// received buffers -> one list in the reference's injection order (each buffer back to front)
+__global__ void __launch_bounds__(256) gather_injectors_kernel(float4 *__restrict__ list, const float4 *__restrict__ buf, int n, int off) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = (int)(t / 3), piece = (int)(t - 3L * j);
+  if (j >= n) return;
+  list[3 * (size_t)(off + j) + piece] = buf[3 * (size_t)(n - 1 - j) + piece];
+}
+
+struct SpeciesTable {
+  int n;
+  int id[7];
+  vpb_particle_t *p[7];
+  vpb_particle_mover_t *pm[7];
+  int np[7];
+};
+
+__global__ void __launch_bounds__(256) species_code_kernel(const float4 *__restrict__ list, int n, const SpeciesTable T,
+                                                           unsigned char *__restrict__ code) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const int id = __float_as_int(list[3 * (size_t)q + 2].w);
+  int c = 7;
+  for (int s = 0; s < T.n; s++) if (T.id[s] == id) c = s;
+  code[q] = (unsigned char)c;
+}
+
+// boundary_p.c:478-496: append, then finish the move.  Leaves the remaining displacement and the
+// particle's new index in list[q] and marks unresolved movers in code2.
+__global__ void __launch_bounds__(128) inject_kernel(float4 *__restrict__ list, int n, const unsigned char *__restrict__ code,
+                                                     const int *__restrict__ rank, const SpeciesTable T, float *__restrict__ a0,
+                                                     const int32_t *__restrict__ nbr, unsigned char *__restrict__ code2) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const int s = code[q];
+  if (s >= 7) { code2[q] = 7; return; }
+  const float4 a = list[3 * (size_t)q], b = list[3 * (size_t)q + 1], c = list[3 * (size_t)q + 2];
+  Mover m;
+  m.dx = a.x; m.dy = a.y; m.dz = a.z; m.i = __float_as_int(a.w);
+  m.ux = b.x; m.uy = b.y; m.uz = b.z; m.q = b.w;
+  m.dispx = c.x; m.dispy = c.y; m.dispz = c.z;
+  const int pos = T.np[s] + rank[q];
+  const int unresolved = move_p_dev(m, a0, nbr);
+  float4 *pp = reinterpret_cast<float4 *>(T.p[s] + pos);   // tags are left as they were (boundary_p.c:488-491)
+  pp[0] = make_float4(m.dx, m.dy, m.dz, __int_as_float(m.i));
+  pp[1] = make_float4(m.ux, m.uy, m.uz, m.q);
+  list[3 * (size_t)q + 2] = make_float4(m.dispx, m.dispy, m.dispz, __int_as_float(pos));
+  code2[q] = unresolved ? (unsigned char)s : (unsigned char)7;
+}
+
+__global__ void __launch_bounds__(256) compact_movers_kernel(const float4 *__restrict__ list, int n, const unsigned char *__restrict__ code2,
+                                                             const int *__restrict__ rank2, const SpeciesTable T) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const int s = code2[q];
+  if (s >= 7) return;
+  reinterpret_cast<float4 *>(T.pm[s])[rank2[q]] = list[3 * (size_t)q + 2];
+}
+
+// single-mover / single-particle entry points (host code of the reference calls these one at a time:
+// inject_particle, misc.cxx:102; custom boundary handlers)
+__global__ void move_p_one_kernel(vpb_particle_t *p, vpb_particle_mover_t *pm, float *a0, const int32_t *nbr, int *result) {
+  Mover s;
+  const int k = pm->i;
+  const float4 a = reinterpret_cast<const float4 *>(p + k)[0], b = reinterpret_cast<const float4 *>(p + k)[1];
+  s.dx = a.x; s.dy = a.y; s.dz = a.z; s.i = __float_as_int(a.w);
+  s.ux = b.x; s.uy = b.y; s.uz = b.z; s.q = b.w;
+  s.dispx = pm->dispx; s.dispy = pm->dispy; s.dispz = pm->dispz;
+  *result = move_p_dev(s, a0, nbr);
+  reinterpret_cast<float4 *>(p + k)[0] = make_float4(s.dx, s.dy, s.dz, __int_as_float(s.i));
+  reinterpret_cast<float4 *>(p + k)[1] = make_float4(s.ux, s.uy, s.uz, s.q);
+  pm->dispx = s.dispx; pm->dispy = s.dispy; pm->dispz = s.dispz;
+}
+
+__global__ void accumulate_rhob_one_kernel(vpb_field_t *f, const vpb_particle_t *p, const DomainDev g) {
+  accumulate_rhob_dev(f, p->dx, p->dy, p->dz, p->i, p->q, g);
+}
+
+struct BoundaryBuffers {
+  float4 *send[6] = {}, *recv[6] = {};
+  size_t cap[6] = {};          // injectors
+  float4 **d_send_table = nullptr;
+  int *d_counts = nullptr;     // [0..7] send bins, [8..15] recv counts, [16..23] species bins, [24..31] mover bins, [32] nh, [33] unknown
+};
+static BoundaryBuffers g_bb;
+
+static void ensure_cap(int face, size_t n) {
+  if (g_bb.cap[face] >= n) return;
+  cudaStream_t st = ctx().stream;
+  VPB_CUDA(cudaStreamSynchronize(st));
+  if (g_bb.send[face]) { cudaFree(g_bb.send[face]); cudaFree(g_bb.recv[face]); }
+  const size_t want = n + n / 4 + 1024;
+  VPB_CUDA(cudaMalloc(&g_bb.send[face], want * 48));
+  VPB_CUDA(cudaMalloc(&g_bb.recv[face], want * 48));
+  g_bb.cap[face] = want;
+  if (!g_bb.d_send_table) VPB_CUDA(cudaMalloc(&g_bb.d_send_table, 6 * sizeof(float4 *)));
+  VPB_CUDA(cudaMemcpy(g_bb.d_send_table, g_bb.send, 6 * sizeof(float4 *), cudaMemcpyHostToDevice));
+}
+
+static inline int blocks(long n, int tb) { return (int)((n + tb - 1) / tb); }
+
+}  // namespace vpb
+
+using namespace vpb;
+
+extern "C" {
+
+void vpb_move_p_one(vpb_domain_t *dom, vpb_particle_t *d_p, vpb_particle_mover_t *d_pm, vpb_accumulator_t *d_a, int *d_result) {
+  move_p_one_kernel<<<1, 1, 0, ctx().stream>>>(d_p, d_pm, reinterpret_cast<float *>(d_a), dom->d.nbr, d_result);
+  count_launch();
+  VPB_CUDA(cudaGetLastError());
+}
+
+void vpb_accumulate_rhob_one(vpb_domain_t *dom, vpb_field_t *d_f, const vpb_particle_t *d_particle) {
+  accumulate_rhob_one_kernel<<<1, 1, 0, ctx().stream>>>(d_f, d_particle, dom->d);
+  count_launch();
+  VPB_CUDA(cudaGetLastError());
+}
+
+// One round of boundary_p over n_sp species (at most 7).  sp[s].nm is the number of movers in
+// sp[s].pm (ascending particle index); on return np/nm are updated.  Synchronises the stream.
+void vpb_boundary_p(vpb_domain_t *dom, vpb_species_state_t *sp, int n_sp, vpb_field_t *d_f, vpb_accumulator_t *d_a) {
+  if (!dom) VPB_ERROR("Bad grid");
+  if (n_sp < 0 || n_sp > 7) VPB_ERROR("boundary_p handles at most 7 species per call (got %d)", n_sp);
+  if (n_sp && !sp) VPB_ERROR("Bad species");
+  Context &c = ctx();
+  cudaStream_t st = c.stream;
+  const DomainDev &g = dom->d;
+  static const int fbound[6] = {VPB_BOUNDARY(-1, 0, 0), VPB_BOUNDARY(0, -1, 0), VPB_BOUNDARY(0, 0, -1),
+                                VPB_BOUNDARY(1, 0, 0),  VPB_BOUNDARY(0, 1, 0),  VPB_BOUNDARY(0, 0, 1)};
+  bool remote[6];
+  int peer[6];
+  FaceInfo fi;
+  bool any_remote = false;
+  for (int f = 0; f < 6; f++) {
+    const int b = g.bc[fbound[f]];
+    remote[f] = b >= 0 && b < g.nproc && b != g.rank;   // SHARED_REMOTELY (boundary_p.c:103-104)
+    peer[f] = remote[f] ? b : -1;
+    fi.rbase[f] = remote[f] ? dom->range[b] : 0;
+    any_remote |= remote[f];
+  }
+  fi.rangem = dom->range[g.nproc];
+  if (!g_bb.d_counts) VPB_CUDA(cudaMalloc(&g_bb.d_counts, 64 * sizeof(int)));
+  int *dc = g_bb.d_counts;
+  VPB_CUDA(cudaMemsetAsync(dc, 0, 64 * sizeof(int), st));
+
+  long total = 0;
+  for (int s = 0; s < n_sp; s++) {
+    if (sp[s].nm < 0 || sp[s].nm > sp[s].max_nm) VPB_ERROR("Bad mover count");
+    total += sp[s].nm;
+  }
+  if (total == 0 && !any_remote) return;
+  if (total > 0 && !d_f) VPB_ERROR("Bad field");
+
+  // scratch: code[total] | rank[total] | tail_code[maxnm] | tail_rank[maxnm]
+  int maxnm = 0;
+  for (int s = 0; s < n_sp; s++) maxnm = sp[s].nm > maxnm ? sp[s].nm : maxnm;
+  auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t o_rank = al((size_t)total), o_tcode = o_rank + al((size_t)total * 4), o_trank = o_tcode + al((size_t)maxnm),
+               o_end = o_trank + al((size_t)maxnm * 4);
+  char *scr = (char *)scratch(o_end + 256);
+  unsigned char *code = (unsigned char *)scr, *tcode = (unsigned char *)(scr + o_tcode);
+  int *rank = (int *)(scr + o_rank), *trank = (int *)(scr + o_trank);
+
+  int ns[6] = {0, 0, 0, 0, 0, 0}, nr[6] = {0, 0, 0, 0, 0, 0};
+  static const int rorder[6] = {3, 4, 5, 0, 1, 2};
+  Xfer x[12];
+  int nx = 0;
+  if (total > 0) {
+    long off = 0;
+    for (int s = 0; s < n_sp; s++) {
+      const int nm = sp[s].nm;
+      if (nm) {
+        classify_kernel<<<blocks(nm, 256), 256, 0, st>>>(sp[s].p, sp[s].pm, nm, code + off, d_f, g, fi, dc + 33);
+        rank_bins_kernel<<<1, kRankThreads, 0, st>>>(code + off, nm, 1, rank + off, dc);
+        count_launch(2);
+      }
+      off += nm;
+    }
+  }
+  // per-face counts first (boundary_p.c:330-365): both sides then know every payload size
+  if (any_remote) {
+    for (int f = 0; f < 6; f++)
+      if (remote[f]) x[nx++] = {dc + f, sizeof(int), peer[f], nullptr, 0, -1};
+    for (int k = 0; k < 6; k++) {
+      const int f = rorder[k];
+      if (remote[f]) x[nx++] = {nullptr, 0, -1, dc + 8 + f, sizeof(int), peer[f]};
+    }
+    comm_exchange(x, nx);
+  }
+  VPB_CUDA(cudaMemcpyAsync(c.h_pinned_i, dc, 40 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  VPB_CUDA(cudaStreamSynchronize(st));
+  for (int f = 0; f < 6; f++) { ns[f] = c.h_pinned_i[f]; nr[f] = remote[f] ? c.h_pinned_i[8 + f] : 0; }
+  if (c.h_pinned_i[33])
+    VPB_WARNING("Unknown boundary interaction ... using absorption (%d particles, rank=%d)", c.h_pinned_i[33], g.rank);
+  for (int f = 0; f < 6; f++) {
+    if (ns[f] && !remote[f]) VPB_ERROR("movers classified for face %d which is not shared with another rank", f);
+    const int need = ns[f] > nr[f] ? ns[f] : nr[f];
+    if (need) ensure_cap(f, (size_t)need);
+  }
+  if (total > 0) {
+    long off = 0;
+    bool sends = false;
+    for (int f = 0; f < 6; f++) sends |= ns[f] > 0;
+    for (int s = 0; s < n_sp; s++) {
+      const int nm = sp[s].nm;
+      if (nm) {
+        if (sends) {
+          pack_injectors_kernel<<<blocks(nm, 256), 256, 0, st>>>(sp[s].p, sp[s].pm, nm, code + off, rank + off, sp[s].id, g, fi,
+                                                                  g_bb.d_send_table);
+          count_launch();
+        }
+        // remove all nm particles: holes below np' are filled from the tail
+        const int np_new = sp[s].np - nm;
+        if (np_new < 0) VPB_ERROR("more movers than particles");
+        VPB_CUDA(cudaMemsetAsync(tcode, 0, (size_t)nm, st));
+        VPB_CUDA(cudaMemsetAsync(dc + 32, 0, sizeof(int), st));
+        VPB_CUDA(cudaMemsetAsync(dc + 40, 0, 8 * sizeof(int), st));
+        mark_tail_kernel<<<blocks(nm, 256), 256, 0, st>>>(sp[s].pm, nm, np_new, tcode, dc + 32);
+        rank_bins_kernel<<<1, kRankThreads, 0, st>>>(tcode, nm, 1, trank, dc + 40);
+        backfill_kernel<<<blocks(3L * nm, 256), 256, 0, st>>>(sp[s].p, sp[s].pm, nm, np_new, tcode, trank, dc + 32);
+        count_launch(3);
+        sp[s].np = np_new;
+      }
+      off += nm;
+      sp[s].nm = 0;
+    }
+  }
+  // payloads (boundary_p.c:369-384)
+  if (any_remote) {
+    nx = 0;
+    for (int f = 0; f < 6; f++)
+      if (remote[f] && ns[f]) x[nx++] = {g_bb.send[f], (size_t)ns[f] * 48, peer[f], nullptr, 0, -1};
+    for (int k = 0; k < 6; k++) {
+      const int f = rorder[k];
+      if (remote[f] && nr[f]) x[nx++] = {nullptr, 0, -1, g_bb.recv[f], (size_t)nr[f] * 48, peer[f]};
+    }
+    if (nx) comm_exchange(x, nx);
+  }
+
+  long n_in = 0;
+  for (int f = 0; f < 6; f++) n_in += nr[f];
+  if (n_in == 0) { VPB_CUDA(cudaStreamSynchronize(st)); return; }
+  if (!d_a) VPB_ERROR("Bad accumulator");
+
+  // injection (boundary_p.c:388-497)
+  const size_t o_list = 0, o_c1 = al((size_t)n_in * 48), o_r1 = o_c1 + al((size_t)n_in), o_c2 = o_r1 + al((size_t)n_in * 4),
+               o_r2 = o_c2 + al((size_t)n_in), o_fin = o_r2 + al((size_t)n_in * 4);
+  char *s2 = (char *)scratch(o_fin + 256);
+  float4 *list = (float4 *)(s2 + o_list);
+  unsigned char *c1 = (unsigned char *)(s2 + o_c1), *c2 = (unsigned char *)(s2 + o_c2);
+  int *r1 = (int *)(s2 + o_r1), *r2 = (int *)(s2 + o_r2);
+  int off = 0;
+  for (int k = 0; k < 6; k++) {   // the reference's receive loop: what arrived from +x first (rf2b order)
+    const int f = rorder[k];
+    if (!nr[f]) continue;
+    gather_injectors_kernel<<<blocks(3L * nr[f], 256), 256, 0, st>>>(list, g_bb.recv[f], nr[f], off);
+    count_launch();
+    off += nr[f];
+  }
+  SpeciesTable T;
+  T.n = n_sp;
+  for (int s = 0; s < n_sp; s++) { T.id[s] = sp[s].id; T.p[s] = sp[s].p; T.pm[s] = sp[s].pm; T.np[s] = sp[s].np; }
+  const int n = (int)n_in;
+  species_code_kernel<<<blocks(n, 256), 256, 0, st>>>(list, n, T, c1);
+  rank_bins_kernel<<<1, kRankThreads, 0, st>>>(c1, n, 0, r1, dc + 16);
+  VPB_CUDA(cudaMemcpyAsync(c.h_pinned_i, dc + 16, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  VPB_CUDA(cudaStreamSynchronize(st));
+  int cnt[7];
+  for (int s = 0; s < n_sp; s++) {
+    cnt[s] = c.h_pinned_i[s];
+    if (sp[s].np + cnt[s] > sp[s].max_np)
+      VPB_ERROR("species %d: %d particles + %d arrivals exceed max_np=%d (the reference would grow the array by 31%%, "
+                "boundary_p.c:416-430; size max_np with head-room)", sp[s].id, sp[s].np, cnt[s], sp[s].max_np);
+    if (cnt[s] > sp[s].max_nm) VPB_ERROR("species %d: %d arrivals exceed max_nm=%d", sp[s].id, cnt[s], sp[s].max_nm);
+  }
+  inject_kernel<<<blocks(n, 128), 128, 0, st>>>(list, n, c1, r1, T, reinterpret_cast<float *>(d_a), g.nbr, c2);
+  rank_bins_kernel<<<1, kRankThreads, 0, st>>>(c2, n, 0, r2, dc + 24);
+  compact_movers_kernel<<<blocks(n, 256), 256, 0, st>>>(list, n, c2, r2, T);
+  count_launch(5);
+  VPB_CUDA(cudaMemcpyAsync(c.h_pinned_i, dc + 24, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  VPB_CUDA(cudaStreamSynchronize(st));
+  for (int s = 0; s < n_sp; s++) {
+    sp[s].np += cnt[s];
+    sp[s].nm = c.h_pinned_i[s];
+  }
+  VPB_CUDA(cudaGetLastError());
+}
+
+}  // extern "C"

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <vector>
 #include "../../include/vpic_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -93,6 +94,7 @@ struct vpb_domain {
   int32_t *nbr = nullptr;  // device allocations owned by the domain
   int64_t *nbr64 = nullptr;
   const vpb_grid_t *host_grid = nullptr;
+  std::vector<int64_t> range;   // copy of grid_t.range[0..nproc] (global voxel-id range of every rank)
   // per-face message buffers (vpb_faces.cu), sized for the largest message kind
   float *face_send[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   float *face_recv[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

@@ -218,6 +218,8 @@ vpb_domain_t *vpb_domain_create(const vpb_grid_t *g, int rank, int nproc) {
   d.rank = rank; d.nproc = nproc;
   d.rangel = g->rangel; d.rangeh = g->rangeh;
   dom->host_grid = g;
+  dom->range.assign((size_t)nproc + 1, 0);
+  for (int r = 0; r <= nproc; r++) dom->range[r] = g->range ? g->range[r] : (int64_t)r * nv;
   if (g->neighbor) {
     // compress: local ids to int32, everything else to a negative code
     std::vector<int32_t> nb((size_t)6 * nv);

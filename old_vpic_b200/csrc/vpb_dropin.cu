@@ -246,6 +246,71 @@ void accumulate_rho_p(vpb_field_t *f, const vpb_particle_t *p0, int np, const vp
   r.finish();
 }
 
+// move_p.c:20-136 for ONE mover.  Host code of the reference calls this per injected particle
+// (misc.cxx:102); it costs a kernel launch here and is meant for set-up paths only.
+int move_p(vpb_particle_t *p0, vpb_particle_mover_t *m, vpb_accumulator_t *a0, const vpb_grid_t *g) {
+  vpb_domain_t *dom = domain_of(g);
+  Context &c = ctx();
+  Residency r;
+  // only the one particle the mover names is touched; stage just that record when p0 is host memory
+  vpb_particle_mover_t hm = *m;
+  vpb_particle_t *pk = p0 + hm.i;
+  cudaPointerAttributes at;
+  bool on_device = cudaPointerGetAttributes(&at, p0) == cudaSuccess && (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged);
+  cudaGetLastError();
+  vpb_particle_t *dp = on_device ? p0 : ((vpb_particle_t *)r.get(pk, sizeof(*pk), RW)) - hm.i;
+  vpb_accumulator_t *da = (vpb_accumulator_t *)r.get(a0, nvox(g) * sizeof(*a0), RW);
+  char *d_tmp = nullptr;
+  VPB_CUDA(cudaMallocAsync(&d_tmp, 64, c.stream));
+  VPB_CUDA(cudaMemcpyAsync(d_tmp, &hm, sizeof(hm), cudaMemcpyHostToDevice, c.stream));
+  vpb_move_p_one(dom, dp, (vpb_particle_mover_t *)d_tmp, da, (int *)(d_tmp + 32));
+  VPB_CUDA(cudaMemcpyAsync(c.h_pinned_i, d_tmp, 48, cudaMemcpyDeviceToHost, c.stream));
+  VPB_CUDA(cudaFreeAsync(d_tmp, c.stream));
+  r.finish();
+  memcpy(m, c.h_pinned_i, sizeof(*m));
+  return c.h_pinned_i[8];
+}
+
+// boundary_p.c:9-71 for ONE particle
+void accumulate_rhob(vpb_field_t *f0, const vpb_particle_t *p, const vpb_grid_t *g) {
+  if (!f0 || !p) VPB_ERROR("Bad field or particle");
+  vpb_domain_t *dom = domain_of(g);
+  Context &c = ctx();
+  Residency r;
+  vpb_field_t *df = (vpb_field_t *)r.get(f0, nvox(g) * sizeof(*f0), RW);
+  vpb_particle_t hp = *p, *d_one = nullptr;
+  VPB_CUDA(cudaMallocAsync(&d_one, sizeof(hp), c.stream));
+  VPB_CUDA(cudaMemcpyAsync(d_one, &hp, sizeof(hp), cudaMemcpyHostToDevice, c.stream));
+  vpb_accumulate_rhob_one(dom, df, d_one);
+  VPB_CUDA(cudaFreeAsync(d_one, c.stream));
+  r.finish();
+}
+
+// boundary_p.c:77-505: one round over the species list.  rng is only used by custom boundary
+// handlers in the reference (host callbacks), which the device path does not run.
+void boundary_p(vpb_species_t *sp_list, vpb_field_t *f0, vpb_accumulator_t *a0, const vpb_grid_t *g, void *rng) {
+  (void)rng;
+  if (!g) VPB_ERROR("Bad grid");
+  vpb_domain_t *dom = domain_of(g);
+  Residency r;
+  std::vector<vpb_species_t *> list;
+  for (vpb_species_t *sp = sp_list; sp; sp = sp->next) list.push_back(sp);
+  if (list.size() > 7) VPB_ERROR("boundary_p handles at most 7 species per call");
+  std::vector<vpb_species_state_t> st(list.size());
+  for (size_t s = 0; s < list.size(); s++) {
+    vpb_species_t *sp = list[s];
+    if (sp->id < 0 || sp->id >= 64) VPB_ERROR("Invalid sp->id");   // boundary_p.c:396
+    st[s].p = (vpb_particle_t *)r.get(sp->p, (size_t)sp->max_np * sizeof(vpb_particle_t), RW);
+    st[s].pm = (vpb_particle_mover_t *)r.get(sp->pm, (size_t)sp->max_nm * sizeof(vpb_particle_mover_t), RW);
+    st[s].np = sp->np; st[s].max_np = sp->max_np; st[s].nm = sp->nm; st[s].max_nm = sp->max_nm; st[s].id = sp->id;
+  }
+  vpb_field_t *df = f0 ? (vpb_field_t *)r.get(f0, nvox(g) * sizeof(*f0), RW) : nullptr;
+  vpb_accumulator_t *da = a0 ? (vpb_accumulator_t *)r.get(a0, nvox(g) * sizeof(*a0), RW) : nullptr;
+  vpb_boundary_p(dom, st.data(), (int)st.size(), df, da);
+  for (size_t s = 0; s < list.size(); s++) { list[s]->np = st[s].np; list[s]->nm = st[s].nm; }
+  r.finish();
+}
+
 void sort_p(vpb_species_t *sp, const vpb_grid_t *g) {
   if (!sp) VPB_ERROR("Bad species");
   if (!g) VPB_ERROR("Bad grid");

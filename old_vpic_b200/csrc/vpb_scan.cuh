@@ -12,8 +12,11 @@ constexpr int kScanItems = 8;
 constexpr int kScanBlock = kScanThreads * kScanItems;  // 4096
 
 // block_sums[b] = sum of in[b*4096 .. )
-static __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const int *__restrict__ in, int *__restrict__ block_sums, int n) {
+// skip (may be NULL): device int; when it reads 0 the kernel has nothing to do and returns
+static __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const int *__restrict__ in, int *__restrict__ block_sums, int n,
+                                                                          const int *__restrict__ skip) {
   __shared__ int ws[kScanThreads / 32];
+  if (skip && *skip == 0) return;
   const int base = blockIdx.x * kScanBlock;
   int s = 0;
 #pragma unroll
@@ -32,8 +35,10 @@ static __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const 
 }
 
 // out[i] = block_off[b] + exclusive prefix of in within block b (in may alias out)
-static __global__ void __launch_bounds__(kScanThreads) scan_block_kernel(const int *in, int *out, const int *__restrict__ block_off, int n) {
+static __global__ void __launch_bounds__(kScanThreads) scan_block_kernel(const int *in, int *out, const int *__restrict__ block_off, int n,
+                                                                         const int *__restrict__ skip) {
   __shared__ int ws[kScanThreads / 32];
+  if (skip && *skip == 0) return;
   const int base = blockIdx.x * kScanBlock + threadIdx.x * kScanItems;  // each thread owns 8 consecutive items
   int v[kScanItems];
   int s = 0;
@@ -77,18 +82,18 @@ inline int scan_launches(long n) {
 }
 
 // in may alias out.  tmp must hold scan_scratch_bytes(n).
-inline void exclusive_scan_i32(const int *in, int *out, int n, void *tmp, cudaStream_t st) {
+inline void exclusive_scan_i32(const int *in, int *out, int n, void *tmp, cudaStream_t st, const int *skip = nullptr) {
   if (n <= 0) return;
   const int nb = (n + kScanBlock - 1) / kScanBlock;
   if (nb == 1) {
-    scan_block_kernel<<<1, kScanThreads, 0, st>>>(in, out, nullptr, n);
+    scan_block_kernel<<<1, kScanThreads, 0, st>>>(in, out, nullptr, n, skip);
     return;
   }
   int *sums = (int *)tmp;
   void *next = (char *)tmp + (((size_t)nb * sizeof(int) + 255) & ~(size_t)255);
-  scan_reduce_kernel<<<nb, kScanThreads, 0, st>>>(in, sums, n);
-  exclusive_scan_i32(sums, sums, nb, next, st);
-  scan_block_kernel<<<nb, kScanThreads, 0, st>>>(in, out, sums, n);
+  scan_reduce_kernel<<<nb, kScanThreads, 0, st>>>(in, sums, n, skip);
+  exclusive_scan_i32(sums, sums, nb, next, st, skip);
+  scan_block_kernel<<<nb, kScanThreads, 0, st>>>(in, out, sums, n, skip);
 }
 
 }  // namespace vpb

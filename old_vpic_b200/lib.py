@@ -19,11 +19,14 @@ _vp, _i, _f, _d, _sz, _l = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_size_
 SIGNATURES = {
     # (A) reference-named entry points
     "advance_p": (_i, [_vp, _i, _f, _vp, _i, _vp, _vp, _vp]),
+    "move_p": (_i, [_vp, _vp, _vp, _vp]),
     "sort_p": (None, [_vp, _vp]),
     "center_p": (None, [_vp, _i, _f, _vp, _vp]),
     "uncenter_p": (None, [_vp, _i, _f, _vp, _vp]),
     "energy_p": (_d, [_vp, _i, _f, _vp, _vp]),
     "accumulate_rho_p": (None, [_vp, _vp, _i, _vp]),
+    "accumulate_rhob": (None, [_vp, _vp, _vp]),
+    "boundary_p": (None, [_vp, _vp, _vp, _vp, _vp]),
     "new_interpolator": (_vp, [_vp]),
     "delete_interpolator": (None, [_vp]),
     "new_accumulators": (_vp, [_vp]),
@@ -76,10 +79,14 @@ SIGNATURES = {
     "vpb_domain_destroy": (None, [_vp]),
     "vpb_domain_nvoxel": (_l, [_vp]),
     "vpb_advance_p": (None, [_vp, _vp, _i, _f, _vp, _i, _vp, _vp, _vp]),
+    "vpb_advance_p_ignored": (_i, []),
     "vpb_center_p": (None, [_vp, _vp, _i, _f, _vp]),
     "vpb_uncenter_p": (None, [_vp, _vp, _i, _f, _vp]),
     "vpb_energy_p": (None, [_vp, _vp, _i, _f, _vp, _vp]),
     "vpb_accumulate_rho_p": (None, [_vp, _vp, _vp, _i]),
+    "vpb_move_p_one": (None, [_vp, _vp, _vp, _vp, _vp]),
+    "vpb_accumulate_rhob_one": (None, [_vp, _vp, _vp]),
+    "vpb_boundary_p": (None, [_vp, _vp, _i, _vp, _vp]),
     "vpb_sort_p": (None, [_vp, _vp, _vp, _i, _vp]),
     "vpb_load_interpolator": (None, [_vp, _vp, _vp]),
     "vpb_clear_accumulators": (None, [_vp, _vp]),

@@ -1,0 +1,70 @@
+"""The drop-in boundary: struct layouts agree with the reference compiled from source, and
+libvpic_b200.so loads and exports every entry point include/vpic_b200.h declares (no GPU needed)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import ROOT, abi, loader
+from old_vpic_b200 import lib
+
+
+def test_layouts_match_reference(ref_scalar):
+    out = (C.c_long * 128)()
+    n = ref_scalar.refh_layout(out, 128)
+    got = list(out[:n])
+    P, Mv, I, F, A, Fd, G, S = (abi.particle_dtype, abi.mover_dtype, abi.injector_dtype, abi.interpolator_dtype,
+                                abi.accumulator_dtype, abi.field_dtype, abi.GridStruct, abi.SpeciesStruct)
+    off = lambda dt, name: dt.fields[name][1]
+    want = [
+        P.itemsize, off(P, "i"), off(P, "ux"), off(P, "q"), off(P, "tag"), off(P, "tag2"),
+        Mv.itemsize, off(Mv, "i"),
+        I.itemsize, off(I, "dispx"), off(I, "sp_id"),
+        F.itemsize, off(F, "ey"), off(F, "cbx"), off(F, "dcbzdz"),
+        A.itemsize, off(A, "jy"), off(A, "jz"),
+        Fd.itemsize, off(Fd, "cbx"), off(Fd, "tcax"), off(Fd, "rhob"), off(Fd, "jfx"), off(Fd, "rhof"), off(Fd, "ematx"),
+        off(Fd, "fmatx"), off(Fd, "cmat"),
+        64,
+        C.sizeof(G), G.dt.offset, G.damp.offset, G.x0.offset, G.dx.offset, G.rdx.offset, G.nx.offset, G.bc.offset,
+        G.range.offset, G.neighbor.offset, G.rangel.offset, G.rangeh.offset, G.nb.offset, G.boundary.offset,
+        C.sizeof(S), S.np.offset, S.max_np.offset, S.p.offset, S.nm.offset, S.max_nm.offset, S.pm.offset, S.q_m.offset,
+        S.sort_interval.offset, S.sort_out_of_place.offset, S.partition.offset, S.next.offset, S.name.offset,
+        C.sizeof(abi.FieldAdvanceMethods), abi.FieldAdvanceMethods.advance_b.offset, abi.FieldAdvanceMethods.energy_f.offset,
+        abi.FieldAdvanceMethods.clean_div_b.offset,
+    ]
+    assert got[:len(want)] == want
+    # field_advance_t {f,m,g,method[1]} and material_t (field_advance.h:307-312, material.h:42-50)
+    assert got[len(want):len(want) + 2] == [184, 24]
+    assert got[len(want) + 2:] == [72, 4, 56, 64]
+
+
+def test_c_header_static_asserts_compile(tmp_path):
+    """include/*.h carries the same numbers as static asserts; compile it as C and as C++."""
+    src = tmp_path / "t.c"
+    src.write_text('#include "vpic_b200.h"\nint main(void){return 0;}\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.check_call(["gcc", "-std=c11", "-I", inc, "-c", str(src), "-o", str(tmp_path / "t.o")])
+    subprocess.check_call(["g++", "-std=c++17", "-x", "c++", "-I", inc, "-c", str(src), "-o", str(tmp_path / "t2.o")])
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "vpic_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", text))
+    names -= {"defined", "VPB_STATIC_ASSERT", "sizeof", "offsetof"}
+    # function-pointer parameter names etc. do not occur in this header; keep only real prototypes
+    return sorted(n for n in names if re.search(r"\b%s\s*\([^;{]*\)\s*;" % re.escape(n), text))
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(lib.SO), "run python -m old_vpic_b200.build"
+    L = C.CDLL(lib.SO)      # loading must not need a GPU
+    missing = [n for n in _declared_functions() if not hasattr(L, n)]
+    assert not missing, missing
+    for name in lib.DATA_SYMBOLS:
+        tab = abi.FieldAdvanceMethods.in_dll(L, name)
+        assert all(getattr(tab, n) for n in abi.FieldAdvanceMethods.NAMES), name
+    assert set(lib.SIGNATURES) >= set(_declared_functions()), sorted(set(_declared_functions()) - set(lib.SIGNATURES))
