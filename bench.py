@@ -248,6 +248,9 @@ def run_b200(args):
         tot, cnt = C.c_double(0), C.c_int(0)
         L.vpb_prof_collect(cls, C.byref(tot), C.byref(cnt), 0)
         prof[nm] = (tot.value, cnt.value)
+    lst = (C.c_float * 4096)()
+    nl = L.vpb_prof_list(0, lst, 4096)
+    adv_list = [round(float(lst[i]), 3) for i in range(nl)]
     L.vpb_prof_collect(0, None, None, 1)
     L.vpb_prof_enable(0)
 
@@ -279,6 +282,9 @@ def run_b200(args):
         "field_cell_updates_per_s": {"advance_b": (2 * cells * args.steps / (prof["advance_b"][0] * 1e-3)) if prof["advance_b"][0] else None,
                                      "advance_e": (cells * args.steps / (prof["advance_e"][0] * 1e-3)) if prof["advance_e"][0] else None},
         "host_wall_ms_per_step": 1e3 * wall / args.steps,
+        "advance_p_ms_by_launch": adv_list,
+        "tuning": {k: L.vpb_get_tuning(k.encode()) for k in ("advance_p.deposit", "advance_p.l2hint", "advance_p.prefetch",
+                                                             "advance_p.ctas_per_sm")},
     }
     if not args.no_e2e:
         line["e2e"] = e2e_measure(L, args, abi, helpers)

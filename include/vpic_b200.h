@@ -125,6 +125,7 @@ float vpb_timer_ms(int slot);                /* synchronises on the stop event *
  * 5 unload_accumulator, 6 other. */
 void vpb_prof_enable(int on);
 void vpb_prof_collect(int cls, double *total_ms, int *count, int reset);
+int vpb_prof_list(int cls, float *out_ms, int max);   /* per-launch durations in launch order */
 
 /* Count of kernel launches made by this library since the last reset. */
 long vpb_launch_count(int reset);

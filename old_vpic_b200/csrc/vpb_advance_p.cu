@@ -51,7 +51,21 @@ struct AdvanceArgs {
 
 // Segmented warp reduction of the 12 deposit values over runs of consecutive
 // lanes that share a voxel; the head lane of each run issues three REDG.128.
-__device__ __forceinline__ void deposit_runs(float (&v)[12], int key, bool active, float *__restrict__ a0) {
+template <bool HINT>
+__device__ __forceinline__ void red3(float *a, const float (&v)[12], uint64_t pol) {
+  if (HINT) {
+    red_add_v4_hint(a, v[0], v[1], v[2], v[3], pol);
+    red_add_v4_hint(a + 4, v[4], v[5], v[6], v[7], pol);
+    red_add_v4_hint(a + 8, v[8], v[9], v[10], v[11], pol);
+  } else {
+    red_add_v4(a, v[0], v[1], v[2], v[3]);
+    red_add_v4(a + 4, v[4], v[5], v[6], v[7]);
+    red_add_v4(a + 8, v[8], v[9], v[10], v[11]);
+  }
+}
+
+template <bool HINT>
+__device__ __forceinline__ void deposit_runs(float (&v)[12], int key, bool active, float *__restrict__ a0, uint64_t pol) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int k = active ? key : -1;
@@ -70,12 +84,7 @@ __device__ __forceinline__ void deposit_runs(float (&v)[12], int key, bool activ
       }
     }
   }
-  if (active && ((heads >> lane) & 1u)) {
-    float *a = a0 + 12 * (size_t)key;
-    red_add_v4(a, v[0], v[1], v[2], v[3]);
-    red_add_v4(a + 4, v[4], v[5], v[6], v[7]);
-    red_add_v4(a + 8, v[8], v[9], v[10], v[11]);
-  }
+  if (active && ((heads >> lane) & 1u)) red3<HINT>(a0 + 12 * (size_t)key, v, pol);
 }
 
 // Run move_p on up to 32 queued movers (one per lane), write the particles back and
@@ -118,7 +127,10 @@ __device__ __noinline__ void drain_movers(vpb_particle_t *__restrict__ p, float 
   }
 }
 
-template <int DEPOSIT>  // 0: one REDG.128 triple per particle, 1: warp run reduction first
+// DEPOSIT 0: one REDG.128 triple per particle, 1: warp run reduction first.
+// HINT: L2 eviction hints (particle stream evict_first, interpolator/accumulator evict_last).
+// PREFETCH: the next chunk's particle words are requested before the current chunk is computed.
+template <int DEPOSIT, bool HINT, bool PREFETCH>
 __global__ void __launch_bounds__(kWarps * 32, 4) advance_p_kernel(const AdvanceArgs A) {
   __shared__ float4 q_pos[kWarps][kQueue];    // dx,dy,dz,i
   __shared__ float4 q_mom[kWarps][kQueue];    // ux,uy,uz,q
@@ -130,11 +142,28 @@ __global__ void __launch_bounds__(kWarps * 32, 4) advance_p_kernel(const Advance
   const float one_third = (float)(1. / 3.);
   const float qdt_2mc = A.qdt_2mc, cdt_dx = A.cdt_dx, cdt_dy = A.cdt_dy, cdt_dz = A.cdt_dz;
   int q_head = 0, q_n = 0;   // warp-uniform ring state
+  const uint64_t pol_stream = HINT ? l2_policy_evict_first() : 0, pol_keep = HINT ? l2_policy_evict_last() : 0;
 
   const int stride = gridDim.x * kWarps;
+  float4 n0 = make_float4(0, 0, 0, 0), n1 = n0;
+  if (PREFETCH) {
+    const int k0 = (blockIdx.x * kWarps + w) * 32 + lane;
+    if (k0 < A.np) {
+      const float4 *pp = reinterpret_cast<const float4 *>(A.p + k0);
+      if (HINT) { n0 = ld_hint4(pp, pol_stream); n1 = ld_hint4(pp + 1, pol_stream); } else { n0 = pp[0]; n1 = pp[1]; }
+    }
+  }
   for (int chunk = blockIdx.x * kWarps + w; chunk < A.nchunks; chunk += stride) {
     const int k = chunk * 32 + lane;
     const bool valid = k < A.np;
+    float4 c0 = n0, c1 = n1;
+    if (PREFETCH) {
+      const int kn = k + stride * 32;
+      if (kn < A.np) {
+        const float4 *pn = reinterpret_cast<const float4 *>(A.p + kn);
+        if (HINT) { n0 = ld_hint4(pn, pol_stream); n1 = ld_hint4(pn + 1, pol_stream); } else { n0 = pn[0]; n1 = pn[1]; }
+      }
+    }
     bool inbnds = false, outbnds = false;
     int ii = 0;
     float dep[12];
@@ -145,16 +174,22 @@ __global__ void __launch_bounds__(kWarps * 32, 4) advance_p_kernel(const Advance
 
     if (valid) {
       float4 *pp = reinterpret_cast<float4 *>(A.p + k);
-      r0 = pp[0];
-      const float4 r1 = pp[1];
+      if (!PREFETCH) {
+        if (HINT) { c0 = ld_hint4(pp, pol_stream); c1 = ld_hint4(pp + 1, pol_stream); } else { c0 = pp[0]; c1 = pp[1]; }
+      }
+      r0 = c0;
+      const float4 r1 = c1;
       float dx = r0.x, dy = r0.y, dz = r0.z;
       ii = __float_as_int(r0.w);
       const char *fp = reinterpret_cast<const char *>(A.f + ii);
-      const float4 fe_x = ldg4(fp);        // ex dexdy dexdz d2exdydz
-      const float4 fe_y = ldg4(fp + 16);   // ey deydz deydx d2eydzdx
-      const float4 fe_z = ldg4(fp + 32);   // ez dezdx dezdy d2ezdxdy
-      const float4 fb_0 = ldg4(fp + 48);   // cbx dcbxdx cby dcbydy
-      const float2 fb_1 = ldg2(fp + 64);   // cbz dcbzdz
+      float4 fe_x, fe_y, fe_z, fb_0;   // {ex dexdy dexdz d2exdydz} {ey deydz deydx d2eydzdx} {ez dezdx dezdy d2ezdxdy} {cbx dcbxdx cby dcbydy}
+      float2 fb_1;                     // {cbz dcbzdz}
+      if (HINT) {
+        fe_x = ldg_hint4(fp, pol_keep); fe_y = ldg_hint4(fp + 16, pol_keep); fe_z = ldg_hint4(fp + 32, pol_keep);
+        fb_0 = ldg_hint4(fp + 48, pol_keep); fb_1 = ldg_hint2(fp + 64, pol_keep);
+      } else {
+        fe_x = ldg4(fp); fe_y = ldg4(fp + 16); fe_z = ldg4(fp + 32); fb_0 = ldg4(fp + 48); fb_1 = ldg2(fp + 64);
+      }
       const float hax = qdt_2mc * ((fe_x.x + dy * fe_x.y) + dz * (fe_x.z + dy * fe_x.w));
       const float hay = qdt_2mc * ((fe_y.x + dz * fe_y.y) + dx * (fe_y.z + dz * fe_y.w));
       const float haz = qdt_2mc * ((fe_z.x + dx * fe_z.y) + dy * (fe_z.z + dx * fe_z.w));
@@ -188,8 +223,8 @@ __global__ void __launch_bounds__(kWarps * 32, 4) advance_p_kernel(const Advance
       inbnds = v3 <= one && v4 <= one && v5 <= one && -v3 <= one && -v4 <= one && -v5 <= one;
       outbnds = !inbnds;
       if (inbnds) {
-        pp[0] = make_float4(v3, v4, v5, r0.w);
-        pp[1] = mom;
+        if (HINT) { st_hint4(pp, make_float4(v3, v4, v5, r0.w), pol_stream); st_hint4(pp + 1, mom, pol_stream); }
+        else { pp[0] = make_float4(v3, v4, v5, r0.w); pp[1] = mom; }
         dx = v0; dy = v1; dz = v2;
         v5 = q * ux * uy * uz * one_third;
         accumulate_j(q, ux, dy, dz, v5, dep[0], dep[1], dep[2], dep[3]);
@@ -201,14 +236,9 @@ __global__ void __launch_bounds__(kWarps * 32, 4) advance_p_kernel(const Advance
     }
 
     if (DEPOSIT == 0) {
-      if (inbnds) {
-        float *a = A.a + 12 * (size_t)ii;
-        red_add_v4(a, dep[0], dep[1], dep[2], dep[3]);
-        red_add_v4(a + 4, dep[4], dep[5], dep[6], dep[7]);
-        red_add_v4(a + 8, dep[8], dep[9], dep[10], dep[11]);
-      }
+      if (inbnds) red3<HINT>(A.a + 12 * (size_t)ii, dep, pol_keep);
     } else {
-      deposit_runs(dep, ii, inbnds, A.a);
+      deposit_runs<HINT>(dep, ii, inbnds, A.a, pol_keep);
     }
 
     // park the out-of-cell particles (in particle order) in this warp's ring
@@ -307,10 +337,19 @@ extern "C" void vpb_advance_p(vpb_domain_t *dom, vpb_particle_t *d_p, int np, fl
   if (grid > max_grid) grid = max_grid;
   {
     ProfScope prof(0);
-    if (tuning("advance_p.deposit", 1) == 0)
-      advance_p_kernel<0><<<grid, kWarps * 32, 0, c.stream>>>(A);
-    else
-      advance_p_kernel<1><<<grid, kWarps * 32, 0, c.stream>>>(A);
+    const int variant = (tuning("advance_p.deposit", 1) ? 4 : 0) | (tuning("advance_p.l2hint", 1) ? 2 : 0) |
+                        (tuning("advance_p.prefetch", 1) ? 1 : 0);
+    const dim3 gd(grid), bd(kWarps * 32);
+    switch (variant) {
+    case 0: advance_p_kernel<0, false, false><<<gd, bd, 0, c.stream>>>(A); break;
+    case 1: advance_p_kernel<0, false, true><<<gd, bd, 0, c.stream>>>(A); break;
+    case 2: advance_p_kernel<0, true, false><<<gd, bd, 0, c.stream>>>(A); break;
+    case 3: advance_p_kernel<0, true, true><<<gd, bd, 0, c.stream>>>(A); break;
+    case 4: advance_p_kernel<1, false, false><<<gd, bd, 0, c.stream>>>(A); break;
+    case 5: advance_p_kernel<1, false, true><<<gd, bd, 0, c.stream>>>(A); break;
+    case 6: advance_p_kernel<1, true, false><<<gd, bd, 0, c.stream>>>(A); break;
+    default: advance_p_kernel<1, true, true><<<gd, bd, 0, c.stream>>>(A); break;
+    }
   }
   const int tg = c.sm_count * 4;
   mover_popc_kernel<<<tg, 256, 0, c.stream>>>(A.bitmap, nwords, word_off, A.counters);

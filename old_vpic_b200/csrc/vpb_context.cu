@@ -67,6 +67,15 @@ void prof_end(int cls) {
 
 using namespace vpb;
 
+// individual durations (ms) of one kernel class in launch order; returns how many were written
+extern "C" int vpb_prof_list(int cls, float *out_ms, int max) {
+  VPB_CUDA(cudaStreamSynchronize(ctx().stream));
+  int n = 0;
+  for (size_t i = 0; i < g_prof_used && n < max; i++)
+    if (g_prof[i].cls == cls) VPB_CUDA(cudaEventElapsedTime(&out_ms[n++], g_prof[i].a, g_prof[i].b));
+  return n;
+}
+
 extern "C" void vpb_prof_enable(int on) { g_prof_on = on != 0; g_prof_used = 0; }
 
 // Sum of the recorded durations of one kernel class since the last collect of

@@ -111,39 +111,43 @@ void faces_local_adjust(vpb_domain_t *dom, vpb_field_t *d_f, AdjKind which) {
   const int n[3] = {g.nx, g.ny, g.nz};
   LocalOps ops;
   ops.n = 0;
-  for (int face = 0; face < 6; face++) {
-    const int X = face % 3, s = face < 3 ? -1 : 1, Y = (X + 1) % 3, Z = (X + 2) % 3;
-    const int bc = face_bc(g, X, s);
-    if (!is_local(g, bc)) continue;
-    const int fp = s < 0 ? 1 : n[X] + 1;
-    const bool pec = bc == vpb_pec_fields, sym = bc == vpb_symmetric_fields, pmc = bc == vpb_pmc_fields,
-               absb = bc == vpb_absorb_fields;
-    if (!(pec || sym || pmc || absb)) VPB_ERROR("Bad boundary condition encountered.");
-    switch (which) {
-    case ADJ_TANG_E:   // local.c:232-262
-      if (pec) {
-        add_op(ops, plane(g, X, fp, 0, 1), L_ZERO, cEX + Y); add_op(ops, plane(g, X, fp, 0, 1), L_ZERO, cTCAX + Y);
-        add_op(ops, plane(g, X, fp, 1, 0), L_ZERO, cEX + Z); add_op(ops, plane(g, X, fp, 1, 0), L_ZERO, cTCAX + Z);
+  // Boundary planes of different axes share edges, and "double it" is not idempotent: the two faces
+  // of one axis (disjoint planes) go into one launch, the three axes into consecutive launches.
+  for (int X = 0; X < 3; X++) {
+    for (int s = -1; s <= 1; s += 2) {
+      const int Y = (X + 1) % 3, Z = (X + 2) % 3;
+      const int bc = face_bc(g, X, s);
+      if (!is_local(g, bc)) continue;
+      const int fp = s < 0 ? 1 : n[X] + 1;
+      const bool pec = bc == vpb_pec_fields, sym = bc == vpb_symmetric_fields, pmc = bc == vpb_pmc_fields,
+                 absb = bc == vpb_absorb_fields;
+      if (!(pec || sym || pmc || absb)) VPB_ERROR("Bad boundary condition encountered.");
+      switch (which) {
+      case ADJ_TANG_E:   // local.c:232-262
+        if (pec) {
+          add_op(ops, plane(g, X, fp, 0, 1), L_ZERO, cEX + Y); add_op(ops, plane(g, X, fp, 0, 1), L_ZERO, cTCAX + Y);
+          add_op(ops, plane(g, X, fp, 1, 0), L_ZERO, cEX + Z); add_op(ops, plane(g, X, fp, 1, 0), L_ZERO, cTCAX + Z);
+        }
+        break;
+      case ADJ_NORM_B:   // :264-290
+        if (sym) add_op(ops, plane(g, X, fp, 0, 0), L_ZERO, cCBX + X);
+        break;
+      case ADJ_DIV_E:    // :292-318
+        if (pec || absb) add_op(ops, plane(g, X, fp, 1, 1), L_ZERO, cDIVE);
+        break;
+      case ADJ_JF:       // :325-353
+        add_op(ops, plane(g, X, fp, 0, 1), pec ? L_ZERO : L_DOUBLE, cJFX + Y);
+        add_op(ops, plane(g, X, fp, 1, 0), pec ? L_ZERO : L_DOUBLE, cJFX + Z);
+        break;
+      case ADJ_RHOF:     // :361-387
+        add_op(ops, plane(g, X, fp, 1, 1), pec ? L_ZERO : L_DOUBLE, cRHOF);
+        break;
+      case ADJ_RHOB:     // :394-420
+        if (pec) add_op(ops, plane(g, X, fp, 1, 1), L_ZERO, cRHOB);
+        break;
       }
-      break;
-    case ADJ_NORM_B:   // :264-290
-      if (sym) add_op(ops, plane(g, X, fp, 0, 0), L_ZERO, cCBX + X);
-      break;
-    case ADJ_DIV_E:    // :292-318
-      if (pec || absb) add_op(ops, plane(g, X, fp, 1, 1), L_ZERO, cDIVE);
-      break;
-    case ADJ_JF:       // :325-353
-      add_op(ops, plane(g, X, fp, 0, 1), pec ? L_ZERO : L_DOUBLE, cJFX + Y);
-      add_op(ops, plane(g, X, fp, 1, 0), pec ? L_ZERO : L_DOUBLE, cJFX + Z);
-      break;
-    case ADJ_RHOF:     // :361-387
-      add_op(ops, plane(g, X, fp, 1, 1), pec ? L_ZERO : L_DOUBLE, cRHOF);
-      break;
-    case ADJ_RHOB:     // :394-420
-      if (pec) add_op(ops, plane(g, X, fp, 1, 1), L_ZERO, cRHOB);
-      break;
     }
-    if (ops.n > kMaxOps - 4) { run_ops(d_f, ops, g); ops.n = 0; }
+    if (which == ADJ_JF || which == ADJ_RHOF) { run_ops(d_f, ops, g); ops.n = 0; }
   }
   run_ops(d_f, ops, g);
 }

@@ -58,6 +58,7 @@ SIGNATURES = {
     "vpb_launch_count": (_l, [_i]),
     "vpb_prof_enable": (None, [_i]),
     "vpb_prof_collect": (None, [_i, _vp, _vp, _i]),
+    "vpb_prof_list": (_i, [_i, _vp, _i]),
     "vpb_load_thermal": (None, [_vp, _vp, _i, _f, _f, C.c_ulonglong, _l]),
     "vpb_copy_positions": (None, [_vp, _vp, _l]),
     "vpb_comm_unique_id": (None, [_vp]),

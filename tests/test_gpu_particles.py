@@ -150,7 +150,7 @@ def test_accumulate_rho_p(vpb, orc):
     vpb.accumulate_rho_p(ptr(f_g), ptr(p), len(p), g.ref())
     for k in abi.field_dtype.names:
         if k != "rhof":
-            assert np.array_equal(f_g[k].view(np.uint8), f_o[k].view(np.uint8)), k
+            assert np.array_equal(np.ascontiguousarray(f_g[k]).view(np.uint8), np.ascontiguousarray(f_o[k]).view(np.uint8)), k
     assert max_rel(f_g["rhof"], f_o["rhof"]) < ACC_TOL
 
 
