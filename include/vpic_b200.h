@@ -164,6 +164,13 @@ long vpb_domain_nvoxel(const vpb_domain_t *dom);
  * in increasing particle index (boundary_p.c:168-176 relies on that). */
 void vpb_advance_p(vpb_domain_t *dom, vpb_particle_t *d_p, int np, float q_m, vpb_particle_mover_t *d_pm,
                    int max_nm, vpb_accumulator_t *d_a, const vpb_interpolator_t *d_f, int *d_nm);
+/* Same, with a traversal hint: d_partition (int[nvoxel+1], may be NULL) is partition[] as the last
+ * sort of this array left it.  It only decides the ORDER in which chunks of the array are visited
+ * (x-rows, y-blocked, z inner: keeps a voxel's neighbours in L2 once particles have drifted off
+ * their sorted voxel); results do not depend on it. */
+void vpb_advance_p_ordered(vpb_domain_t *dom, vpb_particle_t *d_p, int np, float q_m, vpb_particle_mover_t *d_pm,
+                           int max_nm, vpb_accumulator_t *d_a, const vpb_interpolator_t *d_f, int *d_nm,
+                           const int *d_partition);
 int vpb_advance_p_ignored(void);   /* movers the last vpb_advance_p dropped because pm[] was full (synchronises) */
 void vpb_center_p(vpb_domain_t *dom, vpb_particle_t *d_p, int np, float q_m, const vpb_interpolator_t *d_f);
 void vpb_uncenter_p(vpb_domain_t *dom, vpb_particle_t *d_p, int np, float q_m, const vpb_interpolator_t *d_f);

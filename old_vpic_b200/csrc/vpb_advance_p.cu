@@ -47,25 +47,51 @@ struct AdvanceArgs {
   int max_nm;
   int *counters;                  // [0] staged movers  [1] movers ignored (overflow)
   unsigned *bitmap;               // one bit per particle: has an unresolved mover
+  // traversal: work item -> range of chunks.  With a partition[] from the last sort the items are the
+  // x-rows of voxels visited y-blocked / z-inner (see work_range); without, 64-chunk slabs in order.
+  const int *partition;           // first particle of each voxel at the last sort (NULL: linear)
+  int nwork, by, sx, sy, sz, nv;
 };
+
+// Which chunks does work item t own?  A chunk belongs to the row that contains its first particle.
+// Rows are walked in blocks of `by` consecutive y, all z for a block before the next block, so that a
+// voxel and its z+-1 neighbours are touched within by rows (a few MB of particle stream) of each other
+// and their interpolator/accumulator lines are still in L2 -- the array position of a particle only
+// changes at a sort, its voxel drifts by about a cell every ten steps.
+__device__ __forceinline__ void work_range(const AdvanceArgs &A, int t, int &c0, int &c1) {
+  if (!A.partition) {
+    c0 = t * 64;
+    c1 = c0 + 64 < A.nchunks ? c0 + 64 : A.nchunks;
+    return;
+  }
+  int lo, hi;
+  if (t == A.nwork - 1) {                 // particles appended since the sort
+    lo = A.partition[A.nv];
+    hi = A.np;
+  } else {
+    const int per_block = A.by * A.sz;
+    const int yb = t / per_block, rem = t - yb * per_block;
+    const int z = rem / A.by, y = yb * A.by + (rem - z * A.by);
+    if (y >= A.sy) { c0 = c1 = 0; return; }
+    const int v0 = A.sx * (y + A.sy * z);
+    lo = A.partition[v0];
+    hi = A.partition[v0 + A.sx];
+  }
+  if (lo > A.np) lo = A.np;
+  if (hi > A.np) hi = A.np;
+  c0 = (lo + 31) >> 5;
+  c1 = (hi + 31) >> 5;
+}
+
+__device__ __forceinline__ void red3(float *a, const float (&v)[12]) {
+  red_add_v4(a, v[0], v[1], v[2], v[3]);
+  red_add_v4(a + 4, v[4], v[5], v[6], v[7]);
+  red_add_v4(a + 8, v[8], v[9], v[10], v[11]);
+}
 
 // Segmented warp reduction of the 12 deposit values over runs of consecutive
 // lanes that share a voxel; the head lane of each run issues three REDG.128.
-template <bool HINT>
-__device__ __forceinline__ void red3(float *a, const float (&v)[12], uint64_t pol) {
-  if (HINT) {
-    red_add_v4_hint(a, v[0], v[1], v[2], v[3], pol);
-    red_add_v4_hint(a + 4, v[4], v[5], v[6], v[7], pol);
-    red_add_v4_hint(a + 8, v[8], v[9], v[10], v[11], pol);
-  } else {
-    red_add_v4(a, v[0], v[1], v[2], v[3]);
-    red_add_v4(a + 4, v[4], v[5], v[6], v[7]);
-    red_add_v4(a + 8, v[8], v[9], v[10], v[11]);
-  }
-}
-
-template <bool HINT>
-__device__ __forceinline__ void deposit_runs(float (&v)[12], int key, bool active, float *__restrict__ a0, uint64_t pol) {
+__device__ __forceinline__ void deposit_runs(float (&v)[12], int key, bool active, float *__restrict__ a0) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int k = active ? key : -1;
@@ -84,7 +110,7 @@ __device__ __forceinline__ void deposit_runs(float (&v)[12], int key, bool activ
       }
     }
   }
-  if (active && ((heads >> lane) & 1u)) red3<HINT>(a0 + 12 * (size_t)key, v, pol);
+  if (active && ((heads >> lane) & 1u)) red3(a0 + 12 * (size_t)key, v);
 }
 
 // Run move_p on up to 32 queued movers (one per lane), write the particles back and
@@ -128,9 +154,7 @@ __device__ __noinline__ void drain_movers(vpb_particle_t *__restrict__ p, float 
 }
 
 // DEPOSIT 0: one REDG.128 triple per particle, 1: warp run reduction first.
-// HINT: L2 eviction hints (particle stream evict_first, interpolator/accumulator evict_last).
-// PREFETCH: the next chunk's particle words are requested before the current chunk is computed.
-template <int DEPOSIT, bool HINT, bool PREFETCH>
+template <int DEPOSIT>
 __global__ void __launch_bounds__(kWarps * 32, 4) advance_p_kernel(const AdvanceArgs A) {
   __shared__ float4 q_pos[kWarps][kQueue];    // dx,dy,dz,i
   __shared__ float4 q_mom[kWarps][kQueue];    // ux,uy,uz,q
@@ -142,121 +166,101 @@ __global__ void __launch_bounds__(kWarps * 32, 4) advance_p_kernel(const Advance
   const float one_third = (float)(1. / 3.);
   const float qdt_2mc = A.qdt_2mc, cdt_dx = A.cdt_dx, cdt_dy = A.cdt_dy, cdt_dz = A.cdt_dz;
   int q_head = 0, q_n = 0;   // warp-uniform ring state
-  const uint64_t pol_stream = HINT ? l2_policy_evict_first() : 0, pol_keep = HINT ? l2_policy_evict_last() : 0;
 
-  const int stride = gridDim.x * kWarps;
-  float4 n0 = make_float4(0, 0, 0, 0), n1 = n0;
-  if (PREFETCH) {
-    const int k0 = (blockIdx.x * kWarps + w) * 32 + lane;
-    if (k0 < A.np) {
-      const float4 *pp = reinterpret_cast<const float4 *>(A.p + k0);
-      if (HINT) { n0 = ld_hint4(pp, pol_stream); n1 = ld_hint4(pp + 1, pol_stream); } else { n0 = pp[0]; n1 = pp[1]; }
-    }
-  }
-  for (int chunk = blockIdx.x * kWarps + w; chunk < A.nchunks; chunk += stride) {
-    const int k = chunk * 32 + lane;
-    const bool valid = k < A.np;
-    float4 c0 = n0, c1 = n1;
-    if (PREFETCH) {
-      const int kn = k + stride * 32;
-      if (kn < A.np) {
-        const float4 *pn = reinterpret_cast<const float4 *>(A.p + kn);
-        if (HINT) { n0 = ld_hint4(pn, pol_stream); n1 = ld_hint4(pn + 1, pol_stream); } else { n0 = pn[0]; n1 = pn[1]; }
-      }
-    }
-    bool inbnds = false, outbnds = false;
-    int ii = 0;
-    float dep[12];
+  for (int t = blockIdx.x; t < A.nwork; t += gridDim.x) {
+    int c_begin, c_end;
+    work_range(A, t, c_begin, c_end);
+    for (int chunk = c_begin + w; chunk < c_end; chunk += kWarps) {
+      const int k = chunk * 32 + lane;
+      const bool valid = k < A.np;
+      bool inbnds = false, outbnds = false;
+      int ii = 0;
+      float dep[12];
 #pragma unroll
-    for (int c = 0; c < 12; c++) dep[c] = 0.f;
-    float4 r0 = make_float4(0, 0, 0, 0), mom = r0;
-    float hx = 0, hy = 0, hz = 0;
+      for (int c = 0; c < 12; c++) dep[c] = 0.f;
+      float4 r0 = make_float4(0, 0, 0, 0), mom = r0;
+      float hx = 0, hy = 0, hz = 0;
 
-    if (valid) {
-      float4 *pp = reinterpret_cast<float4 *>(A.p + k);
-      if (!PREFETCH) {
-        if (HINT) { c0 = ld_hint4(pp, pol_stream); c1 = ld_hint4(pp + 1, pol_stream); } else { c0 = pp[0]; c1 = pp[1]; }
+      if (valid) {
+        float4 *pp = reinterpret_cast<float4 *>(A.p + k);
+        r0 = pp[0];
+        const float4 r1 = pp[1];
+        float dx = r0.x, dy = r0.y, dz = r0.z;
+        ii = __float_as_int(r0.w);
+        const char *fp = reinterpret_cast<const char *>(A.f + ii);
+        const float4 fe_x = ldg4(fp);        // ex dexdy dexdz d2exdydz
+        const float4 fe_y = ldg4(fp + 16);   // ey deydz deydx d2eydzdx
+        const float4 fe_z = ldg4(fp + 32);   // ez dezdx dezdy d2ezdxdy
+        const float4 fb_0 = ldg4(fp + 48);   // cbx dcbxdx cby dcbydy
+        const float2 fb_1 = ldg2(fp + 64);   // cbz dcbzdz
+        const float hax = qdt_2mc * ((fe_x.x + dy * fe_x.y) + dz * (fe_x.z + dy * fe_x.w));
+        const float hay = qdt_2mc * ((fe_y.x + dz * fe_y.y) + dx * (fe_y.z + dz * fe_y.w));
+        const float haz = qdt_2mc * ((fe_z.x + dx * fe_z.y) + dy * (fe_z.z + dx * fe_z.w));
+        const float cbx = fb_0.x + dx * fb_0.y;
+        const float cby = fb_0.z + dy * fb_0.w;
+        const float cbz = fb_1.x + dz * fb_1.y;
+        float ux = r1.x, uy = r1.y, uz = r1.z;
+        const float q = r1.w;
+        ux += hax; uy += hay; uz += haz;
+        const float two_fifteenths = (float)(2. / 15.);
+        float v0 = qdt_2mc / sqrtf(one + (ux * ux + (uy * uy + uz * uz)));
+        float v1 = cbx * cbx + (cby * cby + cbz * cbz);
+        float v2 = (v0 * v0) * v1;
+        float v3 = v0 * (one + v2 * (one_third + v2 * two_fifteenths));
+        float v4 = v3 / (one + v1 * (v3 * v3));
+        v4 += v4;
+        v0 = ux + v3 * (uy * cbz - uz * cby);
+        v1 = uy + v3 * (uz * cbx - ux * cbz);
+        v2 = uz + v3 * (ux * cby - uy * cbx);
+        ux += v4 * (v1 * cbz - v2 * cby);
+        uy += v4 * (v2 * cbx - v0 * cbz);
+        uz += v4 * (v0 * cby - v1 * cbx);
+        ux += hax; uy += hay; uz += haz;
+        mom = make_float4(ux, uy, uz, q);   // stored momentum
+        v0 = one / sqrtf(one + (ux * ux + (uy * uy + uz * uz)));
+        ux *= cdt_dx; uy *= cdt_dy; uz *= cdt_dz;
+        ux *= v0; uy *= v0; uz *= v0;
+        v0 = dx + ux; v1 = dy + uy; v2 = dz + uz;      // streak midpoint
+        v3 = v0 + ux; v4 = v1 + uy;                     // new position
+        float v5 = v2 + uz;
+        inbnds = v3 <= one && v4 <= one && v5 <= one && -v3 <= one && -v4 <= one && -v5 <= one;
+        outbnds = !inbnds;
+        if (inbnds) {
+          pp[0] = make_float4(v3, v4, v5, r0.w);
+          pp[1] = mom;
+          dx = v0; dy = v1; dz = v2;
+          v5 = q * ux * uy * uz * one_third;
+          accumulate_j(q, ux, dy, dz, v5, dep[0], dep[1], dep[2], dep[3]);
+          accumulate_j(q, uy, dz, dx, v5, dep[4], dep[5], dep[6], dep[7]);
+          accumulate_j(q, uz, dx, dy, v5, dep[8], dep[9], dep[10], dep[11]);
+        } else {
+          hx = ux; hy = uy; hz = uz;
+        }
       }
-      r0 = c0;
-      const float4 r1 = c1;
-      float dx = r0.x, dy = r0.y, dz = r0.z;
-      ii = __float_as_int(r0.w);
-      const char *fp = reinterpret_cast<const char *>(A.f + ii);
-      float4 fe_x, fe_y, fe_z, fb_0;   // {ex dexdy dexdz d2exdydz} {ey deydz deydx d2eydzdx} {ez dezdx dezdy d2ezdxdy} {cbx dcbxdx cby dcbydy}
-      float2 fb_1;                     // {cbz dcbzdz}
-      if (HINT) {
-        fe_x = ldg_hint4(fp, pol_keep); fe_y = ldg_hint4(fp + 16, pol_keep); fe_z = ldg_hint4(fp + 32, pol_keep);
-        fb_0 = ldg_hint4(fp + 48, pol_keep); fb_1 = ldg_hint2(fp + 64, pol_keep);
+
+      if (DEPOSIT == 0) {
+        if (inbnds) red3(A.a + 12 * (size_t)ii, dep);
       } else {
-        fe_x = ldg4(fp); fe_y = ldg4(fp + 16); fe_z = ldg4(fp + 32); fb_0 = ldg4(fp + 48); fb_1 = ldg2(fp + 64);
+        deposit_runs(dep, ii, inbnds, A.a);
       }
-      const float hax = qdt_2mc * ((fe_x.x + dy * fe_x.y) + dz * (fe_x.z + dy * fe_x.w));
-      const float hay = qdt_2mc * ((fe_y.x + dz * fe_y.y) + dx * (fe_y.z + dz * fe_y.w));
-      const float haz = qdt_2mc * ((fe_z.x + dx * fe_z.y) + dy * (fe_z.z + dx * fe_z.w));
-      const float cbx = fb_0.x + dx * fb_0.y;
-      const float cby = fb_0.z + dy * fb_0.w;
-      const float cbz = fb_1.x + dz * fb_1.y;
-      float ux = r1.x, uy = r1.y, uz = r1.z;
-      const float q = r1.w;
-      ux += hax; uy += hay; uz += haz;
-      const float two_fifteenths = (float)(2. / 15.);
-      float v0 = qdt_2mc / sqrtf(one + (ux * ux + (uy * uy + uz * uz)));
-      float v1 = cbx * cbx + (cby * cby + cbz * cbz);
-      float v2 = (v0 * v0) * v1;
-      float v3 = v0 * (one + v2 * (one_third + v2 * two_fifteenths));
-      float v4 = v3 / (one + v1 * (v3 * v3));
-      v4 += v4;
-      v0 = ux + v3 * (uy * cbz - uz * cby);
-      v1 = uy + v3 * (uz * cbx - ux * cbz);
-      v2 = uz + v3 * (ux * cby - uy * cbx);
-      ux += v4 * (v1 * cbz - v2 * cby);
-      uy += v4 * (v2 * cbx - v0 * cbz);
-      uz += v4 * (v0 * cby - v1 * cbx);
-      ux += hax; uy += hay; uz += haz;
-      mom = make_float4(ux, uy, uz, q);   // stored momentum
-      v0 = one / sqrtf(one + (ux * ux + (uy * uy + uz * uz)));
-      ux *= cdt_dx; uy *= cdt_dy; uz *= cdt_dz;
-      ux *= v0; uy *= v0; uz *= v0;
-      v0 = dx + ux; v1 = dy + uy; v2 = dz + uz;      // streak midpoint
-      v3 = v0 + ux; v4 = v1 + uy;                     // new position
-      float v5 = v2 + uz;
-      inbnds = v3 <= one && v4 <= one && v5 <= one && -v3 <= one && -v4 <= one && -v5 <= one;
-      outbnds = !inbnds;
-      if (inbnds) {
-        if (HINT) { st_hint4(pp, make_float4(v3, v4, v5, r0.w), pol_stream); st_hint4(pp + 1, mom, pol_stream); }
-        else { pp[0] = make_float4(v3, v4, v5, r0.w); pp[1] = mom; }
-        dx = v0; dy = v1; dz = v2;
-        v5 = q * ux * uy * uz * one_third;
-        accumulate_j(q, ux, dy, dz, v5, dep[0], dep[1], dep[2], dep[3]);
-        accumulate_j(q, uy, dz, dx, v5, dep[4], dep[5], dep[6], dep[7]);
-        accumulate_j(q, uz, dx, dy, v5, dep[8], dep[9], dep[10], dep[11]);
-      } else {
-        hx = ux; hy = uy; hz = uz;
-      }
-    }
 
-    if (DEPOSIT == 0) {
-      if (inbnds) red3<HINT>(A.a + 12 * (size_t)ii, dep, pol_keep);
-    } else {
-      deposit_runs<HINT>(dep, ii, inbnds, A.a, pol_keep);
-    }
-
-    // park the out-of-cell particles (in particle order) in this warp's ring
-    const unsigned om = __ballot_sync(full, outbnds);
-    if (om) {
-      if (outbnds) {
-        const int e = (q_head + q_n + __popc(om & ((1u << lane) - 1u))) & (kQueue - 1);
-        q_pos[w][e] = r0;
-        q_mom[w][e] = mom;
-        q_disp[w][e] = make_float4(hx, hy, hz, __int_as_float(k));
-      }
-      q_n += __popc(om);
-      __syncwarp();
-      if (q_n >= 32) {
-        drain_movers(A.p, A.a, A.nbr, A.tmp_pm, A.max_nm, A.counters, A.bitmap, q_pos[w], q_mom[w], q_disp[w], q_head, 32);
-        q_head = (q_head + 32) & (kQueue - 1);
-        q_n -= 32;
+      // park the out-of-cell particles (in particle order) in this warp's ring
+      const unsigned om = __ballot_sync(full, outbnds);
+      if (om) {
+        if (outbnds) {
+          const int e = (q_head + q_n + __popc(om & ((1u << lane) - 1u))) & (kQueue - 1);
+          q_pos[w][e] = r0;
+          q_mom[w][e] = mom;
+          q_disp[w][e] = make_float4(hx, hy, hz, __int_as_float(k));
+        }
+        q_n += __popc(om);
         __syncwarp();
+        if (q_n >= 32) {
+          drain_movers(A.p, A.a, A.nbr, A.tmp_pm, A.max_nm, A.counters, A.bitmap, q_pos[w], q_mom[w], q_disp[w], q_head, 32);
+          q_head = (q_head + 32) & (kQueue - 1);
+          q_n -= 32;
+          __syncwarp();
+        }
       }
     }
   }
@@ -290,8 +294,9 @@ __global__ void __launch_bounds__(256) mover_place_kernel(const unsigned *__rest
 
 using namespace vpb;
 
-extern "C" void vpb_advance_p(vpb_domain_t *dom, vpb_particle_t *d_p, int np, float q_m, vpb_particle_mover_t *d_pm,
-                              int max_nm, vpb_accumulator_t *d_a, const vpb_interpolator_t *d_f, int *d_nm) {
+extern "C" void vpb_advance_p_ordered(vpb_domain_t *dom, vpb_particle_t *d_p, int np, float q_m, vpb_particle_mover_t *d_pm,
+                                      int max_nm, vpb_accumulator_t *d_a, const vpb_interpolator_t *d_f, int *d_nm,
+                                      const int *d_partition) {
   if (!dom) VPB_ERROR("Bad grid");
   if (!d_p) VPB_ERROR("Bad particle array");
   if (np < 0) VPB_ERROR("Bad number of particles");
@@ -331,25 +336,19 @@ extern "C" void vpb_advance_p(vpb_domain_t *dom, vpb_particle_t *d_p, int np, fl
   void *scan_tmp = s + off_scan;
   VPB_CUDA(cudaMemsetAsync(s, 0, off_bits + (size_t)nwords * 4, c.stream));   // counters + bitmap
 
+  A.partition = tuning("advance_p.ordered", 1) ? d_partition : nullptr;
+  A.sx = g.sx; A.sy = g.sy; A.sz = g.sz; A.nv = g.nv;
+  A.by = tuning("advance_p.by", 16);
+  if (A.by < 1) A.by = 1;
+  if (A.partition) A.nwork = ((g.sy + A.by - 1) / A.by) * A.by * g.sz + 1;
+  else A.nwork = (A.nchunks + 63) / 64;
   const int per_sm = tuning("advance_p.ctas_per_sm", 4);
   int grid = c.sm_count * per_sm;
-  const int max_grid = (A.nchunks + kWarps - 1) / kWarps;
-  if (grid > max_grid) grid = max_grid;
+  if (grid > A.nwork) grid = A.nwork;
   {
     ProfScope prof(0);
-    const int variant = (tuning("advance_p.deposit", 1) ? 4 : 0) | (tuning("advance_p.l2hint", 1) ? 2 : 0) |
-                        (tuning("advance_p.prefetch", 1) ? 1 : 0);
-    const dim3 gd(grid), bd(kWarps * 32);
-    switch (variant) {
-    case 0: advance_p_kernel<0, false, false><<<gd, bd, 0, c.stream>>>(A); break;
-    case 1: advance_p_kernel<0, false, true><<<gd, bd, 0, c.stream>>>(A); break;
-    case 2: advance_p_kernel<0, true, false><<<gd, bd, 0, c.stream>>>(A); break;
-    case 3: advance_p_kernel<0, true, true><<<gd, bd, 0, c.stream>>>(A); break;
-    case 4: advance_p_kernel<1, false, false><<<gd, bd, 0, c.stream>>>(A); break;
-    case 5: advance_p_kernel<1, false, true><<<gd, bd, 0, c.stream>>>(A); break;
-    case 6: advance_p_kernel<1, true, false><<<gd, bd, 0, c.stream>>>(A); break;
-    default: advance_p_kernel<1, true, true><<<gd, bd, 0, c.stream>>>(A); break;
-    }
+    if (tuning("advance_p.deposit", 1) == 0) advance_p_kernel<0><<<grid, kWarps * 32, 0, c.stream>>>(A);
+    else advance_p_kernel<1><<<grid, kWarps * 32, 0, c.stream>>>(A);
   }
   const int tg = c.sm_count * 4;
   mover_popc_kernel<<<tg, 256, 0, c.stream>>>(A.bitmap, nwords, word_off, A.counters);
@@ -357,6 +356,11 @@ extern "C" void vpb_advance_p(vpb_domain_t *dom, vpb_particle_t *d_p, int np, fl
   mover_place_kernel<<<tg, 256, 0, c.stream>>>(A.bitmap, word_off, (const float4 *)A.tmp_pm, (float4 *)d_pm, max_nm, A.counters, d_nm);
   count_launch(3 + scan_launches(nwords));
   VPB_CUDA(cudaGetLastError());
+}
+
+extern "C" void vpb_advance_p(vpb_domain_t *dom, vpb_particle_t *d_p, int np, float q_m, vpb_particle_mover_t *d_pm, int max_nm,
+                              vpb_accumulator_t *d_a, const vpb_interpolator_t *d_f, int *d_nm) {
+  vpb_advance_p_ordered(dom, d_p, np, q_m, d_pm, max_nm, d_a, d_f, d_nm, nullptr);
 }
 
 // number of movers the last vpb_advance_p had to drop because pm[] was full (advance_p.cxx:463-465)

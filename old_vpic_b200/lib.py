@@ -80,6 +80,7 @@ SIGNATURES = {
     "vpb_domain_destroy": (None, [_vp]),
     "vpb_domain_nvoxel": (_l, [_vp]),
     "vpb_advance_p": (None, [_vp, _vp, _i, _f, _vp, _i, _vp, _vp, _vp]),
+    "vpb_advance_p_ordered": (None, [_vp, _vp, _i, _f, _vp, _i, _vp, _vp, _vp, _vp]),
     "vpb_advance_p_ignored": (_i, []),
     "vpb_center_p": (None, [_vp, _vp, _i, _f, _vp]),
     "vpb_uncenter_p": (None, [_vp, _vp, _i, _f, _vp]),

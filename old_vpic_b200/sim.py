@@ -47,6 +47,7 @@ class Species:
         self.p = DevArray(L, max_np, abi.particle_dtype)
         self.pm = DevArray(L, max_nm, abi.mover_dtype)
         self.nm = DevArray(L, 4, np.int32)
+        self.partition = None        # int[nv+1] from the last sort of this species (traversal hint)
 
 
 class Simulation:
@@ -74,7 +75,6 @@ class Simulation:
             self.m.upload(from_vac)
         self.species = []
         self.sort_tmp = None
-        self.partition = DevArray(self.L, self.nv + 1, np.int32)
         self.step = 0
         self.clean_div_e_interval = 0
         self.clean_div_b_interval = 0
@@ -103,7 +103,9 @@ class Simulation:
             if self.sort_tmp is not None:
                 self.sort_tmp.free()
             self.sort_tmp = DevArray(L, sp.max_np, abi.particle_dtype)
-        L.vpb_sort_p(self.dom, sp.p.ptr, self.sort_tmp.ptr, sp.np, self.partition.ptr)
+        if sp.partition is None:
+            sp.partition = DevArray(L, self.nv + 1, np.int32)
+        L.vpb_sort_p(self.dom, sp.p.ptr, self.sort_tmp.ptr, sp.np, sp.partition.ptr)
         sp.p, self.sort_tmp = self.sort_tmp, sp.p     # out-of-place: swap (sort_p.c:76-77)
 
     def advance_fields(self):
@@ -120,7 +122,8 @@ class Simulation:
             if sp.sort_interval > 0 and self.step % sp.sort_interval == 0:
                 self.sort(sp)
         for sp in self.species:                                         # :70-73
-            L.vpb_advance_p(dom, sp.p.ptr, sp.np, sp.q_m, sp.pm.ptr, sp.max_nm, self.a.ptr, self.fi.ptr, sp.nm.ptr)
+            L.vpb_advance_p_ordered(dom, sp.p.ptr, sp.np, sp.q_m, sp.pm.ptr, sp.max_nm, self.a.ptr, self.fi.ptr, sp.nm.ptr,
+                                    None if sp.partition is None else sp.partition.ptr)
         # reduce_accumulators (:74) is a no-op with one replica; boundary_p (:94-96): see Simulation.migrate
         self.migrate()
         L.vpb_clear_jf(dom, self.f.ptr)                                 # :109
