@@ -123,7 +123,7 @@ def cpu_reference_rate(cells, ppc, steps, warmup):
     acc = abi.aligned_zeros(nrep * stride, abi.accumulator_dtype)
     fi = abi.aligned_zeros(g.nv, abi.interpolator_dtype)
     species = []
-    for q, q_m in ((-1.0, -1.0), (1.0, 1.0)):
+    for q, q_m in ((-1.0 / ppc, -1.0), (1.0 / ppc, 1.0)):   # q = +-V/N: plasma frequency 1 (SURVEY.md 8d, C1 recipe)
         p = abi.aligned_zeros(np_, abi.particle_dtype)
         p["i"] = np.repeat(helpers.interior_voxels(g), ppc)
         for k in ("dx", "dy", "dz"):
@@ -208,7 +208,9 @@ def run_b200(args):
     sim = Simulation(g, n_mat=1, L=L)
     np_ = n ** 3 * args.ppc
     max_np = int(np_ * (1.0 if world == 1 else 1.02)) + 1024
-    for name, q_m, q, seed in (("electron", -1.0, -1.0, 7 + rank), ("ion", 1.0, 1.0, 1007 + rank)):
+    # macro-charge q = +-(cell volume)/ppc so that the plasma frequency is 1 (the reference's thermal recipe,
+    # q = +-L^3/Ne); dt*wpe = 0.55
+    for name, q_m, q, seed in (("electron", -1.0, -1.0 / args.ppc, 7 + rank), ("ion", 1.0, 1.0 / args.ppc, 1007 + rank)):
         sp = sim.define_species(name, q_m, max_np, sort_interval=SORT_INTERVAL)
         sim.load_thermal(sp, args.ppc, VTH, q, seed, tag0=rank * (1 << 40))
     L.vpb_sync()
@@ -318,7 +320,7 @@ def e2e_measure(L, args, abi, helpers):
         p[k] = rng.uniform(-1, 1, np_).astype(np.float32)
     for k in ("ux", "uy", "uz"):
         p[k] = (VTH * rng.standard_normal(np_)).astype(np.float32)
-    p["q"] = -1.0
+    p["q"] = -1.0 / ppc
     max_nm = max(2 * np_ // 25, 16)
     pm = pinned(max_nm, abi.mover_dtype)
     acc = pinned(g.nv, abi.accumulator_dtype)

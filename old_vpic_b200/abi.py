@@ -74,6 +74,12 @@ assert C.sizeof(GridStruct) == 240 and GridStruct.bc.offset == 84 and GridStruct
 assert SpeciesStruct.p.offset == 16 and SpeciesStruct.partition.offset == 56 and SpeciesStruct.name.offset == 72
 
 
+class SpeciesState(C.Structure):
+    """include/vpic_b200.h vpb_species_state_t: one species' device arrays for vpb_boundary_p."""
+    _fields_ = [("p", C.c_void_p), ("pm", C.c_void_p), ("np", C.c_int), ("max_np", C.c_int), ("nm", C.c_int),
+                ("max_nm", C.c_int), ("id", C.c_int), ("_pad", C.c_int)]
+
+
 class FieldAdvanceMethods(C.Structure):
     """src/field_advance/field_advance.h:185-302: 20 function pointers."""
     NAMES = ("new_field", "delete_field", "new_material_coefficients", "delete_material_coefficients", "advance_b",

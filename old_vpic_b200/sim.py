@@ -139,10 +139,35 @@ class Simulation:
             L.vpb_load_interpolator(dom, self.fi.ptr, self.f.ptr)       # :214
         self.step += 1
 
+    NUM_COMM_ROUND = 3     # vpic.cxx:17
+
+    def _needs_boundary_p(self):
+        """advance_p can only leave movers where a face is shared with another rank or absorbs particles."""
+        if getattr(self, "_nbp", None) is None:
+            g = self.grid
+            remote = any(0 <= g.struct.bc[b] < g.nproc and g.struct.bc[b] != g.rank
+                         for b in (abi.boundary(-1, 0, 0), abi.boundary(1, 0, 0), abi.boundary(0, -1, 0), abi.boundary(0, 1, 0),
+                                   abi.boundary(0, 0, -1), abi.boundary(0, 0, 1)))
+            absorbing = bool(np.any((g.neighbor < 0) & (g.neighbor != abi.REFLECT_PARTICLES)))
+            self._nbp = remote or absorbing
+        return self._nbp
+
     def migrate(self):
-        """boundary_p (advance.cxx:94-96).  Filled in by the multi-GPU driver; on a single periodic or
-        reflecting rank advance_p leaves no movers."""
-        return
+        """boundary_p x num_comm_round (advance.cxx:94-103)."""
+        if not self.species or not self._needs_boundary_p():
+            return
+        L = self.L
+        st = (abi.SpeciesState * len(self.species))()
+        nms = self.mover_counts()                     # one small read-back (synchronises)
+        for k, sp in enumerate(self.species):
+            st[k].p, st[k].pm, st[k].np, st[k].max_np = sp.p.ptr, sp.pm.ptr, sp.np, sp.max_np
+            st[k].nm, st[k].max_nm, st[k].id = nms[k], sp.max_nm, sp.id
+        for _ in range(self.NUM_COMM_ROUND):
+            L.vpb_boundary_p(self.dom, st, len(self.species), self.f.ptr, self.a.ptr)
+        for k, sp in enumerate(self.species):
+            sp.np = st[k].np
+            if st[k].nm:
+                print("Warning: ignoring %d unprocessed %s movers (increase num_comm_round)" % (st[k].nm, sp.name))
 
     def clean_div_e(self):                                               # advance.cxx:151-173
         L, dom, f = self.L, self.dom, self.f.ptr
