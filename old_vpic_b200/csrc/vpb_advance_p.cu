@@ -26,7 +26,7 @@
 //    popcount so pm[] comes out in increasing particle index, which
 //    boundary_p.c:168-176 relies on.  The post-pass kernels return at once when
 //    nothing was staged (the usual case on a periodic or reflecting rank).
-#include "vpb_common.cuh"
+#include "vpb_advance_p.cuh"
 #include "vpb_move_p.cuh"
 #include "vpb_scan.cuh"
 
@@ -35,24 +35,6 @@ namespace vpb {
 constexpr int kWarps = 8;            // warps per CTA
 constexpr int kQueue = 64;           // ring capacity per warp (>= 31 + 32)
 
-struct AdvanceArgs {
-  vpb_particle_t *p;
-  int np;
-  int nchunks;                    // ceil(np/32)
-  float qdt_2mc, cdt_dx, cdt_dy, cdt_dz;
-  float *a;                       // accumulator_t[nv] viewed as float[12*nv]
-  const vpb_interpolator_t *f;
-  const int32_t *nbr;
-  vpb_particle_mover_t *tmp_pm;   // unordered staging, capacity max_nm
-  int max_nm;
-  int *counters;                  // [0] staged movers  [1] movers ignored (overflow)
-  unsigned *bitmap;               // one bit per particle: has an unresolved mover
-  // traversal: work item -> range of chunks.  With a partition[] from the last sort the items are the
-  // x-rows of voxels visited y-blocked / z-inner (see work_range); without, 64-chunk slabs in order.
-  const int *partition;           // first particle of each voxel at the last sort (NULL: linear)
-  int nwork, by, sx, sy, sz, nv;
-};
-
 // Which chunks does work item t own?  A chunk belongs to the row that contains its first particle.
 // Rows are walked in blocks of `by` consecutive y, all z for a block before the next block, so that a
 // voxel and its z+-1 neighbours are touched within by rows (a few MB of particle stream) of each other
@@ -60,8 +42,8 @@ struct AdvanceArgs {
 // changes at a sort, its voxel drifts by about a cell every ten steps.
 __device__ __forceinline__ void work_range(const AdvanceArgs &A, int t, int &c0, int &c1) {
   if (!A.partition) {
-    c0 = t * 64;
-    c1 = c0 + 64 < A.nchunks ? c0 + 64 : A.nchunks;
+    c0 = A.chunk_lo + t * 64;
+    c1 = c0 + 64 < A.chunk_hi ? c0 + 64 : A.chunk_hi;
     return;
   }
   int lo, hi;
@@ -267,6 +249,202 @@ __global__ void __launch_bounds__(kWarps * 32, 4) advance_p_kernel(const Advance
   if (q_n) drain_movers(A.p, A.a, A.nbr, A.tmp_pm, A.max_nm, A.counters, A.bitmap, q_pos[w], q_mom[w], q_disp[w], q_head, q_n);
 }
 
+// ---------------------------------------------------------------------------
+// TMA variant.  The particle stream goes global -> shared -> global with 1-D bulk
+// async copies (cp.async.bulk, SASS UBLKCP) carrying an L2 evict-first policy:
+// each warp owns a ring of kStages 1536-byte tiles (32 particles x 48 B) with one
+// mbarrier per tile, keeps kStages-1 tiles in flight ahead of the one it computes
+// on, reads/writes its particle with conflict-free LDS.128/STS.128 (48-byte lane
+// stride), and writes the whole tile back with one bulk store.  Full 128-byte
+// lines travel to and from DRAM exactly once, and because the stream no longer
+// competes for L2, the interpolator/accumulator lines the particles gather from
+// and scatter to stay resident there even after the particles have drifted off
+// their sorted voxels (profiles/: DRAM bytes per particle 195 -> ~100 when
+// drifted).
+// ---------------------------------------------------------------------------
+constexpr int kStages = 3;
+constexpr int kTileBytes = 32 * 48;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tma_load_tile(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void tma_store_tile(void *dst, uint32_t src, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(src), "r"(bytes), "l"(pol) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+
+struct TmaSmem {
+  float4 tile[kWarps][kStages][96];
+  float4 q_pos[kWarps][kQueue], q_mom[kWarps][kQueue], q_disp[kWarps][kQueue];
+  uint64_t full[kWarps][kStages];
+};
+
+template <int DEPOSIT>
+__global__ void __launch_bounds__(kWarps * 32, 3) advance_p_tma_kernel(const AdvanceArgs A) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  TmaSmem &S = *reinterpret_cast<TmaSmem *>(smem_raw);
+
+  const unsigned fullmask = 0xffffffffu;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const float one = 1.f;
+  const float one_third = (float)(1. / 3.);
+  const float qdt_2mc = A.qdt_2mc, cdt_dx = A.cdt_dx, cdt_dy = A.cdt_dy, cdt_dz = A.cdt_dz;
+  int q_head = 0, q_n = 0;
+  const uint64_t pol = l2_policy_evict_first();
+  char *const gbase = reinterpret_cast<char *>(A.p);
+
+  if (lane == 0) {
+    for (int s = 0; s < kStages; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&S.full[w][s])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  const int gw_stride = gridDim.x * kWarps;
+  const int first = A.chunk_lo + blockIdx.x * kWarps + w;
+  auto tile_bytes = [&](int chunk) -> uint32_t {
+    const int n = A.np - chunk * 32;
+    return (uint32_t)((n < 32 ? n : 32) * 48);
+  };
+  if (lane == 0) {
+    for (int j = 0; j < kStages - 1; j++) {
+      const int c = first + j * gw_stride;
+      if (c < A.chunk_hi)
+        tma_load_tile(smem_u32(&S.tile[w][j][0]), gbase + (size_t)c * kTileBytes, tile_bytes(c), smem_u32(&S.full[w][j]), pol);
+    }
+  }
+
+  int it = 0;
+  for (int chunk = first; chunk < A.chunk_hi; chunk += gw_stride, ++it) {
+    const int stage = it % kStages;
+    mbar_wait(smem_u32(&S.full[w][stage]), (uint32_t)((it / kStages) & 1));
+    const int k = chunk * 32 + lane;
+    const bool valid = k < A.np;
+    bool inbnds = false, outbnds = false;
+    int ii = 0;
+    float dep[12];
+#pragma unroll
+    for (int c = 0; c < 12; c++) dep[c] = 0.f;
+    float4 r0 = make_float4(0, 0, 0, 0), mom = r0;
+    float hx = 0, hy = 0, hz = 0;
+    float4 *tp = &S.tile[w][stage][lane * 3];
+
+    if (valid) {
+      r0 = tp[0];
+      const float4 r1 = tp[1];
+      float dx = r0.x, dy = r0.y, dz = r0.z;
+      ii = __float_as_int(r0.w);
+      const char *fp = reinterpret_cast<const char *>(A.f + ii);
+      const float4 fe_x = ldg4(fp);
+      const float4 fe_y = ldg4(fp + 16);
+      const float4 fe_z = ldg4(fp + 32);
+      const float4 fb_0 = ldg4(fp + 48);
+      const float2 fb_1 = ldg2(fp + 64);
+      const float hax = qdt_2mc * ((fe_x.x + dy * fe_x.y) + dz * (fe_x.z + dy * fe_x.w));
+      const float hay = qdt_2mc * ((fe_y.x + dz * fe_y.y) + dx * (fe_y.z + dz * fe_y.w));
+      const float haz = qdt_2mc * ((fe_z.x + dx * fe_z.y) + dy * (fe_z.z + dx * fe_z.w));
+      const float cbx = fb_0.x + dx * fb_0.y;
+      const float cby = fb_0.z + dy * fb_0.w;
+      const float cbz = fb_1.x + dz * fb_1.y;
+      float ux = r1.x, uy = r1.y, uz = r1.z;
+      const float q = r1.w;
+      ux += hax; uy += hay; uz += haz;
+      const float two_fifteenths = (float)(2. / 15.);
+      float v0 = qdt_2mc / sqrtf(one + (ux * ux + (uy * uy + uz * uz)));
+      float v1 = cbx * cbx + (cby * cby + cbz * cbz);
+      float v2 = (v0 * v0) * v1;
+      float v3 = v0 * (one + v2 * (one_third + v2 * two_fifteenths));
+      float v4 = v3 / (one + v1 * (v3 * v3));
+      v4 += v4;
+      v0 = ux + v3 * (uy * cbz - uz * cby);
+      v1 = uy + v3 * (uz * cbx - ux * cbz);
+      v2 = uz + v3 * (ux * cby - uy * cbx);
+      ux += v4 * (v1 * cbz - v2 * cby);
+      uy += v4 * (v2 * cbx - v0 * cbz);
+      uz += v4 * (v0 * cby - v1 * cbx);
+      ux += hax; uy += hay; uz += haz;
+      mom = make_float4(ux, uy, uz, q);
+      v0 = one / sqrtf(one + (ux * ux + (uy * uy + uz * uz)));
+      ux *= cdt_dx; uy *= cdt_dy; uz *= cdt_dz;
+      ux *= v0; uy *= v0; uz *= v0;
+      v0 = dx + ux; v1 = dy + uy; v2 = dz + uz;
+      v3 = v0 + ux; v4 = v1 + uy;
+      float v5 = v2 + uz;
+      inbnds = v3 <= one && v4 <= one && v5 <= one && -v3 <= one && -v4 <= one && -v5 <= one;
+      outbnds = !inbnds;
+      if (inbnds) {
+        tp[0] = make_float4(v3, v4, v5, r0.w);
+        tp[1] = mom;
+        dx = v0; dy = v1; dz = v2;
+        v5 = q * ux * uy * uz * one_third;
+        accumulate_j(q, ux, dy, dz, v5, dep[0], dep[1], dep[2], dep[3]);
+        accumulate_j(q, uy, dz, dx, v5, dep[4], dep[5], dep[6], dep[7]);
+        accumulate_j(q, uz, dx, dy, v5, dep[8], dep[9], dep[10], dep[11]);
+      } else {
+        hx = ux; hy = uy; hz = uz;
+      }
+    }
+    // the tile goes back as one bulk store (out-of-cell particles unchanged; drain_movers rewrites them later)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_tile(gbase + (size_t)chunk * kTileBytes, smem_u32(&S.tile[w][stage][0]), tile_bytes(chunk), pol);
+      // refill the stage used one iteration ago (its store must have finished reading shared memory)
+      const int cn = chunk + (kStages - 1) * gw_stride;
+      if (cn < A.chunk_hi) {
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        const int sn = (it + kStages - 1) % kStages;
+        tma_load_tile(smem_u32(&S.tile[w][sn][0]), gbase + (size_t)cn * kTileBytes, tile_bytes(cn), smem_u32(&S.full[w][sn]), pol);
+      }
+    }
+
+    if (DEPOSIT == 0) {
+      if (inbnds) red3(A.a + 12 * (size_t)ii, dep);
+    } else {
+      deposit_runs(dep, ii, inbnds, A.a);
+    }
+
+    const unsigned om = __ballot_sync(fullmask, outbnds);
+    if (om) {
+      if (outbnds) {
+        const int e = (q_head + q_n + __popc(om & ((1u << lane) - 1u))) & (kQueue - 1);
+        S.q_pos[w][e] = r0;
+        S.q_mom[w][e] = mom;
+        S.q_disp[w][e] = make_float4(hx, hy, hz, __int_as_float(k));
+      }
+      q_n += __popc(om);
+      __syncwarp();
+      if (q_n >= 32) {
+        // the movers' tiles must have landed in global memory before their final state is written over them
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+          asm volatile("fence.proxy.async;" ::: "memory");
+        }
+        __syncwarp();
+        drain_movers(A.p, A.a, A.nbr, A.tmp_pm, A.max_nm, A.counters, A.bitmap, S.q_pos[w], S.q_mom[w], S.q_disp[w], q_head, 32);
+        q_head = (q_head + 32) & (kQueue - 1);
+        q_n -= 32;
+        __syncwarp();
+      }
+    }
+  }
+  if (lane == 0) {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    asm volatile("fence.proxy.async;" ::: "memory");
+  }
+  __syncwarp();
+  if (q_n) drain_movers(A.p, A.a, A.nbr, A.tmp_pm, A.max_nm, A.counters, A.bitmap, S.q_pos[w], S.q_mom[w], S.q_disp[w], q_head, q_n);
+}
+
 // ---- ordered mover emission (post-pass; every kernel leaves at once if nothing was staged) ----
 
 __global__ void __launch_bounds__(256) mover_popc_kernel(const unsigned *__restrict__ bitmap, int nwords, int *__restrict__ cnt,
@@ -292,6 +470,91 @@ __global__ void __launch_bounds__(256) mover_place_kernel(const unsigned *__rest
 
 }  // namespace vpb
 
+namespace vpb {
+
+// An advance_p call in three parts so that a caller can feed the particle array in pieces (the staged
+// host-buffer path of vpb_dropin.cu overlaps H2D / kernel / D2H per piece).
+void advance_p_begin(vpb_domain_t *dom, int np, float q_m, int max_nm, vpb_accumulator_t *d_a, const vpb_interpolator_t *d_f,
+                     AdvanceJob &J, cudaStream_t st) {
+  const DomainDev &g = dom->d;
+  AdvanceArgs &A = J.A;
+  A.p = nullptr;
+  A.np = np;
+  A.nchunks = (np + 31) / 32;
+  // same expressions, same types as advance_p.cxx:425-428
+  A.qdt_2mc = (float)(0.5 * q_m * g.dt / g.cvac);
+  A.cdt_dx = g.cvac * g.dt * g.rdx;
+  A.cdt_dy = g.cvac * g.dt * g.rdy;
+  A.cdt_dz = g.cvac * g.dt * g.rdz;
+  A.a = reinterpret_cast<float *>(d_a);
+  A.f = d_f;
+  A.nbr = g.nbr;
+  A.max_nm = max_nm;
+  A.sx = g.sx; A.sy = g.sy; A.sz = g.sz; A.nv = g.nv;
+  A.by = tuning("advance_p.by", 16);
+  if (A.by < 1) A.by = 1;
+  // scratch: counters | bitmap[nwords] | word_cnt/off[nwords] | tmp_pm[max_nm] | scan scratch
+  J.nwords = A.nchunks > 0 ? A.nchunks : 1;
+  auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t off_bits = 256, off_cnt = off_bits + al((size_t)J.nwords * 4), off_tmp = off_cnt + al((size_t)J.nwords * 4),
+               off_scan = off_tmp + al((size_t)max_nm * 16 + 16);
+  char *s = (char *)scratch(off_scan + scan_scratch_bytes(J.nwords));
+  A.counters = (int *)s;
+  A.bitmap = (unsigned *)(s + off_bits);
+  J.word_off = (int *)(s + off_cnt);
+  A.tmp_pm = (vpb_particle_mover_t *)(s + off_tmp);
+  J.scan_tmp = s + off_scan;
+  VPB_CUDA(cudaMemsetAsync(s, 0, off_bits + (size_t)J.nwords * 4, st));   // counters + bitmap
+}
+
+// particles k0..k1-1 (k0 a multiple of 32); d_base[k] must address particle k
+void advance_p_range(AdvanceJob &J, vpb_particle_t *d_base, int k0, int k1, const int *d_partition, cudaStream_t st) {
+  if (k1 <= k0) return;
+  Context &c = ctx();
+  AdvanceArgs A = J.A;
+  A.p = d_base;
+  A.np = k1;
+  A.chunk_lo = k0 / 32;
+  A.chunk_hi = (k1 + 31) / 32;
+  A.partition = (k0 == 0 && k1 == J.A.np && tuning("advance_p.ordered", 1)) ? d_partition : nullptr;
+  if (A.partition) A.nwork = ((A.sy + A.by - 1) / A.by) * A.by * A.sz + 1;
+  else A.nwork = (A.chunk_hi - A.chunk_lo + 63) / 64;
+  const bool tma = tuning("advance_p.tma", 1) != 0 && (reinterpret_cast<uintptr_t>(d_base) & 15) == 0;
+  if (tma) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      VPB_CUDA(cudaFuncSetAttribute(advance_p_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmaSmem)));
+      VPB_CUDA(cudaFuncSetAttribute(advance_p_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmaSmem)));
+      attr_set = true;
+    }
+    const int nch = A.chunk_hi - A.chunk_lo;
+    int grid = c.sm_count * tuning("advance_p.tma_ctas_per_sm", 3);
+    if (grid > (nch + kWarps - 1) / kWarps) grid = (nch + kWarps - 1) / kWarps;
+    if (tuning("advance_p.deposit", 1) == 0) advance_p_tma_kernel<0><<<grid, kWarps * 32, sizeof(TmaSmem), st>>>(A);
+    else advance_p_tma_kernel<1><<<grid, kWarps * 32, sizeof(TmaSmem), st>>>(A);
+  } else {
+    int grid = c.sm_count * tuning("advance_p.ctas_per_sm", 4);
+    if (grid > A.nwork) grid = A.nwork;
+    if (tuning("advance_p.deposit", 1) == 0) advance_p_kernel<0><<<grid, kWarps * 32, 0, st>>>(A);
+    else advance_p_kernel<1><<<grid, kWarps * 32, 0, st>>>(A);
+  }
+  count_launch();
+  VPB_CUDA(cudaGetLastError());
+}
+
+void advance_p_end(AdvanceJob &J, vpb_particle_mover_t *d_pm, int *d_nm, cudaStream_t st) {
+  Context &c = ctx();
+  const AdvanceArgs &A = J.A;
+  const int tg = c.sm_count * 4;
+  mover_popc_kernel<<<tg, 256, 0, st>>>(A.bitmap, J.nwords, J.word_off, A.counters);
+  exclusive_scan_i32(J.word_off, J.word_off, J.nwords, J.scan_tmp, st, A.counters);
+  mover_place_kernel<<<tg, 256, 0, st>>>(A.bitmap, J.word_off, (const float4 *)A.tmp_pm, (float4 *)d_pm, A.max_nm, A.counters, d_nm);
+  count_launch(2 + scan_launches(J.nwords));
+  VPB_CUDA(cudaGetLastError());
+}
+
+}  // namespace vpb
+
 using namespace vpb;
 
 extern "C" void vpb_advance_p_ordered(vpb_domain_t *dom, vpb_particle_t *d_p, int np, float q_m, vpb_particle_mover_t *d_pm,
@@ -305,57 +568,17 @@ extern "C" void vpb_advance_p_ordered(vpb_domain_t *dom, vpb_particle_t *d_p, in
   if (!d_a) VPB_ERROR("Bad accumulator");
   if (!d_f) VPB_ERROR("Bad interpolator");
   Context &c = ctx();
-  const DomainDev &g = dom->d;
   if (np == 0) {
     if (d_nm) VPB_CUDA(cudaMemsetAsync(d_nm, 0, sizeof(int), c.stream));
     return;
   }
-  AdvanceArgs A;
-  A.p = d_p;
-  A.np = np;
-  A.nchunks = (np + 31) / 32;
-  // same expressions, same types as advance_p.cxx:425-428
-  A.qdt_2mc = (float)(0.5 * q_m * g.dt / g.cvac);
-  A.cdt_dx = g.cvac * g.dt * g.rdx;
-  A.cdt_dy = g.cvac * g.dt * g.rdy;
-  A.cdt_dz = g.cvac * g.dt * g.rdz;
-  A.a = reinterpret_cast<float *>(d_a);
-  A.f = d_f;
-  A.nbr = g.nbr;
-  A.max_nm = max_nm;
-  // scratch: counters | bitmap[nwords] | word_cnt/off[nwords] | tmp_pm[max_nm] | scan scratch
-  const int nwords = A.nchunks;
-  auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-  const size_t off_bits = 256, off_cnt = off_bits + al((size_t)nwords * 4), off_tmp = off_cnt + al((size_t)nwords * 4),
-               off_scan = off_tmp + al((size_t)max_nm * 16 + 16);
-  char *s = (char *)scratch(off_scan + scan_scratch_bytes(nwords));
-  A.counters = (int *)s;
-  A.bitmap = (unsigned *)(s + off_bits);
-  int *word_off = (int *)(s + off_cnt);
-  A.tmp_pm = (vpb_particle_mover_t *)(s + off_tmp);
-  void *scan_tmp = s + off_scan;
-  VPB_CUDA(cudaMemsetAsync(s, 0, off_bits + (size_t)nwords * 4, c.stream));   // counters + bitmap
-
-  A.partition = tuning("advance_p.ordered", 1) ? d_partition : nullptr;
-  A.sx = g.sx; A.sy = g.sy; A.sz = g.sz; A.nv = g.nv;
-  A.by = tuning("advance_p.by", 16);
-  if (A.by < 1) A.by = 1;
-  if (A.partition) A.nwork = ((g.sy + A.by - 1) / A.by) * A.by * g.sz + 1;
-  else A.nwork = (A.nchunks + 63) / 64;
-  const int per_sm = tuning("advance_p.ctas_per_sm", 4);
-  int grid = c.sm_count * per_sm;
-  if (grid > A.nwork) grid = A.nwork;
+  AdvanceJob J;
+  advance_p_begin(dom, np, q_m, max_nm, d_a, d_f, J, c.stream);
   {
     ProfScope prof(0);
-    if (tuning("advance_p.deposit", 1) == 0) advance_p_kernel<0><<<grid, kWarps * 32, 0, c.stream>>>(A);
-    else advance_p_kernel<1><<<grid, kWarps * 32, 0, c.stream>>>(A);
+    advance_p_range(J, d_p, 0, np, d_partition, c.stream);
   }
-  const int tg = c.sm_count * 4;
-  mover_popc_kernel<<<tg, 256, 0, c.stream>>>(A.bitmap, nwords, word_off, A.counters);
-  exclusive_scan_i32(word_off, word_off, nwords, scan_tmp, c.stream, A.counters);
-  mover_place_kernel<<<tg, 256, 0, c.stream>>>(A.bitmap, word_off, (const float4 *)A.tmp_pm, (float4 *)d_pm, max_nm, A.counters, d_nm);
-  count_launch(3 + scan_launches(nwords));
-  VPB_CUDA(cudaGetLastError());
+  advance_p_end(J, d_pm, d_nm, c.stream);
 }
 
 extern "C" void vpb_advance_p(vpb_domain_t *dom, vpb_particle_t *d_p, int np, float q_m, vpb_particle_mover_t *d_pm, int max_nm,

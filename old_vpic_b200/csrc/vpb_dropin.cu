@@ -13,6 +13,7 @@
 #include <math.h>
 #include <unordered_map>
 #include <vector>
+#include "vpb_advance_p.cuh"
 #include "vpb_common.cuh"
 
 namespace vpb {
@@ -168,6 +169,47 @@ void util_free_aligned(void *mem_ref) {
 // ---------------------------------------------------------------------------
 // species_advance (spa.h)
 // ---------------------------------------------------------------------------
+// Host particle arrays larger than this many particles are streamed through the device in pieces:
+// H2D of piece i+1, the kernel on piece i and D2H of piece i-1 run concurrently (three streams, three
+// rotating device buffers), so a call costs about max(PCIe in, PCIe out, kernel) instead of their sum.
+struct PipeBuffers {
+  vpb_particle_t *buf[3] = {nullptr, nullptr, nullptr};
+  size_t cap = 0;   // particles per buffer
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[3], ev_k[3], ev_free[3], ev_aux;
+  bool ready = false;
+};
+static PipeBuffers g_pipe;
+
+static void pipe_prepare(size_t piece) {
+  PipeBuffers &P = g_pipe;
+  if (!P.ready) {
+    VPB_CUDA(cudaStreamCreateWithFlags(&P.s_in, cudaStreamNonBlocking));
+    VPB_CUDA(cudaStreamCreateWithFlags(&P.s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 3; i++) {
+      VPB_CUDA(cudaEventCreateWithFlags(&P.ev_in[i], cudaEventDisableTiming));
+      VPB_CUDA(cudaEventCreateWithFlags(&P.ev_k[i], cudaEventDisableTiming));
+      VPB_CUDA(cudaEventCreateWithFlags(&P.ev_free[i], cudaEventDisableTiming));
+    }
+    VPB_CUDA(cudaEventCreateWithFlags(&P.ev_aux, cudaEventDisableTiming));
+    P.ready = true;
+  }
+  if (P.cap < piece) {
+    VPB_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < 3; i++) {
+      if (P.buf[i]) cudaFree(P.buf[i]);
+      VPB_CUDA(cudaMalloc(&P.buf[i], piece * sizeof(vpb_particle_t)));
+    }
+    P.cap = piece;
+  }
+}
+
+static bool is_plain_host(const void *p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+  return at.type == cudaMemoryTypeUnregistered || at.type == cudaMemoryTypeHost;
+}
+
 int advance_p(vpb_particle_t *p0, int np, const float q_m, vpb_particle_mover_t *pm, int max_nm, vpb_accumulator_t *a0,
               const vpb_interpolator_t *f0, const vpb_grid_t *g) {
   if (!p0) VPB_ERROR("Bad particle array");
@@ -178,22 +220,74 @@ int advance_p(vpb_particle_t *p0, int np, const float q_m, vpb_particle_mover_t 
   if (!f0) VPB_ERROR("Bad interpolator");
   if (!g) VPB_ERROR("Bad grid");
   vpb_domain_t *dom = domain_of(g);
-  Residency r;
-  vpb_particle_t *dp = (vpb_particle_t *)r.get(p0, (size_t)np * sizeof(*p0), RW);
-  vpb_particle_mover_t *dpm = (vpb_particle_mover_t *)r.get(pm, (size_t)max_nm * sizeof(*pm), WR);
-  vpb_accumulator_t *da = (vpb_accumulator_t *)r.get(a0, nvox(g) * sizeof(*a0), RW);
-  const vpb_interpolator_t *df = (const vpb_interpolator_t *)r.get(f0, nvox(g) * sizeof(*f0), RD);
   Context &c = ctx();
+  Residency r;
+  const int piece = tuning("dropin.piece", 4 << 20) & ~31;   // particles per piece
+  const bool streamed = is_plain_host(p0) && np > 2 * piece && tuning("dropin.pipeline", 1);
   int *d_out = nullptr;
   VPB_CUDA(cudaMallocAsync(&d_out, 2 * sizeof(int), c.stream));
-  const int *d_part = nullptr;
-  auto ph = g_part_hint.find(p0);
-  if (ph != g_part_hint.end() && ph->second.np == np && ph->second.n == nvox(g) + 1) d_part = ph->second.dev;
-  vpb_advance_p_ordered(dom, dp, np, q_m, dpm, max_nm, da, df, d_out, d_part);
+  // movers: staged without copying max_nm records back; only the nm that exist are returned
+  vpb_particle_mover_t *dpm = pm;
+  const bool pm_host = is_plain_host(pm);
+  if (pm_host) {
+    StageBuf &sb = g_stage[pm];
+    const size_t bytes = (size_t)max_nm * sizeof(*pm) + 16;
+    if (sb.cap < bytes) {
+      if (sb.dev) { VPB_CUDA(cudaStreamSynchronize(c.stream)); VPB_CUDA(cudaFree(sb.dev)); }
+      VPB_CUDA(cudaMalloc(&sb.dev, bytes));
+      sb.cap = bytes;
+    }
+    dpm = (vpb_particle_mover_t *)sb.dev;
+  }
+  if (!streamed) {
+    vpb_particle_t *dp = (vpb_particle_t *)r.get(p0, (size_t)np * sizeof(*p0), RW);
+    vpb_accumulator_t *da = (vpb_accumulator_t *)r.get(a0, nvox(g) * sizeof(*a0), RW);
+    const vpb_interpolator_t *df = (const vpb_interpolator_t *)r.get(f0, nvox(g) * sizeof(*f0), RD);
+    const int *d_part = nullptr;
+    auto ph = g_part_hint.find(p0);
+    if (ph != g_part_hint.end() && ph->second.np == np && ph->second.n == nvox(g) + 1) d_part = ph->second.dev;
+    vpb_advance_p_ordered(dom, dp, np, q_m, dpm, max_nm, da, df, d_out, d_part);
+  } else {
+    PipeBuffers &P = g_pipe;
+    pipe_prepare((size_t)piece);
+    // field-sized arrays go over whole, on the input stream, before the first piece
+    vpb_accumulator_t *da = (vpb_accumulator_t *)r.get(a0, nvox(g) * sizeof(*a0), RW);
+    const vpb_interpolator_t *df = (const vpb_interpolator_t *)r.get(f0, nvox(g) * sizeof(*f0), RD);
+    AdvanceJob J;
+    advance_p_begin(dom, np, q_m, max_nm, da, df, J, c.stream);
+    VPB_CUDA(cudaEventRecord(P.ev_aux, c.stream));
+    VPB_CUDA(cudaStreamWaitEvent(P.s_in, P.ev_aux, 0));    // buffers of a previous call are idle by now
+    VPB_CUDA(cudaStreamWaitEvent(P.s_out, P.ev_aux, 0));
+    const int npieces = (np + piece - 1) / piece;
+    for (int i = 0; i < npieces; i++) {
+      const int b = i % 3, k0 = i * piece, k1 = (k0 + piece < np) ? k0 + piece : np;
+      const size_t bytes = (size_t)(k1 - k0) * sizeof(vpb_particle_t);
+      if (i >= 3) VPB_CUDA(cudaStreamWaitEvent(P.s_in, P.ev_free[b], 0));
+      VPB_CUDA(cudaMemcpyAsync(P.buf[b], p0 + k0, bytes, cudaMemcpyHostToDevice, P.s_in));
+      VPB_CUDA(cudaEventRecord(P.ev_in[b], P.s_in));
+      VPB_CUDA(cudaStreamWaitEvent(c.stream, P.ev_in[b], 0));
+      advance_p_range(J, P.buf[b] - k0, k0, k1, nullptr, c.stream);
+      VPB_CUDA(cudaEventRecord(P.ev_k[b], c.stream));
+      VPB_CUDA(cudaStreamWaitEvent(P.s_out, P.ev_k[b], 0));
+      VPB_CUDA(cudaMemcpyAsync(p0 + k0, P.buf[b], bytes, cudaMemcpyDeviceToHost, P.s_out));
+      VPB_CUDA(cudaEventRecord(P.ev_free[b], P.s_out));
+      g_h2d_total += bytes; g_d2h_total += bytes;
+    }
+    advance_p_end(J, dpm, d_out, c.stream);
+    VPB_CUDA(cudaStreamSynchronize(P.s_out));
+  }
   VPB_CUDA(cudaMemcpyAsync(c.h_pinned_i, d_out, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
   VPB_CUDA(cudaFreeAsync(d_out, c.stream));
   r.finish();
-  return c.h_pinned_i[0];
+  const int nm = c.h_pinned_i[0];
+  if (pm_host && nm > 0) {
+    VPB_CUDA(cudaMemcpyAsync(pm, dpm, (size_t)nm * sizeof(*pm), cudaMemcpyDeviceToHost, c.stream));
+    VPB_CUDA(cudaStreamSynchronize(c.stream));
+    g_d2h_total += (size_t)nm * sizeof(*pm);
+  }
+  const int ignored = nm >= max_nm ? vpb_advance_p_ignored() : 0;
+  if (ignored) VPB_WARNING("advance_p ran out of storage for %d movers", ignored);   // advance_p.cxx:463-465
+  return nm;
 }
 
 void center_p(vpb_particle_t *p0, int np, const float q_m, const vpb_interpolator_t *f0, const vpb_grid_t *g) {

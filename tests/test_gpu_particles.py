@@ -25,17 +25,18 @@ def acc_floats(a):
     return np.ascontiguousarray(a).view(np.float32).reshape(-1, 12)
 
 
-@pytest.mark.parametrize("deposit", [1, 0])
+@pytest.mark.parametrize("deposit,tma", [(1, 1), (0, 1), (1, 0), (0, 0)])
 @pytest.mark.parametrize("kind", ["periodic", "metal", "absorbing"])
 @pytest.mark.parametrize("n,np_,sort", [((6, 5, 4), 5000, True), ((8, 1, 6), 7001, False), ((1, 1, 16), 300, True),
                                         ((16, 16, 16), 16 * 16 * 16 * 40, True)])
-def test_advance_p(vpb, orc, deposit, kind, n, np_, sort):
+def test_advance_p(vpb, orc, deposit, tma, kind, n, np_, sort):
     g = host_grid(n, kind)
     rng = np.random.default_rng(21)
     p = random_particles(rng, g, np_, vth=0.6, sort=sort, edge_frac=0.02)
     fi = random_interpolator(rng, g, amp=0.3)
     q_m, max_nm = -1.0, np_
     vpb.vpb_set_tuning(b"advance_p.deposit", deposit)
+    vpb.vpb_set_tuning(b"advance_p.tma", tma)
     p_o, p_g = p.copy(), p.copy()
     a_o = abi.aligned_zeros(g.nv, abi.accumulator_dtype)
     a_g = a_o.copy()
@@ -43,6 +44,8 @@ def test_advance_p(vpb, orc, deposit, kind, n, np_, sort):
     pm_g = pm_o.copy()
     nm_o = orc.orc_advance_p(ptr(p_o), np_, q_m, ptr(pm_o), max_nm, ptr(a_o), ptr(fi), g.ref())
     nm_g = vpb.advance_p(ptr(p_g), np_, q_m, ptr(pm_g), max_nm, ptr(a_g), ptr(fi), g.ref())
+    vpb.vpb_set_tuning(b"advance_p.deposit", 1)
+    vpb.vpb_set_tuning(b"advance_p.tma", 1)
     assert nm_g == nm_o
     if kind == "absorbing":
         assert nm_o > 0
@@ -103,6 +106,32 @@ def test_advance_p_managed_memory_in_place(vpb, orc):
     assert nm == orc.orc_advance_p(ptr(p_o), np_, -1.0, ptr(pm_o), np_, ptr(a_o), ptr(fi), g.ref())
     assert_bits_equal(p_m, p_o, "particles (managed)")
     assert max_rel(acc_floats(a_m), acc_floats(a_o)) < ACC_TOL
+
+
+@pytest.mark.parametrize("kind", ["periodic", "absorbing"])
+def test_advance_p_streamed_in_pieces(vpb, orc, kind):
+    """Large host arrays go through the device in pieces (H2D / kernel / D2H overlapped); same results,
+    movers still ordered by particle index across pieces."""
+    g = host_grid((10, 9, 8), kind)
+    rng = np.random.default_rng(23)
+    np_ = 20000 + 17
+    p = random_particles(rng, g, np_, vth=0.6, edge_frac=0.02)
+    fi = random_interpolator(rng, g, amp=0.3)
+    vpb.vpb_set_tuning(b"dropin.piece", 2048)
+    try:
+        p_o, p_g = p.copy(), p.copy()
+        a_o = abi.aligned_zeros(g.nv, abi.accumulator_dtype)
+        a_g = a_o.copy()
+        pm_o = abi.aligned_zeros(np_, abi.mover_dtype)
+        pm_g = pm_o.copy()
+        nm_o = orc.orc_advance_p(ptr(p_o), np_, -1.0, ptr(pm_o), np_, ptr(a_o), ptr(fi), g.ref())
+        nm_g = vpb.advance_p(ptr(p_g), np_, -1.0, ptr(pm_g), np_, ptr(a_g), ptr(fi), g.ref())
+    finally:
+        vpb.vpb_set_tuning(b"dropin.piece", 4 << 20)
+    assert nm_g == nm_o and (kind != "absorbing" or nm_o > 0)
+    assert_bits_equal(p_g, p_o, "particles")
+    assert_bits_equal(pm_g[:nm_g], pm_o[:nm_o], "movers")
+    assert max_rel(acc_floats(a_g), acc_floats(a_o)) < ACC_TOL
 
 
 @pytest.mark.parametrize("which", ["center_p", "uncenter_p"])
