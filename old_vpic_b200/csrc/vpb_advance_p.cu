@@ -309,22 +309,39 @@ __global__ void __launch_bounds__(kWarps * 32, 3) advance_p_tma_kernel(const Adv
   }
   __syncwarp();
 
-  const int gw_stride = gridDim.x * kWarps;
-  const int first = A.chunk_lo + blockIdx.x * kWarps + w;
   auto tile_bytes = [&](int chunk) -> uint32_t {
     const int n = A.np - chunk * 32;
     return (uint32_t)((n < 32 ? n : 32) * 48);
   };
-  if (lane == 0) {
-    for (int j = 0; j < kStages - 1; j++) {
-      const int c = first + j * gw_stride;
-      if (c < A.chunk_hi)
-        tma_load_tile(smem_u32(&S.tile[w][j][0]), gbase + (size_t)c * kTileBytes, tile_bytes(c), smem_u32(&S.full[w][j]), pol);
+  // Dynamic scheduling: chunks are handed out kGrab at a time from a global ticket counter, so the chunks in
+  // flight on the chip are always the most recently issued ones however unevenly the warps progress.  With
+  // a static stride the warps drift apart by whole z-planes within a launch and a voxel's interpolator /
+  // accumulator lines are then touched at times too far apart to still be in L2 (profiles/r1f: 55-59 % L2
+  // miss on gathers and REDs once particles have left their sorted voxels).
+  constexpr int kGrab = 4;
+  int g_cur = 0, g_end = 0;   // warp-uniform: current group of chunks [g_cur, g_end)
+  auto next_chunk = [&]() -> int {
+    if (g_cur >= g_end) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&A.counters[2], kGrab);
+      base = __shfl_sync(fullmask, base, 0) + A.chunk_lo;
+      g_cur = base;
+      g_end = base + kGrab < A.chunk_hi ? base + kGrab : A.chunk_hi;
+      if (g_cur >= g_end) { g_cur = g_end = A.chunk_hi; return -1; }
     }
+    return g_cur++;
+  };
+  // chunks this warp will compute on next, oldest first; their tiles are in flight
+  int pend[kStages - 1];
+#pragma unroll
+  for (int j = 0; j < kStages - 1; j++) {
+    pend[j] = next_chunk();
+    if (lane == 0 && pend[j] >= 0)
+      tma_load_tile(smem_u32(&S.tile[w][j][0]), gbase + (size_t)pend[j] * kTileBytes, tile_bytes(pend[j]), smem_u32(&S.full[w][j]), pol);
   }
 
-  int it = 0;
-  for (int chunk = first; chunk < A.chunk_hi; chunk += gw_stride, ++it) {
+  for (int it = 0; pend[0] >= 0; ++it) {
+    const int chunk = pend[0];
     const int stage = it % kStages;
     mbar_wait(smem_u32(&S.full[w][stage]), (uint32_t)((it / kStages) & 1));
     const int k = chunk * 32 + lane;
@@ -398,13 +415,17 @@ __global__ void __launch_bounds__(kWarps * 32, 3) advance_p_tma_kernel(const Adv
     __syncwarp();
     if (lane == 0) {
       tma_store_tile(gbase + (size_t)chunk * kTileBytes, smem_u32(&S.tile[w][stage][0]), tile_bytes(chunk), pol);
-      // refill the stage used one iteration ago (its store must have finished reading shared memory)
-      const int cn = chunk + (kStages - 1) * gw_stride;
-      if (cn < A.chunk_hi) {
-        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        const int sn = (it + kStages - 1) % kStages;
-        tma_load_tile(smem_u32(&S.tile[w][sn][0]), gbase + (size_t)cn * kTileBytes, tile_bytes(cn), smem_u32(&S.full[w][sn]), pol);
-      }
+    }
+    // take the next chunk and refill the stage used one iteration ago (its store must have finished
+    // reading shared memory first)
+    const int cn = next_chunk();
+#pragma unroll
+    for (int j = 0; j < kStages - 2; j++) pend[j] = pend[j + 1];
+    pend[kStages - 2] = cn;
+    if (lane == 0 && cn >= 0) {
+      asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      const int sn = (it + kStages - 1) % kStages;
+      tma_load_tile(smem_u32(&S.tile[w][sn][0]), gbase + (size_t)cn * kTileBytes, tile_bytes(cn), smem_u32(&S.full[w][sn]), pol);
     }
 
     if (DEPOSIT == 0) {
@@ -528,6 +549,7 @@ void advance_p_range(AdvanceJob &J, vpb_particle_t *d_base, int k0, int k1, cons
       attr_set = true;
     }
     const int nch = A.chunk_hi - A.chunk_lo;
+    VPB_CUDA(cudaMemsetAsync(&A.counters[2], 0, sizeof(int), st));   // ticket counter of the dynamic scheduler
     int grid = c.sm_count * tuning("advance_p.tma_ctas_per_sm", 3);
     if (grid > (nch + kWarps - 1) / kWarps) grid = (nch + kWarps - 1) / kWarps;
     if (tuning("advance_p.deposit", 1) == 0) advance_p_tma_kernel<0><<<grid, kWarps * 32, sizeof(TmaSmem), st>>>(A);

@@ -1,0 +1,15 @@
+#!/usr/bin/env bash
+set -u
+cd "$GRAFT_REPO_ROOT"
+O=gpurun_out
+mkdir -p $O
+timeout 900 python -m pytest tests -m gpu -q -n 4 -p no:cacheprovider > $O/pytest_gpu7.log 2>&1; echo "pytest exit $?" >> $O/pytest_gpu7.log
+timeout 600 python bench.py --cells 128 --ppc 64 --steps 20 --warmup 3 --no-e2e --no-cpu-baseline > $O/b7_128.json 2> $O/b7_128.err
+for c in 3 2; do
+  VPB_ADVANCE_P_TMA_CTAS_PER_SM=$c timeout 900 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e > $O/b7_256_c$c.json 2> $O/b7_256_c$c.err
+done
+if timeout 300 python bench.py --steps 19 --warmup 1 --no-e2e --no-cpu-baseline > $O/plain7.log 2>&1; then
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:advance_p_tma -s 36 -c 1 -o $O/prof_advance_p_r1g_256_drift \
+      python bench.py --steps 19 --warmup 1 --no-e2e --no-cpu-baseline > $O/ncu_full11.log 2>&1
+fi
+ls $O | tail -3
