@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--ppc", type=int, default=64, help="particles per cell per species")
     ap.add_argument("--e2e-particles", type=int, default=64 * 1024 * 1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--field-cells", type=int, default=1024, help="cells per axis of the field-only leg (configs[1]); 0 = skip")
+    ap.add_argument("--workload", default="thermal", choices=["thermal", "fields"])
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
@@ -202,6 +204,13 @@ def run_b200(args):
         ub = (C.c_uint8 * 128)(*uid.cpu().tolist())
         L.vpb_comm_init(rank, world, ub)
 
+    fields_c2 = None
+    if world == 1 and args.field_cells > 0:
+        fields_c2 = fields_measure(L, args.field_cells, 5, 3)
+        if args.workload == "fields":
+            print(json.dumps(fields_c2), flush=True)
+            return
+
     n = args.cells
     topo = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
     g = helpers.make_grid((n * topo[0], n * topo[1], n * topo[2]), "periodic", topo=topo, rank=rank)
@@ -285,9 +294,11 @@ def run_b200(args):
                                      "advance_e": (cells * args.steps / (prof["advance_e"][0] * 1e-3)) if prof["advance_e"][0] else None},
         "host_wall_ms_per_step": 1e3 * wall / args.steps,
         "advance_p_ms_by_launch": adv_list,
-        "tuning": {k: L.vpb_get_tuning(k.encode()) for k in ("advance_p.deposit", "advance_p.l2hint", "advance_p.prefetch",
-                                                             "advance_p.ctas_per_sm")},
+        "tuning": {k: L.vpb_get_tuning(k.encode()) for k in ("advance_p.deposit", "advance_p.tma", "advance_p.stream_ctas_per_sm",
+                                                             "advance_p.tma_ctas_per_sm", "advance_p.ctas_per_sm")},
     }
+    if fields_c2 is not None:
+        line["fields_c2"] = fields_c2
     if not args.no_e2e:
         line["e2e"] = e2e_measure(L, args, abi, helpers)
     if not args.no_cpu_baseline and world == 1:
@@ -295,6 +306,52 @@ def run_b200(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+
+
+def fields_measure(L, n, steps, warmup):
+    """BASELINE configs[1]: field-only Yee vacuum plane wave on n^3 cells (advance_b x2 + vacuum advance_e per step).
+    Returns cell-update rates and the roofline fractions of the two stencil kernels, timed with CUDA events around
+    each kernel launch (vpb_prof classes 2 and 3) over `steps` steps."""
+    from old_vpic_b200 import grid as helpers
+    from old_vpic_b200.sim import Simulation
+    g = helpers.make_grid((n, n, n), "periodic", field_only=True)
+    sim = Simulation(g, n_mat=1, vacuum=True, L=L)
+    L.vpb_load_plane_wave(sim.dom, sim.f.ptr, 8, 1.0)
+    e0 = sum(sim.energies()[:6])
+    for _ in range(warmup):
+        sim.advance()
+    L.vpb_sync()
+    L.vpb_prof_enable(1)
+    L.vpb_timer_start(1)
+    for _ in range(steps):
+        sim.advance()
+    L.vpb_timer_stop(1)
+    ms = L.vpb_timer_ms(1)
+    out = {}
+    for cls, nm in ((2, "advance_b"), (3, "advance_e")):
+        tot, cnt = C.c_double(0), C.c_int(0)
+        L.vpb_prof_collect(cls, C.byref(tot), C.byref(cnt), 0)
+        out[nm] = (tot.value, cnt.value)
+    L.vpb_prof_collect(0, None, None, 1)
+    L.vpb_prof_enable(0)
+    e1 = sum(sim.energies()[:6])
+    sim.free()
+    peak, _ = measured_peak()
+    cells = float(n) ** 3
+    res = {"workload": "BASELINE configs[1]: field-only Yee vacuum plane wave, %d^3 cells, periodic, 1 GPU" % n,
+           "steps": steps, "ms_per_step": ms / steps, "field_cell_updates_per_s": 3 * cells * steps / (ms * 1e-3),
+           "em_energy_drift_rel": abs(e1 - e0) / e0}
+    # algorithmic bytes per cell (SURVEY.md 8d) and what the reference's 80-byte AoS field_t makes DRAM move at
+    # 32-byte sector granularity (DESIGN.md 4): advance_b 36 vs 80, vacuum advance_e 48 vs 96
+    for nm, alg, layout in (("advance_b", 36.0, 80.0), ("advance_e", 48.0, 96.0)):
+        tot, cnt = out[nm]
+        if not cnt:
+            continue
+        rate = cells * cnt / (tot * 1e-3)
+        res[nm] = {"cell_updates_per_s": rate, "avg_launch_ms": tot / cnt, "algorithmic_bytes_per_cell": alg,
+                   "layout_imposed_bytes_per_cell": layout, "achieved_GBs": rate * alg / 1e9, "frac": rate * alg / 1e9 / peak,
+                   "frac_of_layout_bound": rate * layout / 1e9 / peak}
+    return res
 
 
 def e2e_measure(L, args, abi, helpers):

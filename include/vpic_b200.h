@@ -183,6 +183,9 @@ void vpb_accumulate_rho_p(vpb_domain_t *dom, vpb_field_t *d_f, const vpb_particl
 void vpb_load_thermal(vpb_domain_t *dom, vpb_particle_t *d_p, int ppc, float vth, float q,
                       unsigned long long seed, long tag0);
 void vpb_copy_positions(vpb_particle_t *d_dst, const vpb_particle_t *d_src, long np);
+/* Synthetic field state: an x-propagating vacuum plane wave (ey, cbz) with `mode` wavelengths across
+ * the local nx cells; everything else zero. */
+void vpb_load_plane_wave(vpb_domain_t *dom, vpb_field_t *d_f, int mode, float amp);
 
 /* One species' device arrays as boundary_p needs them (the device-side part of species_t). */
 typedef struct vpb_species_state {

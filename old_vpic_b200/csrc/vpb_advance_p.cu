@@ -466,6 +466,313 @@ __global__ void __launch_bounds__(kWarps * 32, 3) advance_p_tma_kernel(const Adv
   if (q_n) drain_movers(A.p, A.a, A.nbr, A.tmp_pm, A.max_nm, A.counters, A.bitmap, S.q_pos[w], S.q_mom[w], S.q_disp[w], q_head, q_n);
 }
 
+// ---------------------------------------------------------------------------
+// Streaming variant (default).  What the ncu captures of the kernel above showed (profiles/README.md):
+// a fifth of the stall samples sat on the first use of the interpolator, a sixth on the scheduler's
+// ticket atomic, an eighth on the proxy fence in front of the bulk store, and a third of the issued
+// instructions were the segmented shuffle reduction.  Here
+//  * particles still ARRIVE by bulk async copy (kStagesS tiles per warp in flight), but results leave
+//    by two STG.128 per lane straight from registers (streaming policy): no proxy fence, no wait
+//    before movers are drained, and the tile can be refilled as soon as it has been read;
+//  * the interpolator of chunk n+1 is requested (voxel index read from its staged tile) BEFORE chunk n
+//    is computed and held in registers across it;
+//  * the next ticket is requested one grab ahead of its use;
+//  * deposit: all in-cell lanes in one voxel (the usual case after a sort) -> halving butterfly
+//    (54 instructions instead of ~180) ending in 12 scalar REDs from four lanes; many short runs
+//    (drifted) -> no reduction at all, each lane issues its own three REDG.128; otherwise the
+//    segmented reduction, with out-of-cell lanes made transparent so they do not split a run.
+// ---------------------------------------------------------------------------
+constexpr int kStagesS = 4;
+constexpr int kGrabS = 16;
+
+struct StreamSmem {
+  float4 tile[kWarps][kStagesS][96];
+  float4 q_pos[kWarps][kQueue], q_disp[kWarps][kQueue];   // the momentum waits in global memory (already stored)
+  uint64_t full[kWarps][kStagesS];
+};
+
+struct Interp {
+  float4 ex, ey, ez, b0;
+  float2 b1;
+};
+
+__device__ __forceinline__ void load_interp(Interp &I, const vpb_interpolator_t *f, int ii) {
+  const char *fp = reinterpret_cast<const char *>(f + ii);
+  I.ex = ldg4(fp);        // ex dexdy dexdz d2exdydz
+  I.ey = ldg4(fp + 16);   // ey deydz deydx d2eydzdx
+  I.ez = ldg4(fp + 32);   // ez dezdx dezdy d2ezdxdy
+  I.b0 = ldg4(fp + 48);   // cbx dcbxdx cby dcbydy
+  I.b1 = ldg2(fp + 64);   // cbz dcbzdz
+}
+
+__device__ __forceinline__ void st_stream4(void *p, float4 v) { __stcs(reinterpret_cast<float4 *>(p), v); }
+
+// Deposit for one chunk.  A few steps after a sort a warp's 32 particles are mostly still in one or two voxels
+// with strays mixed in at random lanes, so runs of equal voxel are short even though one voxel dominates.
+// The dominant voxel (the more populous of the first and the last in-cell lane's) is summed over the warp by
+// a halving butterfly -- 18 shuffles instead of the 60 of a full 12-value reduction -- and leaves as 12 scalar
+// REDs from four lanes; every other in-cell lane issues its own three REDG.128.
+__device__ __forceinline__ void deposit_dominant(float (&v)[12], int key, bool active, float *__restrict__ a0) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const unsigned am = __ballot_sync(full, active);
+  if (am == 0) return;
+  const int ka = __shfl_sync(full, key, __ffs(am) - 1), kb = __shfl_sync(full, key, 31 - __clz(am));
+  const unsigned ma = __ballot_sync(full, active && key == ka), mb = __ballot_sync(full, active && key == kb);
+  const bool pick_a = __popc(ma) >= __popc(mb);
+  const int k0 = pick_a ? ka : kb;
+  const unsigned dm = pick_a ? ma : mb;
+  const bool mine = (dm >> lane) & 1u;
+  if (active && (!mine || __popc(dm) < 3)) red3(a0 + 12 * (size_t)key, v);
+  if (__popc(dm) < 3) return;
+  // component c = 4g+j of the dominant voxel ends up summed in the lanes with j = 2*bit4 + bit3
+  const bool h16 = lane & 16, h8 = lane & 8;
+  float w[6];
+#pragma unroll
+  for (int g = 0; g < 3; g++) {
+#pragma unroll
+    for (int jj = 0; jj < 2; jj++) {
+      const float lo = mine ? v[4 * g + jj] : 0.f, hi = mine ? v[4 * g + 2 + jj] : 0.f;
+      w[2 * g + jj] = (h16 ? hi : lo) + __shfl_xor_sync(full, h16 ? lo : hi, 16);
+    }
+  }
+  float u[3];
+#pragma unroll
+  for (int g = 0; g < 3; g++) u[g] = (h8 ? w[2 * g + 1] : w[2 * g]) + __shfl_xor_sync(full, h8 ? w[2 * g] : w[2 * g + 1], 8);
+#pragma unroll
+  for (int d = 4; d >= 1; d >>= 1) {
+#pragma unroll
+    for (int g = 0; g < 3; g++) u[g] += __shfl_xor_sync(full, u[g], d);
+  }
+  if ((lane & 7) == 0) {
+    float *a = a0 + 12 * (size_t)k0 + (lane >> 3);
+    red_add(a, u[0]);
+    red_add(a + 4, u[1]);
+    red_add(a + 8, u[2]);
+  }
+}
+
+// drain_movers for the streaming kernel: the updated momentum is read back from the particle array
+// (stored by the main loop, as advance_p.cxx:131-133 does before it calls move_p)
+__device__ __noinline__ void drain_movers_slim(vpb_particle_t *__restrict__ p, float *__restrict__ acc, const int32_t *__restrict__ nbr,
+                                               vpb_particle_mover_t *__restrict__ tmp_pm, int max_nm, int *__restrict__ counters,
+                                               unsigned *__restrict__ bitmap, const float4 *q_pos, const float4 *q_disp, int head,
+                                               int count) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  int unresolved = 0, k = 0;
+  Mover s;
+  s.dispx = s.dispy = s.dispz = 0.f;
+  if (lane < count) {
+    const int e = (head + lane) & (kQueue - 1);
+    const float4 a = q_pos[e], c = q_disp[e];
+    k = __float_as_int(c.w);
+    float4 *pp = reinterpret_cast<float4 *>(p + k);
+    const float4 b = __ldcg(pp + 1);
+    s.dx = a.x; s.dy = a.y; s.dz = a.z; s.i = __float_as_int(a.w);
+    s.ux = b.x; s.uy = b.y; s.uz = b.z; s.q = b.w;
+    s.dispx = c.x; s.dispy = c.y; s.dispz = c.z;
+    unresolved = move_p_dev(s, acc, nbr);
+    pp[0] = make_float4(s.dx, s.dy, s.dz, __int_as_float(s.i));   // move_p never changes the momentum
+  }
+  const unsigned um = __ballot_sync(full, unresolved);
+  if (um) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&counters[0], __popc(um));
+    base = __shfl_sync(full, base, 0);
+    if (unresolved) {
+      const int dst = base + __popc(um & ((1u << lane) - 1u));
+      if (dst < max_nm) {
+        reinterpret_cast<float4 *>(tmp_pm)[dst] = make_float4(s.dispx, s.dispy, s.dispz, __int_as_float(k));
+        atomicOr(&bitmap[k >> 5], 1u << (k & 31));
+      } else {
+        atomicAdd(&counters[1], 1);
+      }
+    }
+  }
+}
+
+template <int DEPOSIT, int MINB>
+__global__ void __launch_bounds__(kWarps * 32, MINB) advance_p_stream_kernel(const AdvanceArgs A) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  StreamSmem &S = *reinterpret_cast<StreamSmem *>(smem_raw);
+
+  const unsigned fullmask = 0xffffffffu;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const float one = 1.f;
+  const float one_third = (float)(1. / 3.);
+  const float two_fifteenths = (float)(2. / 15.);
+  const float qdt_2mc = A.qdt_2mc, cdt_dx = A.cdt_dx, cdt_dy = A.cdt_dy, cdt_dz = A.cdt_dz;
+  int q_head = 0, q_n = 0;
+  const uint64_t pol = l2_policy_evict_first();
+  char *const gbase = reinterpret_cast<char *>(A.p);
+
+  if (lane == 0) {
+    for (int s = 0; s < kStagesS; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&S.full[w][s])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  auto tile_bytes = [&](int chunk) -> uint32_t {
+    const int n = A.np - chunk * 32;
+    return (uint32_t)((n < 32 ? n : 32) * 48);
+  };
+  // dynamic scheduling (see advance_p_tma_kernel); the ticket for the NEXT group is already in flight
+  int g_cur = 0, g_end = 0;
+  int ticket = 0;                                  // lane 0: result of the outstanding atomic
+  // (inline PTX: nvcc turns a lane-0 atomicAdd into a warp-aggregated one whose result is shuffled out at
+  // once, which would wait for the atomic right here)
+  auto take_ticket = [&]() {
+    if (lane == 0) asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(ticket) : "l"(A.counters + 2), "r"(kGrabS) : "memory");
+  };
+  take_ticket();
+  auto next_chunk = [&]() -> int {
+    if (g_cur >= g_end) {
+      const int base = __shfl_sync(fullmask, ticket, 0) + A.chunk_lo;
+      if (base >= A.chunk_hi) { g_cur = g_end = A.chunk_hi; return -1; }
+      take_ticket();
+      g_cur = base;
+      g_end = base + kGrabS < A.chunk_hi ? base + kGrabS : A.chunk_hi;
+    }
+    return g_cur++;
+  };
+  auto issue_load = [&](int chunk, int stage) {
+    if (lane == 0 && chunk >= 0)
+      tma_load_tile(smem_u32(&S.tile[w][stage][0]), gbase + (size_t)chunk * kTileBytes, tile_bytes(chunk), smem_u32(&S.full[w][stage]),
+                    pol);
+  };
+
+  // pend[j]: chunk whose tile sits (or is landing) in stage (it+j) % kStagesS
+  int pend[kStagesS];
+#pragma unroll
+  for (int j = 0; j < kStagesS; j++) {
+    pend[j] = next_chunk();
+    issue_load(pend[j], j);
+  }
+  Interp cur;
+  cur.ex = cur.ey = cur.ez = cur.b0 = make_float4(0, 0, 0, 0);
+  cur.b1 = make_float2(0, 0);
+  if (pend[0] >= 0) {
+    mbar_wait(smem_u32(&S.full[w][0]), 0);
+    const int k = pend[0] * 32 + lane;
+    const int ii = k < A.np ? __float_as_int(S.tile[w][0][lane * 3].w) : 0;
+    load_interp(cur, A.f, ii);
+  }
+
+  for (int it = 0; pend[0] >= 0; ++it) {
+    const int chunk = pend[0];
+    const int stage = it % kStagesS;
+    const int k = chunk * 32 + lane;
+    const bool valid = k < A.np;
+    const float4 *tp = &S.tile[w][stage][lane * 3];
+    float4 r0 = make_float4(0, 0, 0, 0), r1 = r0;
+    if (valid) { r0 = tp[0]; r1 = tp[1]; }
+
+    // request the interpolator of the next chunk before computing on this one
+    Interp nxt = cur;
+    if (pend[1] >= 0) {
+      const int sn = (it + 1) % kStagesS;
+      mbar_wait(smem_u32(&S.full[w][sn]), (uint32_t)(((it + 1) / kStagesS) & 1));
+      const int kn = pend[1] * 32 + lane;
+      const int iin = kn < A.np ? __float_as_int(S.tile[w][sn][lane * 3].w) : 0;
+      load_interp(nxt, A.f, iin);
+    }
+
+    bool inbnds = false, outbnds = false;
+    const int ii = __float_as_int(r0.w);
+    float dep[12];
+#pragma unroll
+    for (int c = 0; c < 12; c++) dep[c] = 0.f;
+    float4 mom = r1;
+    float hx = 0, hy = 0, hz = 0;
+
+    if (valid) {
+      float dx = r0.x, dy = r0.y, dz = r0.z;
+      const float hax = qdt_2mc * ((cur.ex.x + dy * cur.ex.y) + dz * (cur.ex.z + dy * cur.ex.w));
+      const float hay = qdt_2mc * ((cur.ey.x + dz * cur.ey.y) + dx * (cur.ey.z + dz * cur.ey.w));
+      const float haz = qdt_2mc * ((cur.ez.x + dx * cur.ez.y) + dy * (cur.ez.z + dx * cur.ez.w));
+      const float cbx = cur.b0.x + dx * cur.b0.y;
+      const float cby = cur.b0.z + dy * cur.b0.w;
+      const float cbz = cur.b1.x + dz * cur.b1.y;
+      float ux = r1.x, uy = r1.y, uz = r1.z;
+      const float q = r1.w;
+      ux += hax; uy += hay; uz += haz;
+      float v0 = qdt_2mc / sqrtf(one + (ux * ux + (uy * uy + uz * uz)));
+      float v1 = cbx * cbx + (cby * cby + cbz * cbz);
+      float v2 = (v0 * v0) * v1;
+      float v3 = v0 * (one + v2 * (one_third + v2 * two_fifteenths));
+      float v4 = v3 / (one + v1 * (v3 * v3));
+      v4 += v4;
+      v0 = ux + v3 * (uy * cbz - uz * cby);
+      v1 = uy + v3 * (uz * cbx - ux * cbz);
+      v2 = uz + v3 * (ux * cby - uy * cbx);
+      ux += v4 * (v1 * cbz - v2 * cby);
+      uy += v4 * (v2 * cbx - v0 * cbz);
+      uz += v4 * (v0 * cby - v1 * cbx);
+      ux += hax; uy += hay; uz += haz;
+      mom = make_float4(ux, uy, uz, q);
+      v0 = one / sqrtf(one + (ux * ux + (uy * uy + uz * uz)));
+      ux *= cdt_dx; uy *= cdt_dy; uz *= cdt_dz;
+      ux *= v0; uy *= v0; uz *= v0;
+      v0 = dx + ux; v1 = dy + uy; v2 = dz + uz;
+      v3 = v0 + ux; v4 = v1 + uy;
+      float v5 = v2 + uz;
+      inbnds = v3 <= one && v4 <= one && v5 <= one && -v3 <= one && -v4 <= one && -v5 <= one;
+      outbnds = !inbnds;
+      // all 48 bytes of every particle leave here, so a warp writes 1536 contiguous bytes and no sector is
+      // written partially (a partial write makes L2 fetch the rest from DRAM first: +25 GB per launch in
+      // profiles/r1h).  Out-of-cell particles keep their old position until move_p has run.
+      float4 *pp = reinterpret_cast<float4 *>(A.p + k);
+      st_stream4(pp, inbnds ? make_float4(v3, v4, v5, r0.w) : r0);
+      st_stream4(pp + 1, mom);
+      st_stream4(pp + 2, tp[2]);
+      if (inbnds) {
+        dx = v0; dy = v1; dz = v2;
+        v5 = q * ux * uy * uz * one_third;
+        accumulate_j(q, ux, dy, dz, v5, dep[0], dep[1], dep[2], dep[3]);
+        accumulate_j(q, uy, dz, dx, v5, dep[4], dep[5], dep[6], dep[7]);
+        accumulate_j(q, uz, dx, dy, v5, dep[8], dep[9], dep[10], dep[11]);
+      } else {
+        hx = ux; hy = uy; hz = uz;
+      }
+    }
+
+    // this stage has been read by every lane (the push consumed r0/r1): refill it
+    __syncwarp();
+    const int cn = next_chunk();
+    issue_load(cn, stage);
+#pragma unroll
+    for (int j = 0; j < kStagesS - 1; j++) pend[j] = pend[j + 1];
+    pend[kStagesS - 1] = cn;
+
+    if (DEPOSIT == 0) {
+      if (inbnds) red3(A.a + 12 * (size_t)ii, dep);
+    } else {
+      deposit_dominant(dep, ii, inbnds, A.a);
+    }
+
+    const unsigned om = __ballot_sync(fullmask, outbnds);
+    if (om) {
+      if (outbnds) {
+        const int e = (q_head + q_n + __popc(om & ((1u << lane) - 1u))) & (kQueue - 1);
+        S.q_pos[w][e] = r0;
+        S.q_disp[w][e] = make_float4(hx, hy, hz, __int_as_float(k));
+      }
+      q_n += __popc(om);
+      __syncwarp();
+      if (q_n >= 32) {
+        drain_movers_slim(A.p, A.a, A.nbr, A.tmp_pm, A.max_nm, A.counters, A.bitmap, S.q_pos[w], S.q_disp[w], q_head, 32);
+        q_head = (q_head + 32) & (kQueue - 1);
+        q_n -= 32;
+        __syncwarp();
+      }
+    }
+    cur = nxt;
+  }
+  __syncwarp();
+  if (q_n) drain_movers_slim(A.p, A.a, A.nbr, A.tmp_pm, A.max_nm, A.counters, A.bitmap, S.q_pos[w], S.q_disp[w], q_head, q_n);
+}
+
 // ---- ordered mover emission (post-pass; every kernel leaves at once if nothing was staged) ----
 
 __global__ void __launch_bounds__(256) mover_popc_kernel(const unsigned *__restrict__ bitmap, int nwords, int *__restrict__ cnt,
@@ -540,8 +847,27 @@ void advance_p_range(AdvanceJob &J, vpb_particle_t *d_base, int k0, int k1, cons
   A.partition = (k0 == 0 && k1 == J.A.np && tuning("advance_p.ordered", 1)) ? d_partition : nullptr;
   if (A.partition) A.nwork = ((A.sy + A.by - 1) / A.by) * A.by * A.sz + 1;
   else A.nwork = (A.chunk_hi - A.chunk_lo + 63) / 64;
-  const bool tma = tuning("advance_p.tma", 1) != 0 && (reinterpret_cast<uintptr_t>(d_base) & 15) == 0;
-  if (tma) {
+  const int tma_mode = (reinterpret_cast<uintptr_t>(d_base) & 15) == 0 ? tuning("advance_p.tma", 2) : 0;
+  if (tma_mode == 2) {
+    const int nch = A.chunk_hi - A.chunk_lo;
+    VPB_CUDA(cudaMemsetAsync(&A.counters[2], 0, sizeof(int), st));   // ticket counter of the dynamic scheduler
+    const int per_sm = tuning("advance_p.stream_ctas_per_sm", 3);
+    int grid = c.sm_count * per_sm;
+    if (grid > (nch + kWarps - 1) / kWarps) grid = (nch + kWarps - 1) / kWarps;
+    const bool dep = tuning("advance_p.deposit", 1) != 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+      const int sm = (int)sizeof(StreamSmem);
+      VPB_CUDA(cudaFuncSetAttribute(advance_p_stream_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      VPB_CUDA(cudaFuncSetAttribute(advance_p_stream_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      VPB_CUDA(cudaFuncSetAttribute(advance_p_stream_kernel<0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      VPB_CUDA(cudaFuncSetAttribute(advance_p_stream_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      attr_set = true;
+    }
+    auto launch = [&](void (*kern)(AdvanceArgs)) { kern<<<grid, kWarps * 32, sizeof(StreamSmem), st>>>(A); };
+    if (per_sm >= 3) { if (dep) launch(advance_p_stream_kernel<1, 3>); else launch(advance_p_stream_kernel<0, 3>); }
+    else { if (dep) launch(advance_p_stream_kernel<1, 2>); else launch(advance_p_stream_kernel<0, 2>); }
+  } else if (tma_mode == 1) {
     static bool attr_set = false;
     if (!attr_set) {
       VPB_CUDA(cudaFuncSetAttribute(advance_p_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmaSmem)));

@@ -217,8 +217,10 @@ vpb_domain_t *vpb_domain_create(const vpb_grid_t *g, int rank, int nproc) {
   d.sx = g->nx + 2; d.sy = g->ny + 2; d.sz = g->nz + 2;
   d.sxy = d.sx * d.sy;
   long nv = (long)d.sxy * d.sz;
-  // the reference's own limit (grid.h:132-135): 6*voxel must fit an int
-  if (6 * nv > 0x7fffffffL) VPB_ERROR("local domain of %ld voxels exceeds the 2^31/6 voxel limit of grid_t", nv);
+  // the reference's own limit (grid.h:132-135): 6*voxel must fit an int.  A grid without a neighbor
+  // table (field-only use; particles cannot move on it) only needs the voxel index itself to fit.
+  if (g->neighbor && 6 * nv > 0x7fffffffL) VPB_ERROR("local domain of %ld voxels exceeds the 2^31/6 voxel limit of grid_t", nv);
+  if (nv > 0x7fffffffL) VPB_ERROR("local domain of %ld voxels exceeds 2^31", nv);
   d.nv = (int)nv;
   d.dt = g->dt; d.cvac = g->cvac; d.eps0 = g->eps0; d.damp = g->damp;
   d.dx = g->dx; d.dy = g->dy; d.dz = g->dz;

@@ -49,6 +49,20 @@ __global__ void __launch_bounds__(256) copy_positions_kernel(vpb_particle_t *__r
     reinterpret_cast<float4 *>(dst + k)[0] = reinterpret_cast<const float4 *>(src + k)[0];
 }
 
+// x-propagating vacuum plane wave on the Yee mesh (ey on x nodes, cbz half a cell further): a synthetic
+// field state for the field-only benchmark and its energy-conservation property test
+__global__ void __launch_bounds__(256) load_plane_wave_kernel(vpb_field_t *__restrict__ f, const DomainDev g, double kdx, float amp) {
+  const size_t nv = (size_t)g.sxy * g.sz;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (size_t)gridDim.x * blockDim.x) {
+    const int ix = (int)(v % g.sx);
+    float4 *q = reinterpret_cast<float4 *>(f) + 5 * v;
+    const float4 z = make_float4(0, 0, 0, 0);
+    q[0] = make_float4(0, amp * (float)cos(kdx * (ix - 1)), 0, 0);
+    q[1] = make_float4(0, 0, amp * (float)cos(kdx * (ix - 0.5)), 0);
+    q[2] = z; q[3] = z; q[4] = z;
+  }
+}
+
 }  // namespace vpb
 
 using namespace vpb;
@@ -63,6 +77,17 @@ void vpb_load_thermal(vpb_domain_t *dom, vpb_particle_t *d_p, int ppc, float vth
   const DomainDev &g = dom->d;
   const long np = (long)ppc * g.nx * g.ny * g.nz;
   load_thermal_kernel<<<ctx().sm_count * 16, 256, 0, ctx().stream>>>(d_p, np, ppc, vth, q, seed, tag0, g);
+  count_launch();
+  VPB_CUDA(cudaGetLastError());
+}
+
+// mode = number of wavelengths across the local nx cells (periodic in x)
+void vpb_load_plane_wave(vpb_domain_t *dom, vpb_field_t *d_f, int mode, float amp) {
+  if (!dom) VPB_ERROR("Bad grid");
+  if (!d_f) VPB_ERROR("Bad field");
+  const DomainDev &g = dom->d;
+  const double kdx = 2.0 * 3.14159265358979323846 * mode / g.nx;
+  load_plane_wave_kernel<<<ctx().sm_count * 16, 256, 0, ctx().stream>>>(d_f, g, kdx, amp);
   count_launch();
   VPB_CUDA(cudaGetLastError());
 }

@@ -36,6 +36,7 @@ class Grid:
         self.struct.bc[abi.boundary(0, 0, 0)] = rank
         self.range = None
         self.neighbor = None
+        self.field_only = False     # True: no neighbor[] (6 int64 per voxel); particles cannot move on such a grid
 
     # convenience -----------------------------------------------------------
     @property
@@ -80,6 +81,9 @@ class Grid:
         s.range = self.range.ctypes.data
         s.rangel = int(self.range[self.rank])
         s.rangeh = int(self.range[self.rank + 1]) - 1
+        if self.field_only:
+            s.neighbor = None
+            return
         sx, sy, sz = lnx + 2, lny + 2, lnz + 2
         z, y, x = np.meshgrid(np.arange(sz), np.arange(sy), np.arange(sx), indexing="ij")
         lid = (x + sx * (y + sy * z)).astype(np.int64)
@@ -119,6 +123,8 @@ class Grid:
             raise ValueError("Bad rank")
         s = self.struct
         s.bc[bound] = rank
+        if self.field_only:
+            return
         ln = list(self.n)
         ax = face % 3
         Y, Z = (ax + 1) % 3, (ax + 2) % 3
@@ -151,6 +157,8 @@ class Grid:
             raise ValueError("Bad boundary")
         if pbc not in (abi.ABSORB_PARTICLES, abi.REFLECT_PARTICLES):
             raise ValueError("Bad particle bc")
+        if self.field_only:
+            return
         z, y, x = self._face_cells(face)
         nx, ny, _ = self.n
         lid = x + (nx + 2) * (y + (ny + 2) * z)
@@ -220,12 +228,14 @@ def courant_dt(dx, dy, dz, cvac=1.0, frac=0.95):
     return frac / (cvac * np.sqrt(inv))
 
 
-def make_grid(n, kind="periodic", topo=(1, 1, 1), rank=0, L=None, dt=None, damp=0.0, pbc=abi.ABSORB_PARTICLES):
+def make_grid(n, kind="periodic", topo=(1, 1, 1), rank=0, L=None, dt=None, damp=0.0, pbc=abi.ABSORB_PARTICLES,
+              field_only=False):
     """One rank's grid_t for a global box of n=(gnx,gny,gnz) cells (cell size 1 unless L is given),
     cvac=eps0=1 and dt=0.95 Courant unless given."""
     nx, ny, nz = n
     L = L or (float(nx), float(ny), float(nz))
     g = Grid(rank=rank, nproc=topo[0] * topo[1] * topo[2])
+    g.field_only = field_only
     args = (g, 0.0, 0.0, 0.0, L[0], L[1], L[2], nx, ny, nz, topo[0], topo[1], topo[2])
     if kind == "periodic":
         partition_periodic_box(*args)

@@ -61,6 +61,7 @@ SIGNATURES = {
     "vpb_prof_list": (_i, [_i, _vp, _i]),
     "vpb_load_thermal": (None, [_vp, _vp, _i, _f, _f, C.c_ulonglong, _l]),
     "vpb_copy_positions": (None, [_vp, _vp, _l]),
+    "vpb_load_plane_wave": (None, [_vp, _vp, _i, _f]),
     "vpb_comm_unique_id": (None, [_vp]),
     "vpb_comm_init": (None, [_i, _i, _vp]),
     "vpb_comm_finalize": (None, []),

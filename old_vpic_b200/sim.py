@@ -61,8 +61,9 @@ class Simulation:
         self.nv = grid.nv
         self.vacuum = vacuum
         self.f = DevArray(self.L, self.nv, abi.field_dtype)
-        self.fi = DevArray(self.L, self.nv, abi.interpolator_dtype)
-        self.a = DevArray(self.L, self.nv + 1, abi.accumulator_dtype)
+        # a field-only grid (no neighbor table, grid.py) carries no particles: no interpolator / accumulators
+        self.fi = None if grid.field_only else DevArray(self.L, self.nv, abi.interpolator_dtype)
+        self.a = None if grid.field_only else DevArray(self.L, self.nv + 1, abi.accumulator_dtype)
         self.m_host = None
         self.m = None
         self.n_mat = n_mat
@@ -84,7 +85,17 @@ class Simulation:
     def m_ptr(self):
         return None if self.m is None else self.m.ptr
 
+    def free(self):
+        """Release every device array of this run."""
+        for arr in [self.f, self.fi, self.a, self.m, self.sort_tmp, self.scalars] + \
+                [x for sp in self.species for x in (sp.p, sp.pm, sp.nm, sp.partition)]:
+            if arr is not None:
+                arr.free()
+        self.L.vpb_domain_destroy(self.dom)
+        self.dom = None
+
     def define_species(self, name, q_m, max_np, max_nm=None, sort_interval=20):
+        assert not self.grid.field_only, "a field-only grid cannot carry particles"
         max_nm = max_nm if max_nm is not None else max(2 * max_np // 25, 16)   # vpic.hxx:416-420
         sp = Species(self.L, name, q_m, max_np, max_nm, sort_interval, len(self.species))
         self.species.append(sp)
