@@ -482,14 +482,7 @@ __global__ void __launch_bounds__(kWarps * 32, 3) advance_p_tma_kernel(const Adv
 //    (drifted) -> no reduction at all, each lane issues its own three REDG.128; otherwise the
 //    segmented reduction, with out-of-cell lanes made transparent so they do not split a run.
 // ---------------------------------------------------------------------------
-constexpr int kStagesS = 4;
 constexpr int kGrabS = 16;
-
-struct StreamSmem {
-  float4 tile[kWarps][kStagesS][96];
-  float4 q_pos[kWarps][kQueue], q_disp[kWarps][kQueue];   // the momentum waits in global memory (already stored)
-  uint64_t full[kWarps][kStagesS];
-};
 
 struct Interp {
   float4 ex, ey, ez, b0;
@@ -573,7 +566,8 @@ __device__ __noinline__ void drain_movers_slim(vpb_particle_t *__restrict__ p, f
     s.ux = b.x; s.uy = b.y; s.uz = b.z; s.q = b.w;
     s.dispx = c.x; s.dispy = c.y; s.dispz = c.z;
     unresolved = move_p_dev(s, acc, nbr);
-    pp[0] = make_float4(s.dx, s.dy, s.dz, __int_as_float(s.i));   // move_p never changes the momentum
+    pp[0] = make_float4(s.dx, s.dy, s.dz, __int_as_float(s.i));
+    pp[1] = make_float4(s.ux, s.uy, s.uz, s.q);                   // a reflection flips a momentum component
   }
   const unsigned um = __ballot_sync(full, unresolved);
   if (um) {
@@ -592,10 +586,26 @@ __device__ __noinline__ void drain_movers_slim(vpb_particle_t *__restrict__ p, f
   }
 }
 
-template <int DEPOSIT, int MINB>
+// STORE 0: results leave by three STG.128 per lane (all 48 bytes of the record, so that no sector is written
+//          partially -- a partial write makes L2 fetch the rest from DRAM first: +25 GB per launch in profiles/r1h);
+// STORE 1: results are put back into the staged tile and the tile leaves as one bulk async store, which takes
+//          the 96 store sectors per chunk off the LSU (its wavefronts were 70 % busy in profiles/r1i) at the
+//          price of a proxy fence per chunk and one more stage (a tile is refilled one iteration after its store).
+template <int STORE> struct StreamCfg { static constexpr int stages = STORE ? 5 : 4; };
+
+template <int STORE>
+struct StreamSmem {
+  float4 tile[kWarps][StreamCfg<STORE>::stages][96];
+  float4 q_pos[kWarps][kQueue], q_disp[kWarps][kQueue];   // the momentum waits in global memory (already stored)
+  uint64_t full[kWarps][StreamCfg<STORE>::stages];
+};
+
+template <int DEPOSIT, int MINB, int STORE>
 __global__ void __launch_bounds__(kWarps * 32, MINB) advance_p_stream_kernel(const AdvanceArgs A) {
+  constexpr int NS = StreamCfg<STORE>::stages;
+  constexpr int AHEAD = STORE ? NS - 1 : NS;      // tiles landed or landing, the current one included
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  StreamSmem &S = *reinterpret_cast<StreamSmem *>(smem_raw);
+  StreamSmem<STORE> &S = *reinterpret_cast<StreamSmem<STORE> *>(smem_raw);
 
   const unsigned fullmask = 0xffffffffu;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -608,7 +618,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) advance_p_stream_kernel(con
   char *const gbase = reinterpret_cast<char *>(A.p);
 
   if (lane == 0) {
-    for (int s = 0; s < kStagesS; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&S.full[w][s])));
+    for (int s = 0; s < NS; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&S.full[w][s])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
@@ -618,10 +628,10 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) advance_p_stream_kernel(con
     return (uint32_t)((n < 32 ? n : 32) * 48);
   };
   // dynamic scheduling (see advance_p_tma_kernel); the ticket for the NEXT group is already in flight
-  int g_cur = 0, g_end = 0;
-  int ticket = 0;                                  // lane 0: result of the outstanding atomic
   // (inline PTX: nvcc turns a lane-0 atomicAdd into a warp-aggregated one whose result is shuffled out at
   // once, which would wait for the atomic right here)
+  int g_cur = 0, g_end = 0;
+  int ticket = 0;                                  // lane 0: result of the outstanding atomic
   auto take_ticket = [&]() {
     if (lane == 0) asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(ticket) : "l"(A.counters + 2), "r"(kGrabS) : "memory");
   };
@@ -641,109 +651,121 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) advance_p_stream_kernel(con
       tma_load_tile(smem_u32(&S.tile[w][stage][0]), gbase + (size_t)chunk * kTileBytes, tile_bytes(chunk), smem_u32(&S.full[w][stage]),
                     pol);
   };
+  auto drain = [&](int count) {
+    if (STORE) {   // the movers' tiles must have landed in global memory before their final state is written over them
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+      }
+    }
+    __syncwarp();
+    drain_movers_slim(A.p, A.a, A.nbr, A.tmp_pm, A.max_nm, A.counters, A.bitmap, S.q_pos[w], S.q_disp[w], q_head, count);
+  };
 
-  // pend[j]: chunk whose tile sits (or is landing) in stage (it+j) % kStagesS
-  int pend[kStagesS];
+  // pend[j]: chunk whose tile sits (or is landing) in stage (it+j) % NS
+  int pend[AHEAD];
 #pragma unroll
-  for (int j = 0; j < kStagesS; j++) {
+  for (int j = 0; j < AHEAD; j++) {
     pend[j] = next_chunk();
     issue_load(pend[j], j);
   }
-  Interp cur;
-  cur.ex = cur.ey = cur.ez = cur.b0 = make_float4(0, 0, 0, 0);
-  cur.b1 = make_float2(0, 0);
+  Interp fa, fb;    // interpolators of the chunk being computed / of the next one; roles alternate
+  fa.ex = fa.ey = fa.ez = fa.b0 = make_float4(0, 0, 0, 0);
+  fa.b1 = make_float2(0, 0);
+  fb = fa;
   if (pend[0] >= 0) {
     mbar_wait(smem_u32(&S.full[w][0]), 0);
     const int k = pend[0] * 32 + lane;
     const int ii = k < A.np ? __float_as_int(S.tile[w][0][lane * 3].w) : 0;
-    load_interp(cur, A.f, ii);
+    load_interp(fa, A.f, ii);
   }
 
-  for (int it = 0; pend[0] >= 0; ++it) {
+  int it = 0;
+  // one chunk: compute with `cur`, request `nxt` for the following chunk.  Every lane runs the whole push; lanes
+  // past the end of the array carry zeros and are masked out of every store.
+  auto step = [&](const Interp &cur, Interp &nxt) {
     const int chunk = pend[0];
-    const int stage = it % kStagesS;
+    const int stage = it % NS;
     const int k = chunk * 32 + lane;
     const bool valid = k < A.np;
-    const float4 *tp = &S.tile[w][stage][lane * 3];
+    float4 *tp = &S.tile[w][stage][lane * 3];
     float4 r0 = make_float4(0, 0, 0, 0), r1 = r0;
     if (valid) { r0 = tp[0]; r1 = tp[1]; }
 
     // request the interpolator of the next chunk before computing on this one
-    Interp nxt = cur;
     if (pend[1] >= 0) {
-      const int sn = (it + 1) % kStagesS;
-      mbar_wait(smem_u32(&S.full[w][sn]), (uint32_t)(((it + 1) / kStagesS) & 1));
+      const int sn = (it + 1) % NS;
+      mbar_wait(smem_u32(&S.full[w][sn]), (uint32_t)(((it + 1) / NS) & 1));
       const int kn = pend[1] * 32 + lane;
       const int iin = kn < A.np ? __float_as_int(S.tile[w][sn][lane * 3].w) : 0;
       load_interp(nxt, A.f, iin);
     }
 
-    bool inbnds = false, outbnds = false;
     const int ii = __float_as_int(r0.w);
     float dep[12];
-#pragma unroll
-    for (int c = 0; c < 12; c++) dep[c] = 0.f;
-    float4 mom = r1;
-    float hx = 0, hy = 0, hz = 0;
-
-    if (valid) {
-      float dx = r0.x, dy = r0.y, dz = r0.z;
-      const float hax = qdt_2mc * ((cur.ex.x + dy * cur.ex.y) + dz * (cur.ex.z + dy * cur.ex.w));
-      const float hay = qdt_2mc * ((cur.ey.x + dz * cur.ey.y) + dx * (cur.ey.z + dz * cur.ey.w));
-      const float haz = qdt_2mc * ((cur.ez.x + dx * cur.ez.y) + dy * (cur.ez.z + dx * cur.ez.w));
-      const float cbx = cur.b0.x + dx * cur.b0.y;
-      const float cby = cur.b0.z + dy * cur.b0.w;
-      const float cbz = cur.b1.x + dz * cur.b1.y;
-      float ux = r1.x, uy = r1.y, uz = r1.z;
-      const float q = r1.w;
-      ux += hax; uy += hay; uz += haz;
-      float v0 = qdt_2mc / sqrtf(one + (ux * ux + (uy * uy + uz * uz)));
-      float v1 = cbx * cbx + (cby * cby + cbz * cbz);
-      float v2 = (v0 * v0) * v1;
-      float v3 = v0 * (one + v2 * (one_third + v2 * two_fifteenths));
-      float v4 = v3 / (one + v1 * (v3 * v3));
-      v4 += v4;
-      v0 = ux + v3 * (uy * cbz - uz * cby);
-      v1 = uy + v3 * (uz * cbx - ux * cbz);
-      v2 = uz + v3 * (ux * cby - uy * cbx);
-      ux += v4 * (v1 * cbz - v2 * cby);
-      uy += v4 * (v2 * cbx - v0 * cbz);
-      uz += v4 * (v0 * cby - v1 * cbx);
-      ux += hax; uy += hay; uz += haz;
-      mom = make_float4(ux, uy, uz, q);
-      v0 = one / sqrtf(one + (ux * ux + (uy * uy + uz * uz)));
-      ux *= cdt_dx; uy *= cdt_dy; uz *= cdt_dz;
-      ux *= v0; uy *= v0; uz *= v0;
-      v0 = dx + ux; v1 = dy + uy; v2 = dz + uz;
-      v3 = v0 + ux; v4 = v1 + uy;
-      float v5 = v2 + uz;
-      inbnds = v3 <= one && v4 <= one && v5 <= one && -v3 <= one && -v4 <= one && -v5 <= one;
-      outbnds = !inbnds;
-      // all 48 bytes of every particle leave here, so a warp writes 1536 contiguous bytes and no sector is
-      // written partially (a partial write makes L2 fetch the rest from DRAM first: +25 GB per launch in
-      // profiles/r1h).  Out-of-cell particles keep their old position until move_p has run.
+    float dx = r0.x, dy = r0.y, dz = r0.z;
+    const float hax = qdt_2mc * ((cur.ex.x + dy * cur.ex.y) + dz * (cur.ex.z + dy * cur.ex.w));
+    const float hay = qdt_2mc * ((cur.ey.x + dz * cur.ey.y) + dx * (cur.ey.z + dz * cur.ey.w));
+    const float haz = qdt_2mc * ((cur.ez.x + dx * cur.ez.y) + dy * (cur.ez.z + dx * cur.ez.w));
+    const float cbx = cur.b0.x + dx * cur.b0.y;
+    const float cby = cur.b0.z + dy * cur.b0.w;
+    const float cbz = cur.b1.x + dz * cur.b1.y;
+    float ux = r1.x, uy = r1.y, uz = r1.z;
+    const float q = r1.w;
+    ux += hax; uy += hay; uz += haz;
+    float v0 = qdt_2mc / sqrtf(one + (ux * ux + (uy * uy + uz * uz)));
+    float v1 = cbx * cbx + (cby * cby + cbz * cbz);
+    float v2 = (v0 * v0) * v1;
+    float v3 = v0 * (one + v2 * (one_third + v2 * two_fifteenths));
+    float v4 = v3 / (one + v1 * (v3 * v3));
+    v4 += v4;
+    v0 = ux + v3 * (uy * cbz - uz * cby);
+    v1 = uy + v3 * (uz * cbx - ux * cbz);
+    v2 = uz + v3 * (ux * cby - uy * cbx);
+    ux += v4 * (v1 * cbz - v2 * cby);
+    uy += v4 * (v2 * cbx - v0 * cbz);
+    uz += v4 * (v0 * cby - v1 * cbx);
+    ux += hax; uy += hay; uz += haz;
+    const float4 mom = make_float4(ux, uy, uz, q);
+    v0 = one / sqrtf(one + (ux * ux + (uy * uy + uz * uz)));
+    ux *= cdt_dx; uy *= cdt_dy; uz *= cdt_dz;
+    ux *= v0; uy *= v0; uz *= v0;
+    v0 = dx + ux; v1 = dy + uy; v2 = dz + uz;
+    v3 = v0 + ux; v4 = v1 + uy;
+    float v5 = v2 + uz;
+    const bool in_cell = v3 <= one && v4 <= one && v5 <= one && -v3 <= one && -v4 <= one && -v5 <= one;
+    const bool inbnds = valid && in_cell, outbnds = valid && !in_cell;
+    const float4 pos = in_cell ? make_float4(v3, v4, v5, r0.w) : r0;   // out-of-cell: old position until move_p has run
+    if (STORE) {
+      if (valid) { tp[0] = pos; tp[1] = mom; }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) tma_store_tile(gbase + (size_t)chunk * kTileBytes, smem_u32(&S.tile[w][stage][0]), tile_bytes(chunk), pol);
+    } else if (valid) {
       float4 *pp = reinterpret_cast<float4 *>(A.p + k);
-      st_stream4(pp, inbnds ? make_float4(v3, v4, v5, r0.w) : r0);
+      st_stream4(pp, pos);
       st_stream4(pp + 1, mom);
       st_stream4(pp + 2, tp[2]);
-      if (inbnds) {
-        dx = v0; dy = v1; dz = v2;
-        v5 = q * ux * uy * uz * one_third;
-        accumulate_j(q, ux, dy, dz, v5, dep[0], dep[1], dep[2], dep[3]);
-        accumulate_j(q, uy, dz, dx, v5, dep[4], dep[5], dep[6], dep[7]);
-        accumulate_j(q, uz, dx, dy, v5, dep[8], dep[9], dep[10], dep[11]);
-      } else {
-        hx = ux; hy = uy; hz = uz;
-      }
     }
+    // the 12 contributions (garbage in out-of-cell lanes, which are masked out of the deposit)
+    v5 = q * ux * uy * uz * one_third;
+    accumulate_j(q, ux, v1, v2, v5, dep[0], dep[1], dep[2], dep[3]);
+    accumulate_j(q, uy, v2, v0, v5, dep[4], dep[5], dep[6], dep[7]);
+    accumulate_j(q, uz, v0, v1, v5, dep[8], dep[9], dep[10], dep[11]);
 
-    // this stage has been read by every lane (the push consumed r0/r1): refill it
+    // refill: STORE 0 this stage (read by every lane: the push consumed r0/r1); STORE 1 the stage whose bulk
+    // store was issued one iteration ago (it must have finished reading shared memory)
     __syncwarp();
     const int cn = next_chunk();
-    issue_load(cn, stage);
+    if (STORE) {
+      if (lane == 0 && cn >= 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      issue_load(cn, (it + NS - 1) % NS);
+    } else {
+      issue_load(cn, stage);
+    }
 #pragma unroll
-    for (int j = 0; j < kStagesS - 1; j++) pend[j] = pend[j + 1];
-    pend[kStagesS - 1] = cn;
+    for (int j = 0; j < AHEAD - 1; j++) pend[j] = pend[j + 1];
+    pend[AHEAD - 1] = cn;
 
     if (DEPOSIT == 0) {
       if (inbnds) red3(A.a + 12 * (size_t)ii, dep);
@@ -756,21 +778,28 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) advance_p_stream_kernel(con
       if (outbnds) {
         const int e = (q_head + q_n + __popc(om & ((1u << lane) - 1u))) & (kQueue - 1);
         S.q_pos[w][e] = r0;
-        S.q_disp[w][e] = make_float4(hx, hy, hz, __int_as_float(k));
+        S.q_disp[w][e] = make_float4(ux, uy, uz, __int_as_float(k));
       }
       q_n += __popc(om);
-      __syncwarp();
       if (q_n >= 32) {
-        drain_movers_slim(A.p, A.a, A.nbr, A.tmp_pm, A.max_nm, A.counters, A.bitmap, S.q_pos[w], S.q_disp[w], q_head, 32);
+        drain(32);
         q_head = (q_head + 32) & (kQueue - 1);
         q_n -= 32;
         __syncwarp();
       }
     }
-    cur = nxt;
+    ++it;
+  };
+
+  while (pend[0] >= 0) {
+    step(fa, fb);
+    if (pend[0] < 0) break;
+    step(fb, fa);
   }
-  __syncwarp();
-  if (q_n) drain_movers_slim(A.p, A.a, A.nbr, A.tmp_pm, A.max_nm, A.counters, A.bitmap, S.q_pos[w], S.q_disp[w], q_head, q_n);
+  if (q_n) drain(q_n);
+  if (STORE) {
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
 }
 
 // ---- ordered mover emission (post-pass; every kernel leaves at once if nothing was staged) ----
@@ -851,22 +880,26 @@ void advance_p_range(AdvanceJob &J, vpb_particle_t *d_base, int k0, int k1, cons
   if (tma_mode == 2) {
     const int nch = A.chunk_hi - A.chunk_lo;
     VPB_CUDA(cudaMemsetAsync(&A.counters[2], 0, sizeof(int), st));   // ticket counter of the dynamic scheduler
-    const int per_sm = tuning("advance_p.stream_ctas_per_sm", 3);
+    const int per_sm = tuning("advance_p.stream_ctas_per_sm", 2);
     int grid = c.sm_count * per_sm;
     if (grid > (nch + kWarps - 1) / kWarps) grid = (nch + kWarps - 1) / kWarps;
     const bool dep = tuning("advance_p.deposit", 1) != 0;
+    const int store = tuning("advance_p.stream_store", 0) ? 1 : 0;
+    typedef void (*kern_t)(AdvanceArgs);
+    static const kern_t table[2][2][2] = {   // [store][per_sm >= 3][deposit]
+        {{advance_p_stream_kernel<0, 2, 0>, advance_p_stream_kernel<1, 2, 0>}, {advance_p_stream_kernel<0, 3, 0>, advance_p_stream_kernel<1, 3, 0>}},
+        {{advance_p_stream_kernel<0, 2, 1>, advance_p_stream_kernel<1, 2, 1>}, {advance_p_stream_kernel<0, 2, 1>, advance_p_stream_kernel<1, 2, 1>}}};
+    static const int smem_bytes[2] = {(int)sizeof(StreamSmem<0>), (int)sizeof(StreamSmem<1>)};
     static bool attr_set = false;
     if (!attr_set) {
-      const int sm = (int)sizeof(StreamSmem);
-      VPB_CUDA(cudaFuncSetAttribute(advance_p_stream_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-      VPB_CUDA(cudaFuncSetAttribute(advance_p_stream_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-      VPB_CUDA(cudaFuncSetAttribute(advance_p_stream_kernel<0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-      VPB_CUDA(cudaFuncSetAttribute(advance_p_stream_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+      for (int a = 0; a < 2; a++)
+        for (int b = 0; b < 2; b++)
+          for (int d = 0; d < 2; d++)
+            VPB_CUDA(cudaFuncSetAttribute(table[a][b][d], cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes[a]));
       attr_set = true;
     }
-    auto launch = [&](void (*kern)(AdvanceArgs)) { kern<<<grid, kWarps * 32, sizeof(StreamSmem), st>>>(A); };
-    if (per_sm >= 3) { if (dep) launch(advance_p_stream_kernel<1, 3>); else launch(advance_p_stream_kernel<0, 3>); }
-    else { if (dep) launch(advance_p_stream_kernel<1, 2>); else launch(advance_p_stream_kernel<0, 2>); }
+    if (store && grid > c.sm_count * 2) grid = c.sm_count * 2;   // 76 KB of shared memory per CTA: two per SM
+    table[store][per_sm >= 3][dep]<<<grid, kWarps * 32, smem_bytes[store], st>>>(A);
   } else if (tma_mode == 1) {
     static bool attr_set = false;
     if (!attr_set) {

@@ -185,9 +185,9 @@ def test_field_only_grid_and_plane_wave_loader(vpb, orc):
         sim.advance()
         orc.orc_clear_jf(ptr(f_o), go.ref())
         orc.orc_synchronize_jf(ptr(f_o), go.ref())
-        orc.orc_advance_b(ptr(f_o), go.ref(), 0.5)
+        orc.orc_advance_b(ptr(f_o), go.ref(), 0.5, 1)
         orc.orc_advance_e(ptr(f_o), None, go.ref(), 1)
-        orc.orc_advance_b(ptr(f_o), go.ref(), 0.5)
+        orc.orc_advance_b(ptr(f_o), go.ref(), 0.5, 1)
     assert_bits_equal(sim.f.download(), f_o, "field-only advance")
     assert abs(sum(sim.energies()[:6]) - en0) / en0 < 2e-3
     sim.free()

@@ -25,11 +25,12 @@ def acc_floats(a):
     return np.ascontiguousarray(a).view(np.float32).reshape(-1, 12)
 
 
-@pytest.mark.parametrize("deposit,tma,per_sm", [(1, 2, 3), (0, 2, 3), (1, 2, 2), (0, 2, 2), (1, 1, 3), (0, 1, 3), (1, 0, 3), (0, 0, 3)])
+@pytest.mark.parametrize("deposit,tma,per_sm,store", [(1, 2, 2, 0), (0, 2, 2, 0), (1, 2, 3, 0), (0, 2, 3, 0), (1, 2, 2, 1), (0, 2, 2, 1),
+                                                      (1, 1, 3, 0), (0, 1, 3, 0), (1, 0, 3, 0), (0, 0, 3, 0)])
 @pytest.mark.parametrize("kind", ["periodic", "metal", "absorbing"])
 @pytest.mark.parametrize("n,np_,sort", [((6, 5, 4), 5000, True), ((8, 1, 6), 7001, False), ((1, 1, 16), 300, True),
                                         ((16, 16, 16), 16 * 16 * 16 * 40, True)])
-def test_advance_p(vpb, orc, deposit, tma, per_sm, kind, n, np_, sort):
+def test_advance_p(vpb, orc, deposit, tma, per_sm, store, kind, n, np_, sort):
     g = host_grid(n, kind)
     rng = np.random.default_rng(21)
     p = random_particles(rng, g, np_, vth=0.6, sort=sort, edge_frac=0.02)
@@ -38,6 +39,7 @@ def test_advance_p(vpb, orc, deposit, tma, per_sm, kind, n, np_, sort):
     vpb.vpb_set_tuning(b"advance_p.deposit", deposit)
     vpb.vpb_set_tuning(b"advance_p.tma", tma)
     vpb.vpb_set_tuning(b"advance_p.stream_ctas_per_sm", per_sm)
+    vpb.vpb_set_tuning(b"advance_p.stream_store", store)
     p_o, p_g = p.copy(), p.copy()
     a_o = abi.aligned_zeros(g.nv, abi.accumulator_dtype)
     a_g = a_o.copy()
@@ -47,7 +49,8 @@ def test_advance_p(vpb, orc, deposit, tma, per_sm, kind, n, np_, sort):
     nm_g = vpb.advance_p(ptr(p_g), np_, q_m, ptr(pm_g), max_nm, ptr(a_g), ptr(fi), g.ref())
     vpb.vpb_set_tuning(b"advance_p.deposit", 1)
     vpb.vpb_set_tuning(b"advance_p.tma", 2)
-    vpb.vpb_set_tuning(b"advance_p.stream_ctas_per_sm", 3)
+    vpb.vpb_set_tuning(b"advance_p.stream_ctas_per_sm", 2)
+    vpb.vpb_set_tuning(b"advance_p.stream_store", 0)
     assert nm_g == nm_o
     if kind == "absorbing":
         assert nm_o > 0
