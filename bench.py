@@ -214,7 +214,7 @@ def run_b200(args):
     n = args.cells
     topo = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
     g = helpers.make_grid((n * topo[0], n * topo[1], n * topo[2]), "periodic", topo=topo, rank=rank)
-    sim = Simulation(g, n_mat=1, L=L)
+    sim = Simulation(g, n_mat=1, L=L, planar=L.vpb_get_tuning(b"sim.aos_fields") == 0)
     np_ = n ** 3 * args.ppc
     max_np = int(np_ * (1.0 if world == 1 else 1.02)) + 1024
     # macro-charge q = +-(cell volume)/ppc so that the plasma frequency is 1 (the reference's thermal recipe,
@@ -315,7 +315,7 @@ def fields_measure(L, n, steps, warmup):
     from old_vpic_b200 import grid as helpers
     from old_vpic_b200.sim import Simulation
     g = helpers.make_grid((n, n, n), "periodic", field_only=True)
-    sim = Simulation(g, n_mat=1, vacuum=True, L=L)
+    sim = Simulation(g, n_mat=1, vacuum=True, L=L, planar=L.vpb_get_tuning(b"sim.aos_fields") == 0)
     L.vpb_load_plane_wave(sim.dom, sim.f.ptr, 8, 1.0)
     e0 = sum(sim.energies()[:6])
     for _ in range(warmup):
@@ -341,15 +341,18 @@ def fields_measure(L, n, steps, warmup):
     res = {"workload": "BASELINE configs[1]: field-only Yee vacuum plane wave, %d^3 cells, periodic, 1 GPU" % n,
            "steps": steps, "ms_per_step": ms / steps, "field_cell_updates_per_s": 3 * cells * steps / (ms * 1e-3),
            "em_energy_drift_rel": abs(e1 - e0) / e0}
-    # algorithmic bytes per cell and what the reference's 80-byte AoS field_t makes DRAM move at
-    # 32-byte sector granularity: advance_b 36 vs 80, vacuum advance_e 48 vs 96
-    for nm, alg, layout in (("advance_b", 36.0, 80.0), ("advance_e", 48.0, 96.0)):
+    # algorithmic bytes per cell and what the quad-planar device layout moves (DESIGN.md "field
+    # layout"): advance_b reads the e quad and reads+writes the cb quad = 48 B; vacuum advance_e reads cb and jf
+    # quads and reads+writes the e quad = 64 B.  (On the reference's 80-byte AoS array ncu measures 112 B per
+    # cell for either kernel, profiles/r1j.)
+    res["field_layout"] = "planar" if L.vpb_get_tuning(b"sim.aos_fields") == 0 else "aos"
+    for nm, alg, layout in (("advance_b", 36.0, 48.0), ("advance_e", 48.0, 64.0)):
         tot, cnt = out[nm]
         if not cnt:
             continue
         rate = cells * cnt / (tot * 1e-3)
         res[nm] = {"cell_updates_per_s": rate, "avg_launch_ms": tot / cnt, "algorithmic_bytes_per_cell": alg,
-                   "layout_imposed_bytes_per_cell": layout, "achieved_GBs": rate * alg / 1e9, "frac": rate * alg / 1e9 / peak,
+                   "layout_bytes_per_cell": layout, "achieved_GBs": rate * alg / 1e9, "frac": rate * alg / 1e9 / peak,
                    "frac_of_layout_bound": rate * layout / 1e9 / peak}
     return res
 

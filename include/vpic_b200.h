@@ -183,6 +183,17 @@ void vpb_accumulate_rho_p(vpb_domain_t *dom, vpb_field_t *d_f, const vpb_particl
 void vpb_load_thermal(vpb_domain_t *dom, vpb_particle_t *d_p, int ppc, float vth, float q,
                       unsigned long long seed, long tag0);
 void vpb_copy_positions(vpb_particle_t *d_dst, const vpb_particle_t *d_src, long np);
+/* Device field layout.  A domain starts out with the reference's 80-byte AoS field_t (what every layer-A entry
+ * point uses).  A caller that keeps the field array resident on the device can switch the domain to the PLANAR
+ * layout: five planes (e|div_e, cb|div_b, tca|rhob, jf|rhof, material ids) of one 16-byte quad per voxel, so a
+ * stencil kernel only moves the quads it uses (advance_b: 48 B per cell instead of the 112 B ncu measures on the
+ * AoS array).  All vpb_* field functions follow the domain's current layout; vpb_field_bytes() is the size to
+ * allocate, vpb_field_convert() copies between the two layouts (out of place). */
+void vpb_domain_set_field_layout(vpb_domain_t *dom, int planar);
+int vpb_domain_field_layout(const vpb_domain_t *dom);
+size_t vpb_field_bytes(const vpb_domain_t *dom);
+void vpb_field_convert(vpb_domain_t *dom, vpb_field_t *d_dst, const vpb_field_t *d_src, int to_planar);
+
 /* Synthetic field state: an x-propagating vacuum plane wave (ey, cbz) with `mode` wavelengths across
  * the local nx cells; everything else zero. */
 void vpb_load_plane_wave(vpb_domain_t *dom, vpb_field_t *d_f, int mode, float amp);

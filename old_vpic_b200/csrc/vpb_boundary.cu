@@ -87,8 +87,8 @@ __device__ void accumulate_rhob_dev(vpb_field_t *__restrict__ f, float dx, float
   if (j == g.ny) { w2 += w2; w3 += w3; w6 += w6; w7 += w7; }
   if (k == 1) { w0 += w0; w1 += w1; w2 += w2; w3 += w3; }
   if (k == g.nz) { w4 += w4; w5 += w5; w6 += w6; w7 += w7; }
-  float *rhob = &f[vi].rhob;
-  const size_t X = 20, Y = 20 * (size_t)g.sx, Z = 20 * (size_t)g.sxy;
+  float *rhob = &FCOMP(f, g, vi, 11);                                      // rhob = component 11
+  const size_t X = 4 * (size_t)g.fqv, Y = X * (size_t)g.sx, Z = X * (size_t)g.sxy;
   red_add(rhob, w0); red_add(rhob + X, w1); red_add(rhob + Y, w2); red_add(rhob + X + Y, w3);
   red_add(rhob + Z, w4); red_add(rhob + Z + X, w5); red_add(rhob + Z + Y, w6); red_add(rhob + Z + Y + X, w7);
 }

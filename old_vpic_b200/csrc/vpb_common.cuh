@@ -55,7 +55,17 @@ struct DomainDev {
   // original 64-bit table, only read by migration (boundary_p.c:304-309)
   const int64_t *nbr64;
   int64_t rangel, rangeh;
+  // field_t addressing in 16-byte quads {e,div_e | cb,div_b | tca,rhob | jf,rhof | material ids}: quad q of voxel
+  // v sits at float4 index v*fqv + q*fqq.  Reference layout (80-byte AoS): fqv=5, fqq=1.  Planar layout (five
+  // planes of nvp quads, device-resident runs): fqv=1, fqq=nvp.  See DESIGN.md "field layout".
+  long fqv, fqq;
 };
+
+#define FQ(f, g, v, q) (reinterpret_cast<float4 *>(f) + ((size_t)(v) * (size_t)(g).fqv + (size_t)(q) * (size_t)(g).fqq))
+#define CFQ(f, g, v, q) (reinterpret_cast<const float4 *>(f) + ((size_t)(v) * (size_t)(g).fqv + (size_t)(q) * (size_t)(g).fqq))
+// float component c (0..19, the reference's member order) of voxel v
+#define FCOMP(f, g, v, c) \
+  (reinterpret_cast<float *>(f)[4 * ((size_t)(v) * (size_t)(g).fqv + (size_t)((c) >> 2) * (size_t)(g).fqq) + ((c) & 3)])
 
 struct Context {
   int device = -1;

@@ -61,9 +61,35 @@ struct Residency {
     return sb.dev;
   }
 
+  // A field array: like get(), and when the array had to be staged anyway (plain host memory) and the tuning
+  // "dropin.planar" is on, the staged copy is re-laid out planar for the duration of the call (the layout the
+  // device-resident driver uses; tests run the whole layer-A suite through it with VPB_DROPIN_PLANAR=1).
+  struct PlanarAcq { vpb_domain_t *dom; void *aos, *planar; int mode; };
+  std::vector<PlanarAcq> planar;
+  void *get_field(vpb_domain_t *dom, const void *host, size_t bytes, int mode) {
+    void *d = get(host, bytes, mode);
+    if (d == host || !host || !tuning("dropin.planar", 0)) return d;
+    Context &c = ctx();
+    for (auto &pa : planar)
+      if (pa.aos == d) return pa.planar;
+    vpb_domain_set_field_layout(dom, 1);
+    void *pl = nullptr;
+    VPB_CUDA(cudaMallocAsync(&pl, vpb_field_bytes(dom), c.stream));
+    VPB_CUDA(cudaMemsetAsync(pl, 0, vpb_field_bytes(dom), c.stream));
+    if (mode & RD) vpb_field_convert(dom, (vpb_field_t *)pl, (const vpb_field_t *)d, 1);
+    planar.push_back({dom, d, pl, mode});
+    return pl;
+  }
+
   // copy results back and drain the stream
   void finish() {
     Context &c = ctx();
+    for (auto &pa : planar) {
+      if (pa.mode & WR) vpb_field_convert(pa.dom, (vpb_field_t *)pa.aos, (const vpb_field_t *)pa.planar, 0);
+      VPB_CUDA(cudaFreeAsync(pa.planar, c.stream));
+      vpb_domain_set_field_layout(pa.dom, 0);
+    }
+    planar.clear();
     for (auto &a : staged)
       if (a.mode & WR) { VPB_CUDA(cudaMemcpyAsync(a.host, a.dev, a.bytes, cudaMemcpyDeviceToHost, c.stream)); d2h += a.bytes; }
     VPB_CUDA(cudaStreamSynchronize(c.stream));
@@ -340,7 +366,7 @@ void accumulate_rho_p(vpb_field_t *f, const vpb_particle_t *p0, int np, const vp
   if (!g) VPB_ERROR("Bad grid");
   vpb_domain_t *dom = domain_of(g);
   Residency r;
-  vpb_field_t *df = (vpb_field_t *)r.get(f, nvox(g) * sizeof(*f), RW);
+  vpb_field_t *df = (vpb_field_t *)r.get_field(dom, f, nvox(g) * sizeof(*f), RW);
   const vpb_particle_t *dp = (const vpb_particle_t *)r.get(p0, (size_t)np * sizeof(*p0), RD);
   vpb_accumulate_rho_p(dom, df, dp, np);
   r.finish();
@@ -377,7 +403,7 @@ void accumulate_rhob(vpb_field_t *f0, const vpb_particle_t *p, const vpb_grid_t 
   vpb_domain_t *dom = domain_of(g);
   Context &c = ctx();
   Residency r;
-  vpb_field_t *df = (vpb_field_t *)r.get(f0, nvox(g) * sizeof(*f0), RW);
+  vpb_field_t *df = (vpb_field_t *)r.get_field(dom, f0, nvox(g) * sizeof(*f0), RW);
   vpb_particle_t hp = *p, *d_one = nullptr;
   VPB_CUDA(cudaMallocAsync(&d_one, sizeof(hp), c.stream));
   VPB_CUDA(cudaMemcpyAsync(d_one, &hp, sizeof(hp), cudaMemcpyHostToDevice, c.stream));
@@ -404,7 +430,7 @@ void boundary_p(vpb_species_t *sp_list, vpb_field_t *f0, vpb_accumulator_t *a0, 
     st[s].pm = (vpb_particle_mover_t *)r.get(sp->pm, (size_t)sp->max_nm * sizeof(vpb_particle_mover_t), RW);
     st[s].np = sp->np; st[s].max_np = sp->max_np; st[s].nm = sp->nm; st[s].max_nm = sp->max_nm; st[s].id = sp->id;
   }
-  vpb_field_t *df = f0 ? (vpb_field_t *)r.get(f0, nvox(g) * sizeof(*f0), RW) : nullptr;
+  vpb_field_t *df = f0 ? (vpb_field_t *)r.get_field(dom, f0, nvox(g) * sizeof(*f0), RW) : nullptr;
   vpb_accumulator_t *da = a0 ? (vpb_accumulator_t *)r.get(a0, nvox(g) * sizeof(*a0), RW) : nullptr;
   vpb_boundary_p(dom, st.data(), (int)st.size(), df, da);
   for (size_t s = 0; s < list.size(); s++) { list[s]->np = st[s].np; list[s]->nm = st[s].nm; }
@@ -468,7 +494,7 @@ void load_interpolator(vpb_interpolator_t *fi, const vpb_field_t *f, const vpb_g
   Residency r;
   // RW, not WR: ghost voxels and _pad of the caller's array are left as they were
   vpb_interpolator_t *dfi = (vpb_interpolator_t *)r.get(fi, nvox(g) * sizeof(*fi), RW);
-  const vpb_field_t *df = (const vpb_field_t *)r.get(f, nvox(g) * sizeof(*f), RD);
+  const vpb_field_t *df = (const vpb_field_t *)r.get_field(dom, f, nvox(g) * sizeof(*f), RD);
   vpb_load_interpolator(dom, dfi, df);
   r.finish();
 }
@@ -495,7 +521,7 @@ void unload_accumulator(vpb_field_t *f, const vpb_accumulator_t *a, const vpb_gr
   if (!g) VPB_ERROR("Bad grid");
   vpb_domain_t *dom = domain_of(g);
   Residency r;
-  vpb_field_t *df = (vpb_field_t *)r.get(f, nvox(g) * sizeof(*f), RW);
+  vpb_field_t *df = (vpb_field_t *)r.get_field(dom, f, nvox(g) * sizeof(*f), RW);
   const vpb_accumulator_t *da = (const vpb_accumulator_t *)r.get(a, nvox(g) * sizeof(*a), RD);
   vpb_unload_accumulator(dom, df, da);
   r.finish();
@@ -576,7 +602,7 @@ struct FieldCall {
     if (need_m && !m) VPB_ERROR("Bad material coefficients");
     if (!g) VPB_ERROR("Bad grid");
     dom = domain_of(g);
-    df = (vpb_field_t *)r.get(f, nvox(g) * sizeof(*f), mode);
+    df = (vpb_field_t *)r.get_field(dom, f, nvox(g) * sizeof(*f), mode);
     if (m) {
       n_mat = nmat_of(m);
       dm = (const vpb_material_coefficient_t *)r.get(m, (size_t)n_mat * sizeof(*m), RD);

@@ -51,7 +51,7 @@ struct LocalOp {
 constexpr int kMaxOps = 24;
 struct LocalOps { int n; LocalOp op[kMaxOps]; };
 
-#define FV(f, v, c) (reinterpret_cast<float *>(f)[20 * (size_t)(v) + (c)])
+#define FV(f, v, c) FCOMP(f, g, v, c)
 
 __device__ __forceinline__ size_t box_voxel(const Box &b, long cell, const DomainDev &g) {
   const int wx = b.hi[0] - b.lo[0] + 1, wy = b.hi[1] - b.lo[1] + 1;
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(128) pack_kernel(const vpb_field_t *__restrict
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < j.plan.nfloats; e += gridDim.x * blockDim.x) {
     if (e < j.plan.header) { j.buf[e] = j.dX; continue; }   // leading cell size (remote.c:82)
     const Elem el = decode(j.plan, e, g);
-    j.buf[e] = reinterpret_cast<const float *>(f)[20 * el.v + el.comp];
+    j.buf[e] = FCOMP(const_cast<vpb_field_t *>(f), g, el.v, el.comp);
   }
 }
 

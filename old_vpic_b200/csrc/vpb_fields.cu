@@ -44,8 +44,8 @@ __device__ __forceinline__ VoxelIdx voxel_of_thread(const DomainDev &g) {
   return i;
 }
 
-#define QUAD(f, v, q) (reinterpret_cast<float4 *>(f) + 5 * (v) + (q))
-#define CQUAD(f, v, q) (reinterpret_cast<const float4 *>(f) + 5 * (v) + (q))
+#define QUAD(f, v, q) FQ(f, g, v, q)
+#define CQUAD(f, v, q) CFQ(f, g, v, q)
 
 // cbX -= pY*(eZ(+Y) - eZ) - pZ*(eY(+Z) - eY)  on X faces (X in 1..nX+1, others 1..n)
 __global__ void __launch_bounds__(256) advance_b_kernel(vpb_field_t *__restrict__ f, const DomainDev g, float px, float py, float pz) {
@@ -198,7 +198,8 @@ __global__ void __launch_bounds__(256) clean_div_b_kernel(vpb_field_t *__restric
 }
 
 // which: 0 clear jfx,jfy,jfz   1 clear rhof   (all voxels, ghosts included)
-__global__ void __launch_bounds__(256) clear_quad3_kernel(vpb_field_t *__restrict__ f, size_t nv, int which) {
+__global__ void __launch_bounds__(256) clear_quad3_kernel(vpb_field_t *__restrict__ f, const DomainDev g, int which) {
+  const size_t nv = (size_t)g.nv;
   for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (size_t)gridDim.x * blockDim.x) {
     float4 q = *QUAD(f, v, 3);
     if (which == 0) { q.x = 0; q.y = 0; q.z = 0; } else { q.w = 0; }
@@ -276,6 +277,17 @@ __global__ void __launch_bounds__(256) rms_kernel(const vpb_field_t *__restrict_
   block_sum_to(s, 1, out);
 }
 
+// AoS <-> planar copy, one thread per quad
+__global__ void __launch_bounds__(256) field_convert_kernel(float4 *__restrict__ dst, const float4 *__restrict__ src, size_t nv,
+                                                            size_t nvp, int to_planar) {
+  const size_t n5 = 5 * nv;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n5; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t v = t / 5, q = t - 5 * v;
+    if (to_planar) dst[q * nvp + v] = src[t];
+    else dst[t] = src[q * nvp + v];
+  }
+}
+
 static inline int tb_for(int n) { return n >= 256 ? 256 : (n >= 128 ? 128 : (n >= 64 ? 64 : 32)); }
 static inline dim3 node_grid(const DomainDev &g, int tb) { return dim3((g.nx + 1 + tb - 1) / tb, g.ny + 1, g.nz + 1); }
 
@@ -304,6 +316,36 @@ static const vpb_material_coefficient_t *uniform_vacuum() {
   (void)st; (void)tb; (void)grid
 
 extern "C" {
+
+// ---- field layout (DESIGN.md "field layout") ----
+static size_t planar_quads(const DomainDev &g) { return ((size_t)g.nv + 7) & ~(size_t)7; }
+
+void vpb_domain_set_field_layout(vpb_domain_t *dom, int planar) {
+  if (!dom) VPB_ERROR("Bad grid");
+  DomainDev &g = dom->d;
+  if (planar) { g.fqv = 1; g.fqq = (long)planar_quads(g); }
+  else { g.fqv = 5; g.fqq = 1; }
+}
+
+int vpb_domain_field_layout(const vpb_domain_t *dom) {
+  if (!dom) VPB_ERROR("Bad grid");
+  return dom->d.fqv == 1;
+}
+
+size_t vpb_field_bytes(const vpb_domain_t *dom) {
+  if (!dom) VPB_ERROR("Bad grid");
+  return dom->d.fqv == 1 ? 5 * planar_quads(dom->d) * sizeof(float4) : (size_t)dom->d.nv * sizeof(vpb_field_t);
+}
+
+void vpb_field_convert(vpb_domain_t *dom, vpb_field_t *d_dst, const vpb_field_t *d_src, int to_planar) {
+  if (!dom) VPB_ERROR("Bad grid");
+  if (!d_dst || !d_src) VPB_ERROR("Bad field");
+  const DomainDev &g = dom->d;
+  field_convert_kernel<<<ctx().sm_count * 16, 256, 0, ctx().stream>>>((float4 *)d_dst, (const float4 *)d_src, (size_t)g.nv,
+                                                                       planar_quads(g), to_planar);
+  count_launch();
+  VPB_CUDA(cudaGetLastError());
+}
 
 void vpb_advance_b(vpb_domain_t *dom, vpb_field_t *d_f, float frac) {
   CHECK_FG();
@@ -361,13 +403,13 @@ void vpb_compute_curl_b(vpb_domain_t *dom, vpb_field_t *d_f, const vpb_material_
 
 void vpb_clear_jf(vpb_domain_t *dom, vpb_field_t *d_f) {
   CHECK_FG();
-  clear_quad3_kernel<<<ctx().sm_count * 8, 256, 0, st>>>(d_f, (size_t)g.nv, 0);
+  clear_quad3_kernel<<<ctx().sm_count * 8, 256, 0, st>>>(d_f, g, 0);
   count_launch();
 }
 
 void vpb_clear_rhof(vpb_domain_t *dom, vpb_field_t *d_f) {
   CHECK_FG();
-  clear_quad3_kernel<<<ctx().sm_count * 8, 256, 0, st>>>(d_f, (size_t)g.nv, 1);
+  clear_quad3_kernel<<<ctx().sm_count * 8, 256, 0, st>>>(d_f, g, 1);
   count_launch();
 }
 

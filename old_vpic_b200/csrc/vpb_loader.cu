@@ -55,11 +55,10 @@ __global__ void __launch_bounds__(256) load_plane_wave_kernel(vpb_field_t *__res
   const size_t nv = (size_t)g.sxy * g.sz;
   for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (size_t)gridDim.x * blockDim.x) {
     const int ix = (int)(v % g.sx);
-    float4 *q = reinterpret_cast<float4 *>(f) + 5 * v;
     const float4 z = make_float4(0, 0, 0, 0);
-    q[0] = make_float4(0, amp * (float)cos(kdx * (ix - 1)), 0, 0);
-    q[1] = make_float4(0, 0, amp * (float)cos(kdx * (ix - 0.5)), 0);
-    q[2] = z; q[3] = z; q[4] = z;
+    *FQ(f, g, v, 0) = make_float4(0, amp * (float)cos(kdx * (ix - 1)), 0, 0);
+    *FQ(f, g, v, 1) = make_float4(0, 0, amp * (float)cos(kdx * (ix - 0.5)), 0);
+    *FQ(f, g, v, 2) = z; *FQ(f, g, v, 3) = z; *FQ(f, g, v, 4) = z;
   }
 }
 

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) energy_p_kernel(const vpb_particle_t *__r
 
 // rho_p.c:43-78: trilinear deposit of q/8V onto the 8 nodes of the particle's voxel
 __global__ void __launch_bounds__(256) rho_p_kernel(vpb_field_t *__restrict__ f, const vpb_particle_t *__restrict__ p, int np,
-                                                    float r8V, int sx, int sxy) {
+                                                    float r8V, const DomainDev g) {
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x) {
     const float4 *pp = reinterpret_cast<const float4 *>(p + k);
     const float4 r0 = __ldg(pp), r1 = __ldg(pp + 1);
@@ -97,8 +97,8 @@ __global__ void __launch_bounds__(256) rho_p_kernel(vpb_field_t *__restrict__ f,
     t = r0.y; w3 = 1 + t; w2 = w0 * w3; w3 *= w1; t = 1 - t; w0 *= t; w1 *= t;
     t = r0.z; w7 = 1 + t; w4 = w0 * w7; w5 = w1 * w7; w6 = w2 * w7; w7 *= w3;
     t = 1 - t; w0 *= t; w1 *= t; w2 *= t; w3 *= t;
-    float *rho = &f[__float_as_int(r0.w)].rhof;
-    const size_t X = 20, Y = 20 * (size_t)sx, Z = 20 * (size_t)sxy;   // field_t = 20 floats
+    float *rho = &FCOMP(f, g, __float_as_int(r0.w), 15);                    // rhof = component 15
+    const size_t X = 4 * (size_t)g.fqv, Y = X * (size_t)g.sx, Z = X * (size_t)g.sxy;   // floats per voxel step
     red_add(rho, w0); red_add(rho + X, w1); red_add(rho + Y, w2); red_add(rho + X + Y, w3);
     red_add(rho + Z, w4); red_add(rho + Z + X, w5); red_add(rho + Z + Y, w6); red_add(rho + Z + Y + X, w7);
   }
@@ -213,7 +213,7 @@ void vpb_accumulate_rho_p(vpb_domain_t *dom, vpb_field_t *d_f, const vpb_particl
   if (np == 0) return;
   const DomainDev &g = dom->d;
   const float r8V = (float)(0.125 * g.rdx * g.rdy * g.rdz);             // rho_p.c:37
-  rho_p_kernel<<<grid_for(np, 256), 256, 0, ctx().stream>>>(d_f, d_p, np, r8V, g.sx, g.sxy);
+  rho_p_kernel<<<grid_for(np, 256), 256, 0, ctx().stream>>>(d_f, d_p, np, r8V, g);
   count_launch();
   VPB_CUDA(cudaGetLastError());
 }

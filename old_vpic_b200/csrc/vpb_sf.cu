@@ -19,15 +19,14 @@ __global__ void __launch_bounds__(256) load_interpolator_kernel(vpb_interpolator
   const int z = 1 + blockIdx.z;
   if (x > g.nx) return;
   const size_t v = (size_t)x + (size_t)g.sx * ((size_t)y + (size_t)g.sy * z);
-  const float4 *f4 = reinterpret_cast<const float4 *>(f);  // 5 float4 per field_t
-  const size_t s0 = 5 * v, sX = 5, sY = 5 * (size_t)g.sx, sZ = 5 * (size_t)g.sxy;
-  const float4 e0 = __ldg(f4 + s0), b0 = __ldg(f4 + s0 + 1);
-  const float4 ex_ = __ldg(f4 + s0 + sX), bx_ = __ldg(f4 + s0 + sX + 1);
-  const float4 ey_ = __ldg(f4 + s0 + sY), by_ = __ldg(f4 + s0 + sY + 1);
-  const float4 ez_ = __ldg(f4 + s0 + sZ), bz_ = __ldg(f4 + s0 + sZ + 1);
-  const float4 eyz = __ldg(f4 + s0 + sY + sZ);
-  const float4 ezx = __ldg(f4 + s0 + sZ + sX);
-  const float4 exy = __ldg(f4 + s0 + sX + sY);
+  const size_t sX = 1, sY = (size_t)g.sx, sZ = (size_t)g.sxy;
+  const float4 e0 = __ldg(CFQ(f, g, v, 0)), b0 = __ldg(CFQ(f, g, v, 1));
+  const float4 ex_ = __ldg(CFQ(f, g, v + sX, 0)), bx_ = __ldg(CFQ(f, g, v + sX, 1));
+  const float4 ey_ = __ldg(CFQ(f, g, v + sY, 0)), by_ = __ldg(CFQ(f, g, v + sY, 1));
+  const float4 ez_ = __ldg(CFQ(f, g, v + sZ, 0)), bz_ = __ldg(CFQ(f, g, v + sZ, 1));
+  const float4 eyz = __ldg(CFQ(f, g, v + sY + sZ, 0));
+  const float4 ezx = __ldg(CFQ(f, g, v + sZ + sX, 0));
+  const float4 exy = __ldg(CFQ(f, g, v + sX + sY, 0));
   const float fourth = 0.25f, half = 0.5f;
   float w0, w1, w2, w3;
   float4 o0, o1, o2, o3;
@@ -78,7 +77,7 @@ __global__ void __launch_bounds__(256) unload_accumulator_kernel(vpb_field_t *__
   const float4 ayz_x = __ldg(a + 3 * (v - sY - sZ));         // ayz: jx
   const float4 azx_y = __ldg(a + 3 * (v - sZ - sX) + 1);     // azx: jy
   const float4 axy_z = __ldg(a + 3 * (v - sX - sY) + 2);     // axy: jz
-  float4 *jf = reinterpret_cast<float4 *>(f + v) + 3;        // jfx,jfy,jfz,rhof
+  float4 *jf = FQ(f, g, v, 3);                               // jfx,jfy,jfz,rhof
   float4 j = *jf;
   j.x += cx * (a0x.x + ayx_.y + azx_.z + ayz_x.w);
   j.y += cy * (a0y.x + azy_.y + axy_.z + azx_y.w);

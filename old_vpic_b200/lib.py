@@ -62,6 +62,10 @@ SIGNATURES = {
     "vpb_load_thermal": (None, [_vp, _vp, _i, _f, _f, C.c_ulonglong, _l]),
     "vpb_copy_positions": (None, [_vp, _vp, _l]),
     "vpb_load_plane_wave": (None, [_vp, _vp, _i, _f]),
+    "vpb_domain_set_field_layout": (None, [_vp, _i]),
+    "vpb_domain_field_layout": (_i, [_vp]),
+    "vpb_field_bytes": (C.c_size_t, [_vp]),
+    "vpb_field_convert": (None, [_vp, _vp, _vp, _i]),
     "vpb_comm_unique_id": (None, [_vp]),
     "vpb_comm_init": (None, [_i, _i, _vp]),
     "vpb_comm_finalize": (None, []),

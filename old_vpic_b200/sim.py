@@ -39,6 +39,52 @@ class DevArray:
             self.ptr = None
 
 
+class FieldArray:
+    """The device field array of one domain in the domain's layout (include/vpic_b200.h "Device field layout").
+    upload()/download() speak the reference's AoS field_t[nv] and convert on the device."""
+
+    def __init__(self, L, dom, nv):
+        self.L, self.dom, self.n, self.dtype = L, dom, int(nv), abi.field_dtype
+        self.nbytes = int(L.vpb_field_bytes(dom))
+        self.ptr = L.vpb_dev_alloc(self.nbytes)     # zero-filled
+
+    def _planar(self):
+        return bool(self.L.vpb_domain_field_layout(self.dom))
+
+    def upload(self, host):
+        host = np.ascontiguousarray(host, dtype=self.dtype)
+        assert len(host) == self.n
+        L = self.L
+        if not self._planar():
+            L.vpb_h2d(self.ptr, host.ctypes.data, host.nbytes)
+        else:
+            tmp = L.vpb_dev_alloc(host.nbytes)
+            L.vpb_h2d(tmp, host.ctypes.data, host.nbytes)
+            L.vpb_field_convert(self.dom, self.ptr, tmp, 1)
+            L.vpb_sync()
+            L.vpb_dev_free(tmp)
+        L.vpb_sync()
+
+    def download(self):
+        L = self.L
+        out = abi.aligned_empty(self.n, self.dtype)
+        if not self._planar():
+            L.vpb_d2h(out.ctypes.data, self.ptr, out.nbytes)
+        else:
+            tmp = L.vpb_dev_alloc(out.nbytes)
+            L.vpb_field_convert(self.dom, tmp, self.ptr, 0)
+            L.vpb_d2h(out.ctypes.data, tmp, out.nbytes)
+            L.vpb_sync()
+            L.vpb_dev_free(tmp)
+        L.vpb_sync()
+        return out
+
+    def free(self):
+        if self.ptr:
+            self.L.vpb_dev_free(self.ptr)
+            self.ptr = None
+
+
 class Species:
     def __init__(self, L, name, q_m, max_np, max_nm, sort_interval, sp_id):
         self.name, self.q_m, self.id = name, float(q_m), sp_id
@@ -53,14 +99,16 @@ class Species:
 class Simulation:
     """One rank's share of a PIC run on one GPU."""
 
-    def __init__(self, grid, n_mat=1, vacuum=False, L=None):
+    def __init__(self, grid, n_mat=1, vacuum=False, L=None, planar=True):
         self.L = L or lib.load()
         self.L.vpb_init(-1)
         self.grid = grid
         self.dom = self.L.vpb_domain_create(grid.ref(), grid.rank, grid.nproc)
+        # the field array never leaves the device in this driver: keep it in the planar layout
+        self.L.vpb_domain_set_field_layout(self.dom, 1 if planar else 0)
         self.nv = grid.nv
         self.vacuum = vacuum
-        self.f = DevArray(self.L, self.nv, abi.field_dtype)
+        self.f = FieldArray(self.L, self.dom, self.nv)
         # a field-only grid (no neighbor table, grid.py) carries no particles: no interpolator / accumulators
         self.fi = None if grid.field_only else DevArray(self.L, self.nv, abi.interpolator_dtype)
         self.a = None if grid.field_only else DevArray(self.L, self.nv + 1, abi.accumulator_dtype)
