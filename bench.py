@@ -214,7 +214,8 @@ def run_b200(args):
     n = args.cells
     topo = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
     g = helpers.make_grid((n * topo[0], n * topo[1], n * topo[2]), "periodic", topo=topo, rank=rank)
-    sim = Simulation(g, n_mat=1, L=L, planar=L.vpb_get_tuning(b"sim.aos_fields") == 0)
+    sim = Simulation(g, n_mat=1, L=L, planar=L.vpb_get_tuning(b"sim.aos_fields") == 0,
+                     wide_interpolator=L.vpb_get_tuning(b"sim.narrow_interpolator") == 0)
     np_ = n ** 3 * args.ppc
     max_np = int(np_ * (1.0 if world == 1 else 1.02)) + 1024
     # macro-charge q = +-(cell volume)/ppc so that the plasma frequency is 1 (the reference's thermal recipe,
@@ -268,6 +269,7 @@ def run_b200(args):
     if rank != 0:
         if world > 1:
             dist.barrier()
+            dist.destroy_process_group()
         return
     total_particles = 2 * np_ * world
     value = total_particles * args.steps / (ms_max * 1e-3)
@@ -294,7 +296,7 @@ def run_b200(args):
                                      "advance_e": (cells * args.steps / (prof["advance_e"][0] * 1e-3)) if prof["advance_e"][0] else None},
         "host_wall_ms_per_step": 1e3 * wall / args.steps,
         "advance_p_ms_by_launch": adv_list,
-        "tuning": {k: L.vpb_get_tuning(k.encode()) for k in ("advance_p.deposit", "advance_p.tma", "advance_p.stream_ctas_per_sm", "advance_p.stream_store",
+        "tuning": {k: L.vpb_get_tuning(k.encode()) for k in ("advance_p.deposit", "advance_p.tma", "advance_p.stream_store", "sim.aos_fields", "sim.narrow_interpolator",
                                                              "advance_p.tma_ctas_per_sm", "advance_p.ctas_per_sm")},
     }
     if fields_c2 is not None:
@@ -306,6 +308,7 @@ def run_b200(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        dist.destroy_process_group()
 
 
 def fields_measure(L, n, steps, warmup):

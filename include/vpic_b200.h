@@ -194,6 +194,13 @@ int vpb_domain_field_layout(const vpb_domain_t *dom);
 size_t vpb_field_bytes(const vpb_domain_t *dom);
 void vpb_field_convert(vpb_domain_t *dom, vpb_field_t *d_dst, const vpb_field_t *d_src, int to_planar);
 
+/* Device interpolator layout.  Default: the reference's 80-byte interpolator_t.  wide=1: the same 72 useful
+ * bytes in 96-byte records (three aligned 32-byte sectors), which advance_p gathers with two 256-bit loads and
+ * one 64-bit load instead of five loads that request the record's sectors five times.  load_interpolator,
+ * advance_p, center_p, uncenter_p and energy_p follow the domain's setting. */
+void vpb_domain_set_interpolator_layout(vpb_domain_t *dom, int wide);
+size_t vpb_interpolator_bytes(const vpb_domain_t *dom);
+
 /* Synthetic field state: an x-propagating vacuum plane wave (ey, cbz) with `mode` wavelengths across
  * the local nx cells; everything else zero. */
 void vpb_load_plane_wave(vpb_domain_t *dom, vpb_field_t *d_f, int mode, float amp);

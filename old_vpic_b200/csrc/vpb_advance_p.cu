@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) advance_p_kernel(const Advance
         const float4 r1 = pp[1];
         float dx = r0.x, dy = r0.y, dz = r0.z;
         ii = __float_as_int(r0.w);
-        const char *fp = reinterpret_cast<const char *>(A.f + ii);
+        const char *fp = reinterpret_cast<const char *>(A.f) + (size_t)ii * A.fi_bytes;
         const float4 fe_x = ldg4(fp);        // ex dexdy dexdz d2exdydz
         const float4 fe_y = ldg4(fp + 16);   // ey deydz deydx d2eydzdx
         const float4 fe_z = ldg4(fp + 32);   // ez dezdx dezdy d2ezdxdy
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(kWarps * 32, 3) advance_p_tma_kernel(const Adv
       const float4 r1 = tp[1];
       float dx = r0.x, dy = r0.y, dz = r0.z;
       ii = __float_as_int(r0.w);
-      const char *fp = reinterpret_cast<const char *>(A.f + ii);
+      const char *fp = reinterpret_cast<const char *>(A.f) + (size_t)ii * A.fi_bytes;
       const float4 fe_x = ldg4(fp);
       const float4 fe_y = ldg4(fp + 16);
       const float4 fe_z = ldg4(fp + 32);
@@ -489,13 +489,27 @@ struct Interp {
   float2 b1;
 };
 
+// WIDE: 96-byte records (32-byte aligned): the 72 useful bytes arrive with two LDG.256 and one LDG.64, each
+// of the record's three sectors requested once; otherwise the reference's 80-byte record, five loads.
+template <int WIDE>
 __device__ __forceinline__ void load_interp(Interp &I, const vpb_interpolator_t *f, int ii) {
-  const char *fp = reinterpret_cast<const char *>(f + ii);
-  I.ex = ldg4(fp);        // ex dexdy dexdz d2exdydz
-  I.ey = ldg4(fp + 16);   // ey deydz deydx d2eydzdx
-  I.ez = ldg4(fp + 32);   // ez dezdx dezdy d2ezdxdy
-  I.b0 = ldg4(fp + 48);   // cbx dcbxdx cby dcbydy
-  I.b1 = ldg2(fp + 64);   // cbz dcbzdz
+  if (WIDE) {
+    const char *fp = reinterpret_cast<const char *>(f) + (size_t)ii * 96;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(I.ex.x), "=f"(I.ex.y), "=f"(I.ex.z), "=f"(I.ex.w), "=f"(I.ey.x), "=f"(I.ey.y), "=f"(I.ey.z), "=f"(I.ey.w)
+                 : "l"(fp));
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(I.ez.x), "=f"(I.ez.y), "=f"(I.ez.z), "=f"(I.ez.w), "=f"(I.b0.x), "=f"(I.b0.y), "=f"(I.b0.z), "=f"(I.b0.w)
+                 : "l"(fp + 32));
+    I.b1 = ldg2(fp + 64);
+  } else {
+    const char *fp = reinterpret_cast<const char *>(f + ii);
+    I.ex = ldg4(fp);        // ex dexdy dexdz d2exdydz
+    I.ey = ldg4(fp + 16);   // ey deydz deydx d2eydzdx
+    I.ez = ldg4(fp + 32);   // ez dezdx dezdy d2ezdxdy
+    I.b0 = ldg4(fp + 48);   // cbx dcbxdx cby dcbydy
+    I.b1 = ldg2(fp + 64);   // cbz dcbzdz
+  }
 }
 
 __device__ __forceinline__ void st_stream4(void *p, float4 v) { __stcs(reinterpret_cast<float4 *>(p), v); }
@@ -600,8 +614,8 @@ struct StreamSmem {
   uint64_t full[kWarps][StreamCfg<STORE>::stages];
 };
 
-template <int DEPOSIT, int MINB, int STORE>
-__global__ void __launch_bounds__(kWarps * 32, MINB) advance_p_stream_kernel(const AdvanceArgs A) {
+template <int DEPOSIT, int WIDE, int STORE>
+__global__ void __launch_bounds__(kWarps * 32, 2) advance_p_stream_kernel(const AdvanceArgs A) {
   constexpr int NS = StreamCfg<STORE>::stages;
   constexpr int AHEAD = STORE ? NS - 1 : NS;      // tiles landed or landing, the current one included
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -677,7 +691,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) advance_p_stream_kernel(con
     mbar_wait(smem_u32(&S.full[w][0]), 0);
     const int k = pend[0] * 32 + lane;
     const int ii = k < A.np ? __float_as_int(S.tile[w][0][lane * 3].w) : 0;
-    load_interp(fa, A.f, ii);
+    load_interp<WIDE>(fa, A.f, ii);
   }
 
   int it = 0;
@@ -698,7 +712,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) advance_p_stream_kernel(con
       mbar_wait(smem_u32(&S.full[w][sn]), (uint32_t)(((it + 1) / NS) & 1));
       const int kn = pend[1] * 32 + lane;
       const int iin = kn < A.np ? __float_as_int(S.tile[w][sn][lane * 3].w) : 0;
-      load_interp(nxt, A.f, iin);
+      load_interp<WIDE>(nxt, A.f, iin);
     }
 
     const int ii = __float_as_int(r0.w);
@@ -845,6 +859,7 @@ void advance_p_begin(vpb_domain_t *dom, int np, float q_m, int max_nm, vpb_accum
   A.cdt_dz = g.cvac * g.dt * g.rdz;
   A.a = reinterpret_cast<float *>(d_a);
   A.f = d_f;
+  A.fi_bytes = g.fi_bytes;
   A.nbr = g.nbr;
   A.max_nm = max_nm;
   A.sx = g.sx; A.sy = g.sy; A.sz = g.sz; A.nv = g.nv;
@@ -880,15 +895,15 @@ void advance_p_range(AdvanceJob &J, vpb_particle_t *d_base, int k0, int k1, cons
   if (tma_mode == 2) {
     const int nch = A.chunk_hi - A.chunk_lo;
     VPB_CUDA(cudaMemsetAsync(&A.counters[2], 0, sizeof(int), st));   // ticket counter of the dynamic scheduler
-    const int per_sm = tuning("advance_p.stream_ctas_per_sm", 2);
-    int grid = c.sm_count * per_sm;
+    int grid = c.sm_count * 2;   // ~125 registers x 256 threads, 66-76 KB of shared memory: two CTAs per SM
     if (grid > (nch + kWarps - 1) / kWarps) grid = (nch + kWarps - 1) / kWarps;
     const bool dep = tuning("advance_p.deposit", 1) != 0;
     const int store = tuning("advance_p.stream_store", 0) ? 1 : 0;
     typedef void (*kern_t)(AdvanceArgs);
-    static const kern_t table[2][2][2] = {   // [store][per_sm >= 3][deposit]
-        {{advance_p_stream_kernel<0, 2, 0>, advance_p_stream_kernel<1, 2, 0>}, {advance_p_stream_kernel<0, 3, 0>, advance_p_stream_kernel<1, 3, 0>}},
-        {{advance_p_stream_kernel<0, 2, 1>, advance_p_stream_kernel<1, 2, 1>}, {advance_p_stream_kernel<0, 2, 1>, advance_p_stream_kernel<1, 2, 1>}}};
+    const int wide = A.fi_bytes == 96;
+    static const kern_t table[2][2][2] = {   // [store][wide interpolator][deposit]
+        {{advance_p_stream_kernel<0, 0, 0>, advance_p_stream_kernel<1, 0, 0>}, {advance_p_stream_kernel<0, 1, 0>, advance_p_stream_kernel<1, 1, 0>}},
+        {{advance_p_stream_kernel<0, 0, 1>, advance_p_stream_kernel<1, 0, 1>}, {advance_p_stream_kernel<0, 1, 1>, advance_p_stream_kernel<1, 1, 1>}}};
     static const int smem_bytes[2] = {(int)sizeof(StreamSmem<0>), (int)sizeof(StreamSmem<1>)};
     static bool attr_set = false;
     if (!attr_set) {
@@ -898,8 +913,7 @@ void advance_p_range(AdvanceJob &J, vpb_particle_t *d_base, int k0, int k1, cons
             VPB_CUDA(cudaFuncSetAttribute(table[a][b][d], cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes[a]));
       attr_set = true;
     }
-    if (store && grid > c.sm_count * 2) grid = c.sm_count * 2;   // 76 KB of shared memory per CTA: two per SM
-    table[store][per_sm >= 3][dep]<<<grid, kWarps * 32, smem_bytes[store], st>>>(A);
+    table[store][wide][dep]<<<grid, kWarps * 32, smem_bytes[store], st>>>(A);
   } else if (tma_mode == 1) {
     static bool attr_set = false;
     if (!attr_set) {

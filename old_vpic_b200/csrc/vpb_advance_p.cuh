@@ -11,6 +11,7 @@ struct AdvanceArgs {
   float qdt_2mc, cdt_dx, cdt_dy, cdt_dz;
   float *a;                       // accumulator_t[nv] viewed as float[12*nv]
   const vpb_interpolator_t *f;
+  int fi_bytes;                   // interpolator record stride (80 or 96, DomainDev::fi_bytes)
   const int32_t *nbr;
   vpb_particle_mover_t *tmp_pm;   // unordered staging, capacity max_nm
   int max_nm;

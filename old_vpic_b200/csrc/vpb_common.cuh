@@ -59,6 +59,9 @@ struct DomainDev {
   // v sits at float4 index v*fqv + q*fqq.  Reference layout (80-byte AoS): fqv=5, fqq=1.  Planar layout (five
   // planes of nvp quads, device-resident runs): fqv=1, fqq=nvp.  See DESIGN.md "field layout".
   long fqv, fqq;
+  // interpolator record stride in bytes: 80 = the reference's interpolator_t; 96 = the same 72 bytes padded to
+  // three aligned 32-byte sectors, which advance_p gathers with two 256-bit loads and one 64-bit load
+  int fi_bytes;
 };
 
 #define FQ(f, g, v, q) (reinterpret_cast<float4 *>(f) + ((size_t)(v) * (size_t)(g).fqv + (size_t)(q) * (size_t)(g).fqq))

@@ -14,9 +14,9 @@ struct Gather {
 };
 
 // advance_p.cxx:73-83: half E kick and B at the particle from the 18 coefficients
-__device__ __forceinline__ Gather gather_fields(const vpb_interpolator_t *__restrict__ f0, int ii, float qdt_2mc, float dx,
-                                                float dy, float dz) {
-  const char *fp = reinterpret_cast<const char *>(f0 + ii);
+__device__ __forceinline__ Gather gather_fields(const vpb_interpolator_t *__restrict__ f0, int fi_bytes, int ii, float qdt_2mc,
+                                                float dx, float dy, float dz) {
+  const char *fp = reinterpret_cast<const char *>(f0) + (size_t)ii * fi_bytes;
   const float4 fe_x = ldg4(fp), fe_y = ldg4(fp + 16), fe_z = ldg4(fp + 32), fb_0 = ldg4(fp + 48);
   const float2 fb_1 = ldg2(fp + 64);
   Gather g;
@@ -50,12 +50,12 @@ __device__ __forceinline__ void boris_rotate(float &ux, float &uy, float &uz, co
 // negated, half rotate then half kick).
 template <int MODE>
 __global__ void __launch_bounds__(256) center_kernel(vpb_particle_t *__restrict__ p, int np, float qdt_2mc, float qdt_4mc,
-                                                     const vpb_interpolator_t *__restrict__ f0) {
+                                                     const vpb_interpolator_t *__restrict__ f0, int fi_bytes) {
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x) {
     float4 *pp = reinterpret_cast<float4 *>(p + k);
     const float4 r0 = pp[0];
     float4 r1 = pp[1];
-    const Gather g = gather_fields(f0, __float_as_int(r0.w), qdt_2mc, r0.x, r0.y, r0.z);
+    const Gather g = gather_fields(f0, fi_bytes, __float_as_int(r0.w), qdt_2mc, r0.x, r0.y, r0.z);
     if (MODE == 0) { r1.x += g.hax; r1.y += g.hay; r1.z += g.haz; }
     boris_rotate(r1.x, r1.y, r1.z, g, qdt_4mc);
     if (MODE == 1) { r1.x += g.hax; r1.y += g.hay; r1.z += g.haz; }
@@ -64,13 +64,14 @@ __global__ void __launch_bounds__(256) center_kernel(vpb_particle_t *__restrict_
 }
 
 __global__ void __launch_bounds__(256) energy_p_kernel(const vpb_particle_t *__restrict__ p, int np, float qdt_2mc,
-                                                       const vpb_interpolator_t *__restrict__ f0, double *__restrict__ out) {
+                                                       const vpb_interpolator_t *__restrict__ f0, int fi_bytes,
+                                                       double *__restrict__ out) {
   __shared__ double ws[8];
   double en = 0;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x) {
     const float4 *pp = reinterpret_cast<const float4 *>(p + k);
     const float4 r0 = __ldg(pp), r1 = __ldg(pp + 1);
-    const Gather g = gather_fields(f0, __float_as_int(r0.w), qdt_2mc, r0.x, r0.y, r0.z);
+    const Gather g = gather_fields(f0, fi_bytes, __float_as_int(r0.w), qdt_2mc, r0.x, r0.y, r0.z);
     float v0 = r1.x + g.hax, v1 = r1.y + g.hay, v2 = r1.z + g.haz;   // energy_p.cxx:37-43
     v0 = v0 * v0 + v1 * v1 + v2 * v2;
     v0 /= sqrtf(1.f + v0) + 1.f;
@@ -175,7 +176,7 @@ void vpb_center_p(vpb_domain_t *dom, vpb_particle_t *d_p, int np, float q_m, con
   if (np == 0) return;
   const float qdt_2mc = (float)(0.5 * q_m * dom->d.dt / dom->d.cvac);   // center_p.cxx:171
   const float qdt_4mc = (float)(0.5 * qdt_2mc);                         // center_p.cxx:15
-  center_kernel<0><<<grid_for(np, 256), 256, 0, ctx().stream>>>(d_p, np, qdt_2mc, qdt_4mc, d_f);
+  center_kernel<0><<<grid_for(np, 256), 256, 0, ctx().stream>>>(d_p, np, qdt_2mc, qdt_4mc, d_f, dom->d.fi_bytes);
   count_launch();
   VPB_CUDA(cudaGetLastError());
 }
@@ -188,7 +189,7 @@ void vpb_uncenter_p(vpb_domain_t *dom, vpb_particle_t *d_p, int np, float q_m, c
   const float fwd = (float)(0.5 * q_m * dom->d.dt / dom->d.cvac);       // uncenter_p.cxx:171
   const float qdt_2mc = -fwd;                                           // uncenter_p.cxx:14
   const float qdt_4mc = (float)(-0.5 * fwd);                            // uncenter_p.cxx:15
-  center_kernel<1><<<grid_for(np, 256), 256, 0, ctx().stream>>>(d_p, np, qdt_2mc, qdt_4mc, d_f);
+  center_kernel<1><<<grid_for(np, 256), 256, 0, ctx().stream>>>(d_p, np, qdt_2mc, qdt_4mc, d_f, dom->d.fi_bytes);
   count_launch();
   VPB_CUDA(cudaGetLastError());
 }
@@ -200,7 +201,7 @@ void vpb_energy_p(vpb_domain_t *dom, const vpb_particle_t *d_p, int np, float q_
   VPB_CUDA(cudaMemsetAsync(d_en, 0, sizeof(double), ctx().stream));
   if (np == 0) return;
   const float qdt_2mc = (float)(0.5 * q_m * dom->d.dt / dom->d.cvac);
-  energy_p_kernel<<<grid_for(np, 256), 256, 0, ctx().stream>>>(d_p, np, qdt_2mc, d_f, d_en);
+  energy_p_kernel<<<grid_for(np, 256), 256, 0, ctx().stream>>>(d_p, np, qdt_2mc, d_f, dom->d.fi_bytes, d_en);
   count_launch();
   VPB_CUDA(cudaGetLastError());
 }

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) load_interpolator_kernel(vpb_interpolator
   o3.z = half * (w1 + w0); o3.w = half * (w1 - w0);
   w0 = b0.z; w1 = bz_.z;
   o4.x = half * (w1 + w0); o4.y = half * (w1 - w0);
-  float4 *o = reinterpret_cast<float4 *>(fi + v);
+  float4 *o = reinterpret_cast<float4 *>(reinterpret_cast<char *>(fi) + v * (size_t)g.fi_bytes);
   o[0] = o0; o[1] = o1; o[2] = o2; o[3] = o3;
   *reinterpret_cast<float2 *>(o + 4) = o4;   // _pad[2] is left untouched, like the reference
 }
@@ -90,6 +90,16 @@ __global__ void __launch_bounds__(256) unload_accumulator_kernel(vpb_field_t *__
 using namespace vpb;
 
 extern "C" {
+
+void vpb_domain_set_interpolator_layout(vpb_domain_t *dom, int wide) {
+  if (!dom) VPB_ERROR("Bad grid");
+  dom->d.fi_bytes = wide ? 96 : 80;
+}
+
+size_t vpb_interpolator_bytes(const vpb_domain_t *dom) {
+  if (!dom) VPB_ERROR("Bad grid");
+  return (size_t)dom->d.nv * (size_t)dom->d.fi_bytes;
+}
 
 void vpb_load_interpolator(vpb_domain_t *dom, vpb_interpolator_t *d_fi, const vpb_field_t *d_f) {
   if (!d_fi) VPB_ERROR("Bad interpolator");

@@ -65,6 +65,8 @@ SIGNATURES = {
     "vpb_domain_set_field_layout": (None, [_vp, _i]),
     "vpb_domain_field_layout": (_i, [_vp]),
     "vpb_field_bytes": (C.c_size_t, [_vp]),
+    "vpb_domain_set_interpolator_layout": (None, [_vp, _i]),
+    "vpb_interpolator_bytes": (C.c_size_t, [_vp]),
     "vpb_field_convert": (None, [_vp, _vp, _vp, _i]),
     "vpb_comm_unique_id": (None, [_vp]),
     "vpb_comm_init": (None, [_i, _i, _vp]),

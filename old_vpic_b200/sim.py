@@ -99,7 +99,7 @@ class Species:
 class Simulation:
     """One rank's share of a PIC run on one GPU."""
 
-    def __init__(self, grid, n_mat=1, vacuum=False, L=None, planar=True):
+    def __init__(self, grid, n_mat=1, vacuum=False, L=None, planar=True, wide_interpolator=True):
         self.L = L or lib.load()
         self.L.vpb_init(-1)
         self.grid = grid
@@ -110,7 +110,9 @@ class Simulation:
         self.vacuum = vacuum
         self.f = FieldArray(self.L, self.dom, self.nv)
         # a field-only grid (no neighbor table, grid.py) carries no particles: no interpolator / accumulators
-        self.fi = None if grid.field_only else DevArray(self.L, self.nv, abi.interpolator_dtype)
+        # ... and the interpolator in 96-byte records (include/vpic_b200.h "Device interpolator layout")
+        self.L.vpb_domain_set_interpolator_layout(self.dom, 1 if wide_interpolator else 0)
+        self.fi = None if grid.field_only else DevArray(self.L, int(self.L.vpb_interpolator_bytes(self.dom)), np.uint8)
         self.a = None if grid.field_only else DevArray(self.L, self.nv + 1, abi.accumulator_dtype)
         self.m_host = None
         self.m = None

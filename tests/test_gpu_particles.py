@@ -25,12 +25,11 @@ def acc_floats(a):
     return np.ascontiguousarray(a).view(np.float32).reshape(-1, 12)
 
 
-@pytest.mark.parametrize("deposit,tma,per_sm,store", [(1, 2, 2, 0), (0, 2, 2, 0), (1, 2, 3, 0), (0, 2, 3, 0), (1, 2, 2, 1), (0, 2, 2, 1),
-                                                      (1, 1, 3, 0), (0, 1, 3, 0), (1, 0, 3, 0), (0, 0, 3, 0)])
+@pytest.mark.parametrize("deposit,tma,store", [(1, 2, 0), (0, 2, 0), (1, 2, 1), (0, 2, 1), (1, 1, 0), (0, 1, 0), (1, 0, 0), (0, 0, 0)])
 @pytest.mark.parametrize("kind", ["periodic", "metal", "absorbing"])
 @pytest.mark.parametrize("n,np_,sort", [((6, 5, 4), 5000, True), ((8, 1, 6), 7001, False), ((1, 1, 16), 300, True),
                                         ((16, 16, 16), 16 * 16 * 16 * 40, True)])
-def test_advance_p(vpb, orc, deposit, tma, per_sm, store, kind, n, np_, sort):
+def test_advance_p(vpb, orc, deposit, tma, store, kind, n, np_, sort):
     g = host_grid(n, kind)
     rng = np.random.default_rng(21)
     p = random_particles(rng, g, np_, vth=0.6, sort=sort, edge_frac=0.02)
@@ -38,7 +37,6 @@ def test_advance_p(vpb, orc, deposit, tma, per_sm, store, kind, n, np_, sort):
     q_m, max_nm = -1.0, np_
     vpb.vpb_set_tuning(b"advance_p.deposit", deposit)
     vpb.vpb_set_tuning(b"advance_p.tma", tma)
-    vpb.vpb_set_tuning(b"advance_p.stream_ctas_per_sm", per_sm)
     vpb.vpb_set_tuning(b"advance_p.stream_store", store)
     p_o, p_g = p.copy(), p.copy()
     a_o = abi.aligned_zeros(g.nv, abi.accumulator_dtype)
@@ -49,7 +47,6 @@ def test_advance_p(vpb, orc, deposit, tma, per_sm, store, kind, n, np_, sort):
     nm_g = vpb.advance_p(ptr(p_g), np_, q_m, ptr(pm_g), max_nm, ptr(a_g), ptr(fi), g.ref())
     vpb.vpb_set_tuning(b"advance_p.deposit", 1)
     vpb.vpb_set_tuning(b"advance_p.tma", 2)
-    vpb.vpb_set_tuning(b"advance_p.stream_ctas_per_sm", 2)
     vpb.vpb_set_tuning(b"advance_p.stream_store", 0)
     assert nm_g == nm_o
     if kind == "absorbing":
@@ -210,3 +207,65 @@ def test_sort_p(vpb, orc, n, np_):
     assert_bits_equal(p[:np_], p_o, "sorted particles (tags included)")
     assert np.all(np.diff(p["i"][:np_]) >= 0)
     assert part_g[-1] == np_
+
+
+@pytest.mark.parametrize("store", [0, 1])
+@pytest.mark.parametrize("kind", ["periodic", "metal"])
+def test_layer_b_wide_interpolator(vpb, orc, kind, store):
+    """The device-resident layouts (96-byte interpolator records, planar field array) give the same bits as the
+    reference layouts: load_interpolator -> advance_p / center_p / energy_p on device arrays (layer B)."""
+    from old_vpic_b200.sim import DevArray, FieldArray
+    from helpers import random_fields
+    n, np_ = (9, 7, 5), 20000
+    g = host_grid(n, kind)
+    rng = np.random.default_rng(5)
+    p = random_particles(rng, g, np_, vth=0.5, sort=True, edge_frac=0.02)
+    f = random_fields(rng, g)
+    q_m = -1.0
+    # oracle on the reference layouts
+    fi_o = abi.aligned_zeros(g.nv, abi.interpolator_dtype)
+    orc.orc_load_interpolator(ptr(fi_o), ptr(f), g.ref())
+    p_o = p.copy()
+    a_o = abi.aligned_zeros(g.nv, abi.accumulator_dtype)
+    pm_o = abi.aligned_zeros(np_, abi.mover_dtype)
+    en_o = orc.orc_energy_p(ptr(p_o), np_, q_m, ptr(fi_o), g.ref())
+    nm_o = orc.orc_advance_p(ptr(p_o), np_, q_m, ptr(pm_o), np_, ptr(a_o), ptr(fi_o), g.ref())
+    # device, layer B
+    dom = vpb.vpb_domain_create(g.ref(), 0, 1)
+    vpb.vpb_domain_set_field_layout(dom, 1)
+    vpb.vpb_domain_set_interpolator_layout(dom, 1)
+    assert vpb.vpb_interpolator_bytes(dom) == 96 * g.nv
+    d_f = FieldArray(vpb, dom, g.nv)
+    d_f.upload(f)
+    assert_bits_equal(d_f.download(), f, "planar round trip")
+    d_fi = DevArray(vpb, 96 * g.nv, np.uint8)
+    vpb.vpb_load_interpolator(dom, d_fi.ptr, d_f.ptr)
+    wide = d_fi.download().view(np.float32).reshape(g.nv, 24)
+    assert_bits_equal(wide[:, :18].copy(), fi_o.view(np.float32).reshape(g.nv, 20)[:, :18].copy(), "wide interpolator")
+    d_p, d_pm, d_a, d_nm = DevArray(vpb, np_, abi.particle_dtype), DevArray(vpb, np_, abi.mover_dtype), \
+        DevArray(vpb, g.nv, abi.accumulator_dtype), DevArray(vpb, 4, np.int32)
+    d_en = DevArray(vpb, 2, np.float64)
+    d_p.upload(p)
+    vpb.vpb_energy_p(dom, d_p.ptr, np_, q_m, d_fi.ptr, d_en.ptr)
+    en_g = float(d_en.download(1)[0]) * g.struct.cvac ** 2 / q_m
+    assert en_g == pytest.approx(en_o, rel=1e-12)
+    vpb.vpb_set_tuning(b"advance_p.stream_store", store)
+    vpb.vpb_advance_p(dom, d_p.ptr, np_, q_m, d_pm.ptr, np_, d_a.ptr, d_fi.ptr, d_nm.ptr)
+    vpb.vpb_set_tuning(b"advance_p.stream_store", 0)
+    nm_g = int(d_nm.download(1)[0])
+    assert nm_g == nm_o
+    assert_bits_equal(d_p.download(), p_o, "particles")
+    assert_bits_equal(d_pm.download(nm_g), pm_o[:nm_o], "movers")
+    assert max_rel(acc_floats(d_a.download()), acc_floats(a_o)) < ACC_TOL
+    # center_p then uncenter_p against the oracle's
+    p2_o = p.copy()
+    orc.orc_center_p(ptr(p2_o), np_, q_m, ptr(fi_o), g.ref())
+    d_p.upload(p)
+    vpb.vpb_center_p(dom, d_p.ptr, np_, q_m, d_fi.ptr)
+    assert_bits_equal(d_p.download(), p2_o, "center_p")
+    orc.orc_uncenter_p(ptr(p2_o), np_, q_m, ptr(fi_o), g.ref())
+    vpb.vpb_uncenter_p(dom, d_p.ptr, np_, q_m, d_fi.ptr)
+    assert_bits_equal(d_p.download(), p2_o, "uncenter_p")
+    for arr in (d_f, d_fi, d_p, d_pm, d_a, d_nm, d_en):
+        arr.free()
+    vpb.vpb_domain_destroy(dom)
