@@ -285,7 +285,11 @@ def run_b200(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (device-generated thermal load)",
         "config": workload_config(args), "clocks": clocks, "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": None, "kernel": "advance_p_kernel",
+                     "frac": (achieved / peak) if achieved else None,
+                     # DRAM bytes of ONE launch from the ncu --set full capture of this workload (10 steps after a sort)
+                     "traffic": 123.35e9 if (args.cells == 256 and args.ppc == 64) else None,
+                     "traffic_source": "profiles/r1k_256_step10_advance_p_stream_c2.txt (dram__bytes_read.sum + dram__bytes_write.sum)",
+                     "kernel": "advance_p_stream_kernel",
                      "algorithmic_bytes_per_particle": bytes_alg, "particles_per_launch": per_launch_particles,
                      "avg_launch_ms": adv_ms / max(adv_n, 1), "peak_source": peak_src,
                      "layout_imposed_bytes_per_particle": 96.0 + 176.0 / args.ppc,
