@@ -300,7 +300,7 @@ def run_b200(args):
                                      "advance_e": (cells * args.steps / (prof["advance_e"][0] * 1e-3)) if prof["advance_e"][0] else None},
         "host_wall_ms_per_step": 1e3 * wall / args.steps,
         "advance_p_ms_by_launch": adv_list,
-        "tuning": {k: L.vpb_get_tuning(k.encode()) for k in ("advance_p.deposit", "advance_p.tma", "advance_p.stream_store", "sim.aos_fields", "sim.narrow_interpolator",
+        "tuning": {k: L.vpb_get_tuning(k.encode()) for k in ("advance_p.deposit", "advance_p.tma", "advance_p.stream_store", "advance_p.stream_cps", "sim.aos_fields", "sim.narrow_interpolator",
                                                              "advance_p.tma_ctas_per_sm", "advance_p.ctas_per_sm")},
     }
     if fields_c2 is not None:

@@ -607,15 +607,16 @@ __device__ __noinline__ void drain_movers_slim(vpb_particle_t *__restrict__ p, f
 //          price of a proxy fence per chunk and one more stage (a tile is refilled one iteration after its store).
 template <int STORE> struct StreamCfg { static constexpr int stages = STORE ? 5 : 4; };
 
+constexpr int kWarpsS = 4;           // warps per CTA of the streaming kernel
 template <int STORE>
 struct StreamSmem {
-  float4 tile[kWarps][StreamCfg<STORE>::stages][96];
-  float4 q_pos[kWarps][kQueue], q_disp[kWarps][kQueue];   // the momentum waits in global memory (already stored)
-  uint64_t full[kWarps][StreamCfg<STORE>::stages];
+  float4 tile[kWarpsS][StreamCfg<STORE>::stages][96];
+  float4 q_pos[kWarpsS][kQueue], q_disp[kWarpsS][kQueue];   // the momentum waits in global memory (already stored)
+  uint64_t full[kWarpsS][StreamCfg<STORE>::stages];
 };
 
-template <int DEPOSIT, int WIDE, int STORE>
-__global__ void __launch_bounds__(kWarps * 32, 2) advance_p_stream_kernel(const AdvanceArgs A) {
+template <int DEPOSIT, int WIDE, int STORE, int CPS>
+__global__ void __launch_bounds__(kWarpsS * 32, CPS) advance_p_stream_kernel(const AdvanceArgs A) {
   constexpr int NS = StreamCfg<STORE>::stages;
   constexpr int AHEAD = STORE ? NS - 1 : NS;      // tiles landed or landing, the current one included
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -895,25 +896,32 @@ void advance_p_range(AdvanceJob &J, vpb_particle_t *d_base, int k0, int k1, cons
   if (tma_mode == 2) {
     const int nch = A.chunk_hi - A.chunk_lo;
     VPB_CUDA(cudaMemsetAsync(&A.counters[2], 0, sizeof(int), st));   // ticket counter of the dynamic scheduler
-    int grid = c.sm_count * 2;   // ~125 registers x 256 threads, 66-76 KB of shared memory: two CTAs per SM
-    if (grid > (nch + kWarps - 1) / kWarps) grid = (nch + kWarps - 1) / kWarps;
     const bool dep = tuning("advance_p.deposit", 1) != 0;
-    const int store = tuning("advance_p.stream_store", 0) ? 1 : 0;
-    typedef void (*kern_t)(AdvanceArgs);
     const int wide = A.fi_bytes == 96;
-    static const kern_t table[2][2][2] = {   // [store][wide interpolator][deposit]
-        {{advance_p_stream_kernel<0, 0, 0>, advance_p_stream_kernel<1, 0, 0>}, {advance_p_stream_kernel<0, 1, 0>, advance_p_stream_kernel<1, 1, 0>}},
-        {{advance_p_stream_kernel<0, 0, 1>, advance_p_stream_kernel<1, 0, 1>}, {advance_p_stream_kernel<0, 1, 1>, advance_p_stream_kernel<1, 1, 1>}}};
-    static const int smem_bytes[2] = {(int)sizeof(StreamSmem<0>), (int)sizeof(StreamSmem<1>)};
+    const int store = tuning("advance_p.stream_store", 0) ? 1 : 0;
+    // CTAs of 4 warps; 4, 5 or 6 per SM = 16, 20 or 24 warps at <=128, <=96 or <=80 registers per thread
+    int cps = store ? 4 : tuning("advance_p.stream_cps", 5);
+    cps = cps < 5 ? 4 : (cps > 5 ? 6 : 5);
+    typedef void (*kern_t)(AdvanceArgs);
+    static const kern_t table[4][2][2] = {   // [cps-4, or 3 = bulk store][wide interpolator][deposit]
+        {{advance_p_stream_kernel<0, 0, 0, 4>, advance_p_stream_kernel<1, 0, 0, 4>}, {advance_p_stream_kernel<0, 1, 0, 4>, advance_p_stream_kernel<1, 1, 0, 4>}},
+        {{advance_p_stream_kernel<0, 0, 0, 5>, advance_p_stream_kernel<1, 0, 0, 5>}, {advance_p_stream_kernel<0, 1, 0, 5>, advance_p_stream_kernel<1, 1, 0, 5>}},
+        {{advance_p_stream_kernel<0, 0, 0, 6>, advance_p_stream_kernel<1, 0, 0, 6>}, {advance_p_stream_kernel<0, 1, 0, 6>, advance_p_stream_kernel<1, 1, 0, 6>}},
+        {{advance_p_stream_kernel<0, 0, 1, 4>, advance_p_stream_kernel<1, 0, 1, 4>}, {advance_p_stream_kernel<0, 1, 1, 4>, advance_p_stream_kernel<1, 1, 1, 4>}}};
+    const int row = store ? 3 : cps - 4;
+    const int smem = store ? (int)sizeof(StreamSmem<1>) : (int)sizeof(StreamSmem<0>);
     static bool attr_set = false;
     if (!attr_set) {
-      for (int a = 0; a < 2; a++)
+      for (int a = 0; a < 4; a++)
         for (int b = 0; b < 2; b++)
           for (int d = 0; d < 2; d++)
-            VPB_CUDA(cudaFuncSetAttribute(table[a][b][d], cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes[a]));
+            VPB_CUDA(cudaFuncSetAttribute(table[a][b][d], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          a == 3 ? (int)sizeof(StreamSmem<1>) : (int)sizeof(StreamSmem<0>)));
       attr_set = true;
     }
-    table[store][wide][dep]<<<grid, kWarps * 32, smem_bytes[store], st>>>(A);
+    int grid = c.sm_count * cps;
+    if (grid > (nch + kWarpsS - 1) / kWarpsS) grid = (nch + kWarpsS - 1) / kWarpsS;
+    table[row][wide][dep]<<<grid, kWarpsS * 32, smem, st>>>(A);
   } else if (tma_mode == 1) {
     static bool attr_set = false;
     if (!attr_set) {

@@ -25,11 +25,12 @@ def acc_floats(a):
     return np.ascontiguousarray(a).view(np.float32).reshape(-1, 12)
 
 
-@pytest.mark.parametrize("deposit,tma,store", [(1, 2, 0), (0, 2, 0), (1, 2, 1), (0, 2, 1), (1, 1, 0), (0, 1, 0), (1, 0, 0), (0, 0, 0)])
+@pytest.mark.parametrize("deposit,tma,store,cps", [(1, 2, 0, 5), (0, 2, 0, 5), (1, 2, 0, 4), (1, 2, 0, 6), (0, 2, 0, 6), (1, 2, 1, 4), (0, 2, 1, 4),
+                                                   (1, 1, 0, 5), (0, 1, 0, 5), (1, 0, 0, 5), (0, 0, 0, 5)])
 @pytest.mark.parametrize("kind", ["periodic", "metal", "absorbing"])
 @pytest.mark.parametrize("n,np_,sort", [((6, 5, 4), 5000, True), ((8, 1, 6), 7001, False), ((1, 1, 16), 300, True),
                                         ((16, 16, 16), 16 * 16 * 16 * 40, True)])
-def test_advance_p(vpb, orc, deposit, tma, store, kind, n, np_, sort):
+def test_advance_p(vpb, orc, deposit, tma, store, cps, kind, n, np_, sort):
     g = host_grid(n, kind)
     rng = np.random.default_rng(21)
     p = random_particles(rng, g, np_, vth=0.6, sort=sort, edge_frac=0.02)
@@ -38,6 +39,7 @@ def test_advance_p(vpb, orc, deposit, tma, store, kind, n, np_, sort):
     vpb.vpb_set_tuning(b"advance_p.deposit", deposit)
     vpb.vpb_set_tuning(b"advance_p.tma", tma)
     vpb.vpb_set_tuning(b"advance_p.stream_store", store)
+    vpb.vpb_set_tuning(b"advance_p.stream_cps", cps)
     p_o, p_g = p.copy(), p.copy()
     a_o = abi.aligned_zeros(g.nv, abi.accumulator_dtype)
     a_g = a_o.copy()
@@ -48,6 +50,7 @@ def test_advance_p(vpb, orc, deposit, tma, store, kind, n, np_, sort):
     vpb.vpb_set_tuning(b"advance_p.deposit", 1)
     vpb.vpb_set_tuning(b"advance_p.tma", 2)
     vpb.vpb_set_tuning(b"advance_p.stream_store", 0)
+    vpb.vpb_set_tuning(b"advance_p.stream_cps", 5)
     assert nm_g == nm_o
     if kind == "absorbing":
         assert nm_o > 0
