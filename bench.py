@@ -215,7 +215,8 @@ def run_b200(args):
     topo = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
     g = helpers.make_grid((n * topo[0], n * topo[1], n * topo[2]), "periodic", topo=topo, rank=rank)
     sim = Simulation(g, n_mat=1, L=L, planar=L.vpb_get_tuning(b"sim.aos_fields") == 0,
-                     wide_interpolator=L.vpb_get_tuning(b"sim.narrow_interpolator") == 0)
+                     wide_interpolator=L.vpb_get_tuning(b"sim.narrow_interpolator") == 0,
+                     particle_planes=L.vpb_get_tuning(b"sim.aos_particles") == 0)
     np_ = n ** 3 * args.ppc
     max_np = int(np_ * (1.0 if world == 1 else 1.02)) + 1024
     # macro-charge q = +-(cell volume)/ppc so that the plasma frequency is 1 (the reference's thermal recipe,
@@ -300,7 +301,7 @@ def run_b200(args):
                                      "advance_e": (cells * args.steps / (prof["advance_e"][0] * 1e-3)) if prof["advance_e"][0] else None},
         "host_wall_ms_per_step": 1e3 * wall / args.steps,
         "advance_p_ms_by_launch": adv_list,
-        "tuning": {k: L.vpb_get_tuning(k.encode()) for k in ("advance_p.deposit", "advance_p.tma", "advance_p.stream_store", "advance_p.stream_cps", "sim.aos_fields", "sim.narrow_interpolator",
+        "tuning": {k: L.vpb_get_tuning(k.encode()) for k in ("advance_p.deposit", "advance_p.tma", "advance_p.stream_store", "advance_p.stream_cps", "sim.aos_fields", "sim.narrow_interpolator", "sim.aos_particles", "advance_p.pair_cps", "advance_p.pair_pipe", "advance_p.pair_merge",
                                                              "advance_p.tma_ctas_per_sm", "advance_p.ctas_per_sm")},
     }
     if fields_c2 is not None:

@@ -201,6 +201,19 @@ void vpb_field_convert(vpb_domain_t *dom, vpb_field_t *d_dst, const vpb_field_t 
 void vpb_domain_set_interpolator_layout(vpb_domain_t *dom, int wide);
 size_t vpb_interpolator_bytes(const vpb_domain_t *dom);
 
+/* Device particle layout.  Default (plane = 0): the reference's 48-byte particle_t records, what every layer-A entry
+ * point uses.  plane > 0 (a multiple of 64): every species array of the domain is nine COMPONENT PLANES in one
+ * allocation of plane*48 bytes -- eight planes of `plane` 4-byte words (dx, dy, dz, i, ux, uy, uz, q) followed by one
+ * plane of `plane` 16-byte {tag, tag2} pairs -- still passed around as a vpb_particle_t* with capacity max_np <= plane.
+ * advance_p then runs the two-particles-per-lane kernel (vpb_advance_p_pair.cu): one 64-bit word per component and
+ * lane, packed f32x2 arithmetic, and only the six words that change are written back (56 B of particle traffic per
+ * advance instead of the 96 B the 48-byte records impose).  All vpb_* particle functions follow the domain's setting;
+ * vpb_particle_convert() copies between the two layouts (out of place). */
+void vpb_domain_set_particle_layout(vpb_domain_t *dom, long plane);
+long vpb_domain_particle_layout(const vpb_domain_t *dom);
+void vpb_particle_convert(vpb_domain_t *dom, vpb_particle_t *d_dst, const vpb_particle_t *d_src, long np, int to_planes);
+void vpb_copy_positions_dom(vpb_domain_t *dom, vpb_particle_t *d_dst, const vpb_particle_t *d_src, long np);
+
 /* Synthetic field state: an x-propagating vacuum plane wave (ey, cbz) with `mode` wavelengths across
  * the local nx cells; everything else zero. */
 void vpb_load_plane_wave(vpb_domain_t *dom, vpb_field_t *d_f, int mode, float amp);
@@ -226,6 +239,10 @@ void vpb_accumulate_rhob_one(vpb_domain_t *dom, vpb_field_t *d_f, const vpb_part
 /* Stable counting sort by voxel: d_out receives the sorted particles, d_partition
  * (int[nvoxel+1]) the first particle of each voxel (sort_p.c:54-59,74). */
 void vpb_sort_p(vpb_domain_t *dom, const vpb_particle_t *d_in, vpb_particle_t *d_out, int np, int *d_partition);
+/* Same sort for a component-plane array (Device particle layout), in place: d_p holds the sorted planes on return,
+ * d_tmp (same capacity) is scratch.  The permutation is applied to whole 48-byte records staged in d_tmp, which is
+ * several times faster than moving the 4-byte plane words through it one by one. */
+void vpb_sort_p_planes(vpb_domain_t *dom, vpb_particle_t *d_p, vpb_particle_t *d_tmp, int np, int *d_partition);
 
 void vpb_load_interpolator(vpb_domain_t *dom, vpb_interpolator_t *d_fi, const vpb_field_t *d_f);
 void vpb_clear_accumulators(vpb_domain_t *dom, vpb_accumulator_t *d_a);

@@ -979,7 +979,8 @@ extern "C" void vpb_advance_p_ordered(vpb_domain_t *dom, vpb_particle_t *d_p, in
   advance_p_begin(dom, np, q_m, max_nm, d_a, d_f, J, c.stream);
   {
     ProfScope prof(0);
-    advance_p_range(J, d_p, 0, np, d_partition, c.stream);
+    if (dom->d.p_plane > 0) advance_p_pair_launch(J, reinterpret_cast<float *>(d_p), dom->d.p_plane, c.stream);
+    else advance_p_range(J, d_p, 0, np, d_partition, c.stream);
   }
   advance_p_end(J, d_pm, d_nm, c.stream);
 }

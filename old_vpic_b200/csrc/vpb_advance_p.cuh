@@ -34,6 +34,8 @@ struct AdvanceJob {
 void advance_p_begin(vpb_domain_t *dom, int np, float q_m, int max_nm, vpb_accumulator_t *d_a, const vpb_interpolator_t *d_f,
                      AdvanceJob &J, cudaStream_t st);
 void advance_p_range(AdvanceJob &J, vpb_particle_t *d_base, int k0, int k1, const int *d_partition, cudaStream_t st);
+// component-plane arrays (vpb_advance_p_pair.cu): the whole array in one launch
+void advance_p_pair_launch(AdvanceJob &J, float *d_planes, long plane, cudaStream_t st);
 void advance_p_end(AdvanceJob &J, vpb_particle_mover_t *d_pm, int *d_nm, cudaStream_t st);
 
 }  // namespace vpb

@@ -24,6 +24,7 @@
 #include <vector>
 #include "vpb_comm.cuh"
 #include "vpb_move_p.cuh"
+#include "vpb_pview.cuh"
 
 namespace vpb {
 
@@ -100,14 +101,14 @@ struct FaceInfo {
 
 // boundary_p.c:203-316: which face did mover k end on, and what happens there.
 // code: 0..5 = send through that face, 6 = removed locally (absorbed).
-__global__ void __launch_bounds__(256) classify_kernel(const vpb_particle_t *__restrict__ p, const vpb_particle_mover_t *__restrict__ pm,
+__global__ void __launch_bounds__(256) classify_kernel(const PView p, const vpb_particle_mover_t *__restrict__ pm,
                                                        int nm, unsigned char *__restrict__ code, vpb_field_t *__restrict__ f,
                                                        const DomainDev g, const FaceInfo fi, int *__restrict__ n_unknown) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= nm) return;
   const int pi = pm[k].i;
-  const float4 r0 = reinterpret_cast<const float4 *>(p + pi)[0];
-  const float4 r1 = reinterpret_cast<const float4 *>(p + pi)[1];
+  const float4 r0 = p.pos(pi);
+  const float4 r1 = p.mom(pi);
   const int vi = __float_as_int(r0.w);
   const float pos[3] = {r0.x, r0.y, r0.z}, u[3] = {r1.x, r1.y, r1.z};
   int c = -1;
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(256) classify_kernel(const vpb_particle_t *__r
 }
 
 // write the injector records of one species (boundary_p.c:250-263)
-__global__ void __launch_bounds__(256) pack_injectors_kernel(const vpb_particle_t *__restrict__ p, const vpb_particle_mover_t *__restrict__ pm,
+__global__ void __launch_bounds__(256) pack_injectors_kernel(const PView p, const vpb_particle_mover_t *__restrict__ pm,
                                                              int nm, const unsigned char *__restrict__ code, const int *__restrict__ rank,
                                                              int sp_id, const DomainDev g, const FaceInfo fi, float4 *const *__restrict__ sendbuf) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -140,8 +141,8 @@ __global__ void __launch_bounds__(256) pack_injectors_kernel(const vpb_particle_
   if (face >= 6) return;
   const float4 m = reinterpret_cast<const float4 *>(pm)[k];
   const int pi = __float_as_int(m.w);
-  float4 r0 = reinterpret_cast<const float4 *>(p + pi)[0];
-  const float4 r1 = reinterpret_cast<const float4 *>(p + pi)[1];
+  float4 r0 = p.pos(pi);
+  const float4 r1 = p.mom(pi);
   const int ax = face % 3;
   if (ax == 0) r0.x = -r0.x; else if (ax == 1) r0.y = -r0.y; else r0.z = -r0.z;
   const int64_t nn = g.nbr64[6 * (size_t)__float_as_int(r0.w) + face];
@@ -164,14 +165,14 @@ __global__ void __launch_bounds__(256) mark_tail_kernel(const vpb_particle_mover
 }
 
 // survivor j of the tail (rank r among survivors, counted from the top) fills hole pm[nh-1-r]
-__global__ void __launch_bounds__(256) backfill_kernel(vpb_particle_t *__restrict__ p, const vpb_particle_mover_t *__restrict__ pm,
+__global__ void __launch_bounds__(256) backfill_kernel(const PView p, const vpb_particle_mover_t *__restrict__ pm,
                                                        int nm, int np_new, const unsigned char *__restrict__ tail_code,
                                                        const int *__restrict__ rank, const int *__restrict__ nh) {
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;   // 3 float4 per particle
   const int j = (int)(t / 3), piece = (int)(t - 3L * j);
   if (j >= nm || tail_code[j] != 0) return;
   const int hole = pm[*nh - 1 - rank[j]].i;
-  reinterpret_cast<float4 *>(p + hole)[piece] = reinterpret_cast<const float4 *>(p + np_new + j)[piece];
+  p.set_quad(hole, piece, p.quad(np_new + j, piece));
 }
 
 // received buffers -> one list in the reference's injection order (each buffer back to front)
@@ -188,6 +189,7 @@ struct SpeciesTable {
   vpb_particle_t *p[7];
   vpb_particle_mover_t *pm[7];
   int np[7];
+  long plane;       // particle layout of the domain (vpb_pview.cuh)
 };
 
 __global__ void __launch_bounds__(256) species_code_kernel(const float4 *__restrict__ list, int n, const SpeciesTable T,
@@ -216,9 +218,9 @@ __global__ void __launch_bounds__(128) inject_kernel(float4 *__restrict__ list, 
   m.dispx = c.x; m.dispy = c.y; m.dispz = c.z;
   const int pos = T.np[s] + rank[q];
   const int unresolved = move_p_dev(m, a0, nbr);
-  float4 *pp = reinterpret_cast<float4 *>(T.p[s] + pos);   // tags are left as they were (boundary_p.c:488-491)
-  pp[0] = make_float4(m.dx, m.dy, m.dz, __int_as_float(m.i));
-  pp[1] = make_float4(m.ux, m.uy, m.uz, m.q);
+  const PView pv(T.p[s], T.plane);                          // tags are left as they were (boundary_p.c:488-491)
+  pv.set_pos(pos, make_float4(m.dx, m.dy, m.dz, __int_as_float(m.i)));
+  pv.set_mom(pos, make_float4(m.ux, m.uy, m.uz, m.q));
   list[3 * (size_t)q + 2] = make_float4(m.dispx, m.dispy, m.dispz, __int_as_float(pos));
   code2[q] = unresolved ? (unsigned char)s : (unsigned char)7;
 }
@@ -322,6 +324,7 @@ void vpb_boundary_p(vpb_domain_t *dom, vpb_species_state_t *sp, int n_sp, vpb_fi
   long total = 0;
   for (int s = 0; s < n_sp; s++) {
     if (sp[s].nm < 0 || sp[s].nm > sp[s].max_nm) VPB_ERROR("Bad mover count");
+    if (g.p_plane > 0 && sp[s].max_np > g.p_plane) VPB_ERROR("species %d: max_np exceeds the domain's particle plane stride", sp[s].id);
     total += sp[s].nm;
   }
   if (total == 0 && !any_remote) return;
@@ -346,7 +349,7 @@ void vpb_boundary_p(vpb_domain_t *dom, vpb_species_state_t *sp, int n_sp, vpb_fi
     for (int s = 0; s < n_sp; s++) {
       const int nm = sp[s].nm;
       if (nm) {
-        classify_kernel<<<blocks(nm, 256), 256, 0, st>>>(sp[s].p, sp[s].pm, nm, code + off, d_f, g, fi, dc + 33);
+        classify_kernel<<<blocks(nm, 256), 256, 0, st>>>(PView(sp[s].p, g.p_plane), sp[s].pm, nm, code + off, d_f, g, fi, dc + 33);
         rank_bins_kernel<<<1, kRankThreads, 0, st>>>(code + off, nm, 1, rank + off, dc);
         count_launch(2);
       }
@@ -381,7 +384,7 @@ void vpb_boundary_p(vpb_domain_t *dom, vpb_species_state_t *sp, int n_sp, vpb_fi
       const int nm = sp[s].nm;
       if (nm) {
         if (sends) {
-          pack_injectors_kernel<<<blocks(nm, 256), 256, 0, st>>>(sp[s].p, sp[s].pm, nm, code + off, rank + off, sp[s].id, g, fi,
+          pack_injectors_kernel<<<blocks(nm, 256), 256, 0, st>>>(PView(sp[s].p, g.p_plane), sp[s].pm, nm, code + off, rank + off, sp[s].id, g, fi,
                                                                   g_bb.d_send_table);
           count_launch();
         }
@@ -393,7 +396,7 @@ void vpb_boundary_p(vpb_domain_t *dom, vpb_species_state_t *sp, int n_sp, vpb_fi
         VPB_CUDA(cudaMemsetAsync(dc + 40, 0, 8 * sizeof(int), st));
         mark_tail_kernel<<<blocks(nm, 256), 256, 0, st>>>(sp[s].pm, nm, np_new, tcode, dc + 32);
         rank_bins_kernel<<<1, kRankThreads, 0, st>>>(tcode, nm, 1, trank, dc + 40);
-        backfill_kernel<<<blocks(3L * nm, 256), 256, 0, st>>>(sp[s].p, sp[s].pm, nm, np_new, tcode, trank, dc + 32);
+        backfill_kernel<<<blocks(3L * nm, 256), 256, 0, st>>>(PView(sp[s].p, g.p_plane), sp[s].pm, nm, np_new, tcode, trank, dc + 32);
         count_launch(3);
         sp[s].np = np_new;
       }
@@ -435,6 +438,7 @@ void vpb_boundary_p(vpb_domain_t *dom, vpb_species_state_t *sp, int n_sp, vpb_fi
   }
   SpeciesTable T;
   T.n = n_sp;
+  T.plane = g.p_plane;
   for (int s = 0; s < n_sp; s++) { T.id[s] = sp[s].id; T.p[s] = sp[s].p; T.pm[s] = sp[s].pm; T.np[s] = sp[s].np; }
   const int n = (int)n_in;
   species_code_kernel<<<blocks(n, 256), 256, 0, st>>>(list, n, T, c1);

@@ -62,6 +62,9 @@ struct DomainDev {
   // interpolator record stride in bytes: 80 = the reference's interpolator_t; 96 = the same 72 bytes padded to
   // three aligned 32-byte sectors, which advance_p gathers with two 256-bit loads and one 64-bit load
   int fi_bytes;
+  // particle arrays of device-resident runs: 0 = the reference's 48-byte particle_t records; > 0 = component
+  // planes of p_plane words each (vpb_pview.cuh), every species array of the domain with that capacity
+  long p_plane;
 };
 
 #define FQ(f, g, v, q) (reinterpret_cast<float4 *>(f) + ((size_t)(v) * (size_t)(g).fqv + (size_t)(q) * (size_t)(g).fqq))

@@ -229,6 +229,7 @@ vpb_domain_t *vpb_domain_create(const vpb_grid_t *g, int rank, int nproc) {
   d.rank = rank; d.nproc = nproc;
   d.rangel = g->rangel; d.rangeh = g->rangeh;
   d.fi_bytes = 80;
+  d.p_plane = 0;
   d.fqv = 5; d.fqq = 1;    // the reference's 80-byte field_t until vpb_domain_set_field_layout says otherwise
   dom->host_grid = g;
   dom->range.assign((size_t)nproc + 1, 0);

@@ -81,9 +81,35 @@ struct Residency {
     return pl;
   }
 
+  // A particle array: like get(), and with the tuning "dropin.particle_planes" on, a staged array is re-laid out
+  // as component planes for the duration of the call (the layout the device-resident driver uses), so that the
+  // layer-A parity suite also exercises the two-particles-per-lane advance_p and the plane accessors
+  // (VPB_DROPIN_PARTICLE_PLANES=1).
+  struct PlaneAcq { vpb_domain_t *dom; void *aos, *planes; long np; int mode; };
+  std::vector<PlaneAcq> pplanes;
+  void *get_particles(vpb_domain_t *dom, const void *host, long np, int mode) {
+    void *d = get(host, (size_t)np * sizeof(vpb_particle_t), mode);
+    if (d == host || !host || np <= 0 || !tuning("dropin.particle_planes", 0)) return d;
+    Context &c = ctx();
+    const long plane = (np + 63) / 64 * 64;
+    void *pl = nullptr;
+    VPB_CUDA(cudaMallocAsync(&pl, (size_t)plane * sizeof(vpb_particle_t), c.stream));
+    VPB_CUDA(cudaMemsetAsync(pl, 0, (size_t)plane * sizeof(vpb_particle_t), c.stream));
+    vpb_domain_set_particle_layout(dom, plane);
+    vpb_particle_convert(dom, (vpb_particle_t *)pl, (const vpb_particle_t *)d, np, 1);
+    pplanes.push_back({dom, d, pl, np, mode});
+    return pl;
+  }
+
   // copy results back and drain the stream
   void finish() {
     Context &c = ctx();
+    for (auto &pa : pplanes) {
+      if (pa.mode & WR) vpb_particle_convert(pa.dom, (vpb_particle_t *)pa.aos, (const vpb_particle_t *)pa.planes, pa.np, 0);
+      VPB_CUDA(cudaFreeAsync(pa.planes, c.stream));
+      vpb_domain_set_particle_layout(pa.dom, 0);
+    }
+    pplanes.clear();
     for (auto &pa : planar) {
       if (pa.mode & WR) vpb_field_convert(pa.dom, (vpb_field_t *)pa.aos, (const vpb_field_t *)pa.planar, 0);
       VPB_CUDA(cudaFreeAsync(pa.planar, c.stream));
@@ -249,7 +275,7 @@ int advance_p(vpb_particle_t *p0, int np, const float q_m, vpb_particle_mover_t 
   Context &c = ctx();
   Residency r;
   const int piece = tuning("dropin.piece", 4 << 20) & ~31;   // particles per piece
-  const bool streamed = is_plain_host(p0) && np > 2 * piece && tuning("dropin.pipeline", 1);
+  const bool streamed = is_plain_host(p0) && np > 2 * piece && tuning("dropin.pipeline", 1) && !tuning("dropin.particle_planes", 0);
   int *d_out = nullptr;
   VPB_CUDA(cudaMallocAsync(&d_out, 2 * sizeof(int), c.stream));
   // movers: staged without copying max_nm records back; only the nm that exist are returned
@@ -266,7 +292,7 @@ int advance_p(vpb_particle_t *p0, int np, const float q_m, vpb_particle_mover_t 
     dpm = (vpb_particle_mover_t *)sb.dev;
   }
   if (!streamed) {
-    vpb_particle_t *dp = (vpb_particle_t *)r.get(p0, (size_t)np * sizeof(*p0), RW);
+    vpb_particle_t *dp = (vpb_particle_t *)r.get_particles(dom, p0, np, RW);
     vpb_accumulator_t *da = (vpb_accumulator_t *)r.get(a0, nvox(g) * sizeof(*a0), RW);
     const vpb_interpolator_t *df = (const vpb_interpolator_t *)r.get(f0, nvox(g) * sizeof(*f0), RD);
     const int *d_part = nullptr;
@@ -322,7 +348,7 @@ void center_p(vpb_particle_t *p0, int np, const float q_m, const vpb_interpolato
   if (!g) VPB_ERROR("Bad grid");
   vpb_domain_t *dom = domain_of(g);
   Residency r;
-  vpb_particle_t *dp = (vpb_particle_t *)r.get(p0, (size_t)np * sizeof(*p0), RW);
+  vpb_particle_t *dp = (vpb_particle_t *)r.get_particles(dom, p0, np, RW);
   const vpb_interpolator_t *df = (const vpb_interpolator_t *)r.get(f0, nvox(g) * sizeof(*f0), RD);
   vpb_center_p(dom, dp, np, q_m, df);
   r.finish();
@@ -334,7 +360,7 @@ void uncenter_p(vpb_particle_t *p0, int np, const float q_m, const vpb_interpola
   if (!g) VPB_ERROR("Bad grid");
   vpb_domain_t *dom = domain_of(g);
   Residency r;
-  vpb_particle_t *dp = (vpb_particle_t *)r.get(p0, (size_t)np * sizeof(*p0), RW);
+  vpb_particle_t *dp = (vpb_particle_t *)r.get_particles(dom, p0, np, RW);
   const vpb_interpolator_t *df = (const vpb_interpolator_t *)r.get(f0, nvox(g) * sizeof(*f0), RD);
   vpb_uncenter_p(dom, dp, np, q_m, df);
   r.finish();
@@ -347,7 +373,7 @@ double energy_p(const vpb_particle_t *p0, int np, float q_m, const vpb_interpola
   vpb_domain_t *dom = domain_of(g);
   Context &c = ctx();
   Residency r;
-  const vpb_particle_t *dp = (const vpb_particle_t *)r.get(p0, (size_t)np * sizeof(*p0), RD);
+  const vpb_particle_t *dp = (const vpb_particle_t *)r.get_particles(dom, p0, np, RD);
   const vpb_interpolator_t *df = (const vpb_interpolator_t *)r.get(f0, nvox(g) * sizeof(*f0), RD);
   double *d_en = nullptr;
   VPB_CUDA(cudaMallocAsync(&d_en, sizeof(double), c.stream));
@@ -367,7 +393,7 @@ void accumulate_rho_p(vpb_field_t *f, const vpb_particle_t *p0, int np, const vp
   vpb_domain_t *dom = domain_of(g);
   Residency r;
   vpb_field_t *df = (vpb_field_t *)r.get_field(dom, f, nvox(g) * sizeof(*f), RW);
-  const vpb_particle_t *dp = (const vpb_particle_t *)r.get(p0, (size_t)np * sizeof(*p0), RD);
+  const vpb_particle_t *dp = (const vpb_particle_t *)r.get_particles(dom, p0, np, RD);
   vpb_accumulate_rho_p(dom, df, dp, np);
   r.finish();
 }

@@ -7,6 +7,7 @@
 // so this uses a counter-based generator (reproducible for a given seed and
 // independent of launch geometry).
 #include "vpb_common.cuh"
+#include "vpb_pview.cuh"
 
 namespace vpb {
 
@@ -18,7 +19,7 @@ __device__ __forceinline__ uint64_t mix64(uint64_t z) {   // splitmix64 finalise
 }
 __device__ __forceinline__ float u01(uint64_t r) { return ((r >> 40) + 0.5f) * (1.0f / 16777216.0f); }   // (0,1)
 
-__global__ void __launch_bounds__(256) load_thermal_kernel(vpb_particle_t *__restrict__ p, long np, int ppc, float vth,
+__global__ void __launch_bounds__(256) load_thermal_kernel(const PView p, long np, int ppc, float vth,
                                                            float q, uint64_t seed, long tag0, const DomainDev g) {
   for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < np; k += (long)gridDim.x * blockDim.x) {
     const long cell = k / ppc;
@@ -36,17 +37,17 @@ __global__ void __launch_bounds__(256) load_thermal_kernel(vpb_particle_t *__res
     sincospif(2.f * u01(r4), &s0, &c0);
     sincospif(2.f * u01(r6), &s1, &c1);
     (void)r7; (void)s1;
-    float4 *pp = reinterpret_cast<float4 *>(p + k);
-    pp[0] = make_float4(dx, dy, dz, __int_as_float(v));
-    pp[1] = make_float4(vth * a0 * c0, vth * a0 * s0, vth * a1 * c1, q);
-    reinterpret_cast<longlong2 *>(pp)[2] = make_longlong2(tag0 + k, 0);
+    p.set_pos(k, make_float4(dx, dy, dz, __int_as_float(v)));
+    p.set_mom(k, make_float4(vth * a0 * c0, vth * a0 * s0, vth * a1 * c1, q));
+    const longlong2 tags = make_longlong2(tag0 + k, 0);
+    p.set_tag(k, *reinterpret_cast<const float4 *>(&tags));
   }
 }
 
 // copy only dx,dy,dz,i (the first quad) from one species to another: co-located ions
-__global__ void __launch_bounds__(256) copy_positions_kernel(vpb_particle_t *__restrict__ dst, const vpb_particle_t *__restrict__ src, long np) {
+__global__ void __launch_bounds__(256) copy_positions_kernel(const PView dst, const PView src, long np) {
   for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < np; k += (long)gridDim.x * blockDim.x)
-    reinterpret_cast<float4 *>(dst + k)[0] = reinterpret_cast<const float4 *>(src + k)[0];
+    dst.set_pos(k, src.pos(k));
 }
 
 // x-propagating vacuum plane wave on the Yee mesh (ey on x nodes, cbz half a cell further): a synthetic
@@ -75,7 +76,7 @@ void vpb_load_thermal(vpb_domain_t *dom, vpb_particle_t *d_p, int ppc, float vth
   if (ppc < 1) VPB_ERROR("Bad ppc");
   const DomainDev &g = dom->d;
   const long np = (long)ppc * g.nx * g.ny * g.nz;
-  load_thermal_kernel<<<ctx().sm_count * 16, 256, 0, ctx().stream>>>(d_p, np, ppc, vth, q, seed, tag0, g);
+  load_thermal_kernel<<<ctx().sm_count * 16, 256, 0, ctx().stream>>>(PView(d_p, g.p_plane), np, ppc, vth, q, seed, tag0, g);
   count_launch();
   VPB_CUDA(cudaGetLastError());
 }
@@ -92,7 +93,15 @@ void vpb_load_plane_wave(vpb_domain_t *dom, vpb_field_t *d_f, int mode, float am
 }
 
 void vpb_copy_positions(vpb_particle_t *d_dst, const vpb_particle_t *d_src, long np) {
-  copy_positions_kernel<<<ctx().sm_count * 16, 256, 0, ctx().stream>>>(d_dst, d_src, np);
+  copy_positions_kernel<<<ctx().sm_count * 16, 256, 0, ctx().stream>>>(PView(d_dst, 0), PView(d_src, 0), np);
+  count_launch();
+  VPB_CUDA(cudaGetLastError());
+}
+
+// same, for arrays in the domain's particle layout
+void vpb_copy_positions_dom(vpb_domain_t *dom, vpb_particle_t *d_dst, const vpb_particle_t *d_src, long np) {
+  if (!dom) VPB_ERROR("Bad grid");
+  copy_positions_kernel<<<ctx().sm_count * 16, 256, 0, ctx().stream>>>(PView(d_dst, dom->d.p_plane), PView(d_src, dom->d.p_plane), np);
   count_launch();
   VPB_CUDA(cudaGetLastError());
 }

@@ -5,6 +5,7 @@
 //   sort_p                  sort_p.c:16-77 (stable counting sort + partition[])
 // Arithmetic follows the reference's scalar flavour (built with -fmad=false).
 #include "vpb_common.cuh"
+#include "vpb_pview.cuh"
 #include "vpb_scan.cuh"
 
 namespace vpb {
@@ -49,28 +50,26 @@ __device__ __forceinline__ void boris_rotate(float &ux, float &uy, float &uz, co
 // MODE 0: center_p (half kick then half rotate); MODE 1: uncenter_p (constants
 // negated, half rotate then half kick).
 template <int MODE>
-__global__ void __launch_bounds__(256) center_kernel(vpb_particle_t *__restrict__ p, int np, float qdt_2mc, float qdt_4mc,
+__global__ void __launch_bounds__(256) center_kernel(const PView p, int np, float qdt_2mc, float qdt_4mc,
                                                      const vpb_interpolator_t *__restrict__ f0, int fi_bytes) {
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x) {
-    float4 *pp = reinterpret_cast<float4 *>(p + k);
-    const float4 r0 = pp[0];
-    float4 r1 = pp[1];
+    const float4 r0 = p.pos(k);
+    float4 r1 = p.mom(k);
     const Gather g = gather_fields(f0, fi_bytes, __float_as_int(r0.w), qdt_2mc, r0.x, r0.y, r0.z);
     if (MODE == 0) { r1.x += g.hax; r1.y += g.hay; r1.z += g.haz; }
     boris_rotate(r1.x, r1.y, r1.z, g, qdt_4mc);
     if (MODE == 1) { r1.x += g.hax; r1.y += g.hay; r1.z += g.haz; }
-    pp[1] = r1;
+    p.set_mom(k, r1);
   }
 }
 
-__global__ void __launch_bounds__(256) energy_p_kernel(const vpb_particle_t *__restrict__ p, int np, float qdt_2mc,
+__global__ void __launch_bounds__(256) energy_p_kernel(const PView p, int np, float qdt_2mc,
                                                        const vpb_interpolator_t *__restrict__ f0, int fi_bytes,
                                                        double *__restrict__ out) {
   __shared__ double ws[8];
   double en = 0;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x) {
-    const float4 *pp = reinterpret_cast<const float4 *>(p + k);
-    const float4 r0 = __ldg(pp), r1 = __ldg(pp + 1);
+    const float4 r0 = p.pos(k), r1 = p.mom(k);
     const Gather g = gather_fields(f0, fi_bytes, __float_as_int(r0.w), qdt_2mc, r0.x, r0.y, r0.z);
     float v0 = r1.x + g.hax, v1 = r1.y + g.hay, v2 = r1.z + g.haz;   // energy_p.cxx:37-43
     v0 = v0 * v0 + v1 * v1 + v2 * v2;
@@ -88,11 +87,10 @@ __global__ void __launch_bounds__(256) energy_p_kernel(const vpb_particle_t *__r
 }
 
 // rho_p.c:43-78: trilinear deposit of q/8V onto the 8 nodes of the particle's voxel
-__global__ void __launch_bounds__(256) rho_p_kernel(vpb_field_t *__restrict__ f, const vpb_particle_t *__restrict__ p, int np,
+__global__ void __launch_bounds__(256) rho_p_kernel(vpb_field_t *__restrict__ f, const PView p, int np,
                                                     float r8V, const DomainDev g) {
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x) {
-    const float4 *pp = reinterpret_cast<const float4 *>(p + k);
-    const float4 r0 = __ldg(pp), r1 = __ldg(pp + 1);
+    const float4 r0 = p.pos(k), r1 = p.mom(k);
     float t, w0, w1, w2, w3, w4, w5, w6, w7;
     t = r0.x; w0 = r8V * r1.w; t *= w0; w1 = w0 + t; w0 -= t;
     t = r0.y; w3 = 1 + t; w2 = w0 * w3; w3 *= w1; t = 1 - t; w0 *= t; w1 *= t;
@@ -113,17 +111,32 @@ __global__ void __launch_bounds__(256) rho_p_kernel(vpb_field_t *__restrict__ f,
 // to the reference's stable scatter, sort_p.c:74), (5) gather the 48-byte
 // records through the permutation with 128-bit accesses.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sort_hist_kernel(const vpb_particle_t *__restrict__ p, int np, int *__restrict__ count) {
+__global__ void __launch_bounds__(256) sort_hist_kernel(const PView p, int np, int *__restrict__ count) {
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x)
-    atomicAdd(count + __ldg(&p[k].i), 1);
+    atomicAdd(count + p.voxel(k), 1);
 }
 
-__global__ void __launch_bounds__(256) sort_claim_kernel(const vpb_particle_t *__restrict__ p, int np, int *__restrict__ cursor,
+// Slot claim, warp-aggregated: the lanes of a warp that hold the same voxel (most of them, the array being nearly
+// sorted) send ONE atomic for the group and take consecutive slots in lane order.
+__global__ void __launch_bounds__(256) sort_claim_kernel(const PView p, int np, int *__restrict__ cursor,
                                                          int *__restrict__ perm) {
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x)
-    perm[atomicAdd(cursor + __ldg(&p[k].i), 1)] = k;
+  const int lane = threadIdx.x & 31;
+  const int stride = gridDim.x * blockDim.x;
+  for (int k0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); k0 < np; k0 += stride) {   // warp-uniform trip count
+    const int k = k0 + lane;
+    const bool valid = k < np;
+    const int v = valid ? p.voxel(k) : -1 - lane;
+    const unsigned peers = __match_any_sync(0xffffffffu, v);
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (valid && lane == leader) base = atomicAdd(cursor + v, __popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (valid) perm[base + __popc(peers & ((1u << lane) - 1u))] = k;
+  }
 }
 
+// INV = 0: perm_sorted[destination] = source (for a gather); INV = 1: perm_sorted[source] = destination (for a scatter)
+template <int INV>
 __global__ void __launch_bounds__(256) sort_rank_kernel(const int *__restrict__ partition, int nv, const int *__restrict__ perm,
                                                         int *__restrict__ perm_sorted) {
   const int lane = threadIdx.x & 31;
@@ -135,13 +148,13 @@ __global__ void __launch_bounds__(256) sort_rank_kernel(const int *__restrict__ 
       const int mine = lane < n ? perm[b + lane] : 0x7fffffff;
       int r = 0;
       for (int j = 0; j < n; j++) r += (__shfl_sync(0xffffffffu, mine, j) < mine);
-      if (lane < n) perm_sorted[b + r] = mine;
+      if (lane < n) perm_sorted[INV ? mine : b + r] = INV ? b + r : mine;
     } else {
       for (int i = lane; i < n; i += 32) {
         const int mine = perm[b + i];
         int r = 0;
         for (int j = 0; j < n; j++) r += (perm[b + j] < mine);
-        perm_sorted[b + r] = mine;
+        perm_sorted[INV ? mine : b + r] = INV ? b + r : mine;
       }
     }
   }
@@ -157,9 +170,52 @@ __global__ void __launch_bounds__(256) sort_gather_kernel(const vpb_particle_t *
   }
 }
 
+// Component planes, out of place: blockIdx.y = plane (0..7 the 4-byte components, 8 the 16-byte tag pairs); coalesced
+// writes, reads gathered through the permutation.  Moving single 4-byte words through a permutation is slow once the
+// particles have drifted (every word pulls its own 32-byte sector: 142 ms per 2^30 particles 20 steps after a sort;
+// a 4-byte scatter is worse, 300 ms) -- the device-resident driver uses vpb_sort_p_planes below instead.
+__global__ void __launch_bounds__(256) sort_gather_planes_kernel(const float *__restrict__ in, float *__restrict__ out, long plane_in,
+                                                                 long plane_out, int np, const int *__restrict__ perm) {
+  const int c = blockIdx.y;
+  if (c < 8) {
+    const float *src = in + (size_t)c * plane_in;
+    float *dst = out + (size_t)c * plane_out;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x) dst[k] = __ldg(src + perm[k]);
+  } else {
+    const float4 *src = reinterpret_cast<const float4 *>(in + 8 * (size_t)plane_in);
+    float4 *dst = reinterpret_cast<float4 *>(out + 8 * (size_t)plane_out);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x) dst[k] = __ldg(src + perm[k]);
+  }
+}
+
+// The permutation moves whole 48-byte records (three 16-byte requests per particle, as for the reference layout):
+// the planes are first copied to records in the scratch array (both sides coalesced), then records are gathered
+// through the permutation and written straight back as planes.
+__global__ void __launch_bounds__(256) sort_gather_records_to_planes_kernel(const float4 *__restrict__ rec, const PView out, int np,
+                                                                            const int *__restrict__ perm) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x) {
+    const float4 *r = rec + 3 * (size_t)perm[k];
+    const float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2);
+    out.set_pos(k, a);
+    out.set_mom(k, b);
+    out.set_tag(k, c);
+  }
+}
+
+// AoS <-> component planes (uploads, downloads, tests)
+__global__ void __launch_bounds__(256) particle_convert_kernel(const PView dst, const PView src, long np) {
+  for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < np; k += (long)gridDim.x * blockDim.x) {
+    dst.set_pos(k, src.pos(k));
+    dst.set_mom(k, src.mom(k));
+    dst.set_tag(k, src.tag(k));
+  }
+}
+
 }  // namespace vpb
 
 using namespace vpb;
+
+static bool g_sort_in_place = false;
 
 static int grid_for(long n, int tb) {
   long b = (n + tb - 1) / tb;
@@ -176,7 +232,7 @@ void vpb_center_p(vpb_domain_t *dom, vpb_particle_t *d_p, int np, float q_m, con
   if (np == 0) return;
   const float qdt_2mc = (float)(0.5 * q_m * dom->d.dt / dom->d.cvac);   // center_p.cxx:171
   const float qdt_4mc = (float)(0.5 * qdt_2mc);                         // center_p.cxx:15
-  center_kernel<0><<<grid_for(np, 256), 256, 0, ctx().stream>>>(d_p, np, qdt_2mc, qdt_4mc, d_f, dom->d.fi_bytes);
+  center_kernel<0><<<grid_for(np, 256), 256, 0, ctx().stream>>>(PView(d_p, dom->d.p_plane), np, qdt_2mc, qdt_4mc, d_f, dom->d.fi_bytes);
   count_launch();
   VPB_CUDA(cudaGetLastError());
 }
@@ -189,7 +245,7 @@ void vpb_uncenter_p(vpb_domain_t *dom, vpb_particle_t *d_p, int np, float q_m, c
   const float fwd = (float)(0.5 * q_m * dom->d.dt / dom->d.cvac);       // uncenter_p.cxx:171
   const float qdt_2mc = -fwd;                                           // uncenter_p.cxx:14
   const float qdt_4mc = (float)(-0.5 * fwd);                            // uncenter_p.cxx:15
-  center_kernel<1><<<grid_for(np, 256), 256, 0, ctx().stream>>>(d_p, np, qdt_2mc, qdt_4mc, d_f, dom->d.fi_bytes);
+  center_kernel<1><<<grid_for(np, 256), 256, 0, ctx().stream>>>(PView(d_p, dom->d.p_plane), np, qdt_2mc, qdt_4mc, d_f, dom->d.fi_bytes);
   count_launch();
   VPB_CUDA(cudaGetLastError());
 }
@@ -201,7 +257,7 @@ void vpb_energy_p(vpb_domain_t *dom, const vpb_particle_t *d_p, int np, float q_
   VPB_CUDA(cudaMemsetAsync(d_en, 0, sizeof(double), ctx().stream));
   if (np == 0) return;
   const float qdt_2mc = (float)(0.5 * q_m * dom->d.dt / dom->d.cvac);
-  energy_p_kernel<<<grid_for(np, 256), 256, 0, ctx().stream>>>(d_p, np, qdt_2mc, d_f, dom->d.fi_bytes, d_en);
+  energy_p_kernel<<<grid_for(np, 256), 256, 0, ctx().stream>>>(PView(d_p, dom->d.p_plane), np, qdt_2mc, d_f, dom->d.fi_bytes, d_en);
   count_launch();
   VPB_CUDA(cudaGetLastError());
 }
@@ -214,7 +270,7 @@ void vpb_accumulate_rho_p(vpb_domain_t *dom, vpb_field_t *d_f, const vpb_particl
   if (np == 0) return;
   const DomainDev &g = dom->d;
   const float r8V = (float)(0.125 * g.rdx * g.rdy * g.rdz);             // rho_p.c:37
-  rho_p_kernel<<<grid_for(np, 256), 256, 0, ctx().stream>>>(d_f, d_p, np, r8V, g);
+  rho_p_kernel<<<grid_for(np, 256), 256, 0, ctx().stream>>>(d_f, PView(d_p, g.p_plane), np, r8V, g);
   count_launch();
   VPB_CUDA(cudaGetLastError());
 }
@@ -233,16 +289,60 @@ void vpb_sort_p(vpb_domain_t *dom, const vpb_particle_t *d_in, vpb_particle_t *d
   char *s = (char *)scratch(off_scan + scan_scratch_bytes(nv1));
   int *cursor = (int *)s, *perm = (int *)(s + off_perm), *perm2 = (int *)(s + off_perm2);
   VPB_CUDA(cudaMemsetAsync(cursor, 0, (size_t)nv1 * 4, c.stream));
-  if (np > 0) sort_hist_kernel<<<grid_for(np, 256), 256, 0, c.stream>>>(d_in, np, cursor);
+  if (np > 0) sort_hist_kernel<<<grid_for(np, 256), 256, 0, c.stream>>>(PView(d_in, dom->d.p_plane), np, cursor);
   exclusive_scan_i32(cursor, d_partition, nv1, s + off_scan, c.stream);   // partition[nv] = np (sort_p.c:54-59)
   count_launch(1 + scan_launches(nv1));
   if (np == 0) return;
   if (!d_in || !d_out) VPB_ERROR("Bad particle array");
   VPB_CUDA(cudaMemcpyAsync(cursor, d_partition, (size_t)nv1 * 4, cudaMemcpyDeviceToDevice, c.stream));
-  sort_claim_kernel<<<grid_for(np, 256), 256, 0, c.stream>>>(d_in, np, cursor, perm);
-  sort_rank_kernel<<<grid_for((long)nv * 32, 256), 256, 0, c.stream>>>(d_partition, nv, perm, perm2);
-  sort_gather_kernel<<<grid_for(3L * np, 256), 256, 0, c.stream>>>(d_in, d_out, np, perm2);
+  sort_claim_kernel<<<grid_for(np, 256), 256, 0, c.stream>>>(PView(d_in, dom->d.p_plane), np, cursor, perm);
+  sort_rank_kernel<0><<<grid_for((long)nv * 32, 256), 256, 0, c.stream>>>(d_partition, nv, perm, perm2);
+  if (g_sort_in_place) {   // vpb_sort_p_planes: d_out is scratch, the sorted planes return to d_in
+    particle_convert_kernel<<<grid_for(np, 256), 256, 0, c.stream>>>(PView(d_out, 0), PView(d_in, dom->d.p_plane), np);
+    sort_gather_records_to_planes_kernel<<<grid_for(np, 256), 256, 0, c.stream>>>(reinterpret_cast<const float4 *>(d_out),
+                                                                                  PView(d_in, dom->d.p_plane), np, perm2);
+    count_launch();
+  } else if (dom->d.p_plane > 0) {
+    sort_gather_planes_kernel<<<dim3(grid_for(np, 256), 9), 256, 0, c.stream>>>(reinterpret_cast<const float *>(d_in), reinterpret_cast<float *>(d_out),
+                                                                                dom->d.p_plane, dom->d.p_plane, np, perm2);
+  } else {
+    sort_gather_kernel<<<grid_for(3L * np, 256), 256, 0, c.stream>>>(d_in, d_out, np, perm2);
+  }
   count_launch(4);
+  VPB_CUDA(cudaGetLastError());
+}
+
+// Stable counting sort of a component-plane array IN PLACE: d_p holds the sorted planes on return, d_tmp (same
+// capacity) is scratch.  Same permutation as vpb_sort_p.
+void vpb_sort_p_planes(vpb_domain_t *dom, vpb_particle_t *d_p, vpb_particle_t *d_tmp, int np, int *d_partition) {
+  if (!dom) VPB_ERROR("Bad grid");
+  if (dom->d.p_plane <= 0) VPB_ERROR("the domain keeps its particles in the reference layout: use vpb_sort_p");
+  g_sort_in_place = true;
+  vpb_sort_p(dom, d_p, d_tmp, np, d_partition);
+  g_sort_in_place = false;
+}
+
+// Particle layout of a domain's device-resident species arrays (include/vpic_b200.h "Device particle layout")
+void vpb_domain_set_particle_layout(vpb_domain_t *dom, long plane) {
+  if (!dom) VPB_ERROR("Bad grid");
+  if (plane < 0 || (plane & 63)) VPB_ERROR("particle plane stride must be a non-negative multiple of 64 (got %ld)", plane);
+  dom->d.p_plane = plane;
+}
+
+long vpb_domain_particle_layout(const vpb_domain_t *dom) {
+  if (!dom) VPB_ERROR("Bad grid");
+  return dom->d.p_plane;
+}
+
+// to_planes != 0: d_src is particle_t[np], d_dst the domain's component planes; else the other way round
+void vpb_particle_convert(vpb_domain_t *dom, vpb_particle_t *d_dst, const vpb_particle_t *d_src, long np, int to_planes) {
+  if (!dom) VPB_ERROR("Bad grid");
+  if (!d_dst || !d_src) VPB_ERROR("Bad particle array");
+  if (dom->d.p_plane <= 0) VPB_ERROR("the domain keeps its particles in the reference layout");
+  if (np <= 0) return;
+  const PView planes(to_planes ? (const void *)d_dst : (const void *)d_src, dom->d.p_plane), aos(to_planes ? (const void *)d_src : (const void *)d_dst, 0);
+  particle_convert_kernel<<<grid_for(np, 256), 256, 0, ctx().stream>>>(to_planes ? planes : aos, to_planes ? aos : planes, np);
+  count_launch();
   VPB_CUDA(cudaGetLastError());
 }
 

@@ -62,6 +62,10 @@ SIGNATURES = {
     "vpb_load_thermal": (None, [_vp, _vp, _i, _f, _f, C.c_ulonglong, _l]),
     "vpb_copy_positions": (None, [_vp, _vp, _l]),
     "vpb_load_plane_wave": (None, [_vp, _vp, _i, _f]),
+    "vpb_domain_set_particle_layout": (None, [_vp, _l]),
+    "vpb_domain_particle_layout": (_l, [_vp]),
+    "vpb_particle_convert": (None, [_vp, _vp, _vp, _l, _i]),
+    "vpb_copy_positions_dom": (None, [_vp, _vp, _vp, _l]),
     "vpb_domain_set_field_layout": (None, [_vp, _i]),
     "vpb_domain_field_layout": (_i, [_vp]),
     "vpb_field_bytes": (C.c_size_t, [_vp]),
@@ -97,6 +101,7 @@ SIGNATURES = {
     "vpb_accumulate_rhob_one": (None, [_vp, _vp, _vp]),
     "vpb_boundary_p": (None, [_vp, _vp, _i, _vp, _vp]),
     "vpb_sort_p": (None, [_vp, _vp, _vp, _i, _vp]),
+    "vpb_sort_p_planes": (None, [_vp, _vp, _vp, _i, _vp]),
     "vpb_load_interpolator": (None, [_vp, _vp, _vp]),
     "vpb_clear_accumulators": (None, [_vp, _vp]),
     "vpb_unload_accumulator": (None, [_vp, _vp, _vp]),

@@ -85,12 +85,50 @@ class FieldArray:
             self.ptr = None
 
 
+class ParticleArray(DevArray):
+    """One species' device particle array in the domain's particle layout (include/vpic_b200.h "Device particle
+    layout").  upload()/download() speak the reference's particle_t[] and convert on the device."""
+
+    def __init__(self, L, dom, capacity):
+        self.dom = dom
+        plane = int(L.vpb_domain_particle_layout(dom))
+        assert plane == 0 or capacity <= plane, "capacity exceeds the domain's particle plane stride"
+        DevArray.__init__(self, L, plane if plane else capacity, abi.particle_dtype)
+
+    def _planes(self):
+        return int(self.L.vpb_domain_particle_layout(self.dom)) > 0
+
+    def upload(self, host):
+        host = np.ascontiguousarray(host, dtype=self.dtype)
+        if not self._planes() or len(host) == 0:
+            return DevArray.upload(self, host)
+        L = self.L
+        tmp = L.vpb_dev_alloc(host.nbytes)
+        L.vpb_h2d(tmp, host.ctypes.data, host.nbytes)
+        L.vpb_particle_convert(self.dom, self.ptr, tmp, len(host), 1)
+        L.vpb_sync()
+        L.vpb_dev_free(tmp)
+
+    def download(self, n=None):
+        n = self.n if n is None else int(n)
+        if not self._planes() or n == 0:
+            return DevArray.download(self, n)
+        L = self.L
+        out = abi.aligned_empty(n, self.dtype)
+        tmp = L.vpb_dev_alloc(out.nbytes)
+        L.vpb_particle_convert(self.dom, tmp, self.ptr, n, 0)
+        L.vpb_d2h(out.ctypes.data, tmp, out.nbytes)
+        L.vpb_sync()
+        L.vpb_dev_free(tmp)
+        return out
+
+
 class Species:
-    def __init__(self, L, name, q_m, max_np, max_nm, sort_interval, sp_id):
+    def __init__(self, L, dom, name, q_m, max_np, max_nm, sort_interval, sp_id):
         self.name, self.q_m, self.id = name, float(q_m), sp_id
         self.max_np, self.max_nm, self.sort_interval = int(max_np), int(max_nm), int(sort_interval)
         self.np = 0
-        self.p = DevArray(L, max_np, abi.particle_dtype)
+        self.p = ParticleArray(L, dom, max_np)
         self.pm = DevArray(L, max_nm, abi.mover_dtype)
         self.nm = DevArray(L, 4, np.int32)
         self.partition = None        # int[nv+1] from the last sort of this species (traversal hint)
@@ -99,7 +137,7 @@ class Species:
 class Simulation:
     """One rank's share of a PIC run on one GPU."""
 
-    def __init__(self, grid, n_mat=1, vacuum=False, L=None, planar=True, wide_interpolator=True):
+    def __init__(self, grid, n_mat=1, vacuum=False, L=None, planar=True, wide_interpolator=True, particle_planes=True):
         self.L = L or lib.load()
         self.L.vpb_init(-1)
         self.grid = grid
@@ -124,6 +162,9 @@ class Simulation:
                 from_vac[k] = 1.0
             self.m = DevArray(self.L, n_mat, abi.material_coefficient_dtype)
             self.m.upload(from_vac)
+        # species arrays as component planes (two-particles-per-lane advance_p); the plane stride is fixed by the
+        # first define_species() and shared by every species of the domain
+        self.particle_planes = bool(particle_planes)
         self.species = []
         self.sort_tmp = None
         self.step = 0
@@ -147,7 +188,9 @@ class Simulation:
     def define_species(self, name, q_m, max_np, max_nm=None, sort_interval=20):
         assert not self.grid.field_only, "a field-only grid cannot carry particles"
         max_nm = max_nm if max_nm is not None else max(2 * max_np // 25, 16)   # vpic.hxx:416-420
-        sp = Species(self.L, name, q_m, max_np, max_nm, sort_interval, len(self.species))
+        if self.particle_planes and not self.species:
+            self.L.vpb_domain_set_particle_layout(self.dom, (int(max_np) + 63) // 64 * 64)
+        sp = Species(self.L, self.dom, name, q_m, max_np, max_nm, sort_interval, len(self.species))
         self.species.append(sp)
         return sp
 
@@ -163,11 +206,14 @@ class Simulation:
         if self.sort_tmp is None or self.sort_tmp.n < sp.max_np:
             if self.sort_tmp is not None:
                 self.sort_tmp.free()
-            self.sort_tmp = DevArray(L, sp.max_np, abi.particle_dtype)
+            self.sort_tmp = ParticleArray(L, self.dom, sp.max_np)
         if sp.partition is None:
             sp.partition = DevArray(L, self.nv + 1, np.int32)
-        L.vpb_sort_p(self.dom, sp.p.ptr, self.sort_tmp.ptr, sp.np, sp.partition.ptr)
-        sp.p, self.sort_tmp = self.sort_tmp, sp.p     # out-of-place: swap (sort_p.c:76-77)
+        if int(L.vpb_domain_particle_layout(self.dom)) > 0:
+            L.vpb_sort_p_planes(self.dom, sp.p.ptr, self.sort_tmp.ptr, sp.np, sp.partition.ptr)   # sorted planes return to sp.p
+        else:
+            L.vpb_sort_p(self.dom, sp.p.ptr, self.sort_tmp.ptr, sp.np, sp.partition.ptr)
+            sp.p, self.sort_tmp = self.sort_tmp, sp.p     # out-of-place: swap (sort_p.c:76-77)
 
     def advance_fields(self):
         L, dom, f = self.L, self.dom, self.f.ptr

@@ -272,3 +272,154 @@ def test_layer_b_wide_interpolator(vpb, orc, kind, store):
     for arr in (d_f, d_fi, d_p, d_pm, d_a, d_nm, d_en):
         arr.free()
     vpb.vpb_domain_destroy(dom)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Component-plane particle layout + two-particles-per-lane advance_p (vpb_advance_p_pair.cu, packed f32x2)
+# ---------------------------------------------------------------------------------------------------------
+class particle_planes:
+    """Layer-A calls inside this context stage their particle array as component planes on the device."""
+
+    def __init__(self, vpb, cps=4, pipe=1, merge=1):
+        self.vpb, self.cps, self.pipe, self.merge = vpb, cps, pipe, merge
+
+    def __enter__(self):
+        self.vpb.vpb_set_tuning(b"dropin.particle_planes", 1)
+        self.vpb.vpb_set_tuning(b"advance_p.pair_cps", self.cps)
+        self.vpb.vpb_set_tuning(b"advance_p.pair_pipe", self.pipe)
+        self.vpb.vpb_set_tuning(b"advance_p.pair_merge", self.merge)
+
+    def __exit__(self, *a):
+        self.vpb.vpb_set_tuning(b"dropin.particle_planes", 0)
+        self.vpb.vpb_set_tuning(b"advance_p.pair_cps", 4)
+        self.vpb.vpb_set_tuning(b"advance_p.pair_pipe", 1)
+        self.vpb.vpb_set_tuning(b"advance_p.pair_merge", 1)
+
+
+@pytest.mark.parametrize("cps,pipe,merge", [(2, 1, 1), (3, 1, 1), (4, 1, 1), (4, 0, 1), (5, 1, 1), (5, 0, 0), (4, 1, 0)])
+@pytest.mark.parametrize("kind", ["periodic", "metal", "absorbing"])
+@pytest.mark.parametrize("n,np_,sort,vth", [((6, 5, 4), 5000, True, 0.6), ((8, 1, 6), 7001, False, 0.6), ((1, 1, 16), 300, True, 0.6),
+                                            ((16, 16, 16), 16 * 16 * 16 * 40, True, 0.6), ((12, 12, 12), 12 * 12 * 12 * 64, True, 0.1),
+                                            ((7, 6, 5), 20001, True, 3.0)])
+def test_advance_p_pair(vpb, orc, cps, pipe, merge, kind, n, np_, sort, vth):
+    """Bit-exact particles and movers from the packed kernel: every multiply/add is the scalar one per half, the
+    packed sqrt/div refinements are the scalar operators' own."""
+    g = host_grid(n, kind)
+    rng = np.random.default_rng(31)
+    p = random_particles(rng, g, np_, vth=vth, sort=sort, edge_frac=0.02)
+    fi = random_interpolator(rng, g, amp=0.3)
+    q_m, max_nm = -1.0, np_
+    p_o, p_g = p.copy(), p.copy()
+    a_o = abi.aligned_zeros(g.nv, abi.accumulator_dtype)
+    a_g = a_o.copy()
+    pm_o = abi.aligned_zeros(max_nm, abi.mover_dtype)
+    pm_g = pm_o.copy()
+    nm_o = orc.orc_advance_p(ptr(p_o), np_, q_m, ptr(pm_o), max_nm, ptr(a_o), ptr(fi), g.ref())
+    with particle_planes(vpb, cps, pipe, merge):
+        nm_g = vpb.advance_p(ptr(p_g), np_, q_m, ptr(pm_g), max_nm, ptr(a_g), ptr(fi), g.ref())
+    assert nm_g == nm_o
+    if kind == "absorbing":
+        assert nm_o > 0
+    assert_bits_equal(p_g, p_o, "particles")
+    assert_bits_equal(pm_g[:nm_g], pm_o[:nm_o], "movers (ordered by particle index)")
+    assert max_rel(acc_floats(a_g), acc_floats(a_o)) < ACC_TOL
+    untouched = ~np.any(acc_floats(a_o) != 0, axis=1)
+    assert not np.any(acc_floats(a_g)[untouched] != 0)
+
+
+@pytest.mark.parametrize("q_m", [-1.0, 1.0 / 1836.0, 3e-9, 0.0])
+def test_advance_p_pair_extreme_operands(vpb, orc, q_m):
+    """Operands outside the packed fast paths (huge, tiny and zero momenta and charge-to-mass ratios) take the scalar
+    operators: still bit-exact."""
+    g = host_grid((5, 4, 3), "metal")
+    rng = np.random.default_rng(32)
+    np_ = 4099
+    p = random_particles(rng, g, np_, vth=0.5, sort=True)
+    scale = 10.0 ** rng.uniform(-30, 17, size=np_)
+    pick = rng.random(np_) < 0.3
+    for k in ("ux", "uy", "uz"):
+        p[k][pick] = (p[k][pick] * scale[pick]).astype(np.float32)
+    p["ux"][::97] = 0
+    p["uy"][::97] = 0
+    p["uz"][::97] = 0
+    fi = random_interpolator(rng, g, amp=0.3)
+    fi_flat = fi.view(np.float32).reshape(g.nv, 20)
+    fi_flat[::7, :] = 0          # field-free voxels: v3 = 0/..., tiny rotations
+    p_o, p_g = p.copy(), p.copy()
+    a_o = abi.aligned_zeros(g.nv, abi.accumulator_dtype)
+    a_g = a_o.copy()
+    pm_o = abi.aligned_zeros(np_, abi.mover_dtype)
+    pm_g = pm_o.copy()
+    nm_o = orc.orc_advance_p(ptr(p_o), np_, q_m, ptr(pm_o), np_, ptr(a_o), ptr(fi), g.ref())
+    with particle_planes(vpb):
+        nm_g = vpb.advance_p(ptr(p_g), np_, q_m, ptr(pm_g), np_, ptr(a_g), ptr(fi), g.ref())
+    assert nm_g == nm_o
+    assert_bits_equal(p_g, p_o, "particles")
+    assert_bits_equal(pm_g[:nm_g], pm_o[:nm_o], "movers")
+
+
+def test_advance_p_pair_tails(vpb, orc):
+    g = host_grid((4, 4, 4))
+    rng = np.random.default_rng(33)
+    fi = random_interpolator(rng, g)
+    a = abi.aligned_zeros(g.nv, abi.accumulator_dtype)
+    pm = abi.aligned_zeros(8, abi.mover_dtype)
+    with particle_planes(vpb):
+        for np_ in (1, 2, 31, 63, 64, 65, 127, 255, 256, 257, 1023):
+            p = random_particles(rng, g, np_, vth=0.3)
+            p_o, p_g = p.copy(), p.copy()
+            a_o, a_g = a.copy(), a.copy()
+            orc.orc_advance_p(ptr(p_o), np_, 1.0, ptr(pm), 8, ptr(a_o), ptr(fi), g.ref())
+            vpb.advance_p(ptr(p_g), np_, 1.0, ptr(pm), 8, ptr(a_g), ptr(fi), g.ref())
+            assert_bits_equal(p_g, p_o, "np=%d" % np_)
+            assert max_rel(acc_floats(a_g), acc_floats(a_o)) < ACC_TOL
+
+
+def test_particle_planes_other_kernels(vpb, orc):
+    """center_p, uncenter_p, energy_p and accumulate_rho_p through the plane accessors."""
+    g = host_grid((6, 5, 4), "metal")
+    rng = np.random.default_rng(34)
+    p = random_particles(rng, g, 3333, vth=0.4)
+    fi = random_interpolator(rng, g, amp=0.3)
+    f = random_fields(rng, g)
+    with particle_planes(vpb):
+        for which in ("center_p", "uncenter_p"):
+            p_o, p_g = p.copy(), p.copy()
+            getattr(orc, "orc_" + which)(ptr(p_o), len(p), 0.7, ptr(fi), g.ref())
+            getattr(vpb, which)(ptr(p_g), len(p), 0.7, ptr(fi), g.ref())
+            assert_bits_equal(p_g, p_o, which)
+        e_o = orc.orc_energy_p(ptr(p), len(p), -1.0, ptr(fi), g.ref())
+        assert vpb.energy_p(ptr(p), len(p), -1.0, ptr(fi), g.ref()) == pytest.approx(e_o, rel=1e-12)
+        f_o, f_g = f.copy(), f.copy()
+        orc.orc_accumulate_rho_p(ptr(f_o), ptr(p), len(p), g.ref())
+        vpb.accumulate_rho_p(ptr(f_g), ptr(p), len(p), g.ref())
+        assert max_rel(f_g["rhof"], f_o["rhof"]) < ACC_TOL
+
+
+@pytest.mark.parametrize("n,np_", [((6, 5, 4), 3000), ((16, 16, 16), 150000), ((3, 3, 3), 5001)])
+def test_sort_p_planes(vpb, orc, n, np_):
+    """Layer B: the stable counting sort on component planes, bit-exact against the reference's out-of-place sort."""
+    from old_vpic_b200.sim import DevArray, ParticleArray
+    g = host_grid(n)
+    rng = np.random.default_rng(35)
+    p = random_particles(rng, g, np_, sort=False)
+    p_o = abi.aligned_zeros(np_, abi.particle_dtype)
+    part_o = np.zeros(g.nv + 1, np.int32)
+    orc.orc_sort_p(ptr(p.copy()), ptr(p_o), np_, ptr(part_o), g.ref())
+    dom = vpb.vpb_domain_create(g.ref(), 0, 1)
+    vpb.vpb_domain_set_particle_layout(dom, (np_ + 63) // 64 * 64)
+    d_in, d_out = ParticleArray(vpb, dom, np_), ParticleArray(vpb, dom, np_)
+    d_part = DevArray(vpb, g.nv + 1, np.int32)
+    d_in.upload(p)
+    assert_bits_equal(d_in.download(np_), p, "plane round trip")
+    vpb.vpb_sort_p(dom, d_in.ptr, d_out.ptr, np_, d_part.ptr)
+    assert np.array_equal(d_part.download(), part_o)
+    assert_bits_equal(d_out.download(np_), p_o, "sorted particles (tags included)")
+    # the in-place variant the device-resident driver uses (records staged in the scratch array)
+    vpb.vpb_memset(d_part.ptr, 0xff, 4 * (g.nv + 1))
+    vpb.vpb_sort_p_planes(dom, d_in.ptr, d_out.ptr, np_, d_part.ptr)
+    assert np.array_equal(d_part.download(), part_o)
+    assert_bits_equal(d_in.download(np_), p_o, "sorted in place")
+    for arr in (d_in, d_out, d_part):
+        arr.free()
+    vpb.vpb_domain_destroy(dom)
