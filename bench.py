@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--field-cells", type=int, default=1024, help="cells per axis of the field-only leg (configs[1]); 0 = skip")
     ap.add_argument("--workload", default="thermal", choices=["thermal", "fields"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sort-interval", type=int, default=SORT_INTERVAL, help="species sort_interval (the reference recipe: 20)")
     return ap.parse_args()
 
 
@@ -167,7 +168,7 @@ def run_reference(args):
 
 def workload_config(args):
     return {"workload": "BASELINE configs[3]: thermal e-/p+ plasma weak scaling, %d^3 cells and %d ppc per species per GPU, "
-                        "periodic, dt=0.95 Courant, vth=%.1fc, sort every %d steps" % (args.cells, args.ppc, VTH, SORT_INTERVAL),
+                        "periodic, dt=0.95 Courant, vth=%.1fc, sort every %d steps" % (args.cells, args.ppc, VTH, args.sort_interval),
             "cells_per_gpu": [args.cells] * 3, "ppc_per_species": args.ppc, "species": 2,
             "l2_policy": "inputs (>=100 GB of particles per GPU) are far larger than the 126 MB L2; no flush needed",
             "decomposition": "1 rank per GPU"}
@@ -222,7 +223,7 @@ def run_b200(args):
     # macro-charge q = +-(cell volume)/ppc so that the plasma frequency is 1 (the reference's thermal recipe,
     # q = +-L^3/Ne); dt*wpe = 0.55
     for name, q_m, q, seed in (("electron", -1.0, -1.0 / args.ppc, 7 + rank), ("ion", 1.0, 1.0 / args.ppc, 1007 + rank)):
-        sp = sim.define_species(name, q_m, max_np, sort_interval=SORT_INTERVAL)
+        sp = sim.define_species(name, q_m, max_np, sort_interval=args.sort_interval)
         sim.load_thermal(sp, args.ppc, VTH, q, seed, tag0=rank * (1 << 40))
     L.vpb_sync()
 
@@ -273,6 +274,7 @@ def run_b200(args):
             dist.destroy_process_group()
         return
     total_particles = 2 * np_ * world
+    planes = L.vpb_get_tuning(b"sim.aos_particles") == 0
     value = total_particles * args.steps / (ms_max * 1e-3)
     peak, peak_src = measured_peak()
     adv_ms, adv_n = prof["advance_p"]
@@ -288,13 +290,17 @@ def run_b200(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None,
                      # DRAM bytes of ONE launch from the ncu --set full capture of this workload (10 steps after a sort)
-                     "traffic": 123.35e9 if (args.cells == 256 and args.ppc == 64) else None,
-                     "traffic_source": "profiles/r1k_256_step10_advance_p_stream_c2.txt (dram__bytes_read.sum + dram__bytes_write.sum)",
-                     "kernel": "advance_p_stream_kernel",
+                     "traffic": (TRAFFIC_PLANES if planes else TRAFFIC_AOS) if (args.cells == 256 and args.ppc == 64) else None,
+                     "traffic_source": ("profiles/r1p_256_step10_advance_p_pair_c4_pipe.txt" if planes else
+                                        "profiles/r1k_256_step10_advance_p_stream_c2.txt") + " (dram__bytes_read.sum + dram__bytes_write.sum)",
+                     "kernel": "advance_p_pair_kernel" if planes else "advance_p_stream_kernel",
                      "algorithmic_bytes_per_particle": bytes_alg, "particles_per_launch": per_launch_particles,
                      "avg_launch_ms": adv_ms / max(adv_n, 1), "peak_source": peak_src,
-                     "layout_imposed_bytes_per_particle": 96.0 + 176.0 / args.ppc,
-                     "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None},
+                     # what the device layout makes DRAM move at least: component planes read 8 words and write 6 per
+                     # particle; the reference's 48-byte records move whole (every 32-byte sector holds hot bytes)
+                     "layout_imposed_bytes_per_particle": (56.0 if planes else 96.0) + 176.0 / args.ppc,
+                     "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None,
+                     "min_launch_ms": min(adv_list) if adv_list else None, "max_launch_ms": max(adv_list) if adv_list else None},
         "breakdown_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
         "advance_p_only_particle_advances_per_s": (2 * np_ * args.steps / (adv_ms * 1e-3)) if adv_ms else None,
         "field_cell_updates_per_s": {"advance_b": (2 * cells * args.steps / (prof["advance_b"][0] * 1e-3)) if prof["advance_b"][0] else None,
@@ -407,6 +413,10 @@ def e2e_measure(L, args, abi, helpers):
             "d2h_bytes_per_step": int(sz[1] // reps),
             "sample": "advance_p() C-ABI call, pinned host arrays, %d^3 cells x %d ppc = %d particles per call" % (n, ppc, np_),
             "ms_per_call": 1e3 * sec}
+
+
+TRAFFIC_AOS = 123.35e9      # profiles/r1k (48-byte records, advance_p_stream_kernel)
+TRAFFIC_PLANES = 80.96e9    # profiles/r1p (component planes, advance_p_pair_kernel)
 
 
 def main():

@@ -202,7 +202,15 @@ long vpb_launch_count(int reset) {
 }
 
 void vpb_set_tuning(const char *name, int value) { g_tuning[name] = value; }
-int vpb_get_tuning(const char *name) { return tuning(name, 0); }
+// read-only: a knob that was never set or looked up reports 0 and is NOT pinned to 0 by asking
+int vpb_get_tuning(const char *name) {
+  auto it = g_tuning.find(name);
+  if (it != g_tuning.end()) return it->second;
+  std::string env = std::string("VPB_") + name;
+  for (auto &ch : env) ch = (ch == '.') ? '_' : (char)toupper(ch);
+  const char *e = getenv(env.c_str());
+  return e ? atoi(e) : 0;
+}
 
 // ---------------------------------------------------------------------------
 // Domain: device mirror of grid_t

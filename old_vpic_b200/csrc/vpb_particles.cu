@@ -188,6 +188,30 @@ __global__ void __launch_bounds__(256) sort_gather_planes_kernel(const float *__
   }
 }
 
+// planes -> 48-byte records, both sides coalesced: a warp takes 32 consecutive particles, every lane reads its
+// particle's nine plane words, the 96 quads are transposed through shared memory (48-byte lane stride: conflict
+// free) and leave as three fully coalesced 512-byte stores.
+__global__ void __launch_bounds__(256) planes_to_records_kernel(const PView in, float4 *__restrict__ rec, int np) {
+  __shared__ float4 tile[8][96];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nblk = (np + 31) >> 5;
+  for (int blk = blockIdx.x * 8 + w; blk < nblk; blk += gridDim.x * 8) {
+    const int k = blk * 32 + lane;
+    if (k < np) {
+      tile[w][3 * lane] = in.pos(k);
+      tile[w][3 * lane + 1] = in.mom(k);
+      tile[w][3 * lane + 2] = in.tag(k);
+    }
+    __syncwarp();
+    const int nq = 3 * (np - blk * 32 < 32 ? np - blk * 32 : 32);
+    float4 *o = rec + 96 * (size_t)blk;
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+      if (lane + 32 * j < nq) __stcs(o + lane + 32 * j, tile[w][lane + 32 * j]);
+    __syncwarp();
+  }
+}
+
 // The permutation moves whole 48-byte records (three 16-byte requests per particle, as for the reference layout):
 // the planes are first copied to records in the scratch array (both sides coalesced), then records are gathered
 // through the permutation and written straight back as planes.
@@ -298,7 +322,7 @@ void vpb_sort_p(vpb_domain_t *dom, const vpb_particle_t *d_in, vpb_particle_t *d
   sort_claim_kernel<<<grid_for(np, 256), 256, 0, c.stream>>>(PView(d_in, dom->d.p_plane), np, cursor, perm);
   sort_rank_kernel<0><<<grid_for((long)nv * 32, 256), 256, 0, c.stream>>>(d_partition, nv, perm, perm2);
   if (g_sort_in_place) {   // vpb_sort_p_planes: d_out is scratch, the sorted planes return to d_in
-    particle_convert_kernel<<<grid_for(np, 256), 256, 0, c.stream>>>(PView(d_out, 0), PView(d_in, dom->d.p_plane), np);
+    planes_to_records_kernel<<<grid_for(np, 256), 256, 0, c.stream>>>(PView(d_in, dom->d.p_plane), reinterpret_cast<float4 *>(d_out), np);
     sort_gather_records_to_planes_kernel<<<grid_for(np, 256), 256, 0, c.stream>>>(reinterpret_cast<const float4 *>(d_out),
                                                                                   PView(d_in, dom->d.p_plane), np, perm2);
     count_launch();
