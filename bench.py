@@ -306,6 +306,7 @@ def run_b200(args):
         "field_cell_updates_per_s": {"advance_b": (2 * cells * args.steps / (prof["advance_b"][0] * 1e-3)) if prof["advance_b"][0] else None,
                                      "advance_e": (cells * args.steps / (prof["advance_e"][0] * 1e-3)) if prof["advance_e"][0] else None},
         "host_wall_ms_per_step": 1e3 * wall / args.steps,
+        "l2_fetch_granularity_bytes": int(L.vpb_l2_fetch_granularity()),
         "advance_p_ms_by_launch": adv_list,
         "tuning": {k: L.vpb_get_tuning(k.encode()) for k in ("advance_p.deposit", "advance_p.tma", "advance_p.stream_store", "advance_p.stream_cps", "sim.aos_fields", "sim.narrow_interpolator", "sim.aos_particles", "advance_p.pair_cps", "advance_p.pair_pipe", "advance_p.pair_merge",
                                                              "advance_p.tma_ctas_per_sm", "advance_p.ctas_per_sm")},

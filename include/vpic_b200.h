@@ -102,6 +102,7 @@ typedef struct vpb_domain vpb_domain_t;
 int vpb_init(int device_ordinal);
 void vpb_shutdown(void);
 int vpb_device_sm_count(void);
+int vpb_l2_fetch_granularity(void);         /* cudaLimitMaxL2FetchGranularity in effect (tuning l2.fetch_granularity) */
 
 void *vpb_dev_alloc(size_t bytes);           /* cudaMalloc, zero-filled */
 void vpb_dev_free(void *d);

@@ -98,6 +98,9 @@ extern "C" void vpb_prof_collect(int cls, double *total_ms, int *count, int rese
 
 extern "C" {
 
+static int g_l2_fetch = 0;
+extern "C" int vpb_l2_fetch_granularity(void) { return g_l2_fetch; }
+
 int vpb_init(int device_ordinal) {
   if (g_ready) {
     if (device_ordinal >= 0 && device_ordinal != g_ctx.device)
@@ -127,6 +130,17 @@ int vpb_init(int device_ordinal) {
   }
   VPB_CUDA(cudaMallocHost(&g_ctx.h_pinned_i, 64 * sizeof(int)));
   VPB_CUDA(cudaMallocHost(&g_ctx.h_pinned_d, 64 * sizeof(double)));
+  // L2 fetch granularity (bytes fetched from DRAM per missing sector: 32, 64 or 128).  The gathers of this library
+  // (interpolator records, accumulator REDs, the sort's record gather) use a fraction of a 128-byte line per miss.
+  {
+    const int gran = tuning("l2.fetch_granularity", 0);
+    if (gran == 32 || gran == 64 || gran == 128) {
+      VPB_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran));
+    }
+    size_t got = 0;
+    if (cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity) == cudaSuccess) g_l2_fetch = (int)got;
+    cudaGetLastError();
+  }
   // keep freed stream-ordered blocks in the pool instead of returning them to the OS
   cudaMemPool_t pool;
   VPB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device_ordinal));

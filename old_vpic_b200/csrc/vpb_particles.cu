@@ -116,22 +116,24 @@ __global__ void __launch_bounds__(256) sort_hist_kernel(const PView p, int np, i
     atomicAdd(count + p.voxel(k), 1);
 }
 
-// Slot claim, warp-aggregated: the lanes of a warp that hold the same voxel (most of them, the array being nearly
+// Slot claim, warp-aggregated: the lanes of a warp that hold the same voxel (most of them while the array is nearly
 // sorted) send ONE atomic for the group and take consecutive slots in lane order.
 __global__ void __launch_bounds__(256) sort_claim_kernel(const PView p, int np, int *__restrict__ cursor,
                                                          int *__restrict__ perm) {
+  const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
   const int stride = gridDim.x * blockDim.x;
   for (int k0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); k0 < np; k0 += stride) {   // warp-uniform trip count
     const int k = k0 + lane;
     const bool valid = k < np;
     const int v = valid ? p.voxel(k) : -1 - lane;
-    const unsigned peers = __match_any_sync(0xffffffffu, v);
+    const unsigned peers = __match_any_sync(full, v);
     const int leader = __ffs(peers) - 1;
     int base = 0;
     if (valid && lane == leader) base = atomicAdd(cursor + v, __popc(peers));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (valid) perm[base + __popc(peers & ((1u << lane) - 1u))] = k;
+    base = __shfl_sync(full, base, leader);
+    if (valid) perm[base + __popc(peers & lt)] = k;
   }
 }
 
@@ -215,14 +217,22 @@ __global__ void __launch_bounds__(256) planes_to_records_kernel(const PView in, 
 // The permutation moves whole 48-byte records (three 16-byte requests per particle, as for the reference layout):
 // the planes are first copied to records in the scratch array (both sides coalesced), then records are gathered
 // through the permutation and written straight back as planes.
+// Records gathered through the permutation and written back as planes.  Array order: a particle's source lies within
+// a few x-rows (y) or planes (z) of its destination, and the planes z+-1 are 400 MB of records away, so each source
+// line comes from DRAM about three times (170 GB read per 2^30 particles 20 steps after a sort).  Visiting the
+// output in y-blocked / z-inner order was measured: DRAM reads fall to 130 GB but the kernel gets slower (46-62 ms
+// against 38) because the rows in flight no longer cover the chip (profiles/README.md).
 __global__ void __launch_bounds__(256) sort_gather_records_to_planes_kernel(const float4 *__restrict__ rec, const PView out, int np,
                                                                             const int *__restrict__ perm) {
+  const size_t pl = (size_t)out.plane;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x) {
-    const float4 *r = rec + 3 * (size_t)perm[k];
+    const float4 *r = rec + 3 * (size_t)__ldcs(perm + k);
     const float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2);
-    out.set_pos(k, a);
-    out.set_mom(k, b);
-    out.set_tag(k, c);
+    // streaming stores: the output should not push source lines out of L2
+    float *o = out.b + k;
+    __stcs(o, a.x); __stcs(o + pl, a.y); __stcs(o + 2 * pl, a.z); __stcs(o + 3 * pl, a.w);
+    __stcs(o + 4 * pl, b.x); __stcs(o + 5 * pl, b.y); __stcs(o + 6 * pl, b.z); __stcs(o + 7 * pl, b.w);
+    __stcs(reinterpret_cast<float4 *>(out.b + 8 * pl) + k, c);
   }
 }
 

@@ -41,6 +41,7 @@ SIGNATURES = {
     "vpb_init": (_i, [_i]),
     "vpb_shutdown": (None, []),
     "vpb_device_sm_count": (_i, []),
+    "vpb_l2_fetch_granularity": (_i, []),
     "vpb_dev_alloc": (_vp, [_sz]),
     "vpb_dev_free": (None, [_vp]),
     "vpb_malloc_managed": (_vp, [_sz]),
