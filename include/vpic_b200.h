@@ -75,6 +75,16 @@ void clear_accumulators(vpb_accumulator_t *a, const vpb_grid_t *g);
 void reduce_accumulators(vpb_accumulator_t *a, const vpb_grid_t *g);
 void unload_accumulator(vpb_field_t *f, const vpb_accumulator_t *a, const vpb_grid_t *g);
 
+/* src/sf_interface/sf_interface.h:83-91,140-163 and src/species_advance/standard/spa.h:114-123 (hydro_p.c:24-161,
+ * sf_interface/hydro.c:30-184): the 14 hydro moments of a species on the mesh nodes (diagnostic dumps). */
+vpb_hydro_t *new_hydro(vpb_grid_t *g);
+void delete_hydro(vpb_hydro_t *h);
+void clear_hydro(vpb_hydro_t *h, const vpb_grid_t *g);
+void accumulate_hydro_p(vpb_hydro_t *h0, const vpb_particle_t *p0, int n, float q_m, const vpb_interpolator_t *f0,
+                        const vpb_grid_t *g);
+void synchronize_hydro(vpb_hydro_t *h, const vpb_grid_t *g);
+void local_adjust_hydro(vpb_hydro_t *h, const vpb_grid_t *g);
+
 /* src/field_advance/field_advance.h:318-345: the vtables decks name through the
  * standard_field_advance / vacuum_field_advance macros. */
 extern vpb_field_advance_methods_t _standard_field_advance[1];
@@ -244,6 +254,14 @@ void vpb_sort_p(vpb_domain_t *dom, const vpb_particle_t *d_in, vpb_particle_t *d
  * d_tmp (same capacity) is scratch.  The permutation is applied to whole 48-byte records staged in d_tmp, which is
  * several times faster than moving the 4-byte plane words through it one by one. */
 void vpb_sort_p_planes(vpb_domain_t *dom, vpb_particle_t *d_p, vpb_particle_t *d_tmp, int np, int *d_partition);
+
+/* Hydro moments on device arrays (vpb_hydro_t[nvoxel], the reference layout; the particle array in the domain's
+ * particle layout, the interpolator in the domain's interpolator layout). */
+void vpb_clear_hydro(vpb_domain_t *dom, vpb_hydro_t *d_h);
+void vpb_accumulate_hydro_p(vpb_domain_t *dom, vpb_hydro_t *d_h, const vpb_particle_t *d_p, int np, float q_m,
+                            const vpb_interpolator_t *d_f);
+void vpb_local_adjust_hydro(vpb_domain_t *dom, vpb_hydro_t *d_h);
+void vpb_synchronize_hydro(vpb_domain_t *dom, vpb_hydro_t *d_h);
 
 void vpb_load_interpolator(vpb_domain_t *dom, vpb_interpolator_t *d_fi, const vpb_field_t *d_f);
 void vpb_clear_accumulators(vpb_domain_t *dom, vpb_accumulator_t *d_a);

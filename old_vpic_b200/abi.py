@@ -21,6 +21,10 @@ injector_dtype = np.dtype(
 interpolator_dtype = np.dtype(
     [(n, "f4") for n in ("ex", "dexdy", "dexdz", "d2exdydz", "ey", "deydz", "deydx", "d2eydzdx", "ez", "dezdx", "dezdy",
                          "d2ezdxdy", "cbx", "dcbxdx", "cby", "dcbydy", "cbz", "dcbzdz")] + [("_pad", "f4", (2,))], align=True)
+# sf_interface.h:28-38
+hydro_dtype = np.dtype([(n, "f4") for n in ("jx", "jy", "jz", "rho", "px", "py", "pz", "ke", "txx", "tyy", "tzz", "tyz", "tzx", "txy")] +
+                       [("_pad", "f4", (2,))], align=True)
+assert hydro_dtype.itemsize == 64
 # sf_interface.h:68-77
 accumulator_dtype = np.dtype([("jx", "f4", (4,)), ("jy", "f4", (4,)), ("jz", "f4", (4,))], align=True)
 # src/field_advance/field_advance.h:159-171

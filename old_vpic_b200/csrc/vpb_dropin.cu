@@ -512,6 +512,62 @@ vpb_accumulator_t *new_accumulators(vpb_grid_t *g) {
 }
 void delete_accumulators(vpb_accumulator_t *a) { util_free_aligned(&a); }
 
+// src/sf_interface/sf_structors.c: hydro_t[nv], zero-filled
+vpb_hydro_t *new_hydro(vpb_grid_t *g) {
+  if (!g) VPB_ERROR("Bad grid.");
+  if (g->nx < 1 || g->ny < 1 || g->nz < 1) VPB_ERROR("Bad resolution.");
+  return (vpb_hydro_t *)vpb_malloc_managed(nvox(g) * sizeof(vpb_hydro_t));
+}
+void delete_hydro(vpb_hydro_t *h) { util_free_aligned(&h); }
+
+void clear_hydro(vpb_hydro_t *h, const vpb_grid_t *g) {
+  if (!h) VPB_ERROR("Bad hydro");
+  if (!g) VPB_ERROR("Bad grid");
+  vpb_domain_t *dom = domain_of(g);
+  Residency r;
+  vpb_hydro_t *dh = (vpb_hydro_t *)r.get(h, nvox(g) * sizeof(*h), WR);
+  vpb_clear_hydro(dom, dh);
+  r.finish();
+}
+
+// hydro_p.c:24-161
+void accumulate_hydro_p(vpb_hydro_t *h0, const vpb_particle_t *p0, int n, float q_m, const vpb_interpolator_t *f0,
+                        const vpb_grid_t *g) {
+  if (!h0) VPB_ERROR("Bad hydro");
+  if (!p0) VPB_ERROR("Bad particle array");
+  if (n < 0) VPB_ERROR("Bad number of particles");
+  if (!f0) VPB_ERROR("Bad field");
+  if (!g) VPB_ERROR("Bad grid");
+  vpb_domain_t *dom = domain_of(g);
+  Residency r;
+  vpb_hydro_t *dh = (vpb_hydro_t *)r.get(h0, nvox(g) * sizeof(*h0), RW);
+  const vpb_particle_t *dp = (const vpb_particle_t *)r.get_particles(dom, p0, n, RD);
+  const vpb_interpolator_t *df = (const vpb_interpolator_t *)r.get(f0, nvox(g) * sizeof(*f0), RD);
+  vpb_accumulate_hydro_p(dom, dh, dp, n, q_m, df);
+  r.finish();
+}
+
+// sf_interface/hydro.c:30-141, :146-184
+void synchronize_hydro(vpb_hydro_t *h, const vpb_grid_t *g) {
+  if (!h) VPB_ERROR("Bad hydro");
+  if (!g) VPB_ERROR("Bad grid");
+  vpb_domain_t *dom = domain_of(g);
+  Residency r;
+  vpb_hydro_t *dh = (vpb_hydro_t *)r.get(h, nvox(g) * sizeof(*h), RW);
+  vpb_synchronize_hydro(dom, dh);
+  r.finish();
+}
+
+void local_adjust_hydro(vpb_hydro_t *h, const vpb_grid_t *g) {
+  if (!h) VPB_ERROR("Bad hydro");
+  if (!g) VPB_ERROR("Bad grid");
+  vpb_domain_t *dom = domain_of(g);
+  Residency r;
+  vpb_hydro_t *dh = (vpb_hydro_t *)r.get(h, nvox(g) * sizeof(*h), RW);
+  vpb_local_adjust_hydro(dom, dh);
+  r.finish();
+}
+
 void load_interpolator(vpb_interpolator_t *fi, const vpb_field_t *f, const vpb_grid_t *g) {
   if (!fi) VPB_ERROR("Bad interpolator");
   if (!f) VPB_ERROR("Bad field");

@@ -27,6 +27,12 @@ SIGNATURES = {
     "accumulate_rho_p": (None, [_vp, _vp, _i, _vp]),
     "accumulate_rhob": (None, [_vp, _vp, _vp]),
     "boundary_p": (None, [_vp, _vp, _vp, _vp, _vp]),
+    "new_hydro": (_vp, [_vp]),
+    "delete_hydro": (None, [_vp]),
+    "clear_hydro": (None, [_vp, _vp]),
+    "accumulate_hydro_p": (None, [_vp, _vp, _i, _f, _vp, _vp]),
+    "synchronize_hydro": (None, [_vp, _vp]),
+    "local_adjust_hydro": (None, [_vp, _vp]),
     "new_interpolator": (_vp, [_vp]),
     "delete_interpolator": (None, [_vp]),
     "new_accumulators": (_vp, [_vp]),
@@ -103,6 +109,10 @@ SIGNATURES = {
     "vpb_boundary_p": (None, [_vp, _vp, _i, _vp, _vp]),
     "vpb_sort_p": (None, [_vp, _vp, _vp, _i, _vp]),
     "vpb_sort_p_planes": (None, [_vp, _vp, _vp, _i, _vp]),
+    "vpb_clear_hydro": (None, [_vp, _vp]),
+    "vpb_accumulate_hydro_p": (None, [_vp, _vp, _vp, _i, _f, _vp]),
+    "vpb_local_adjust_hydro": (None, [_vp, _vp]),
+    "vpb_synchronize_hydro": (None, [_vp, _vp]),
     "vpb_load_interpolator": (None, [_vp, _vp, _vp]),
     "vpb_clear_accumulators": (None, [_vp, _vp]),
     "vpb_unload_accumulator": (None, [_vp, _vp, _vp]),

@@ -178,7 +178,7 @@ class Simulation:
 
     def free(self):
         """Release every device array of this run."""
-        for arr in [self.f, self.fi, self.a, self.m, self.sort_tmp, self.scalars] + \
+        for arr in [self.f, self.fi, self.a, self.m, self.sort_tmp, self.scalars, getattr(self, "_hydro", None)] + \
                 [x for sp in self.species for x in (sp.p, sp.pm, sp.nm, sp.partition)]:
             if arr is not None:
                 arr.free()
@@ -305,6 +305,19 @@ class Simulation:
             L.vpb_comm_allsum_d(s.ptr, 1)
             out.append(float(s.download(1)[0]) * g.cvac * g.cvac / sp.q_m)
         return out
+
+    def hydro(self, sp, synchronize=True):
+        """The 14 hydro moments of one species on the mesh nodes, as the dump path computes them
+        (dump.cxx: clear_hydro, accumulate_hydro_p, synchronize_hydro): hydro_t[nv] on the host."""
+        L, dom = self.L, self.dom
+        if getattr(self, "_hydro", None) is None:
+            self._hydro = DevArray(L, self.nv, abi.hydro_dtype)
+        h = self._hydro
+        L.vpb_clear_hydro(dom, h.ptr)
+        L.vpb_accumulate_hydro_p(dom, h.ptr, sp.p.ptr, sp.np, sp.q_m, self.fi.ptr)
+        if synchronize:
+            L.vpb_synchronize_hydro(dom, h.ptr)
+        return h.download()
 
     def mover_counts(self):
         return [int(sp.nm.download(1)[0]) for sp in self.species]

@@ -41,6 +41,10 @@ def oracle():
     _sig(L, "orc_energy_p", _d, [_vp, _i, _f, _vp, _vp])
     _sig(L, "orc_accumulate_rho_p", None, [_vp, _vp, _i, _vp])
     _sig(L, "orc_accumulate_rhob", None, [_vp, _vp, _vp])
+    _sig(L, "orc_clear_hydro", None, [_vp, _vp])
+    _sig(L, "orc_accumulate_hydro_p", None, [_vp, _vp, _i, _f, _vp, _vp])
+    _sig(L, "orc_local_adjust_hydro", None, [_vp, _vp, _i])
+    _sig(L, "orc_synchronize_hydro", None, [_vp, _vp, _i, _i])
     _sig(L, "orc_sort_p", None, [_vp, _vp, _i, _vp, _vp])
     _sig(L, "orc_boundary_p_pack", _i, [_vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp])
     _sig(L, "orc_boundary_p_inject", _i, [_vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp])
@@ -121,6 +125,11 @@ def ref(flavour="scalar", tpp=1):
     _sig(L, "energy_p", _d, [_vp, _i, _f, _vp, _vp])
     _sig(L, "accumulate_rho_p", None, [_vp, _vp, _i, _vp])
     _sig(L, "accumulate_rhob", None, [_vp, _vp, _vp])
+    _sig(L, "accumulate_hydro_p", None, [_vp, _vp, _i, _f, _vp, _vp])
+    _sig(L, "synchronize_hydro", None, [_vp, _vp])
+    _sig(L, "local_adjust_hydro", None, [_vp, _vp])
+    _sig(L, "new_hydro", _vp, [_vp])
+    _sig(L, "clear_hydro", None, [_vp, _vp])
     _sig(L, "sort_p", None, [_vp, _vp])
     _sig(L, "boundary_p", None, [_vp, _vp, _vp, _vp, _vp])
     _sig(L, "new_species", _vp, [C.c_char_p, _f, _i, _i, _i, _i, _vp])

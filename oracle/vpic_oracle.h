@@ -32,6 +32,12 @@ void orc_uncenter_p(vpb_particle_t *p0, int np, float q_m, const vpb_interpolato
 double orc_energy_p(const vpb_particle_t *p0, int np, float q_m, const vpb_interpolator_t *f0, const vpb_grid_t *g);
 /* rho_p.c:23-79 */
 void orc_accumulate_rho_p(vpb_field_t *f, const vpb_particle_t *p0, int np, const vpb_grid_t *g);
+/* oracle_hydro.c: hydro_p.c:24-161, sf_interface/hydro.c:30-184 */
+void orc_clear_hydro(vpb_hydro_t *h, const vpb_grid_t *g);
+void orc_accumulate_hydro_p(vpb_hydro_t *h0, const vpb_particle_t *p0, int n, float q_m, const vpb_interpolator_t *f0,
+                            const vpb_grid_t *g);
+void orc_local_adjust_hydro(vpb_hydro_t *h, const vpb_grid_t *g, int nproc);
+void orc_synchronize_hydro(vpb_hydro_t *h, const vpb_grid_t *g, int rank, int nproc);
 /* boundary_p.c:9-71 */
 void orc_accumulate_rhob(vpb_field_t *f, const vpb_particle_t *p, const vpb_grid_t *g);
 /* sort_p.c:16-77 (stable out-of-place counting sort); partition has nv+1 entries */

@@ -68,7 +68,7 @@ def main():
         parts = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(parts, mine)
         shares.append([t.cpu().numpy().view(abi.particle_dtype) for t in parts])
-    ref_hist = None
+    ref_hist = ref_hydro = None
     if rank == 0:
         single = make_sim(L, gn, (1, 1, 1), 0)
         for sp, per_rank in zip(single.species, shares):
@@ -77,6 +77,7 @@ def main():
             sp.p.upload(allp)
         ref_hist = run(single, STEPS)
         assert sum(sp.np for sp in single.species) == total
+        ref_hydro = single.hydro(single.species[0])
         single.free()
 
     # 2. the decomposed run
@@ -101,6 +102,27 @@ def main():
     dist.broadcast(h0, 0)
     assert torch.equal(h, h0)
     assert np.all(np.isfinite(hist)) and hist[-1, 6] != 0
+    # hydro moments of the electrons: every rank's nodes (faces shared with a neighbour included, completed by
+    # synchronize_hydro over NCCL) against the same nodes of the single-domain run
+    my_hydro = sim.hydro(sim.species[0]).view(np.float32).reshape(PER + 2, PER + 2, PER + 2, 16)
+    gshape = (gn[2] + 2, gn[1] + 2, gn[0] + 2, 16)
+    gh = torch.zeros(gshape, dtype=torch.float32, device="cuda")
+    if rank == 0:
+        gh = torch.from_numpy(ref_hydro.view(np.float32).reshape(gshape).copy()).cuda()
+    dist.broadcast(gh, 0)
+    gh = gh.cpu().numpy()
+    cx, cy, cz = G._rank_to_index(rank, *topo)
+    mine = my_hydro[1:PER + 2, 1:PER + 2, 1:PER + 2, :14]
+    theirs = gh[1 + cz * PER:PER + 2 + cz * PER, 1 + cy * PER:PER + 2 + cy * PER, 1 + cx * PER:PER + 2 + cx * PER, :14]
+    hscale = np.abs(gh[..., :14]).reshape(-1, 14).max(axis=0)
+    # One particle whose in-cell test flips on a 1-ulp difference (the two runs add currents in different orders) feels
+    # the next cell's fields for a step and ends up ~1e-4 away: the zero-mean moments of its 8 nodes then differ by
+    # a fraction of ONE particle's contribution.  A wrong exchange would be off by a whole face plane (factor ~2).
+    rel = np.abs(mine - theirs) / hscale
+    herr = float(np.max(rel))
+    assert float(np.max(rel[..., 3])) < 1e-3, float(np.max(rel[..., 3]))      # rho: large mean, tight
+    assert herr < 2e-2, herr
+    assert float(np.mean(rel > 2e-3)) < 1e-3, float(np.mean(rel > 2e-3))       # and such nodes are isolated
     if rank == 0:
         # decomposition parity: same particles, one domain vs `world` domains.  Only the order of float sums differs
         # (deposit atomics, shared-face current sums, allreduce): every energy column within 1e-4 of its own scale
@@ -110,8 +132,8 @@ def main():
         tot = hist.sum(axis=1)
         drift = abs(tot[-1] - tot[0]) / abs(tot[0])
         assert drift < 5e-3, drift
-        print("DIST_GPU_OK world=%d particles=%d decomposition_err=%.2e energy_drift=%.2e field_energy_last=%.4e" % (
-            world, total, err, drift, hist[-1, :6].sum()))
+        print("DIST_GPU_OK world=%d particles=%d decomposition_err=%.2e energy_drift=%.2e field_energy_last=%.4e hydro_err=%.2e" % (
+            world, total, err, drift, hist[-1, :6].sum(), herr))
     dist.barrier()
     L.vpb_comm_finalize()
     dist.destroy_process_group()

@@ -253,3 +253,50 @@ def test_sync_and_div_clean(orc, ref_scalar, fbc, n):
     en_r, en_o = np.zeros(6), np.zeros(6)
     M.energy_f(ptr(en_r), ptr(f_r), ptr(m), g.ref()); orc.orc_energy_f(ptr(en_o), ptr(f_o), ptr(m), g.ref())
     np.testing.assert_allclose(en_o, en_r, rtol=1e-13)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# hydro moments (hydro_p.c, sf_interface/hydro.c)
+# ---------------------------------------------------------------------------------------------------------
+def _hydro_fields(a):
+    return np.ascontiguousarray(a).view(np.float32).reshape(-1, 16)[:, :14]
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("n", SHAPES)
+def test_accumulate_hydro_p(orc, ref_scalar, kind, n):
+    """Serial in the reference (one loop over the particles): the oracle reproduces every bit, including the two
+    expressions the reference evaluates in double (hydro_p.c:86,93)."""
+    L = ref_scalar
+    g = RefGrid(L, n, kind)
+    rng = np.random.default_rng(41)
+    p = random_particles(rng, g, 5000, vth=0.8, sort=False)
+    p["q"] = rng.uniform(0.5, 1.5, len(p)).astype(np.float32)
+    fi = random_interpolator(rng, g, amp=0.4)
+    for q_m in (-1.0, 0.25):
+        h_r = abi.aligned_zeros(g.nv, abi.hydro_dtype)
+        h_o = h_r.copy()
+        L.accumulate_hydro_p(ptr(h_r), ptr(p), len(p), q_m, ptr(fi), g.ref())
+        orc.orc_accumulate_hydro_p(ptr(h_o), ptr(p), len(p), q_m, ptr(fi), g.ref())
+        assert np.any(_hydro_fields(h_r) != 0)
+        assert_bits_equal(h_o, h_r, "hydro moments q_m=%g" % q_m)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("n", SHAPES)
+def test_synchronize_hydro(orc, ref_scalar, kind, n):
+    L = ref_scalar
+    g = RefGrid(L, n, kind)
+    rng = np.random.default_rng(42)
+    h = abi.aligned_zeros(g.nv, abi.hydro_dtype)
+    h.view(np.float32)[:] = rng.standard_normal(h.view(np.float32).shape).astype(np.float32)
+    h_r, h_o = h.copy(), h.copy()
+    L.local_adjust_hydro(ptr(h_r), g.ref())
+    orc.orc_local_adjust_hydro(ptr(h_o), g.ref(), 1)
+    assert_bits_equal(h_o, h_r, "local_adjust_hydro")
+    h_r, h_o = h.copy(), h.copy()
+    L.synchronize_hydro(ptr(h_r), g.ref())
+    orc.orc_synchronize_hydro(ptr(h_o), g.ref(), 0, 1)
+    assert_bits_equal(h_o, h_r, "synchronize_hydro")
+    if kind == "periodic":
+        assert np.any(_hydro_fields(h_o) != _hydro_fields(h))
