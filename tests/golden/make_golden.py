@@ -95,5 +95,28 @@ def main():
         print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def make_hydro():
+    """ref_hydro_<kind>.npz: hydro moments of the advance_p fixture's particles (hydro_p.c, sf_interface/hydro.c),
+    written separately so that the older fixtures stay byte-identical."""
+    L = loader.ref("scalar", tpp=1)
+    for kind, n in CASES:
+        z = np.load(os.path.join(HERE, "ref_%s.npz" % kind))
+        g = RefGrid(L, n, kind, damp=0.01)
+        p, fi = abi.aligned_empty(len(z["adv_p_in"]), abi.particle_dtype), abi.aligned_empty(g.nv, abi.interpolator_dtype)
+        p[:], fi[:] = z["adv_p_in"], z["adv_fi"]
+        out = {}
+        for tag, q_m in (("e", -1.0), ("i", 0.25)):
+            h = abi.aligned_zeros(g.nv, abi.hydro_dtype)
+            L.accumulate_hydro_p(ptr(h), ptr(p), len(p), q_m, ptr(fi), g.ref())
+            out["hydro_%s_accumulated" % tag] = h.copy()
+            L.synchronize_hydro(ptr(h), g.ref())
+            out["hydro_%s_synchronized" % tag] = h.copy()
+        path = os.path.join(HERE, "ref_hydro_%s.npz" % kind)
+        np.savez_compressed(path, **out)
+        print("wrote", path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
-    main()
+    if "--hydro-only" not in sys.argv:
+        main()
+    make_hydro()

@@ -132,3 +132,40 @@ def test_cuda_reproduces_reference(vpb, kind):
     np.testing.assert_allclose(en, z["energy_f"], rtol=1e-12)
     assert M.compute_rms_div_e_err(ptr(f), g.ref()) == pytest.approx(float(z["rms_div_e"]), rel=1e-12)
     assert M.compute_rms_div_b_err(ptr(f), g.ref()) == pytest.approx(float(z["rms_div_b"]), rel=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# hydro moments (tests/golden/ref_hydro_*.npz, make_golden.py::make_hydro)
+# ---------------------------------------------------------------------------------------------------------
+HYDRO_QM = (("e", -1.0), ("i", 0.25))
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_oracle_reproduces_reference_hydro(orc, kind):
+    z, g = load(kind)
+    zh = np.load(os.path.join(GOLDEN, "ref_hydro_%s.npz" % kind))
+    p, fi = al(z["adv_p_in"]), al(z["adv_fi"])
+    for tag, q_m in HYDRO_QM:
+        h = abi.aligned_zeros(g.nv, abi.hydro_dtype)
+        orc.orc_accumulate_hydro_p(ptr(h), ptr(p), len(p), q_m, ptr(fi), g.ref())
+        assert_bits_equal(h, zh["hydro_%s_accumulated" % tag], "accumulate_hydro_p " + tag)
+        orc.orc_synchronize_hydro(ptr(h), g.ref(), 0, 1)
+        assert_bits_equal(h, zh["hydro_%s_synchronized" % tag], "synchronize_hydro " + tag)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", KINDS)
+def test_cuda_reproduces_reference_hydro(vpb, kind):
+    z, g = load(kind)
+    zh = np.load(os.path.join(GOLDEN, "ref_hydro_%s.npz" % kind))
+    p, fi = al(z["adv_p_in"]), al(z["adv_fi"])
+    for tag, q_m in HYDRO_QM:
+        want = zh["hydro_%s_accumulated" % tag]
+        h = abi.aligned_zeros(g.nv, abi.hydro_dtype)
+        vpb.accumulate_hydro_p(ptr(h), ptr(p), len(p), q_m, ptr(fi), g.ref())
+        for n in want.dtype.names:
+            if n != "_pad":
+                assert max_rel(h[n], want[n]) < 2e-5, n
+        h = al(want)      # continue from the reference's sums: the face operations are bit-exact
+        vpb.synchronize_hydro(ptr(h), g.ref())
+        assert_bits_equal(h, zh["hydro_%s_synchronized" % tag], "synchronize_hydro " + tag)
