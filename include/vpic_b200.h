@@ -92,6 +92,10 @@ extern vpb_field_advance_methods_t _vacuum_field_advance[1];
 extern vpb_field_advance_methods_t _standard_v4_field_advance[1];
 extern vpb_field_advance_methods_t _vacuum_v4_field_advance[1];
 
+/* src/field_advance/field_advance.h:304-316 (field_advance.c:3-28) */
+vpb_field_advance_t *new_field_advance(vpb_grid_t *g, vpb_material_t *m_list, vpb_field_advance_methods_t *fam);
+void delete_field_advance(vpb_field_advance_t *fa);
+
 /* src/util/util_base.h:261-280 (util.c:46-91): the reference's single allocation
  * choke-point.  Substituting it puts every large array in CUDA managed memory,
  * so kernels run on deck-visible pointers in place. */

@@ -512,6 +512,25 @@ vpb_accumulator_t *new_accumulators(vpb_grid_t *g) {
 }
 void delete_accumulators(vpb_accumulator_t *a) { util_free_aligned(&a); }
 
+// src/field_advance/field_advance.c:3-28: bind a grid, a material list and a method table
+vpb_field_advance_t *new_field_advance(vpb_grid_t *g, vpb_material_t *m_list, vpb_field_advance_methods_t *fam) {
+  if (!g || !m_list || !fam) VPB_ERROR("Bad args");
+  vpb_field_advance_t *fa = (vpb_field_advance_t *)calloc(1, sizeof(*fa));
+  if (!fa) VPB_ERROR("Could not allocate field_advance_t");
+  fa->method[0] = fam[0];
+  fa->f = fa->method->new_field(g);
+  fa->m = fa->method->new_material_coefficients(g, m_list);
+  fa->g = g;
+  return fa;
+}
+
+void delete_field_advance(vpb_field_advance_t *fa) {
+  if (!fa) return;   // do-nothing request
+  fa->method->delete_material_coefficients(fa->m);
+  fa->method->delete_field(fa->f);
+  free(fa);
+}
+
 // src/sf_interface/sf_structors.c: hydro_t[nv], zero-filled
 vpb_hydro_t *new_hydro(vpb_grid_t *g) {
   if (!g) VPB_ERROR("Bad grid.");

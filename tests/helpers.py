@@ -150,3 +150,35 @@ def max_rel(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+class MaterialStruct(C.Structure):
+    """material_t (src/material/material.h:42-50) with room for a short name."""
+    pass
+
+
+MaterialStruct._fields_ = [("id", C.c_uint16)] + [(n, C.c_float) for n in (
+    "epsx", "epsy", "epsz", "mux", "muy", "muz", "sigmax", "sigmay", "sigmaz", "zetax", "zetay", "zetaz")] + \
+    [("next", C.POINTER(MaterialStruct)), ("name", C.c_char * 24)]
+
+# name, eps(3), mu(3), sigma(3), zeta(3): vacuum, a lossy anisotropic dielectric, a very good conductor
+MATERIAL_TABLE = [("vacuum", (1, 1, 1), (1, 1, 1), (0, 0, 0), (0, 0, 0)),
+                  ("glass", (2.5, 3.0, 2.0), (1.0, 1.5, 1.25), (0.3, 0.0, 0.05), (0, 0, 0)),
+                  ("metal", (1, 1, 1), (1, 1, 1), (1e9, 1e9, 1e9), (0, 0, 0))]
+
+
+def material_list():
+    """A material list built the way new_material does it (newest first, ids counting up from 0).  Returns the
+    head and the list of structs (keep it alive)."""
+    keep, head = [], None
+    for k, (name, eps, mu, sig, zeta) in enumerate(MATERIAL_TABLE):
+        m = MaterialStruct()
+        m.id = k
+        (m.epsx, m.epsy, m.epsz), (m.mux, m.muy, m.muz) = eps, mu
+        (m.sigmax, m.sigmay, m.sigmaz), (m.zetax, m.zetay, m.zetaz) = sig, zeta
+        m.name = name.encode()
+        if head is not None:
+            m.next = C.pointer(head)
+        keep.append(m)
+        head = m
+    return head, keep

@@ -191,3 +191,30 @@ def test_field_only_grid_and_plane_wave_loader(vpb, orc):
     assert_bits_equal(sim.f.download(), f_o, "field-only advance")
     assert abs(sum(sim.energies()[:6]) - en0) / en0 < 2e-3
     sim.free()
+
+
+def test_new_field_advance(vpb, orc):
+    """new_field_advance / delete_field_advance (field_advance.c:3-28): the bound field array is zero-filled and the
+    material coefficients are the reference's (sfa.c:127-168), bit for bit."""
+    import ctypes as C
+    from helpers import MATERIAL_TABLE, material_list
+    g = host_grid((5, 4, 3), "periodic")
+    head, keep = material_list()
+    n = len(MATERIAL_TABLE)
+    want = abi.aligned_zeros(n, abi.material_coefficient_dtype)
+    orc.orc_material_coefficients(ptr(want), C.byref(head), g.ref())
+    for which in (0, 2):
+        fa_addr = vpb.new_field_advance(g.ref(), C.byref(head), vpb.vpb_field_advance_table(which))
+        fa = (C.c_void_p * 3).from_address(fa_addr)          # f, m, g
+        assert fa[2] == C.addressof(g.struct)
+        f = np.ctypeslib.as_array(C.cast(fa[0], C.POINTER(C.c_uint8)), shape=(g.nv * 80,))
+        assert not np.any(f)
+        m = np.ctypeslib.as_array(C.cast(fa[1], C.POINTER(C.c_uint8)), shape=(64 * n,)).view(abi.material_coefficient_dtype)
+        for k in abi.material_coefficient_dtype.names:
+            if not k.startswith("pad"):
+                assert np.array_equal(m[k].view(np.uint32), want[k].view(np.uint32)), k
+        # the bound method table is the library's: one field step through it runs
+        tab = abi.FieldAdvanceMethods.from_address(fa_addr + 24)
+        adv_b = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_float)(tab.advance_b)
+        adv_b(fa[0], g.ref(), 0.5)
+        vpb.delete_field_advance(fa_addr)

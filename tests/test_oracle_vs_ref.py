@@ -300,3 +300,25 @@ def test_synchronize_hydro(orc, ref_scalar, kind, n):
     assert_bits_equal(h_o, h_r, "synchronize_hydro")
     if kind == "periodic":
         assert np.any(_hydro_fields(h_o) != _hydro_fields(h))
+
+
+def test_material_coefficients(orc, ref_scalar):
+    """new_material_coefficients (sfa.c:127-168) through the reference's vtable, from a list made by the reference's
+    own new_material, against the oracle fed a list built in Python."""
+    from helpers import MATERIAL_TABLE, material_list
+    L = ref_scalar
+    g = RefGrid(L, (4, 3, 2), "periodic")
+    M = loader.ref_methods(L, 0)
+    head = C.c_void_p(None)
+    for name, eps, mu, sig, zeta in MATERIAL_TABLE:
+        L.new_material(name.encode(), *[float(v) for v in eps + mu + sig + zeta], C.byref(head))
+    addr = M.new_material_coefficients(g.ref(), head)
+    n = len(MATERIAL_TABLE)
+    ref_m = np.ctypeslib.as_array(C.cast(addr, C.POINTER(C.c_uint8)), shape=(64 * n,)).view(abi.material_coefficient_dtype).copy()
+    mine, keep = material_list()
+    out = abi.aligned_zeros(n, abi.material_coefficient_dtype)
+    orc.orc_material_coefficients(ptr(out), C.byref(mine), g.ref())
+    names = [k for k in abi.material_coefficient_dtype.names if not k.startswith("pad")]
+    for k in names:
+        assert np.array_equal(out[k].view(np.uint32), ref_m[k].view(np.uint32)), k
+    assert out["nonconductive"].tolist() == [1.0, 0.0, 0.0]
