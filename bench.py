@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--field-cells", type=int, default=1024, help="cells per axis of the field-only leg (configs[1]); 0 = skip")
     ap.add_argument("--workload", default="thermal", choices=["thermal", "fields"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--driver", default="native", choices=["native", "python"], help="time-step driver: csrc/vpb_step.cu or sim.py")
     ap.add_argument("--sort-interval", type=int, default=SORT_INTERVAL, help="species sort_interval (the reference recipe: 20)")
     return ap.parse_args()
 
@@ -182,7 +183,7 @@ def run_b200(args):
     import torch.distributed as dist
     from old_vpic_b200 import abi, lib
     from old_vpic_b200 import grid as helpers
-    from old_vpic_b200.sim import Simulation
+    from old_vpic_b200.sim import NativeSimulation, Simulation
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -215,7 +216,9 @@ def run_b200(args):
     n = args.cells
     topo = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
     g = helpers.make_grid((n * topo[0], n * topo[1], n * topo[2]), "periodic", topo=topo, rank=rank)
-    sim = Simulation(g, n_mat=1, L=L, planar=L.vpb_get_tuning(b"sim.aos_fields") == 0,
+    # the library's C++ time-step driver (csrc/vpb_step.cu); --driver python = the same call order issued from sim.py
+    Driver = NativeSimulation if args.driver == "native" else Simulation
+    sim = Driver(g, n_mat=1, L=L, planar=L.vpb_get_tuning(b"sim.aos_fields") == 0,
                      wide_interpolator=L.vpb_get_tuning(b"sim.narrow_interpolator") == 0,
                      particle_planes=L.vpb_get_tuning(b"sim.aos_particles") == 0)
     np_ = n ** 3 * args.ppc
@@ -305,7 +308,7 @@ def run_b200(args):
         "advance_p_only_particle_advances_per_s": (2 * np_ * args.steps / (adv_ms * 1e-3)) if adv_ms else None,
         "field_cell_updates_per_s": {"advance_b": (2 * cells * args.steps / (prof["advance_b"][0] * 1e-3)) if prof["advance_b"][0] else None,
                                      "advance_e": (cells * args.steps / (prof["advance_e"][0] * 1e-3)) if prof["advance_e"][0] else None},
-        "host_wall_ms_per_step": 1e3 * wall / args.steps,
+        "host_wall_ms_per_step": 1e3 * wall / args.steps, "driver": args.driver,
         "l2_fetch_granularity_bytes": int(L.vpb_l2_fetch_granularity()),
         "advance_p_ms_by_launch": adv_list,
         "tuning": {k: L.vpb_get_tuning(k.encode()) for k in ("advance_p.deposit", "advance_p.tma", "advance_p.stream_store", "advance_p.stream_cps", "sim.aos_fields", "sim.narrow_interpolator", "sim.aos_particles", "advance_p.pair_cps", "advance_p.pair_pipe", "advance_p.pair_merge",
@@ -328,10 +331,10 @@ def fields_measure(L, n, steps, warmup):
     Returns cell-update rates and the roofline fractions of the two stencil kernels, timed with CUDA events around
     each kernel launch (vpb_prof classes 2 and 3) over `steps` steps."""
     from old_vpic_b200 import grid as helpers
-    from old_vpic_b200.sim import Simulation
+    from old_vpic_b200.sim import NativeSimulation, Simulation
     g = helpers.make_grid((n, n, n), "periodic", field_only=True)
-    sim = Simulation(g, n_mat=1, vacuum=True, L=L, planar=L.vpb_get_tuning(b"sim.aos_fields") == 0)
-    L.vpb_load_plane_wave(sim.dom, sim.f.ptr, 8, 1.0)
+    sim = NativeSimulation(g, n_mat=1, vacuum=True, L=L, planar=L.vpb_get_tuning(b"sim.aos_fields") == 0)
+    L.vpb_load_plane_wave(sim.dom, sim.field_ptr, 8, 1.0)
     e0 = sum(sim.energies()[:6])
     for _ in range(warmup):
         sim.advance()

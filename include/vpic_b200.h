@@ -290,6 +290,39 @@ void vpb_compute_rhob(vpb_domain_t *dom, vpb_field_t *d_f, const vpb_material_co
 void vpb_compute_curl_b(vpb_domain_t *dom, vpb_field_t *d_f, const vpb_material_coefficient_t *d_m, int n_mat);
 void vpb_synchronize_tang_e_norm_b(vpb_domain_t *dom, vpb_field_t *d_f, double *d_err);
 
+/* ------------------------------------------------------------------------- */
+/* (C) Time-step driver (vpb_step.cu): the call order of vpic_simulation::advance()      */
+/* (src/vpic/advance.cxx:13-244) in host C++ over layer (B), state resident in HBM.     */
+/* ------------------------------------------------------------------------- */
+typedef struct vpb_sim vpb_sim_t;
+
+/* g is this rank's grid_t (partition_* of the reference, or old_vpic_b200/grid.py); the three layout flags select
+ * the device layouts described above (1,1,1 = what bench.py measures).  n_mat vacuum-like materials unless
+ * `vacuum` selects vfa_advance_e. */
+vpb_sim_t *vpb_sim_create(const vpb_grid_t *g, int rank, int nproc, int n_mat, int vacuum, int field_planar, int wide_interpolator,
+                          int particle_planes);
+void vpb_sim_destroy(vpb_sim_t *s);
+void vpb_sim_set_materials(vpb_sim_t *s, const vpb_material_coefficient_t *m, int n_mat);
+/* species in definition order (= species_t.id); max_nm <= 0: the reference's 2*max_np/25 (vpic.hxx:416-420) */
+int vpb_sim_define_species(vpb_sim_t *s, const char *name, float q_m, long max_np, long max_nm, int sort_interval);
+void vpb_sim_load_thermal(vpb_sim_t *s, int species, int ppc, float vth, float q, unsigned long long seed, long tag0);
+void vpb_sim_set_particles(vpb_sim_t *s, int species, const vpb_particle_t *host, long np);
+long vpb_sim_get_particles(vpb_sim_t *s, int species, vpb_particle_t *host, long max);
+void vpb_sim_set_fields(vpb_sim_t *s, const vpb_field_t *host);       /* field_t[nvoxel], reference layout */
+void vpb_sim_get_fields(vpb_sim_t *s, vpb_field_t *host);
+void vpb_sim_set_intervals(vpb_sim_t *s, int clean_div_e_interval, int clean_div_b_interval, int num_comm_round);
+void vpb_sim_advance(vpb_sim_t *s, int nsteps);                        /* enqueues nsteps time steps */
+void vpb_sim_energies(vpb_sim_t *s, double *out6_plus_nspecies);       /* dump_energies (dump.cxx:37-78), over all ranks */
+void vpb_sim_hydro(vpb_sim_t *s, int species, vpb_hydro_t *host);      /* clear + accumulate + synchronize, to the host */
+long vpb_sim_step(const vpb_sim_t *s);
+int vpb_sim_num_species(const vpb_sim_t *s);
+long vpb_sim_np(vpb_sim_t *s, int species);
+vpb_domain_t *vpb_sim_domain(vpb_sim_t *s);
+vpb_field_t *vpb_sim_field_array(vpb_sim_t *s);                        /* device arrays, in the domain's layouts */
+vpb_interpolator_t *vpb_sim_interpolator_array(vpb_sim_t *s);
+vpb_accumulator_t *vpb_sim_accumulator_array(vpb_sim_t *s);
+vpb_particle_t *vpb_sim_particle_array(vpb_sim_t *s, int species);
+
 #ifdef __cplusplus
 }
 #endif

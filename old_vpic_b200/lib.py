@@ -134,6 +134,28 @@ SIGNATURES = {
     "vpb_compute_rhob": (None, [_vp, _vp, _vp, _i]),
     "vpb_compute_curl_b": (None, [_vp, _vp, _vp, _i]),
     "vpb_synchronize_tang_e_norm_b": (None, [_vp, _vp, _vp]),
+    # (C) time-step driver
+    "vpb_sim_create": (_vp, [_vp, _i, _i, _i, _i, _i, _i, _i]),
+    "vpb_sim_destroy": (None, [_vp]),
+    "vpb_sim_set_materials": (None, [_vp, _vp, _i]),
+    "vpb_sim_define_species": (_i, [_vp, C.c_char_p, _f, _l, _l, _i]),
+    "vpb_sim_load_thermal": (None, [_vp, _i, _i, _f, _f, C.c_ulonglong, _l]),
+    "vpb_sim_set_particles": (None, [_vp, _i, _vp, _l]),
+    "vpb_sim_get_particles": (_l, [_vp, _i, _vp, _l]),
+    "vpb_sim_set_fields": (None, [_vp, _vp]),
+    "vpb_sim_get_fields": (None, [_vp, _vp]),
+    "vpb_sim_set_intervals": (None, [_vp, _i, _i, _i]),
+    "vpb_sim_advance": (None, [_vp, _i]),
+    "vpb_sim_energies": (None, [_vp, _vp]),
+    "vpb_sim_hydro": (None, [_vp, _i, _vp]),
+    "vpb_sim_step": (_l, [_vp]),
+    "vpb_sim_num_species": (_i, [_vp]),
+    "vpb_sim_np": (_l, [_vp, _i]),
+    "vpb_sim_domain": (_vp, [_vp]),
+    "vpb_sim_field_array": (_vp, [_vp]),
+    "vpb_sim_interpolator_array": (_vp, [_vp]),
+    "vpb_sim_accumulator_array": (_vp, [_vp]),
+    "vpb_sim_particle_array": (_vp, [_vp, _i]),
 }
 
 DATA_SYMBOLS = ("_standard_field_advance", "_vacuum_field_advance", "_standard_v4_field_advance",

@@ -321,3 +321,88 @@ class Simulation:
 
     def mover_counts(self):
         return [int(sp.nm.download(1)[0]) for sp in self.species]
+
+
+class NativeSimulation:
+    """The same run through the library's own C++ time-step driver (csrc/vpb_step.cu, vpb_sim_*): Python only holds
+    the handle.  Same constructor and the same handful of methods as Simulation, so callers can switch."""
+
+    class _Sp:
+        def __init__(self, owner, idx, name, q_m, max_np, max_nm, sort_interval):
+            self.owner, self.id, self.name, self.q_m = owner, idx, name, float(q_m)
+            self.max_np, self.max_nm, self.sort_interval = int(max_np), max_nm, int(sort_interval)
+
+        @property
+        def np(self):
+            return int(self.owner.L.vpb_sim_np(self.owner.h, self.id))
+
+    def __init__(self, grid, n_mat=1, vacuum=False, L=None, planar=True, wide_interpolator=True, particle_planes=True):
+        self.L = L or lib.load()
+        self.L.vpb_init(-1)
+        self.grid = grid
+        self.nv = grid.nv
+        self.h = self.L.vpb_sim_create(grid.ref(), grid.rank, grid.nproc, n_mat, int(vacuum), int(planar), int(wide_interpolator),
+                                       int(particle_planes))
+        self.species = []
+
+    def free(self):
+        if self.h:
+            self.L.vpb_sim_destroy(self.h)
+            self.h = None
+
+    def define_species(self, name, q_m, max_np, max_nm=None, sort_interval=20):
+        idx = self.L.vpb_sim_define_species(self.h, name.encode(), q_m, int(max_np), int(max_nm or 0), int(sort_interval))
+        sp = NativeSimulation._Sp(self, idx, name, q_m, max_np, max_nm, sort_interval)
+        self.species.append(sp)
+        return sp
+
+    def load_thermal(self, sp, ppc, vth, q, seed, tag0=0):
+        self.L.vpb_sim_load_thermal(self.h, sp.id, ppc, vth, q, seed, tag0)
+
+    def set_particles(self, sp, host):
+        host = np.ascontiguousarray(host, dtype=abi.particle_dtype)
+        self.L.vpb_sim_set_particles(self.h, sp.id, host.ctypes.data, len(host))
+
+    def get_particles(self, sp):
+        out = abi.aligned_empty(sp.np, abi.particle_dtype)
+        n = self.L.vpb_sim_get_particles(self.h, sp.id, out.ctypes.data, len(out))
+        return out[:n]
+
+    def set_fields(self, host):
+        host = np.ascontiguousarray(host, dtype=abi.field_dtype)
+        assert len(host) == self.nv
+        self.L.vpb_sim_set_fields(self.h, host.ctypes.data)
+
+    def get_fields(self):
+        out = abi.aligned_empty(self.nv, abi.field_dtype)
+        self.L.vpb_sim_get_fields(self.h, out.ctypes.data)
+        return out
+
+    def set_intervals(self, clean_div_e=0, clean_div_b=0, num_comm_round=3):
+        self.L.vpb_sim_set_intervals(self.h, clean_div_e, clean_div_b, num_comm_round)
+
+    def advance(self, nsteps=1):
+        self.L.vpb_sim_advance(self.h, nsteps)
+
+    @property
+    def step(self):
+        return int(self.L.vpb_sim_step(self.h))
+
+    @property
+    def dom(self):
+        return self.L.vpb_sim_domain(self.h)
+
+    @property
+    def field_ptr(self):
+        """device field array in the domain's layout (for vpb_* calls on it)"""
+        return self.L.vpb_sim_field_array(self.h)
+
+    def energies(self):
+        out = np.zeros(6 + len(self.species))
+        self.L.vpb_sim_energies(self.h, out.ctypes.data)
+        return list(out)
+
+    def hydro(self, sp):
+        out = abi.aligned_zeros(self.nv, abi.hydro_dtype)
+        self.L.vpb_sim_hydro(self.h, sp.id, out.ctypes.data)
+        return out
