@@ -29,23 +29,66 @@
 namespace vpb {
 
 constexpr int kBins = 8;          // 0..6 real bins, 7 = "none"
-constexpr int kRankThreads = 1024;
+constexpr int kRankThreads = 256;
 
-// Stable multi-bin ranking by ONE block: rank[k] = base[code] + number of earlier
-// elements (in visiting order) with the same code.  reverse!=0 visits k = n-1..0.
-// base[] (device, 7 ints) is read at entry and updated at exit, so consecutive
-// calls continue the numbering (species after species).
-__global__ void __launch_bounds__(kRankThreads) rank_bins_kernel(const unsigned char *__restrict__ code, int n, int reverse,
-                                                                 int *__restrict__ rank, int *__restrict__ base_io) {
+// Stable multi-bin ranking: rank[k] = base[code] + number of earlier elements (in visiting order) with the same
+// code.  reverse!=0 visits k = n-1..0.  base[] (device, 7 ints) is read at entry and updated at exit, so
+// consecutive calls continue the numbering (species after species).  Three small launches: every block counts the
+// bins of its segment of the visiting order, one thread per bin turns the counts into segment bases, every block
+// ranks its segment.  (One block walking a million movers took milliseconds per call at 256^3 cells per GPU.)
+constexpr int kRankSeg = 4096;     // elements per block
+
+__device__ __forceinline__ int rank_code_at(const unsigned char *__restrict__ code, int n, int reverse, int r) {
+  return r < n ? code[reverse ? n - 1 - r : r] : 7;
+}
+
+__global__ void __launch_bounds__(kRankThreads) rank_bins_count_kernel(const unsigned char *__restrict__ code, int n, int reverse,
+                                                                       int *__restrict__ tab) {
+  __shared__ int cnt[kBins];
+  const int tid = threadIdx.x;
+  if (tid < kBins) cnt[tid] = 0;
+  __syncthreads();
+  const int r0 = blockIdx.x * kRankSeg, r1 = min(n, r0 + kRankSeg);
+  int mine[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int r = r0 + tid; r < r1; r += kRankThreads) {
+    const int c = rank_code_at(code, n, reverse, r);
+#pragma unroll
+    for (int b = 0; b < 7; b++) mine[b] += (c == b);
+  }
+#pragma unroll
+  for (int b = 0; b < 7; b++) {
+    int v = mine[b];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((tid & 31) == 0 && v) atomicAdd(&cnt[b], v);
+  }
+  __syncthreads();
+  if (tid < kBins) tab[blockIdx.x * kBins + tid] = tid < 7 ? cnt[tid] : 0;
+}
+
+__global__ void rank_bins_scan_kernel(int *__restrict__ tab, int nblocks, int *__restrict__ base_io) {
+  const int b = threadIdx.x;
+  if (b >= 7) return;
+  int run = base_io[b];
+  for (int k = 0; k < nblocks; k++) {
+    const int t = tab[k * kBins + b];
+    tab[k * kBins + b] = run;
+    run += t;
+  }
+  base_io[b] = run;
+}
+
+__global__ void __launch_bounds__(kRankThreads) rank_bins_rank_kernel(const unsigned char *__restrict__ code, int n, int reverse,
+                                                                      int *__restrict__ rank, const int *__restrict__ tab) {
   __shared__ int base[kBins];
   __shared__ int wcnt[kRankThreads / 32][kBins];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  if (tid < kBins) base[tid] = tid < 7 ? base_io[tid] : 0;
+  if (tid < kBins) base[tid] = tab[blockIdx.x * kBins + tid];
   __syncthreads();
-  for (int r0 = 0; r0 < n; r0 += kRankThreads) {
+  const int seg0 = blockIdx.x * kRankSeg, seg1 = min(n, seg0 + kRankSeg);
+  for (int r0 = seg0; r0 < seg1; r0 += kRankThreads) {
     const int r = r0 + tid;
     const int k = reverse ? n - 1 - r : r;
-    const int c = r < n ? code[k] : 7;
+    const int c = r < seg1 ? rank_code_at(code, n, reverse, r) : 7;
     int mine = 0;
 #pragma unroll
     for (int b = 0; b < 7; b++) {
@@ -67,7 +110,23 @@ __global__ void __launch_bounds__(kRankThreads) rank_bins_kernel(const unsigned 
     }
     __syncthreads();
   }
-  if (tid < 7) base_io[tid] = base[tid];
+}
+
+static int *g_rank_tab = nullptr;
+static int g_rank_tab_blocks = 0;
+
+static void rank_bins(const unsigned char *code, int n, int reverse, int *rank, int *base_io, cudaStream_t st) {
+  if (n <= 0) return;
+  const int nblocks = (n + kRankSeg - 1) / kRankSeg;
+  if (nblocks > g_rank_tab_blocks) {
+    if (g_rank_tab) { VPB_CUDA(cudaStreamSynchronize(st)); cudaFree(g_rank_tab); }
+    g_rank_tab_blocks = nblocks + nblocks / 2 + 64;
+    VPB_CUDA(cudaMalloc(&g_rank_tab, (size_t)g_rank_tab_blocks * kBins * sizeof(int)));
+  }
+  rank_bins_count_kernel<<<nblocks, kRankThreads, 0, st>>>(code, n, reverse, g_rank_tab);
+  rank_bins_scan_kernel<<<1, 32, 0, st>>>(g_rank_tab, nblocks, base_io);
+  rank_bins_rank_kernel<<<nblocks, kRankThreads, 0, st>>>(code, n, reverse, rank, g_rank_tab);
+  count_launch(3);
 }
 
 // boundary_p.c:9-71 on the device: trilinear deposit of a removed particle's charge to rhob,
@@ -350,8 +409,8 @@ void vpb_boundary_p(vpb_domain_t *dom, vpb_species_state_t *sp, int n_sp, vpb_fi
       const int nm = sp[s].nm;
       if (nm) {
         classify_kernel<<<blocks(nm, 256), 256, 0, st>>>(PView(sp[s].p, g.p_plane), sp[s].pm, nm, code + off, d_f, g, fi, dc + 33);
-        rank_bins_kernel<<<1, kRankThreads, 0, st>>>(code + off, nm, 1, rank + off, dc);
-        count_launch(2);
+        rank_bins(code + off, nm, 1, rank + off, dc, st);
+        count_launch(1);
       }
       off += nm;
     }
@@ -395,9 +454,9 @@ void vpb_boundary_p(vpb_domain_t *dom, vpb_species_state_t *sp, int n_sp, vpb_fi
         VPB_CUDA(cudaMemsetAsync(dc + 32, 0, sizeof(int), st));
         VPB_CUDA(cudaMemsetAsync(dc + 40, 0, 8 * sizeof(int), st));
         mark_tail_kernel<<<blocks(nm, 256), 256, 0, st>>>(sp[s].pm, nm, np_new, tcode, dc + 32);
-        rank_bins_kernel<<<1, kRankThreads, 0, st>>>(tcode, nm, 1, trank, dc + 40);
+        rank_bins(tcode, nm, 1, trank, dc + 40, st);
         backfill_kernel<<<blocks(3L * nm, 256), 256, 0, st>>>(PView(sp[s].p, g.p_plane), sp[s].pm, nm, np_new, tcode, trank, dc + 32);
-        count_launch(3);
+        count_launch(2);
         sp[s].np = np_new;
       }
       off += nm;
@@ -442,7 +501,7 @@ void vpb_boundary_p(vpb_domain_t *dom, vpb_species_state_t *sp, int n_sp, vpb_fi
   for (int s = 0; s < n_sp; s++) { T.id[s] = sp[s].id; T.p[s] = sp[s].p; T.pm[s] = sp[s].pm; T.np[s] = sp[s].np; }
   const int n = (int)n_in;
   species_code_kernel<<<blocks(n, 256), 256, 0, st>>>(list, n, T, c1);
-  rank_bins_kernel<<<1, kRankThreads, 0, st>>>(c1, n, 0, r1, dc + 16);
+  rank_bins(c1, n, 0, r1, dc + 16, st);
   VPB_CUDA(cudaMemcpyAsync(c.h_pinned_i, dc + 16, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
   VPB_CUDA(cudaStreamSynchronize(st));
   int cnt[7];
@@ -454,9 +513,9 @@ void vpb_boundary_p(vpb_domain_t *dom, vpb_species_state_t *sp, int n_sp, vpb_fi
     if (cnt[s] > sp[s].max_nm) VPB_ERROR("species %d: %d arrivals exceed max_nm=%d", sp[s].id, cnt[s], sp[s].max_nm);
   }
   inject_kernel<<<blocks(n, 128), 128, 0, st>>>(list, n, c1, r1, T, reinterpret_cast<float *>(d_a), g.nbr, c2);
-  rank_bins_kernel<<<1, kRankThreads, 0, st>>>(c2, n, 0, r2, dc + 24);
+  rank_bins(c2, n, 0, r2, dc + 24, st);
   compact_movers_kernel<<<blocks(n, 256), 256, 0, st>>>(list, n, c2, r2, T);
-  count_launch(5);
+  count_launch(3);
   VPB_CUDA(cudaMemcpyAsync(c.h_pinned_i, dc + 24, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
   VPB_CUDA(cudaStreamSynchronize(st));
   for (int s = 0; s < n_sp; s++) {
