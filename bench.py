@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--field-cells", type=int, default=1024, help="cells per axis of the field-only leg (configs[1]); 0 = skip")
     ap.add_argument("--workload", default="thermal", choices=["thermal", "fields"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sort-lookahead", type=int, default=-1,
+                    help="sort key = voxel the particle reaches this many steps ahead (-1: 0.6 x the sort interval, 0: current voxel)")
     ap.add_argument("--driver", default="native", choices=["native", "python"], help="time-step driver: csrc/vpb_step.cu or sim.py")
     ap.add_argument("--sort-interval", type=int, default=SORT_INTERVAL, help="species sort_interval (the reference recipe: 20)")
     return ap.parse_args()
@@ -170,6 +172,7 @@ def run_reference(args):
 def workload_config(args):
     return {"workload": "BASELINE configs[3]: thermal e-/p+ plasma weak scaling, %d^3 cells and %d ppc per species per GPU, "
                         "periodic, dt=0.95 Courant, vth=%.1fc, sort every %d steps" % (args.cells, args.ppc, VTH, args.sort_interval),
+            "sort_key": ("voxel %s steps ahead (a look-ahead grouping: same particles, same physics, different array order)" % ("0.6 x interval" if args.sort_lookahead < 0 else args.sort_lookahead)) if (args.sort_lookahead != 0 and args.driver == "native") else "current voxel",
             "cells_per_gpu": [args.cells] * 3, "ppc_per_species": args.ppc, "species": 2,
             "l2_policy": "inputs (>=100 GB of particles per GPU) are far larger than the 126 MB L2; no flush needed",
             "decomposition": "1 rank per GPU"}
@@ -221,6 +224,8 @@ def run_b200(args):
     sim = Driver(g, n_mat=1, L=L, planar=L.vpb_get_tuning(b"sim.aos_fields") == 0,
                      wide_interpolator=L.vpb_get_tuning(b"sim.narrow_interpolator") == 0,
                      particle_planes=L.vpb_get_tuning(b"sim.aos_particles") == 0)
+    if args.driver == "native":
+        sim.set_sort_lookahead(args.sort_lookahead)
     np_ = n ** 3 * args.ppc
     max_np = int(np_ * (1.0 if world == 1 else 1.02)) + 1024
     # macro-charge q = +-(cell volume)/ppc so that the plasma frequency is 1 (the reference's thermal recipe,

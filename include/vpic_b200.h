@@ -258,6 +258,13 @@ void vpb_sort_p(vpb_domain_t *dom, const vpb_particle_t *d_in, vpb_particle_t *d
  * d_tmp (same capacity) is scratch.  The permutation is applied to whole 48-byte records staged in d_tmp, which is
  * several times faster than moving the 4-byte plane words through it one by one. */
 void vpb_sort_p_planes(vpb_domain_t *dom, vpb_particle_t *d_p, vpb_particle_t *d_tmp, int np, int *d_partition);
+/* Look-ahead variant for device-resident runs: particles are grouped by the voxel they WILL be in `lookahead` steps
+ * from now at their present velocity (clamped to the local interior), stable within a group.  The order of a
+ * particle array has no physical meaning; this one halves the average distance between a particle and the voxel
+ * its neighbours in the array share over a sort interval (lookahead ~ 0.6 sort_interval), which is what advance_p's
+ * gathers and REDs pay for.  d_partition describes the groups, not the current voxels.  lookahead = 0 is
+ * vpb_sort_p_planes. */
+void vpb_sort_p_planes_ahead(vpb_domain_t *dom, vpb_particle_t *d_p, vpb_particle_t *d_tmp, int np, int *d_partition, int lookahead);
 
 /* Hydro moments on device arrays (vpb_hydro_t[nvoxel], the reference layout; the particle array in the domain's
  * particle layout, the interpolator in the domain's interpolator layout). */
@@ -311,6 +318,7 @@ long vpb_sim_get_particles(vpb_sim_t *s, int species, vpb_particle_t *host, long
 void vpb_sim_set_fields(vpb_sim_t *s, const vpb_field_t *host);       /* field_t[nvoxel], reference layout */
 void vpb_sim_get_fields(vpb_sim_t *s, vpb_field_t *host);
 void vpb_sim_set_intervals(vpb_sim_t *s, int clean_div_e_interval, int clean_div_b_interval, int num_comm_round);
+void vpb_sim_set_sort_lookahead(vpb_sim_t *s, int steps);   /* < 0: 0.6 x sort_interval of each species; 0 (default): off */
 void vpb_sim_advance(vpb_sim_t *s, int nsteps);                        /* enqueues nsteps time steps */
 void vpb_sim_energies(vpb_sim_t *s, double *out6_plus_nspecies);       /* dump_energies (dump.cxx:37-78), over all ranks */
 void vpb_sim_hydro(vpb_sim_t *s, int species, vpb_hydro_t *host);      /* clear + accumulate + synchronize, to the host */

@@ -111,15 +111,43 @@ __global__ void __launch_bounds__(256) rho_p_kernel(vpb_field_t *__restrict__ f,
 // to the reference's stable scatter, sort_p.c:74), (5) gather the 48-byte
 // records through the permutation with 128-bit accesses.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sort_hist_kernel(const PView p, int np, int *__restrict__ count) {
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x)
-    atomicAdd(count + p.voxel(k), 1);
+// Sort key.  L == 0: the particle's voxel (sort_p.c:46-59).  L > 0 ("look-ahead", device-resident driver only): the
+// voxel the particle will be in L steps from now if it keeps its velocity, clamped to the local interior.  Sorting
+// is a locality heuristic -- any order of the array is physically the same -- and between two sorts `interval`
+// steps apart the particles of a chunk are closest to sharing a voxel when they were grouped by where they will be
+// half-way: the age of the drift that advance_p sees runs 10,9,..,0,..,9 steps instead of 0..19.
+struct SortAhead {
+  int L, sx, sy, nx, ny, nz;
+  float kx, ky, kz;        // 2 * L * c dt / d{x,y,z}: displacement in cell-local units (a cell spans [-1,1]) per unit u/gamma
+};
+
+__device__ __forceinline__ int sort_key(const PView &p, int k, const SortAhead &A) {
+  if (A.L == 0) return p.voxel(k);
+  const float4 r = p.pos(k), u = p.mom(k);
+  const int v = __float_as_int(r.w);
+  const int ix = v % A.sx, t = v / A.sx, iy = t % A.sy, iz = t / A.sy;
+  const float rg = rsqrtf(1.f + (u.x * u.x + (u.y * u.y + u.z * u.z)));
+  int cx = ix + (int)floorf((r.x + A.kx * u.x * rg + 1.f) * 0.5f);
+  int cy = iy + (int)floorf((r.y + A.ky * u.y * rg + 1.f) * 0.5f);
+  int cz = iz + (int)floorf((r.z + A.kz * u.z * rg + 1.f) * 0.5f);
+  cx = min(max(cx, 1), A.nx); cy = min(max(cy, 1), A.ny); cz = min(max(cz, 1), A.nz);
+  return cx + A.sx * (cy + A.sy * cz);
+}
+
+// histogram of the keys; with look-ahead the keys are kept for the claim pass
+__global__ void __launch_bounds__(256) sort_hist_kernel(const PView p, int np, int *__restrict__ count, const SortAhead A,
+                                                        int *__restrict__ keys) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x) {
+    const int key = sort_key(p, k, A);
+    if (keys) keys[k] = key;
+    atomicAdd(count + key, 1);
+  }
 }
 
 // Slot claim, warp-aggregated: the lanes of a warp that hold the same voxel (most of them while the array is nearly
 // sorted) send ONE atomic for the group and take consecutive slots in lane order.
 __global__ void __launch_bounds__(256) sort_claim_kernel(const PView p, int np, int *__restrict__ cursor,
-                                                         int *__restrict__ perm) {
+                                                         int *__restrict__ perm, const int *__restrict__ keys) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
@@ -127,7 +155,7 @@ __global__ void __launch_bounds__(256) sort_claim_kernel(const PView p, int np, 
   for (int k0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); k0 < np; k0 += stride) {   // warp-uniform trip count
     const int k = k0 + lane;
     const bool valid = k < np;
-    const int v = valid ? p.voxel(k) : -1 - lane;
+    const int v = valid ? (keys ? keys[k] : p.voxel(k)) : -1 - lane;
     const unsigned peers = __match_any_sync(full, v);
     const int leader = __ffs(peers) - 1;
     int base = 0;
@@ -250,6 +278,7 @@ __global__ void __launch_bounds__(256) particle_convert_kernel(const PView dst, 
 using namespace vpb;
 
 static bool g_sort_in_place = false;
+static int g_sort_lookahead = 0;
 
 static int grid_for(long n, int tb) {
   long b = (n + tb - 1) / tb;
@@ -316,20 +345,28 @@ void vpb_sort_p(vpb_domain_t *dom, const vpb_particle_t *d_in, vpb_particle_t *d
   Context &c = ctx();
   ProfScope prof(1);
   const int nv = dom->d.nv, nv1 = nv + 1;
-  // scratch: cursor[nv1] | perm[np] | perm_sorted[np] | scan scratch
+  // scratch: cursor[nv1] | perm[np] | perm_sorted[np] (also the look-ahead keys until the rank pass) | scan scratch
   auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
   const size_t off_perm = al((size_t)nv1 * 4), off_perm2 = off_perm + al((size_t)np * 4 + 4),
                off_scan = off_perm2 + al((size_t)np * 4 + 4);
   char *s = (char *)scratch(off_scan + scan_scratch_bytes(nv1));
   int *cursor = (int *)s, *perm = (int *)(s + off_perm), *perm2 = (int *)(s + off_perm2);
+  const DomainDev &gd = dom->d;
+  SortAhead ahead;
+  ahead.L = g_sort_lookahead > 0 ? g_sort_lookahead : 0;
+  ahead.sx = gd.sx; ahead.sy = gd.sy; ahead.nx = gd.nx; ahead.ny = gd.ny; ahead.nz = gd.nz;
+  ahead.kx = 2.f * ahead.L * gd.cvac * gd.dt * gd.rdx;
+  ahead.ky = 2.f * ahead.L * gd.cvac * gd.dt * gd.rdy;
+  ahead.kz = 2.f * ahead.L * gd.cvac * gd.dt * gd.rdz;
+  int *keys = ahead.L ? perm2 : nullptr;
   VPB_CUDA(cudaMemsetAsync(cursor, 0, (size_t)nv1 * 4, c.stream));
-  if (np > 0) sort_hist_kernel<<<grid_for(np, 256), 256, 0, c.stream>>>(PView(d_in, dom->d.p_plane), np, cursor);
+  if (np > 0) sort_hist_kernel<<<grid_for(np, 256), 256, 0, c.stream>>>(PView(d_in, dom->d.p_plane), np, cursor, ahead, keys);
   exclusive_scan_i32(cursor, d_partition, nv1, s + off_scan, c.stream);   // partition[nv] = np (sort_p.c:54-59)
   count_launch(1 + scan_launches(nv1));
   if (np == 0) return;
   if (!d_in || !d_out) VPB_ERROR("Bad particle array");
   VPB_CUDA(cudaMemcpyAsync(cursor, d_partition, (size_t)nv1 * 4, cudaMemcpyDeviceToDevice, c.stream));
-  sort_claim_kernel<<<grid_for(np, 256), 256, 0, c.stream>>>(PView(d_in, dom->d.p_plane), np, cursor, perm);
+  sort_claim_kernel<<<grid_for(np, 256), 256, 0, c.stream>>>(PView(d_in, dom->d.p_plane), np, cursor, perm, keys);
   sort_rank_kernel<0><<<grid_for((long)nv * 32, 256), 256, 0, c.stream>>>(d_partition, nv, perm, perm2);
   if (g_sort_in_place) {   // vpb_sort_p_planes: d_out is scratch, the sorted planes return to d_in
     planes_to_records_kernel<<<grid_for(np, 256), 256, 0, c.stream>>>(PView(d_in, dom->d.p_plane), reinterpret_cast<float4 *>(d_out), np);
@@ -354,6 +391,15 @@ void vpb_sort_p_planes(vpb_domain_t *dom, vpb_particle_t *d_p, vpb_particle_t *d
   g_sort_in_place = true;
   vpb_sort_p(dom, d_p, d_tmp, np, d_partition);
   g_sort_in_place = false;
+}
+
+// Same, grouping the particles by the voxel they will be in `lookahead` steps from now (see SortAhead): d_partition
+// then describes those groups, not the particles' current voxels.
+void vpb_sort_p_planes_ahead(vpb_domain_t *dom, vpb_particle_t *d_p, vpb_particle_t *d_tmp, int np, int *d_partition, int lookahead) {
+  if (lookahead < 0) VPB_ERROR("Bad look-ahead");
+  g_sort_lookahead = lookahead;
+  vpb_sort_p_planes(dom, d_p, d_tmp, np, d_partition);
+  g_sort_lookahead = 0;
 }
 
 // Particle layout of a domain's device-resident species arrays (include/vpic_b200.h "Device particle layout")

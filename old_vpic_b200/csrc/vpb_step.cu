@@ -45,6 +45,7 @@ struct vpb_sim {
   long sort_tmp_cap = 0;
   long step = 0;
   int clean_div_e_interval = 0, clean_div_b_interval = 0, num_comm_round = 3;   // vpic.cxx:17
+  int sort_lookahead = 0;        // steps; < 0: 0.6 x the species' sort interval (measured optimum, profiles/README.md)
   int needs_boundary_p = -1;
 };
 
@@ -83,7 +84,8 @@ static void sort_species(vpb_sim *s, Species &sp) {
   }
   if (!sp.partition) sp.partition = (int *)vpb_dev_alloc((size_t)(s->nv + 1) * sizeof(int));
   if (vpb_domain_particle_layout(s->dom) > 0) {
-    vpb_sort_p_planes(s->dom, sp.p, s->sort_tmp, sp.np, sp.partition);      // sorted planes return to sp.p
+    const int ahead = s->sort_lookahead < 0 ? (3 * sp.sort_interval + 2) / 5 : s->sort_lookahead;
+    vpb_sort_p_planes_ahead(s->dom, sp.p, s->sort_tmp, sp.np, sp.partition, ahead);   // sorted planes return to sp.p
   } else {
     vpb_sort_p(s->dom, sp.p, s->sort_tmp, sp.np, sp.partition);
     std::swap(sp.p, s->sort_tmp);                                           // out of place: swap (sort_p.c:76-77)
@@ -328,6 +330,11 @@ void vpb_sim_set_intervals(vpb_sim_t *s, int clean_div_e_interval, int clean_div
   s->clean_div_e_interval = clean_div_e_interval;
   s->clean_div_b_interval = clean_div_b_interval;
   if (num_comm_round > 0) s->num_comm_round = num_comm_round;
+}
+
+void vpb_sim_set_sort_lookahead(vpb_sim_t *s, int steps) {
+  if (!s) VPB_ERROR("Bad run");
+  s->sort_lookahead = steps;
 }
 
 // nsteps time steps; does not synchronise (beyond what migration needs)

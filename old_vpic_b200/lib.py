@@ -111,6 +111,7 @@ SIGNATURES = {
     "vpb_boundary_p": (None, [_vp, _vp, _i, _vp, _vp]),
     "vpb_sort_p": (None, [_vp, _vp, _vp, _i, _vp]),
     "vpb_sort_p_planes": (None, [_vp, _vp, _vp, _i, _vp]),
+    "vpb_sort_p_planes_ahead": (None, [_vp, _vp, _vp, _i, _vp, _i]),
     "vpb_clear_hydro": (None, [_vp, _vp]),
     "vpb_accumulate_hydro_p": (None, [_vp, _vp, _vp, _i, _f, _vp]),
     "vpb_local_adjust_hydro": (None, [_vp, _vp]),
@@ -145,6 +146,7 @@ SIGNATURES = {
     "vpb_sim_set_fields": (None, [_vp, _vp]),
     "vpb_sim_get_fields": (None, [_vp, _vp]),
     "vpb_sim_set_intervals": (None, [_vp, _i, _i, _i]),
+    "vpb_sim_set_sort_lookahead": (None, [_vp, _i]),
     "vpb_sim_advance": (None, [_vp, _i]),
     "vpb_sim_energies": (None, [_vp, _vp]),
     "vpb_sim_hydro": (None, [_vp, _i, _vp]),

@@ -381,6 +381,10 @@ class NativeSimulation:
     def set_intervals(self, clean_div_e=0, clean_div_b=0, num_comm_round=3):
         self.L.vpb_sim_set_intervals(self.h, clean_div_e, clean_div_b, num_comm_round)
 
+    def set_sort_lookahead(self, steps):
+        """< 0: 0.6 x each species' sort interval; 0: off (the reference's sort key)"""
+        self.L.vpb_sim_set_sort_lookahead(self.h, steps)
+
     def advance(self, nsteps=1):
         self.L.vpb_sim_advance(self.h, nsteps)
 

@@ -423,3 +423,59 @@ def test_sort_p_planes(vpb, orc, n, np_):
     for arr in (d_in, d_out, d_part):
         arr.free()
     vpb.vpb_domain_destroy(dom)
+
+
+def test_sort_p_planes_lookahead(vpb):
+    """Look-ahead sort key (vpb_sort_p_planes_ahead): a stable grouping of the SAME particles by the voxel they reach
+    `L` steps ahead at their present velocity; partition[] delimits the groups; L = 0 is the plain sort."""
+    from old_vpic_b200.sim import DevArray, ParticleArray
+    n, np_, L = (10, 9, 8), 60001, 7
+    g = host_grid(n)
+    rng = np.random.default_rng(36)
+    p = random_particles(rng, g, np_, vth=0.5, sort=False)
+    dom = vpb.vpb_domain_create(g.ref(), 0, 1)
+    vpb.vpb_domain_set_particle_layout(dom, (np_ + 63) // 64 * 64)
+    d_p, d_tmp = ParticleArray(vpb, dom, np_), ParticleArray(vpb, dom, np_)
+    d_part = DevArray(vpb, g.nv + 1, np.int32)
+    d_p.upload(p)
+    vpb.vpb_sort_p_planes_ahead(dom, d_p.ptr, d_tmp.ptr, np_, d_part.ptr, L)
+    out, part = d_p.download(np_), d_part.download()
+    # same particles
+    order = np.argsort(out["tag"], kind="stable")
+    assert_bits_equal(out[order], p[np.argsort(p["tag"], kind="stable")], "multiset")
+    # expected keys, computed the same way in float32
+    s = g.struct
+    sx, sy = n[0] + 2, n[1] + 2
+
+    def keys(q):
+        v = q["i"].astype(np.int64)
+        ix, iy, iz = v % sx, (v // sx) % sy, v // (sx * sy)
+        u2 = (q["ux"] * q["ux"] + (q["uy"] * q["uy"] + q["uz"] * q["uz"])).astype(np.float32)
+        rg = (np.float32(1) / np.sqrt(np.float32(1) + u2)).astype(np.float32)
+        res = []
+        for c, d, u, rd, nn in ((ix, q["dx"], q["ux"], s.rdx, n[0]), (iy, q["dy"], q["uy"], s.rdy, n[1]), (iz, q["dz"], q["uz"], s.rdz, n[2])):
+            k = np.float32(2.0 * L * s.cvac * s.dt * rd)
+            pos = (d + k * u * rg + np.float32(1)) * np.float32(0.5)
+            res.append(np.clip(c + np.floor(pos).astype(np.int64), 1, nn))
+        return res[0] + sx * (res[1] + sy * res[2])
+
+    k_out = keys(out)
+    # rsqrt on the device is approximate: a key may differ where the predicted position sits on a cell face; the
+    # grouping the device produced must be sorted by ITS keys, which partition[] reveals
+    dev_key = np.repeat(np.arange(g.nv), np.diff(part))
+    assert len(dev_key) == np_ and part[-1] == np_
+    assert np.mean(dev_key != k_out) < 1e-3
+    assert np.all(np.diff(dev_key) >= 0)
+    # stable within a group: source order (tags were 0..np-1 in source order) increases
+    same = dev_key[1:] == dev_key[:-1]
+    assert np.all(out["tag"][1:][same] > out["tag"][:-1][same])
+    # L = 0 reproduces the plain sort
+    d_p.upload(p)
+    vpb.vpb_sort_p_planes_ahead(dom, d_p.ptr, d_tmp.ptr, np_, d_part.ptr, 0)
+    ref = d_p.download(np_)
+    d_p.upload(p)
+    vpb.vpb_sort_p_planes(dom, d_p.ptr, d_tmp.ptr, np_, d_part.ptr)
+    assert_bits_equal(ref, d_p.download(np_), "lookahead 0")
+    for arr in (d_p, d_tmp, d_part):
+        arr.free()
+    vpb.vpb_domain_destroy(dom)

@@ -11,9 +11,10 @@ from test_gpu_history import SORT, STEPS, cpu_history, gpu_history, make_species
 pytestmark = pytest.mark.gpu
 
 
-def native_history(vpb, g, species, steps, clean_e=0, clean_b=0, **layouts):
+def native_history(vpb, g, species, steps, clean_e=0, clean_b=0, lookahead=0, **layouts):
     sim = NativeSimulation(g, L=vpb, **layouts)
     sim.set_intervals(clean_e, clean_b)
+    sim.set_sort_lookahead(lookahead)
     for k, sp in enumerate(species):
         s = sim.define_species("s%d" % k, sp["q_m"], len(sp["p"]) + 64, sort_interval=SORT)
         sim.set_particles(s, sp["p"])
@@ -69,4 +70,20 @@ def test_native_driver_field_only(vpb):
     sim.advance(50)
     e1 = sum(sim.energies())
     assert abs(e1 - e0) / e0 < 1e-3
+    sim.free()
+
+
+@pytest.mark.parametrize("lookahead", [-1, 3])
+def test_native_driver_sort_lookahead(vpb, orc, lookahead):
+    """Grouping particles by the voxel they reach a few steps ahead only changes the ORDER of the particle arrays:
+    same energy history as the CPU oracle (which sorts by the current voxel), same particles."""
+    g = host_grid((16, 16, 16), "periodic")
+    ppc = 8
+    h_cpu = cpu_history(oracle_kernels(orc), g, make_species(g, ppc, 3), STEPS, 0, 0)
+    h_nat, sim = native_history(vpb, g, make_species(g, ppc, 3), STEPS, 0, 0, lookahead=lookahead)
+    scale = np.maximum(np.abs(h_cpu).max(axis=0), 1e-300)
+    assert (np.abs(h_nat - h_cpu) / scale).max() < 1e-4
+    for sp, inp in zip(sim.species, make_species(g, ppc, 3)):
+        out = sim.get_particles(sp)
+        assert np.array_equal(np.sort(out["tag"]), np.sort(inp["p"]["tag"]))
     sim.free()
