@@ -18,9 +18,11 @@ pytestmark = pytest.mark.gpu
 STEPS, SORT = 20, 5
 
 
-def cpu_history(K, g, species, steps, clean_e=0, clean_b=0):
+def cpu_history(K, g, species, steps, clean_e=0, clean_b=0, f_init=None):
     """K: dict of kernels with the oracle's calling convention."""
     f = abi.aligned_zeros(g.nv, abi.field_dtype)
+    if f_init is not None:
+        f[:] = f_init
     fi = abi.aligned_zeros(g.nv, abi.interpolator_dtype)
     a = abi.aligned_zeros(K["n_acc"](g), abi.accumulator_dtype)
     m = abi.aligned_zeros(1, abi.material_coefficient_dtype)
