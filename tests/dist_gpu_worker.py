@@ -1,6 +1,7 @@
 """Multi-GPU worker (torchrun, one rank per GPU, NCCL): a thermal plasma on a periodic box split over the
-ranks (2x1x1, 2x2x1 or 2x2x2), stepped with the device driver; every rank checks global invariants and rank 0
-compares the energy history with a single-domain run of the SAME particles on its own GPU.
+ranks (2x1x1, 2x2x1 or 2x2x2), stepped with the library's C++ driver (look-ahead sort key on); every rank checks global invariants and rank 0
+compares the energy history and the hydro moments with a single-domain run of the SAME particles (Python driver,
+plain sort key) on its own GPU.
     torchrun --nproc-per-node N tests/dist_gpu_worker.py
 """
 import ctypes as C
@@ -13,16 +14,19 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from old_vpic_b200 import abi, grid as G, lib  # noqa: E402
-from old_vpic_b200.sim import Simulation  # noqa: E402
+from old_vpic_b200.sim import NativeSimulation, Simulation  # noqa: E402
 
 
 SPECIES = (("e", -1.0, 11), ("i", 1.0, 911))
 PER, PPC, STEPS, VTH = 12, 24, 12, 0.3
 
 
-def make_sim(L, gn, topo, rank):
+def make_sim(L, gn, topo, rank, native=False):
+    """native: the library's C++ driver (vpb_sim_*) with the look-ahead sort key; else the Python driver."""
     g = G.make_grid(gn, "periodic", topo=topo, rank=rank)
-    sim = Simulation(g, L=L)
+    sim = (NativeSimulation if native else Simulation)(g, L=L)
+    if native:
+        sim.set_sort_lookahead(-1)
     n = g.n[0] * g.n[1] * g.n[2] * PPC
     for name, q_m, _ in SPECIES:
         sim.define_species(name, q_m, int(n * 1.5) + 4096, max_nm=n // 2 + 4096, sort_interval=5)
@@ -60,11 +64,11 @@ def main():
 
     # 1. every rank loads its share; the shares are gathered so that rank 0 can run the SAME particles on one
     #    domain (done before vpb_comm_init: until then the library's reductions are rank-local)
-    sim = make_sim(L, gn, topo, rank)
+    sim = make_sim(L, gn, topo, rank, native=True)
     shares = []
     for sp, (_, q_m, seed) in zip(sim.species, SPECIES):
         sim.load_thermal(sp, PPC, VTH, (1.0 if q_m > 0 else -1.0) / PPC, seed + rank, tag0=rank << 32)
-        mine = torch.from_numpy(sp.p.download(sp.np).view(np.uint8).copy()).cuda()
+        mine = torch.from_numpy(sim.get_particles(sp).view(np.uint8).copy()).cuda()
         parts = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(parts, mine)
         shares.append([t.cpu().numpy().view(abi.particle_dtype) for t in parts])
