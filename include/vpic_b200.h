@@ -259,7 +259,7 @@ void vpb_sort_p(vpb_domain_t *dom, const vpb_particle_t *d_in, vpb_particle_t *d
  * several times faster than moving the 4-byte plane words through it one by one. */
 void vpb_sort_p_planes(vpb_domain_t *dom, vpb_particle_t *d_p, vpb_particle_t *d_tmp, int np, int *d_partition);
 /* Look-ahead variant for device-resident runs: particles are grouped by the voxel they WILL be in `lookahead` steps
- * from now at their present velocity (clamped to the local interior), stable within a group.  The order of a
+ * from now at their present velocity (clamped to the local interior); the order inside a group is arbitrary.  The order of a
  * particle array has no physical meaning; this one halves the average distance between a particle and the voxel
  * its neighbours in the array share over a sort interval (lookahead ~ 0.6 sort_interval), which is what advance_p's
  * gathers and REDs pay for.  d_partition describes the groups, not the current voxels.  lookahead = 0 is
