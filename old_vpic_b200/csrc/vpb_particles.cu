@@ -121,10 +121,9 @@ struct SortAhead {
   float kx, ky, kz;        // 2 * L * c dt / d{x,y,z}: displacement in cell-local units (a cell spans [-1,1]) per unit u/gamma
 };
 
-__device__ __forceinline__ int sort_key(const PView &p, int k, const SortAhead &A) {
-  if (A.L == 0) return p.voxel(k);
-  const float4 r = p.pos(k), u = p.mom(k);
+__device__ __forceinline__ int sort_key_of(const float4 r, const float4 u, const SortAhead &A) {
   const int v = __float_as_int(r.w);
+  if (A.L == 0) return v;
   const int ix = v % A.sx, t = v / A.sx, iy = t % A.sy, iz = t / A.sy;
   const float rg = rsqrtf(1.f + (u.x * u.x + (u.y * u.y + u.z * u.z)));
   int cx = ix + (int)floorf((r.x + A.kx * u.x * rg + 1.f) * 0.5f);
@@ -132,6 +131,11 @@ __device__ __forceinline__ int sort_key(const PView &p, int k, const SortAhead &
   int cz = iz + (int)floorf((r.z + A.kz * u.z * rg + 1.f) * 0.5f);
   cx = min(max(cx, 1), A.nx); cy = min(max(cy, 1), A.ny); cz = min(max(cz, 1), A.nz);
   return cx + A.sx * (cy + A.sy * cz);
+}
+
+__device__ __forceinline__ int sort_key(const PView &p, int k, const SortAhead &A) {
+  if (A.L == 0) return p.voxel(k);
+  return sort_key_of(p.pos(k), p.mom(k), A);
 }
 
 // histogram of the keys; with look-ahead the keys are kept for the claim pass
@@ -242,16 +246,26 @@ __global__ void __launch_bounds__(256) sort_gather_planes_kernel(const float *__
 // planes -> 48-byte records, both sides coalesced: a warp takes 32 consecutive particles, every lane reads its
 // particle's nine plane words, the 96 quads are transposed through shared memory (48-byte lane stride: conflict
 // free) and leave as three fully coalesced 512-byte stores.
-__global__ void __launch_bounds__(256) planes_to_records_kernel(const PView in, float4 *__restrict__ rec, int np) {
+// HIST: the pass also computes every particle's sort key (it holds the words the key needs), counts it and keeps it
+// for the claim pass, which saves the separate histogram pass over the planes.
+template <int HIST>
+__global__ void __launch_bounds__(256) planes_to_records_kernel(const PView in, float4 *__restrict__ rec, int np, int *__restrict__ count,
+                                                                const SortAhead A, int *__restrict__ keys) {
   __shared__ float4 tile[8][96];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int nblk = (np + 31) >> 5;
   for (int blk = blockIdx.x * 8 + w; blk < nblk; blk += gridDim.x * 8) {
     const int k = blk * 32 + lane;
     if (k < np) {
-      tile[w][3 * lane] = in.pos(k);
-      tile[w][3 * lane + 1] = in.mom(k);
+      const float4 r = in.pos(k), u = in.mom(k);
+      tile[w][3 * lane] = r;
+      tile[w][3 * lane + 1] = u;
       tile[w][3 * lane + 2] = in.tag(k);
+      if (HIST) {
+        const int key = sort_key_of(r, u, A);
+        keys[k] = key;
+        atomicAdd(count + key, 1);
+      }
     }
     __syncwarp();
     const int nq = 3 * (np - blk * 32 < 32 ? np - blk * 32 : 32);
@@ -379,9 +393,17 @@ void vpb_sort_p(vpb_domain_t *dom, const vpb_particle_t *d_in, vpb_particle_t *d
   ahead.kx = 2.f * ahead.L * gd.cvac * gd.dt * gd.rdx;
   ahead.ky = 2.f * ahead.L * gd.cvac * gd.dt * gd.rdy;
   ahead.kz = 2.f * ahead.L * gd.cvac * gd.dt * gd.rdz;
-  int *keys = ahead.L ? perm2 : nullptr;
+  // in place (planes): the transposition to records doubles as the histogram pass and always leaves the keys
+  const bool fused = g_sort_in_place && np > 0;
+  int *keys = (ahead.L || fused) ? perm2 : nullptr;
   VPB_CUDA(cudaMemsetAsync(cursor, 0, (size_t)nv1 * 4, c.stream));
-  if (np > 0) sort_hist_kernel<<<grid_for(np, 256), 256, 0, c.stream>>>(PView(d_in, dom->d.p_plane), np, cursor, ahead, keys);
+  if (fused) {
+    if (!d_in || !d_out) VPB_ERROR("Bad particle array");
+    planes_to_records_kernel<1><<<grid_for(np, 256), 256, 0, c.stream>>>(PView(d_in, dom->d.p_plane), reinterpret_cast<float4 *>(d_out), np,
+                                                                         cursor, ahead, keys);
+  } else if (np > 0) {
+    sort_hist_kernel<<<grid_for(np, 256), 256, 0, c.stream>>>(PView(d_in, dom->d.p_plane), np, cursor, ahead, keys);
+  }
   exclusive_scan_i32(cursor, d_partition, nv1, s + off_scan, c.stream);   // partition[nv] = np (sort_p.c:54-59)
   count_launch(1 + scan_launches(nv1));
   if (np == 0) return;
@@ -394,7 +416,6 @@ void vpb_sort_p(vpb_domain_t *dom, const vpb_particle_t *d_in, vpb_particle_t *d
   if (ahead.L) perm2 = perm;
   else sort_rank_kernel<0><<<grid_for((long)nv * 32, 256), 256, 0, c.stream>>>(d_partition, nv, perm, perm2);
   if (g_sort_in_place) {   // vpb_sort_p_planes: d_out is scratch, the sorted planes return to d_in
-    planes_to_records_kernel<<<grid_for(np, 256), 256, 0, c.stream>>>(PView(d_in, dom->d.p_plane), reinterpret_cast<float4 *>(d_out), np);
     sort_gather_records_to_planes_kernel<<<grid_for(np, 256), 256, 0, c.stream>>>(reinterpret_cast<const float4 *>(d_out),
                                                                                   PView(d_in, dom->d.p_plane), np, perm2);
     count_launch();
