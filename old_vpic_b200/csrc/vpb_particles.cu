@@ -312,8 +312,6 @@ __global__ void __launch_bounds__(256) particle_convert_kernel(const PView dst, 
 
 using namespace vpb;
 
-static bool g_sort_in_place = false;
-static int g_sort_lookahead = 0;
 
 static int grid_for(long n, int tb) {
   long b = (n + tb - 1) / tb;
@@ -373,7 +371,10 @@ void vpb_accumulate_rho_p(vpb_domain_t *dom, vpb_field_t *d_f, const vpb_particl
   VPB_CUDA(cudaGetLastError());
 }
 
-void vpb_sort_p(vpb_domain_t *dom, const vpb_particle_t *d_in, vpb_particle_t *d_out, int np, int *d_partition) {
+// in_place: d_in holds component planes, d_out is scratch and the sorted planes return to d_in.
+// lookahead > 0: look-ahead grouping (SortAhead), in-place only.
+static void sort_particles(vpb_domain_t *dom, const vpb_particle_t *d_in, vpb_particle_t *d_out, int np, int *d_partition, bool in_place,
+                           int lookahead) {
   if (!dom) VPB_ERROR("Bad grid");
   if (!d_partition) VPB_ERROR("Bad partition");
   if (np < 0) VPB_ERROR("Bad number of particles");
@@ -388,13 +389,13 @@ void vpb_sort_p(vpb_domain_t *dom, const vpb_particle_t *d_in, vpb_particle_t *d
   int *cursor = (int *)s, *perm = (int *)(s + off_perm), *perm2 = (int *)(s + off_perm2);
   const DomainDev &gd = dom->d;
   SortAhead ahead;
-  ahead.L = g_sort_lookahead > 0 ? g_sort_lookahead : 0;
+  ahead.L = lookahead > 0 ? lookahead : 0;
   ahead.sx = gd.sx; ahead.sy = gd.sy; ahead.nx = gd.nx; ahead.ny = gd.ny; ahead.nz = gd.nz;
   ahead.kx = 2.f * ahead.L * gd.cvac * gd.dt * gd.rdx;
   ahead.ky = 2.f * ahead.L * gd.cvac * gd.dt * gd.rdy;
   ahead.kz = 2.f * ahead.L * gd.cvac * gd.dt * gd.rdz;
   // in place (planes): the transposition to records doubles as the histogram pass and always leaves the keys
-  const bool fused = g_sort_in_place && np > 0;
+  const bool fused = in_place && np > 0;
   int *keys = (ahead.L || fused) ? perm2 : nullptr;
   VPB_CUDA(cudaMemsetAsync(cursor, 0, (size_t)nv1 * 4, c.stream));
   if (fused) {
@@ -415,7 +416,7 @@ void vpb_sort_p(vpb_domain_t *dom, const vpb_particle_t *d_in, vpb_particle_t *d
   // (the particles of a group in arbitrary order; 15 ms less per 2^30 particles).
   if (ahead.L) perm2 = perm;
   else sort_rank_kernel<0><<<grid_for((long)nv * 32, 256), 256, 0, c.stream>>>(d_partition, nv, perm, perm2);
-  if (g_sort_in_place) {   // vpb_sort_p_planes: d_out is scratch, the sorted planes return to d_in
+  if (in_place) {   // vpb_sort_p_planes: d_out is scratch, the sorted planes return to d_in
     sort_gather_records_to_planes_kernel<<<grid_for(np, 256), 256, 0, c.stream>>>(reinterpret_cast<const float4 *>(d_out),
                                                                                   PView(d_in, dom->d.p_plane), np, perm2);
     count_launch();
@@ -429,23 +430,25 @@ void vpb_sort_p(vpb_domain_t *dom, const vpb_particle_t *d_in, vpb_particle_t *d
   VPB_CUDA(cudaGetLastError());
 }
 
+void vpb_sort_p(vpb_domain_t *dom, const vpb_particle_t *d_in, vpb_particle_t *d_out, int np, int *d_partition) {
+  sort_particles(dom, d_in, d_out, np, d_partition, false, 0);
+}
+
 // Stable counting sort of a component-plane array IN PLACE: d_p holds the sorted planes on return, d_tmp (same
 // capacity) is scratch.  Same permutation as vpb_sort_p.
 void vpb_sort_p_planes(vpb_domain_t *dom, vpb_particle_t *d_p, vpb_particle_t *d_tmp, int np, int *d_partition) {
   if (!dom) VPB_ERROR("Bad grid");
   if (dom->d.p_plane <= 0) VPB_ERROR("the domain keeps its particles in the reference layout: use vpb_sort_p");
-  g_sort_in_place = true;
-  vpb_sort_p(dom, d_p, d_tmp, np, d_partition);
-  g_sort_in_place = false;
+  sort_particles(dom, d_p, d_tmp, np, d_partition, true, 0);
 }
 
 // Same, grouping the particles by the voxel they will be in `lookahead` steps from now (see SortAhead): d_partition
 // then describes those groups, not the particles' current voxels.
 void vpb_sort_p_planes_ahead(vpb_domain_t *dom, vpb_particle_t *d_p, vpb_particle_t *d_tmp, int np, int *d_partition, int lookahead) {
+  if (!dom) VPB_ERROR("Bad grid");
+  if (dom->d.p_plane <= 0) VPB_ERROR("the domain keeps its particles in the reference layout: use vpb_sort_p");
   if (lookahead < 0) VPB_ERROR("Bad look-ahead");
-  g_sort_lookahead = lookahead;
-  vpb_sort_p_planes(dom, d_p, d_tmp, np, d_partition);
-  g_sort_lookahead = 0;
+  sort_particles(dom, d_p, d_tmp, np, d_partition, true, lookahead);
 }
 
 // Particle layout of a domain's device-resident species arrays (include/vpic_b200.h "Device particle layout")
