@@ -45,6 +45,9 @@ def oracle():
     _sig(L, "orc_accumulate_hydro_p", None, [_vp, _vp, _i, _f, _vp, _vp])
     _sig(L, "orc_local_adjust_hydro", None, [_vp, _vp, _i])
     _sig(L, "orc_synchronize_hydro", None, [_vp, _vp, _i, _i])
+    _sig(L, "orc_hydro_face_floats", _i, [_i, _vp])
+    _sig(L, "orc_hydro_face_pack", None, [_i, _vp, _vp, _vp])
+    _sig(L, "orc_hydro_face_unpack", None, [_i, _vp, _vp, _vp])
     _sig(L, "orc_sort_p", None, [_vp, _vp, _i, _vp, _vp])
     _sig(L, "orc_boundary_p_pack", _i, [_vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp])
     _sig(L, "orc_boundary_p_inject", _i, [_vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp])

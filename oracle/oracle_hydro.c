@@ -132,33 +132,47 @@ void orc_local_adjust_hydro(vpb_hydro_t *h, const vpb_grid_t *g, int nproc) {
     }
 }
 
-void orc_synchronize_hydro(vpb_hydro_t *h, const vpb_grid_t *g, int rank, int nproc) {
-  const int n[3] = {g->nx, g->ny, g->nz};
+/* one face message (hydro.c:46-67): [cell size along the face normal, 14 moments of every node of the face plane].
+ * face 0..5 = -x -y -z +x +y +z; a message packed from face F is consumed through the receiver's face (F+3)%6 */
+int orc_hydro_face_floats(int face, const vpb_grid_t *g) {
+  const int n[3] = {g->nx, g->ny, g->nz}, X = face % 3;
+  return 1 + NCOMP * (n[(X + 1) % 3] + 1) * (n[(X + 2) % 3] + 1);
+}
+
+void orc_hydro_face_pack(int face, const vpb_hydro_t *hc, const vpb_grid_t *g, float *buf) {
+  vpb_hydro_t *h = (vpb_hydro_t *)hc;
+  const int n[3] = {g->nx, g->ny, g->nz}, X = face % 3;
   const float cell[3] = {g->dx, g->dy, g->dz};
+  float *q = buf;
+  *(q++) = cell[X];
+  FOR_NODE_PLANE(X, (face < 3 ? 1 : n[X] + 1), { for (int c = 0; c < NCOMP; c++) *(q++) = hv[c]; });
+}
+
+/* hydro.c:69-99: twice weighted sum of my plane and the neighbour's */
+void orc_hydro_face_unpack(int face, vpb_hydro_t *h, const vpb_grid_t *g, const float *buf) {
+  const int n[3] = {g->nx, g->ny, g->nz}, X = face % 3;
+  const float cell[3] = {g->dx, g->dy, g->dz};
+  const float *m = buf;
+  float rw = *(m++), lw = rw + cell[X];
+  rw /= lw;
+  lw = cell[X] / lw;
+  lw += lw;
+  rw += rw;
+  FOR_NODE_PLANE(X, (face < 3 ? 1 : n[X] + 1), { for (int c = 0; c < NCOMP; c++) hv[c] = lw * hv[c] + rw * (*(m++)); });
+}
+
+void orc_synchronize_hydro(vpb_hydro_t *h, const vpb_grid_t *g, int rank, int nproc) {
   orc_local_adjust_hydro(h, g, nproc);
   for (int X = 0; X < 3; X++) {             /* x faces, then y, then z (hydro.c:107-136) */
-    const int Y = (X + 1) % 3, Z = (X + 2) % 3;
-    const size_t count = (size_t)NCOMP * (n[Y] + 1) * (n[Z] + 1);
-    float *msg[2] = {NULL, NULL};           /* [0]: packed from plane 1 (sent towards -X), [1]: from plane n+1 */
-    for (int s = -1; s <= 1; s += 2) {
-      if (face_bc(g, X, s) != rank) continue;   /* only self-joined faces exist on one rank */
-      float *m = (float *)malloc((1 + count) * sizeof(float)), *q = m;
-      *(q++) = cell[X];
-      FOR_NODE_PLANE(X, (s < 0 ? 1 : n[X] + 1), { for (int c = 0; c < NCOMP; c++) *(q++) = hv[c]; });
-      msg[s < 0 ? 0 : 1] = m;
+    float *msg[2] = {NULL, NULL};           /* [0]: packed from the -X face, [1]: from the +X face */
+    for (int s = 0; s < 2; s++) {
+      if (face_bc(g, X, s ? 1 : -1) != rank) continue;   /* only self-joined faces exist on one rank */
+      msg[s] = (float *)malloc((size_t)orc_hydro_face_floats(X + 3 * s, g) * sizeof(float));
+      orc_hydro_face_pack(X + 3 * s, h, g, msg[s]);
     }
-    /* a message sent towards -X arrives through the receiver's +X face and updates plane n+1 (END_RECV(-1,..)
-     * comes first), the one sent towards +X updates plane 1 */
-    for (int k = 0; k < 2; k++) {
-      const float *m = msg[k];
-      if (!m) continue;
-      float rw = *(m++), lw = rw + cell[X];
-      rw /= lw;
-      lw = cell[X] / lw;
-      lw += lw;
-      rw += rw;
-      FOR_NODE_PLANE(X, (k == 0 ? n[X] + 1 : 1), { for (int c = 0; c < NCOMP; c++) hv[c] = lw * hv[c] + rw * (*(m++)); });
-    }
+    /* what was sent through my -X face comes back through my +X face, which the reference unpacks first */
+    if (msg[0]) orc_hydro_face_unpack(X + 3, h, g, msg[0]);
+    if (msg[1]) orc_hydro_face_unpack(X, h, g, msg[1]);
     free(msg[0]);
     free(msg[1]);
   }

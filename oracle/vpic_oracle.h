@@ -38,6 +38,9 @@ void orc_accumulate_hydro_p(vpb_hydro_t *h0, const vpb_particle_t *p0, int n, fl
                             const vpb_grid_t *g);
 void orc_local_adjust_hydro(vpb_hydro_t *h, const vpb_grid_t *g, int nproc);
 void orc_synchronize_hydro(vpb_hydro_t *h, const vpb_grid_t *g, int rank, int nproc);
+int orc_hydro_face_floats(int face, const vpb_grid_t *g);
+void orc_hydro_face_pack(int face, const vpb_hydro_t *h, const vpb_grid_t *g, float *buf);
+void orc_hydro_face_unpack(int face, vpb_hydro_t *h, const vpb_grid_t *g, const float *buf);
 /* boundary_p.c:9-71 */
 void orc_accumulate_rhob(vpb_field_t *f, const vpb_particle_t *p, const vpb_grid_t *g);
 /* sort_p.c:16-77 (stable out-of-place counting sort); partition has nv+1 entries */

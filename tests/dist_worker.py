@@ -187,6 +187,41 @@ def main():
     for r_ in reqs:
         r_.wait()
     assert torch.equal(mine_hi, other_lo), "shared plane differs between the two ranks after synchronize_jf"
+    # 4. hydro moments (hydro_p.c, sf_interface/hydro.c): every rank deposits its own particles, doubles the nodes on
+    #    local faces, then exchanges the face planes axis by axis; the nodes it owns or shares must equal the
+    #    single-domain result up to float summation order, and the two copies of a shared plane must be identical.
+    rngf = np.random.default_rng(13)
+    fi_glob = abi.aligned_zeros(gg.nv, abi.interpolator_dtype)
+    for name in abi.interpolator_dtype.names:
+        if name != "_pad":
+            fi_glob[name] = (0.2 * rngf.standard_normal(gg.nv)).astype(np.float32)
+    fi_loc = abi.aligned_zeros(g.nv, abi.interpolator_dtype)
+    fi_loc.reshape(g.shape)[:, :, :] = fi_glob.reshape(gg.shape)[:, :, x0:x0 + nx + 2]
+    hg, hl = abi.aligned_zeros(gg.nv, abi.hydro_dtype), abi.aligned_zeros(g.nv, abi.hydro_dtype)
+    O.orc_accumulate_hydro_p(ptr(hg), ptr(Pg), npg, 1.0, ptr(fi_glob), gg.ref())
+    O.orc_synchronize_hydro(ptr(hg), gg.ref(), 0, 1)
+    O.orc_accumulate_hydro_p(ptr(hl), ptr(Pl), nl, 1.0, ptr(fi_loc), g.ref())
+    O.orc_local_adjust_hydro(ptr(hl), g.ref(), world)
+    for X in range(3):
+        out = {}
+        for face in (X, X + 3):
+            b = np.zeros(O.orc_hydro_face_floats(face, g.ref()), np.float32)
+            O.orc_hydro_face_pack(face, ptr(hl), g.ref(), ptr(b))
+            out[face] = b
+        got = exchange(out, peers, rank, {face: len(out[face]) for face in out})
+        for face in (X + 3, X):                 # the reference unpacks the +X side first (hydro.c:111-112)
+            O.orc_hydro_face_unpack(face, ptr(hl), g.ref(), ptr(np.ascontiguousarray(got[face])))
+    a4 = hl.view(np.float32).reshape(g.shape + (16,))[1:, 1:, 1:nx + 2, :14]
+    b4 = hg.view(np.float32).reshape(gg.shape + (16,))[1:, 1:, x0 + 1:x0 + nx + 2, :14]
+    hs = np.abs(hg.view(np.float32).reshape(-1, 16)[:, :14]).max(axis=0)
+    assert np.all(np.abs(a4 - b4) <= 2e-5 * hs), ("hydro", rank, float(np.max(np.abs(a4 - b4) / hs)))
+    h_hi = torch.from_numpy(np.ascontiguousarray(a4[:, :, nx, :]))
+    h_lo = torch.from_numpy(np.ascontiguousarray(a4[:, :, 0, :]))
+    o_lo = torch.empty_like(h_lo)
+    reqs = [dist.isend(h_lo, (rank - 1) % world, tag=78), dist.irecv(o_lo, (rank + 1) % world, tag=78)]
+    for r_ in reqs:
+        r_.wait()
+    assert torch.equal(h_hi, o_lo), "shared node plane differs between the two ranks after synchronize_hydro"
     dist.barrier()
     if rank == 0:
         print("DIST_OK world=%d" % world)
