@@ -99,8 +99,7 @@ void delete_field_advance(vpb_field_advance_t *fa);
 /* src/util/util_base.h:261-280 (util.c:46-91): the reference's single allocation
  * choke-point.  Substituting it puts every large array in CUDA managed memory,
  * so kernels run on deck-visible pointers in place. */
-void util_malloc_aligned(const char *err_fmt, const char *file, int line, const char *name,
-                         void *mem_ref, size_t n, size_t a);
+void util_malloc_aligned(const char *err_fmt /* two %lu: bytes, alignment */, void *mem_ref, size_t n, size_t a);
 void util_free_aligned(void *mem_ref);
 
 #endif /* VPB_NO_REFERENCE_NAMES */

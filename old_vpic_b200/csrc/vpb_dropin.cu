@@ -193,17 +193,24 @@ vpb_domain_t *vpb_domain_of_grid(const vpb_grid_t *g) { return domain_of(g); }
 // util_malloc_aligned / util_free_aligned (util.c:46-91): managed memory, so every
 // array the reference allocates is directly usable by the kernels AND by the deck
 // ---------------------------------------------------------------------------
-void util_malloc_aligned(const char *err_fmt, const char *file, int line, const char *name, void *mem_ref, size_t n, size_t a) {
-  (void)a;   // cudaMallocManaged returns at least 256-byte alignment; the reference asks for <=128
+void util_malloc_aligned(const char *err_fmt, void *mem_ref, size_t n, size_t a) {
+  // util.c:46-78: err_fmt has exactly two %lu (bytes, alignment); a must be a power of two.  cudaMallocManaged returns
+  // at least 256-byte alignment; the reference asks for <= 128.
+  if (!err_fmt) err_fmt = "malloc aligned failed (n=%lu, a=%lu)";
   char **mem = (char **)mem_ref;
-  if (!mem) { fprintf(stderr, "Error at %s(%i):\n\tNULL mem_ref\n", file, line); exit(1); }
+  if (!mem || a == 0 || (a & (a - 1)) != 0) {
+    fprintf(stderr, "Error at %s(%i):\n\t", __FILE__, __LINE__);
+    fprintf(stderr, err_fmt, (unsigned long)n, (unsigned long)a);
+    fprintf(stderr, "\n");
+    exit(1);
+  }
   if (n == 0) { *mem = nullptr; return; }
   void *p = nullptr;
   ctx();
   cudaError_t e = cudaMallocManaged(&p, n);
   if (e != cudaSuccess) {
-    fprintf(stderr, "Error at %s(%i):\n\t", file, line);
-    fprintf(stderr, err_fmt, (unsigned long)n, name);
+    fprintf(stderr, "Error at %s(%i):\n\t", __FILE__, __LINE__);
+    fprintf(stderr, err_fmt, (unsigned long)n, (unsigned long)a);
     fprintf(stderr, "\n");
     exit(1);
   }
@@ -469,8 +476,8 @@ void sort_p(vpb_species_t *sp, const vpb_grid_t *g) {
   vpb_domain_t *dom = domain_of(g);
   Context &c = ctx();
   const size_t nv1 = nvox(g) + 1;
-  if (!sp->partition) util_malloc_aligned("Failed to allocate %lu bytes for \"%s\"", __FILE__, __LINE__, "sp->partition",
-                                          &sp->partition, nv1 * sizeof(int), 128);   // sort_p.c:32
+  if (!sp->partition) util_malloc_aligned("MALLOC_ALIGNED( sp->partition, (%lu bytes), 128 (%lu bytes) ) failed", &sp->partition,
+                                          nv1 * sizeof(int), 128);   // sort_p.c:32
   if (sp->np == 0) return;   // sort_p.c:35
   Residency r;
   vpb_particle_t *dp = (vpb_particle_t *)r.get(sp->p, (size_t)sp->np * sizeof(vpb_particle_t), RW);

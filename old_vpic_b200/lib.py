@@ -43,7 +43,7 @@ SIGNATURES = {
     "unload_accumulator": (None, [_vp, _vp, _vp]),
     "new_field_advance": (_vp, [_vp, _vp, _vp]),
     "delete_field_advance": (None, [_vp]),
-    "util_malloc_aligned": (None, [C.c_char_p, C.c_char_p, _i, C.c_char_p, _vp, _sz, _sz]),
+    "util_malloc_aligned": (None, [C.c_char_p, _vp, _sz, _sz]),
     "util_free_aligned": (None, [_vp]),
     # (B) device-resident layer
     "vpb_init": (_i, [_i]),

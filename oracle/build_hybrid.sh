@@ -1,0 +1,41 @@
+#!/usr/bin/env bash
+# TEST INFRASTRUCTURE -- not part of the product.
+#
+# The drop-in link of INTEGRATION.md, done for real: the reference's own host objects (compiled by build_ref.sh)
+# WITHOUT the translation units of the hot path, plus libvpic_b200.so, linked into deck executables exactly the way
+# buildscript.in:9 links a deck.  Proves that the library provides every symbol the rest of the reference needs and
+# gives tests/test_gpu_deck.py an UNMODIFIED reference host program to run on the GPU.
+#   _ref/hybrid/libvpic_host.a              reference minus hot path (util.c with its two allocation symbols localized)
+#   _ref/hybrid/turbulence.b200.op          decks/trecon-part/turbulence.cxx as shipped (link check; it wants 4 ranks)
+#   _ref/hybrid/thermal_small.b200.op       oracle/decks/thermal_small.cxx on the library
+#   _ref/thermal_small.op                   the same deck on the reference alone (scalar flavour of the hot path)
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+REF="${VPIC_REF:-/root/reference}"
+OUT="$HERE/_ref"
+LIBDIR="$HERE/../old_vpic_b200"
+if [ ! -d "$REF/src" ]; then
+  echo "build_hybrid: $REF not present; keeping prebuilt $OUT/hybrid (if any)"; exit 0
+fi
+[ -d "$OUT/obj_sse" ] || bash "$HERE/build_ref.sh"
+[ -e "$LIBDIR/libvpic_b200.so" ] || { echo "build_hybrid: build libvpic_b200.so first"; exit 1; }
+mkdir -p "$OUT/hybrid"
+HOT='src_field_advance_standard_|src_sf_interface_|src_species_advance_standard_|ref_harness|src_util_util.c.o'
+objcopy --localize-symbol=util_malloc_aligned --localize-symbol=util_free_aligned \
+        "$OUT/obj_sse/src_util_util.c.o" "$OUT/hybrid/util_local.o"
+rm -f "$OUT/hybrid/libvpic_host.a"
+ar rcs "$OUT/hybrid/libvpic_host.a" $(ls "$OUT"/obj_sse/*.o | grep -Ev "$HOT") "$OUT/hybrid/util_local.o"
+COMMON="-D_XOPEN_SOURCE=600 -O2 -fno-strict-aliasing -fomit-frame-pointer -mfpmath=sse -fPIC -w -I$OUT/tree/src/include -I$HERE/mpi_shim"
+link_hybrid() { # deck.cxx name
+  g++ -std=gnu++98 $COMMON -DUSE_V4_SSE -DINPUT_DECK="$1" "$OUT/tree/src/main.cxx" "$OUT/tree/src/deck_wrapper.cxx" \
+      "$OUT/hybrid/libvpic_host.a" -L"$LIBDIR" -lvpic_b200 -Wl,-rpath,'$ORIGIN/../../../old_vpic_b200' -lm -lpthread \
+      -o "$OUT/hybrid/$2.b200.op"
+}
+link_hybrid "$REF/decks/trecon-part/turbulence.cxx" turbulence
+link_hybrid "$HERE/decks/thermal_small.cxx" thermal_small
+# the same deck on the reference alone; hot path in its scalar flavour (what the library is bit-compatible with)
+rm -f "$OUT/hybrid/libvpic_ref_scalar.a"
+ar rcs "$OUT/hybrid/libvpic_ref_scalar.a" $(ls "$OUT"/obj_scalar/*.o | grep -v ref_harness)
+g++ -std=gnu++98 $COMMON -DINPUT_DECK="$HERE/decks/thermal_small.cxx" "$OUT/tree/src/main.cxx" "$OUT/tree/src/deck_wrapper.cxx" \
+    "$OUT/hybrid/libvpic_ref_scalar.a" -lm -lpthread -o "$OUT/thermal_small.op"
+echo "build_hybrid: ok -> $OUT/hybrid"

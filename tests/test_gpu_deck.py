@@ -1,0 +1,36 @@
+"""GPU: an unmodified reference HOST PROGRAM on the library.  oracle/decks/thermal_small.cxx (a deck written for this
+repository against the reference's deck API: thermal e-/p+ plasma, 16^3 cells x 8 ppc, periodic, 20 steps, div-clean
+every 10) is built twice by oracle/build_hybrid.sh: on the reference alone (scalar hot path) and on the reference's
+host objects + libvpic_b200.so (link-time substitution, util_malloc_aligned -> CUDA managed memory,
+layer-A entry points working in place).  The `energies` file the deck's dump_energies() writes on the GPU must match
+the one the pure reference wrote here (tests/golden/deck_thermal_small_energies.txt) within 1e-4 per column."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "oracle", "_ref", "hybrid", "thermal_small.b200.op")
+GOLD = os.path.join(ROOT, "tests", "golden", "deck_thermal_small_energies.txt")
+
+pytestmark = pytest.mark.gpu
+
+
+def read_energies(path):
+    rows = [[float(x) for x in line.split()] for line in open(path) if line.strip() and not line.startswith("%")]
+    return np.array(rows)
+
+
+def test_reference_deck_runs_on_the_library(tmp_path):
+    if not os.path.exists(EXE):
+        pytest.skip("oracle/_ref/hybrid/thermal_small.b200.op not built (needs /root/reference at build time)")
+    r = subprocess.run([EXE, "-tpp=1"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    got, want = read_energies(tmp_path / "energies"), read_energies(GOLD)
+    assert got.shape == want.shape == (21, 9)
+    assert np.array_equal(got[:, 0], want[:, 0])                      # step column
+    scale = np.abs(want[:, 1:]).max(axis=0)
+    rel = np.abs(got[:, 1:] - want[:, 1:]) / scale
+    assert rel.max() < 1e-4, rel.max(axis=0)
+    assert want[-1, 1:7].sum() > 0 and got[-1, 7] > 0 and got[-1, 8] > 0
