@@ -68,3 +68,59 @@ def test_library_exports_every_declared_symbol():
         tab = abi.FieldAdvanceMethods.in_dll(L, name)
         assert all(getattr(tab, n) for n in abi.FieldAdvanceMethods.NAMES), name
     assert set(lib.SIGNATURES) >= set(_declared_functions()), sorted(set(_declared_functions()) - set(lib.SIGNATURES))
+
+
+def _prototypes(text):
+    """name -> (return type, [parameter types]) for every C prototype in `text`, types normalised for comparison."""
+    import re
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", " ", text)
+    text = re.sub(r"^\s*#.*$", " ", text, flags=re.M)
+    text = re.sub(r"ALIGNED\(\d+\)|BEGIN_C_DECLS|END_C_DECLS", " ", text)
+    out = {}
+
+    def norm(t):
+        t = re.sub(r"ALIGNED\(\d+\)|\bconst\b|\brestrict\b|\bstruct\b|\bextern\b", " ", t)
+        t = re.sub(r"\bvpb_", "", t)
+        t = t.replace("*", " * ")
+        return " ".join(t.split())
+
+    for m in re.finditer(r"([A-Za-z_][\w\s\*]*?)\b([a-z_][a-z0-9_]*)\s*\(([^;{}()]*)\)\s*;", text):
+        ret, name, params = m.group(1), m.group(2), m.group(3)
+        plist = []
+        for prm in params.split(","):
+            prm = norm(prm)
+            if prm in ("void", ""):
+                continue
+            toks = prm.split()
+            if len(toks) > 1 and toks[-1] != "*" and not toks[-1].endswith("_t"):
+                toks = toks[:-1]                      # drop the parameter name
+            plist.append(" ".join(toks))
+        out[name] = (norm(ret), plist)
+    return out
+
+
+def test_reference_named_prototypes_match_the_reference_headers():
+    """Same names, same argument lists: every layer-A function of include/vpic_b200.h against the reference header
+    that declares it (spa.h, sf_interface.h, field_advance.h, util_base.h), struct names compared modulo the vpb_
+    prefix.  (Layouts are covered by test_layouts_match_reference.)"""
+    ref_root = "/root/reference/src"
+    if not os.path.isdir(ref_root):
+        pytest.skip("needs /root/reference")
+    ref = {}
+    for h in ("species_advance/standard/spa.h", "sf_interface/sf_interface.h", "field_advance/field_advance.h", "util/util_base.h"):
+        ref.update(_prototypes(open(os.path.join(ref_root, h)).read()))
+    mine_text = open(os.path.join(ROOT, "include", "vpic_b200.h")).read()
+    mine_text = mine_text[:mine_text.index("(B) Device-resident layer")]
+    mine = {k: v for k, v in _prototypes(mine_text).items() if not k.startswith("vpb_")}
+    assert len(mine) >= 27
+    checked = 0
+    for name, (ret, params) in mine.items():
+        assert name in ref, "%s is not declared by the reference headers" % name
+        r_ret, r_params = ref[name]
+        assert len(params) == len(r_params), (name, params, r_params)
+        for a, b in zip(params, r_params):       # an opaque pointer (void *) may stand for any pointer of the reference
+            assert a == b or (a == "void *" and b.endswith("*")), (name, params, r_params)
+        assert ret == r_ret, (name, ret, r_ret)
+        checked += 1
+    assert checked >= 27
