@@ -22,6 +22,37 @@ def read_energies(path):
     return np.array(rows)
 
 
+def test_reference_deck_with_walls_sheet_and_hydro_dump(tmp_path):
+    """oracle/decks/sheet_small.cxx: the trecon-part geometry (periodic x/y, conducting reflecting z walls, force-free
+    sheet, hot drifting pair plasma) with an electron hydro dump at the last step -- clear_hydro, accumulate_hydro_p and
+    synchronize_hydro called by the reference's own dump.cxx on the library's arrays."""
+    exe = EXE.replace("thermal_small", "sheet_small")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/hybrid/sheet_small.b200.op not built (needs /root/reference at build time)")
+    r = subprocess.run([exe, "-tpp=1"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    got, want = read_energies(tmp_path / "energies"), read_energies(GOLD.replace("thermal_small", "sheet_small"))
+    assert got.shape == want.shape == (21, 9)
+    # field columns on the scale of the total field energy, kinetic columns on their own (tests/test_gpu_harris.py)
+    scale = np.abs(want[:, 1:]).max(axis=0)
+    scale[:6] = want[:, 1:7].sum(axis=1).max()
+    rel = np.abs(got[:, 1:] - want[:, 1:]) / scale
+    assert rel.max() < 1e-4, rel.max(axis=0)
+    # hydro dump: header + hydro_t[(nx+2)(ny+2)(nz+2)]
+    z = np.load(os.path.join(ROOT, "tests", "golden", "deck_sheet_small_ehydro.npz"))
+    raw = open(tmp_path / "ehydro.0", "rb").read()
+    assert len(raw) == int(z["header_bytes"]) + z["hydro"].size * 4
+    assert raw[:int(z["header_bytes"])] == open(os.path.join(ROOT, "tests", "golden", "deck_sheet_small_ehydro.hdr"), "rb").read()
+    h = np.frombuffer(raw[int(z["header_bytes"]):], dtype=np.float32).reshape(-1, 16)
+    w = z["hydro"]
+    hs = np.abs(w[:, :14]).max(axis=0)
+    hrel = np.abs(h[:, :14] - w[:, :14]) / hs
+    assert hrel[:, 3].max() < 1e-3 and hrel[:, 7].max() < 1e-3         # rho, ke: large means
+    # the zero-mean moments of a node move by a fraction of ONE particle's contribution when that particle's
+    # in-cell test falls the other way in the two runs (DESIGN.md 2); such nodes are isolated
+    assert hrel.max() < 5e-2 and np.mean(hrel > 2e-3) < 2e-3, (hrel.max(), float(np.mean(hrel > 2e-3)))
+
+
 def test_reference_deck_runs_on_the_library(tmp_path):
     if not os.path.exists(EXE):
         pytest.skip("oracle/_ref/hybrid/thermal_small.b200.op not built (needs /root/reference at build time)")
