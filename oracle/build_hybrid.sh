@@ -7,8 +7,8 @@
 # gives tests/test_gpu_deck.py an UNMODIFIED reference host program to run on the GPU.
 #   _ref/hybrid/libvpic_host.a              reference minus hot path (util.c with its two allocation symbols localized)
 #   _ref/hybrid/turbulence.b200.op          decks/trecon-part/turbulence.cxx as shipped (link check; it wants 4 ranks)
-#   _ref/hybrid/{thermal,sheet}_small.b200.op   oracle/decks/*.cxx on the library
-#   _ref/{thermal,sheet}_small.op               the same decks on the reference alone (scalar flavour of the hot path)
+#   _ref/hybrid/{thermal,sheet,absorb}_small.b200.op   oracle/decks/*.cxx on the library
+#   _ref/{thermal,sheet,absorb}_small.op               the same decks on the reference alone (scalar flavour of the hot path)
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 REF="${VPIC_REF:-/root/reference}"
@@ -34,10 +34,11 @@ link_hybrid() { # deck.cxx name
 link_hybrid "$REF/decks/trecon-part/turbulence.cxx" turbulence
 link_hybrid "$HERE/decks/thermal_small.cxx" thermal_small
 link_hybrid "$HERE/decks/sheet_small.cxx" sheet_small
+link_hybrid "$HERE/decks/absorb_small.cxx" absorb_small
 # the same deck on the reference alone; hot path in its scalar flavour (what the library is bit-compatible with)
 rm -f "$OUT/hybrid/libvpic_ref_scalar.a"
 ar rcs "$OUT/hybrid/libvpic_ref_scalar.a" $(ls "$OUT"/obj_scalar/*.o | grep -v ref_harness)
-for deck in thermal_small sheet_small; do
+for deck in thermal_small sheet_small absorb_small; do
   g++ -std=gnu++98 $COMMON -DINPUT_DECK="$HERE/decks/$deck.cxx" "$OUT/tree/src/main.cxx" "$OUT/tree/src/deck_wrapper.cxx" \
       "$OUT/hybrid/libvpic_ref_scalar.a" -lm -lpthread -o "$OUT/$deck.op"
 done

@@ -22,7 +22,7 @@ def dynsyms(path, undefined):
     return {line.split()[-1].split("@")[0] for line in out.splitlines() if line.strip()}
 
 
-@pytest.mark.parametrize("deck", ["turbulence", "thermal_small", "sheet_small"])
+@pytest.mark.parametrize("deck", ["turbulence", "thermal_small", "sheet_small", "absorb_small"])
 def test_deck_links_against_the_library(deck):
     exe = os.path.join(HYB, deck + ".b200.op")
     if not os.path.exists(exe):

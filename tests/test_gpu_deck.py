@@ -53,6 +53,29 @@ def test_reference_deck_with_walls_sheet_and_hydro_dump(tmp_path):
     assert hrel.max() < 5e-2 and np.mean(hrel > 2e-3) < 2e-3, (hrel.max(), float(np.mean(hrel > 2e-3)))
 
 
+def test_reference_deck_with_absorbing_walls(tmp_path):
+    """oracle/decks/absorb_small.cxx: six absorbing faces (Higdon fields, absorbed particles): nearly half of the
+    particles are removed by boundary_p (accumulate_rhob + back-fill) in 20 steps.  Counts are integers that depend on
+    20 steps of history: a particle whose wall hit falls one step later in one of the runs may shift them by one."""
+    exe = EXE.replace("thermal_small", "absorb_small")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/hybrid/absorb_small.b200.op not built (needs /root/reference at build time)")
+    r = subprocess.run([exe, "-tpp=1"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    want_counts = dict(line.split() for line in open(GOLD.replace("thermal_small_energies", "absorb_small_counts")))
+    got_counts = dict(line.split() for line in open(tmp_path / "counts"))
+    assert set(got_counts) == set(want_counts)
+    for name in want_counts:
+        assert abs(int(got_counts[name]) - int(want_counts[name])) <= 2, (got_counts, want_counts)
+        assert int(want_counts[name]) < 12 * 10 * 8 * 16 * 0.6           # the walls did absorb
+    got, want = read_energies(tmp_path / "energies"), read_energies(GOLD.replace("thermal_small", "absorb_small"))
+    assert got.shape == want.shape == (21, 9)
+    scale = np.abs(want[:, 1:]).max(axis=0)
+    scale[:6] = want[:, 1:7].sum(axis=1).max()
+    rel = np.abs(got[:, 1:] - want[:, 1:]) / scale
+    assert rel.max() < 5e-4, rel.max(axis=0)                            # one particle is 1.2e-4 of a kinetic column
+
+
 def test_reference_deck_runs_on_the_library(tmp_path):
     if not os.path.exists(EXE):
         pytest.skip("oracle/_ref/hybrid/thermal_small.b200.op not built (needs /root/reference at build time)")
