@@ -322,3 +322,38 @@ def test_material_coefficients(orc, ref_scalar):
     for k in names:
         assert np.array_equal(out[k].view(np.uint32), ref_m[k].view(np.uint32)), k
     assert out["nonconductive"].tolist() == [1.0, 0.0, 0.0]
+
+
+@pytest.mark.parametrize("n,np_", [((6, 5, 4), 4000), ((1, 1, 16), 500), ((8, 1, 6), 3001)])
+def test_boundary_p_absorbing(orc, ref_scalar, n, np_):
+    """boundary_p.c:77-505 on one rank with absorbing walls: every mover advance_p left is removed, its charge goes to
+    rhob (accumulate_rhob, :9-71) and the holes are back-filled from the tail.  The oracle's serial loop is the
+    reference's, so survivors (ORDER included), counts and rhob are bit-identical."""
+    L = ref_scalar
+    g = RefGrid(L, n, "absorbing")
+    rng = np.random.default_rng(31)
+    p = random_particles(rng, g, np_, vth=0.7, edge_frac=0.02)
+    fi = random_interpolator(rng, g, amp=0.2)
+    f = random_fields(rng, g)
+    a = abi.aligned_zeros(g.nv, abi.accumulator_dtype)
+    pm = abi.aligned_zeros(np_, abi.mover_dtype)
+    nm = orc.orc_advance_p(ptr(p), np_, -1.0, ptr(pm), np_, ptr(a), ptr(fi), g.ref())
+    assert nm > 0
+    # oracle
+    p_o, f_o = p.copy(), f.copy()
+    out = [abi.aligned_zeros(nm + 1, abi.injector_dtype) for _ in range(6)]
+    outp = (C.c_void_p * 6)(*[o.ctypes.data for o in out])
+    n_out = (C.c_int * 6)()
+    np_o = orc.orc_boundary_p_pack(ptr(p_o), np_, ptr(pm), nm, 0, ptr(f_o), g.ref(), 0, 1, outp, n_out)
+    assert sum(n_out) == 0 and np_o == np_ - nm
+    # reference, on a species_t of its own layout
+    p_r, f_r, pm_r = p.copy(), f.copy(), pm.copy()
+    a_r, _ = _accumulators(L, g)
+    sp = abi.SpeciesStruct()
+    sp.id, sp.np, sp.max_np, sp.p = 0, np_, np_, p_r.ctypes.data
+    sp.nm, sp.max_nm, sp.pm = nm, np_, pm_r.ctypes.data
+    sp.q_m = -1.0
+    L.boundary_p(C.byref(sp), ptr(f_r), ptr(a_r), g.ref(), None)
+    assert sp.np == np_o and sp.nm == 0
+    assert_bits_equal(p_r[:sp.np], p_o[:np_o], "survivors, in the reference's order")
+    assert_bits_equal(f_r, f_o, "fields (rhob)")
