@@ -1,0 +1,46 @@
+"""The reference itself on W>1 ranks (separate processes over oracle/mpi_shim's shared-memory transport) against
+the oracle's multi-rank pieces, bit for bit -- see tests/ref_mpi_worker.py.  CPU only; skipped where oracle/_ref
+was not built (it is built in the dev container by __graft_entry__.build())."""
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import pytest
+
+from helpers import loader
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+pytestmark = pytest.mark.skipif(not loader.ref_available("scalar"), reason="oracle/_ref not built")
+
+
+def run_ranks(world, env_extra, timeout=240):
+    with tempfile.NamedTemporaryFile(prefix="vpic_shim_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as shm:
+        procs = []
+        for r in range(world):
+            env = dict(os.environ, VPIC_SHIM_NPROC=str(world), VPIC_SHIM_RANK=str(r), VPIC_SHIM_SHM=shm.name,
+                       VPIC_SHIM_SLOT_MB="1", **env_extra)
+            procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "ref_mpi_worker.py")], env=env,
+                                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+        t0, failed = time.time(), False
+        while any(p.poll() is None for p in procs):
+            if any(p.poll() not in (None, 0) for p in procs) or time.time() - t0 > timeout:
+                failed = True       # a rank died: its peers would spin in the shim for ever
+                for p in procs:
+                    if p.poll() is None:
+                        p.kill()
+                break
+            time.sleep(0.05)
+        outs = [p.communicate()[0] for p in procs]
+    assert not failed and all(p.returncode == 0 for p in procs), "\n".join(o[-3000:] for o in outs)
+    for r, o in enumerate(outs):
+        assert "REF_MPI_OK rank=%d" % r in o, o[-3000:]
+
+
+@pytest.mark.parametrize("topo,kind,gn", [((2, 1, 1), "periodic", (8, 6, 4)), ((1, 1, 2), "absorbing", (5, 4, 6)),
+                                           ((1, 2, 1), "metal", (4, 8, 1)), ((2, 2, 1), "periodic", (8, 6, 3))])
+def test_reference_on_ranks_matches_oracle(topo, kind, gn):
+    run_ranks(topo[0] * topo[1] * topo[2],
+              {"REFW_TOPO": ",".join(map(str, topo)), "REFW_KIND": kind, "REFW_GN": ",".join(map(str, gn))})
