@@ -149,6 +149,12 @@ long vpb_launch_count(int reset);
  * every rank calls vpb_comm_init.  Replaces mp_init/new_mp (util/mp/mp.h:14-40). */
 void vpb_comm_unique_id(void *out128);
 void vpb_comm_init(int rank, int nproc, const void *uid128);
+/* The same bootstrap with no host code at all, for host programs that ARE the reference (link-time substitution):
+ * rank, size and the id exchange go through the reference's own message layer, found in the process by name
+ * (mp_rank_cxx, mp_nproc_cxx, mp_allgather_i_cxx; util/mp/mp.hxx:36-143 -- link the executable with -rdynamic).
+ * `mp` is grid_t::mp.  Collective.  Called by the reference-named entry points on first use; returns the world
+ * size, 0 if there is no such message layer or only one rank. */
+int vpb_comm_autoboot(void *mp);
 void vpb_comm_finalize(void);
 int vpb_comm_rank(void);
 int vpb_comm_nproc(void);

@@ -4,6 +4,7 @@
 // (bench.py broadcasts it with torch.distributed, INTEGRATION.md shows the MPI
 // equivalent).
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <string.h>
 #include "vpb_comm.cuh"
 
@@ -116,6 +117,33 @@ void vpb_comm_finalize(void) {
   }
   g_rank = 0;
   g_nproc = 1;
+}
+
+// Bootstrap without a line of host code: when the host program is the reference itself (link-time
+// substitution) its message layer is in the process -- the *_cxx functions of src/util/mp/mp.hxx:22-143 -- and every
+// grid_t carries its handle (grid.h:113).  Rank and size come from mp_rank_cxx / mp_nproc_cxx and the NCCL unique id
+// travels from rank 0 through ONE mp_allgather_i_cxx of 32 ints.  The executable must export those symbols
+// (-rdynamic).  Returns the world size, or 0 when the reference's message layer is not there or the run has one rank.
+int vpb_comm_autoboot(void *mp_handle) {
+  if (g_comm) return g_nproc;
+  if (!mp_handle) return 0;
+  typedef int (*int_fn)(void *);
+  typedef void (*gather_fn)(int *, int *, int, void *);
+  int_fn rank_of = (int_fn)dlsym(RTLD_DEFAULT, "mp_rank_cxx"), nproc_of = (int_fn)dlsym(RTLD_DEFAULT, "mp_nproc_cxx");
+  gather_fn gather = (gather_fn)dlsym(RTLD_DEFAULT, "mp_allgather_i_cxx");
+  if (!rank_of || !nproc_of || !gather) return 0;
+  const int rank = rank_of(mp_handle), nproc = nproc_of(mp_handle);
+  if (nproc <= 1) return 0;
+  static_assert(sizeof(nccl_uid) == 32 * sizeof(int), "unique id is 32 ints");
+  int mine[32];
+  memset(mine, 0, sizeof(mine));
+  if (rank == 0) vpb_comm_unique_id(mine);
+  int *all = (int *)malloc(sizeof(mine) * (size_t)nproc);
+  if (!all) VPB_ERROR("out of memory");
+  gather(mine, all, 32, mp_handle);
+  vpb_comm_init(rank, nproc, all);      // rank 0's block comes first
+  free(all);
+  return nproc;
 }
 
 int vpb_comm_rank(void) { return g_rank; }

@@ -112,7 +112,11 @@ int vpb_init(int device_ordinal) {
   if (e != cudaSuccess || n <= 0)
     VPB_ERROR("no CUDA device is usable (%s); libvpic_b200 has no CPU fallback", cudaGetErrorString(e));
   if (device_ordinal < 0) {
-    const char *lr = getenv("LOCAL_RANK");
+    // the launcher's local rank: torchrun, Open MPI, MVAPICH2, Intel MPI / MPICH (hydra), Slurm, the test shim
+    static const char *const vars[] = {"LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", "MV2_COMM_WORLD_LOCAL_RANK", "MPI_LOCALRANKID",
+                                       "SLURM_LOCALID", "VPIC_SHIM_RANK", nullptr};
+    const char *lr = nullptr;
+    for (int i = 0; vars[i] && !lr; i++) lr = getenv(vars[i]);
     device_ordinal = lr ? atoi(lr) % n : 0;
   }
   if (device_ordinal >= n) VPB_ERROR("device %d requested, %d present", device_ordinal, n);

@@ -152,6 +152,15 @@ static vpb_domain_t *domain_of(const vpb_grid_t *g) {
     vpb_domain_destroy(it->second);
     g_domains.erase(it);
   }
+  // A host program that is the reference itself never calls vpb_comm_init: bring the communicator up through its own
+  // message layer the first time a grid with an mp handle shows up (collective; every rank reaches its first hot-path
+  // call at the same point of advance()/initialize()).
+  static bool boot_tried = false;
+  if (!boot_tried && g->mp && g_world_nproc == 1) {
+    boot_tried = true;
+    const int n = vpb_comm_autoboot(g->mp);
+    if (n > 1) g_world_nproc = n;
+  }
   // the centre entry of bc[] is this rank (grid_structors.c:22, ops.c:47)
   vpb_domain_t *dom = vpb_domain_create(g, g->bc[VPB_BOUNDARY(0, 0, 0)], g_world_nproc);
   g_domains[g] = dom;

@@ -83,6 +83,7 @@ SIGNATURES = {
     "vpb_field_convert": (None, [_vp, _vp, _vp, _i]),
     "vpb_comm_unique_id": (None, [_vp]),
     "vpb_comm_init": (None, [_i, _i, _vp]),
+    "vpb_comm_autoboot": (_i, [_vp]),
     "vpb_comm_finalize": (None, []),
     "vpb_comm_rank": (_i, []),
     "vpb_comm_nproc": (_i, []),

@@ -28,7 +28,7 @@ ar rcs "$OUT/hybrid/libvpic_host.a" $(ls "$OUT"/obj_sse/*.o | grep -Ev "$HOT") "
 COMMON="-D_XOPEN_SOURCE=600 -O2 -fno-strict-aliasing -fomit-frame-pointer -mfpmath=sse -fPIC -w -I$OUT/tree/src/include -I$HERE/mpi_shim"
 link_hybrid() { # deck.cxx name
   g++ -std=gnu++98 $COMMON -DUSE_V4_SSE -DINPUT_DECK="$1" "$OUT/tree/src/main.cxx" "$OUT/tree/src/deck_wrapper.cxx" \
-      "$OUT/hybrid/libvpic_host.a" -L"$LIBDIR" -lvpic_b200 -Wl,-rpath,'$ORIGIN/../../../old_vpic_b200' -lm -lpthread \
+      "$OUT/hybrid/libvpic_host.a" -L"$LIBDIR" -lvpic_b200 -Wl,-rpath,'$ORIGIN/../../../old_vpic_b200' -lm -lpthread -rdynamic \
       -o "$OUT/hybrid/$2.b200.op"
 }
 link_hybrid "$REF/decks/trecon-part/turbulence.cxx" turbulence

@@ -1,5 +1,6 @@
 // TEST INFRASTRUCTURE -- an input deck written for this repository (not part of the reference): the thermal
-// e-/p+ plasma of BASELINE configs[0] scaled down to 16^3 cells x 8 ppc, periodic, one rank.  It uses only the
+// e-/p+ plasma of BASELINE configs[0] scaled down to 16^3 cells x 8 ppc, periodic, split along x over however many ranks the job has
+// (every rank draws the same random stream; inject_particle keeps the particles of its own slab).  It uses only the
 // reference's deck API (src/vpic/vpic.hxx, deck_wrapper.cxx), so the SAME file builds
 //   * against the reference alone            -> oracle/_ref/thermal_small.op        (golden energies), and
 //   * against the reference's host objects with the hot path taken from libvpic_b200.so
@@ -24,7 +25,7 @@ begin_initialization {
   grid->cvac = 1;
   grid->eps0 = 1;
   grid->damp = 0;
-  define_periodic_grid( 0, 0, 0, L, L, L, n, n, n, 1, 1, 1 );
+  define_periodic_grid( 0, 0, 0, L, L, L, n, n, n, int( nproc() ), 1, 1 );
 
   define_material( "vacuum", 1 );
   finalize_field_advance( standard_field_advance );

@@ -88,3 +88,30 @@ def test_reference_deck_runs_on_the_library(tmp_path):
     rel = np.abs(got[:, 1:] - want[:, 1:]) / scale
     assert rel.max() < 1e-4, rel.max(axis=0)
     assert want[-1, 1:7].sum() > 0 and got[-1, 7] > 0 and got[-1, 8] > 0
+
+
+def _gpu_count():
+    try:
+        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=60).stdout
+    except (OSError, subprocess.TimeoutExpired):
+        return 0
+    return sum(1 for line in out.splitlines() if line.startswith("GPU "))
+
+
+@pytest.mark.parametrize("world", [2])
+def test_reference_deck_on_two_gpus(world, tmp_path):
+    """The same unmodified host program on `world` ranks, one GPU each: the host side talks through the reference's mp
+    layer (here over oracle/mpi_shim's shared-memory transport), the library brings NCCL up by itself through that
+    layer (vpb_comm_autoboot: no line of host code added) and picks its GPU from the launcher's local rank.  The
+    deck splits the box along x; the energies must be those of the one-rank reference run
+    (tests/test_ref_multirank.py checks the same for the pure reference on CPU ranks)."""
+    if _gpu_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    if not os.path.exists(EXE):
+        pytest.skip("oracle/_ref/hybrid/thermal_small.b200.op not built (needs /root/reference at build time)")
+    from test_ref_multirank import run_ranks
+    outs = run_ranks(world, {"VPIC_SHIM_SLOT_MB": "2"}, timeout=600, argv=[EXE, "-tpp=1"], cwd=str(tmp_path), marker=None)
+    got, want = read_energies(tmp_path / "energies"), read_energies(GOLD)
+    assert got.shape == want.shape == (21, 9), outs[0][-2000:]
+    rel = np.abs(got[:, 1:] - want[:, 1:]) / np.abs(want[:, 1:]).max(axis=0)
+    assert rel.max() < 1e-4, rel.max(axis=0)
