@@ -153,7 +153,10 @@ void vpb_comm_init(int rank, int nproc, const void *uid128);
  * rank, size and the id exchange go through the reference's own message layer, found in the process by name
  * (mp_rank_cxx, mp_nproc_cxx, mp_allgather_i_cxx; util/mp/mp.hxx:36-143 -- link the executable with -rdynamic).
  * `mp` is grid_t::mp.  Collective.  Called by the reference-named entry points on first use; returns the world
- * size, 0 if there is no such message layer or only one rank. */
+ * size, 0 if there is no such message layer or only one rank.  Ranks that each have a GPU of their own talk over
+ * NCCL; when two ranks of the job share a GPU (which NCCL refuses) the exchanges are staged through the host
+ * program's message layer instead (mp_begin_send_cxx ... mp_end_recv_cxx, mp_allsum_d_cxx).  Tuning
+ * comm.transport: 0 decide as described, 1 NCCL, 2 the host program's layer. */
 int vpb_comm_autoboot(void *mp);
 void vpb_comm_finalize(void);
 int vpb_comm_rank(void);

@@ -5,20 +5,16 @@
 // (periodic along an axis with one rank) is a device copy, not a message.
 #pragma once
 #include "vpb_common.cuh"
+#include "vpb_mp_transport.hpp"   // struct Xfer and the host-staged second transport
 
 namespace vpb {
-
-struct Xfer {
-  const void *send; size_t send_bytes; int send_peer;   // send_peer < 0: nothing to send
-  void *recv; size_t recv_bytes; int recv_peer;          // recv_peer < 0: nothing to receive
-};
 
 int comm_rank();
 int comm_nproc();
 bool comm_is_multi();
 
 // Posts every send and receive of `x[0..n)` as one NCCL group on the library
-// stream.  Messages between the same pair of ranks are matched in posting order,
+// stream (or, for jobs whose ranks share a GPU, through the host program's message layer: vpb_mp_transport.hpp).  Messages between the same pair of ranks are matched in posting order,
 // so callers list sends by face 0..5 and receives by face 3,4,5,0,1,2 (a message
 // sent through face F arrives through the peer's face (F+3)%6).
 void comm_exchange(const Xfer *x, int n);

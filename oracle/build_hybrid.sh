@@ -9,6 +9,7 @@
 #   _ref/hybrid/turbulence.b200.op          decks/trecon-part/turbulence.cxx as shipped (link check; it wants 4 ranks)
 #   _ref/hybrid/{thermal,sheet,absorb}_small.b200.op   oracle/decks/*.cxx on the library
 #   _ref/{thermal,sheet,absorb}_small.op               the same decks on the reference alone (scalar flavour of the hot path)
+#   _ref/turbulence.op                                 the shipped trecon-part deck on the reference alone
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 REF="${VPIC_REF:-/root/reference}"
@@ -42,4 +43,7 @@ for deck in thermal_small sheet_small absorb_small; do
   g++ -std=gnu++98 $COMMON -DINPUT_DECK="$HERE/decks/$deck.cxx" "$OUT/tree/src/main.cxx" "$OUT/tree/src/deck_wrapper.cxx" \
       "$OUT/hybrid/libvpic_ref_scalar.a" -lm -lpthread -o "$OUT/$deck.op"
 done
+# the reference's own trecon-part deck, as shipped (16x16x1 cells, topology 2x2x1): golden energies for the 4-rank run
+g++ -std=gnu++98 $COMMON -DINPUT_DECK="$REF/decks/trecon-part/turbulence.cxx" "$OUT/tree/src/main.cxx" "$OUT/tree/src/deck_wrapper.cxx" \
+    "$OUT/hybrid/libvpic_ref_scalar.a" -lm -lpthread -o "$OUT/turbulence.op"
 echo "build_hybrid: ok -> $OUT/hybrid"

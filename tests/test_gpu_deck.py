@@ -90,28 +90,53 @@ def test_reference_deck_runs_on_the_library(tmp_path):
     assert want[-1, 1:7].sum() > 0 and got[-1, 7] > 0 and got[-1, 8] > 0
 
 
-def _gpu_count():
-    try:
-        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=60).stdout
-    except (OSError, subprocess.TimeoutExpired):
-        return 0
-    return sum(1 for line in out.splitlines() if line.startswith("GPU "))
+# Written in round 1 after the GPU budget was spent: not yet run on hardware.  First thing to run next round:
+#   VPB_RUN_UNVALIDATED=1 python -m pytest tests/test_gpu_deck.py -m gpu -q      (one GPU is enough, see below)
+unvalidated = pytest.mark.skipif(os.environ.get("VPB_RUN_UNVALIDATED") != "1",
+                                 reason="not yet run on hardware (set VPB_RUN_UNVALIDATED=1)")
 
 
-@pytest.mark.parametrize("world", [2])
-def test_reference_deck_on_two_gpus(world, tmp_path):
-    """The same unmodified host program on `world` ranks, one GPU each: the host side talks through the reference's mp
-    layer (here over oracle/mpi_shim's shared-memory transport), the library brings NCCL up by itself through that
-    layer (vpb_comm_autoboot: no line of host code added) and picks its GPU from the launcher's local rank.  The
-    deck splits the box along x; the energies must be those of the one-rank reference run
-    (tests/test_ref_multirank.py checks the same for the pure reference on CPU ranks)."""
-    if _gpu_count() < world:
-        pytest.skip("needs %d GPUs" % world)
+def _run_ranks(exe, world, cwd):
+    """`world` processes of an unmodified reference host program on the library.  The host side talks through the
+    reference's mp layer (here over oracle/mpi_shim's shared-memory transport, which tests/test_ref_multirank.py
+    exercises with the pure reference); the library finds that layer by itself (vpb_comm_autoboot: no line of host
+    code added), picks its GPU from the launcher's local rank and runs its exchanges over NCCL when every rank has a
+    GPU of its own, or through the host program's message layer when ranks share one (tests/test_mp_transport.py
+    drives that transport on CPU ranks) -- so this runs on a one-GPU box too."""
+    from test_ref_multirank import run_ranks
+    return run_ranks(world, {"VPIC_SHIM_SLOT_MB": "8"}, timeout=900, argv=[exe, "-tpp=1"], cwd=str(cwd), marker=None)
+
+
+@unvalidated
+@pytest.mark.parametrize("world", [2, 4])
+def test_reference_deck_on_ranks(world, tmp_path):
+    """oracle/decks/thermal_small.cxx splits the box along x over the ranks of the job; every rank draws the same
+    particles and keeps its slab, so the energies must be those of the one-rank reference run."""
     if not os.path.exists(EXE):
         pytest.skip("oracle/_ref/hybrid/thermal_small.b200.op not built (needs /root/reference at build time)")
-    from test_ref_multirank import run_ranks
-    outs = run_ranks(world, {"VPIC_SHIM_SLOT_MB": "2"}, timeout=600, argv=[EXE, "-tpp=1"], cwd=str(tmp_path), marker=None)
+    outs = _run_ranks(EXE, world, tmp_path)
     got, want = read_energies(tmp_path / "energies"), read_energies(GOLD)
     assert got.shape == want.shape == (21, 9), outs[0][-2000:]
     rel = np.abs(got[:, 1:] - want[:, 1:]) / np.abs(want[:, 1:]).max(axis=0)
     assert rel.max() < 1e-4, rel.max(axis=0)
+
+
+@unvalidated
+def test_trecon_part_deck_as_shipped(tmp_path):
+    """The reference's own trecon-part deck (decks/trecon-part/turbulence.cxx with its config.h: 16x16x1 cells, 50 ppc,
+    four species + tracers, topology 2x2x1, 2500 steps, field/hydro/particle/tracer dumps), not one character changed,
+    linked against libvpic_b200.so and run on four ranks.  The energies it logs every 100 steps are compared with the
+    pure reference's (tests/golden/deck_turbulence_energies.txt, made by tests/golden/make_deck_golden.py)."""
+    exe = EXE.replace("thermal_small", "turbulence")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/hybrid/turbulence.b200.op not built (needs /root/reference at build time)")
+    outs = _run_ranks(exe, 4, tmp_path)
+    got = read_energies(tmp_path / "rundata" / "energies")
+    want = read_energies(GOLD.replace("thermal_small", "turbulence"))
+    assert got.shape == want.shape, outs[0][-2000:]
+    assert np.array_equal(got[:, 0], want[:, 0])
+    # 2500 steps of a chaotic system: field columns on the scale of the total field energy, species columns on their own
+    scale = np.abs(want[:, 1:]).max(axis=0)
+    scale[:6] = want[:, 1:7].sum(axis=1).max()
+    rel = np.abs(got[:, 1:] - want[:, 1:]) / scale
+    assert rel.max() < 1e-3, rel.max(axis=0)
