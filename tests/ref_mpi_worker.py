@@ -105,7 +105,7 @@ def main():
     # 2. particle migration: two species, advance_p leaves movers on the remote faces, then num_comm_round=3
     #    boundary_p calls (vpic.cxx:17, advance.cxx:58-66).  Survivors, their ORDER, the movers still pending,
     #    rhob and the accumulator are compared after every call.
-    npk, cap = 3000, 6000
+    npk, cap = 16 * 188, 6000      # whole bundles of 16: everything through pipeline 0 (advance_p.cxx:41)
     species, accs, fis = [], [], []
     for k in range(W):
         gk = grids[k]
@@ -115,7 +115,19 @@ def main():
         for sid, q in ((0, -1.0), (1, 0.5)):
             p = make_particles(10 * k + sid + 1, gk, npk, cap, q)
             pm = abi.aligned_zeros(cap, abi.mover_dtype)
-            nm = O.orc_advance_p(ptr(p), npk, q, ptr(pm), cap, ptr(acc), ptr(fi), gk.ref())
+            acc1 = abi.aligned_zeros(gk.nv, abi.accumulator_dtype)     # this species alone, for a bit-exact comparison
+            if k == rank:      # the reference's advance_p on its decomposed grid: movers stop at the remote faces
+                p2, pm2 = p.copy(), pm.copy()
+                a2 = abi.aligned_zeros((1 + L.refh_n_pipeline()) * ((gk.nv + 1) // 2 * 2), abi.accumulator_dtype)
+                nm2 = L.advance_p(ptr(p2), npk, q, ptr(pm2), cap, ptr(a2), ptr(fi), gref)
+                L.reduce_accumulators(ptr(a2), gref)
+            nm = O.orc_advance_p(ptr(p), npk, q, ptr(pm), cap, ptr(acc1), ptr(fi), gk.ref())
+            if k == rank:
+                assert nm2 == nm and nm > 0, (nm2, nm)
+                assert_bits_equal(p2[:npk], p[:npk], "advance_p particles (rank %d)" % rank)
+                assert_bits_equal(pm2[:nm], pm[:nm], "advance_p movers (rank %d)" % rank)
+                assert_bits_equal(a2[:gk.nv], acc1, "advance_p accumulator (rank %d)" % rank)
+            acc.view(np.float32)[:] += acc1.view(np.float32)
             sl.append({"id": sid, "p": p, "np": npk, "pm": pm, "nm": nm})
         species.append(sl); accs.append(acc); fis.append(fi)
     assert sum(s["nm"] for s in species[rank]) > 0
