@@ -1,0 +1,19 @@
+#!/usr/bin/env bash
+# First GPU call of round 2: everything that was written in round 1 after the GPU budget was spent.
+#   gpurun --timeout 2400 -- 'bash scripts/gpu_r2_first.sh'
+# 1. the gated tests (kernel variants of advance_p_pair; multi-rank decks on one GPU through the host program's mp layer)
+# 2. advance_p_pair variants in bench.py: 0 default, 1 FULL, 2 LEAN, 3 both (average launch ms in the JSON line)
+set -u
+mkdir -p gpurun_out
+export VPB_RUN_UNVALIDATED=1
+python -m pytest tests/test_gpu_particles.py -q -m gpu -k "variants" > gpurun_out/r2_variants_pytest.log 2>&1
+echo "variants pytest rc=$?" | tee -a gpurun_out/r2_summary.txt
+timeout 1500 python -m pytest tests/test_gpu_deck.py -q -m gpu > gpurun_out/r2_deck_pytest.log 2>&1
+echo "deck pytest rc=$?" | tee -a gpurun_out/r2_summary.txt
+unset VPB_RUN_UNVALIDATED
+for v in 0 1 2 3; do
+  VPB_ADVANCE_P_PAIR_VARIANT=$v python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu-baseline --field-cells 0 \
+    > gpurun_out/r2_bench_variant$v.json 2> gpurun_out/r2_bench_variant$v.err
+  echo "bench variant $v rc=$?" | tee -a gpurun_out/r2_summary.txt
+done
+tail -n 5 gpurun_out/r2_variants_pytest.log gpurun_out/r2_deck_pytest.log
