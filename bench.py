@@ -47,6 +47,10 @@ def parse():
     ap.add_argument("--field-cells", type=int, default=1024, help="cells per axis of the field-only leg (configs[1]); 0 = skip")
     ap.add_argument("--workload", default="thermal", choices=["thermal", "fields"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--deck-e2e", action="store_true",
+                    help="also time BASELINE configs[0] as an unmodified reference host program (oracle/decks/thermal_c1.cxx): "
+                         "on libvpic_b200.so in the b200 arm, on the reference alone in the reference arm (key deck_e2e)")
+    ap.add_argument("--deck-steps", type=int, default=40)
     ap.add_argument("--sort-lookahead", type=int, default=-1,
                     help="sort key = voxel the particle reaches this many steps ahead (-1: 0.6 x the sort interval, 0: current voxel)")
     ap.add_argument("--driver", default="native", choices=["native", "python"], help="time-step driver: csrc/vpb_step.cu or sim.py")
@@ -166,7 +170,36 @@ def run_reference(args):
             "config": workload_config(args), "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if args.deck_e2e:
+        line["deck_e2e"] = deck_e2e(os.path.join(ROOT, "oracle", "_ref", "thermal_c1.op"), args.deck_steps,
+                                    min(os.cpu_count() or 1, 16), "reference alone (V4/SSE + pthreads hot path)")
     print(json.dumps(line), flush=True)
+
+
+def deck_e2e(exe, steps, tpp, what):
+    """One run of oracle/decks/thermal_c1.cxx (64^3 cells x 32 ppc x 2 species = BASELINE configs[0]) through the
+    reference's own main.cxx + vpic_simulation::advance(); the rate is particle-advances / the `simulation time` its
+    main loop reports (load excluded).  Never raises: a failure is reported in the returned dict."""
+    import re
+    import subprocess
+    import tempfile
+    n, ppc = 64, 32
+    if not os.path.exists(exe):
+        return {"unavailable": "%s not built" % os.path.relpath(exe, ROOT)}
+    try:
+        with tempfile.TemporaryDirectory() as t:
+            env = dict(os.environ, VPB_DECK_STEPS=str(steps), VPB_DECK_CELLS=str(n), VPB_DECK_PPC=str(ppc))
+            r = subprocess.run([exe, "-tpp=%d" % tpp], cwd=t, env=env, capture_output=True, text=True, timeout=900)
+            m = re.search(r"simulation time: ([0-9.eE+-]+)", r.stdout + r.stderr)
+            if r.returncode != 0 or not m:
+                return {"unavailable": "deck exited %d: %s" % (r.returncode, (r.stdout + r.stderr)[-300:])}
+            sec = float(m.group(1))
+    except Exception as e:          # noqa: BLE001 -- an optional leg must not take the bench line down
+        return {"unavailable": repr(e)[:300]}
+    adv = 2.0 * n ** 3 * ppc * steps
+    return {"value": adv / sec, "unit": "particle-advances/s", "ms_per_step": 1e3 * sec / steps, "steps": steps,
+            "sample": "%s: thermal 64^3 x 32 ppc x 2 species, %d steps of vpic_simulation::advance() (sort every 20), "
+                      "unmodified reference host program, -tpp=%d" % (what, steps, tpp)}
 
 
 def workload_config(args):
@@ -316,7 +349,7 @@ def run_b200(args):
         "host_wall_ms_per_step": 1e3 * wall / args.steps, "driver": args.driver,
         "l2_fetch_granularity_bytes": int(L.vpb_l2_fetch_granularity()),
         "advance_p_ms_by_launch": adv_list,
-        "tuning": {k: L.vpb_get_tuning(k.encode()) for k in ("advance_p.deposit", "advance_p.tma", "advance_p.stream_store", "advance_p.stream_cps", "sim.aos_fields", "sim.narrow_interpolator", "sim.aos_particles", "advance_p.pair_cps", "advance_p.pair_pipe", "advance_p.pair_merge",
+        "tuning": {k: L.vpb_get_tuning(k.encode()) for k in ("advance_p.deposit", "advance_p.tma", "advance_p.stream_store", "advance_p.stream_cps", "sim.aos_fields", "sim.narrow_interpolator", "sim.aos_particles", "advance_p.pair_cps", "advance_p.pair_pipe", "advance_p.pair_merge", "advance_p.pair_variant",
                                                              "advance_p.tma_ctas_per_sm", "advance_p.ctas_per_sm")},
     }
     if fields_c2 is not None:
@@ -325,6 +358,9 @@ def run_b200(args):
         line["e2e"] = e2e_measure(L, args, abi, helpers)
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = {k: v for k, v in cpu_reference_rate(64, args.ppc, 3, 1).items() if k != "ms_per_step"}
+    if args.deck_e2e and world == 1:
+        line["deck_e2e"] = deck_e2e(os.path.join(ROOT, "oracle", "_ref", "hybrid", "thermal_c1.b200.op"), args.deck_steps, 1,
+                                    "reference host objects + libvpic_b200.so (link-time substitution)")
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

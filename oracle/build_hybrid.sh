@@ -36,13 +36,18 @@ link_hybrid "$REF/decks/trecon-part/turbulence.cxx" turbulence
 link_hybrid "$HERE/decks/thermal_small.cxx" thermal_small
 link_hybrid "$HERE/decks/sheet_small.cxx" sheet_small
 link_hybrid "$HERE/decks/absorb_small.cxx" absorb_small
+link_hybrid "$HERE/decks/thermal_c1.cxx" thermal_c1
 # the same deck on the reference alone; hot path in its scalar flavour (what the library is bit-compatible with)
-rm -f "$OUT/hybrid/libvpic_ref_scalar.a"
+rm -f "$OUT/hybrid/libvpic_ref_scalar.a" "$OUT/hybrid/libvpic_ref_sse.a"
 ar rcs "$OUT/hybrid/libvpic_ref_scalar.a" $(ls "$OUT"/obj_scalar/*.o | grep -v ref_harness)
 for deck in thermal_small sheet_small absorb_small; do
   g++ -std=gnu++98 $COMMON -DINPUT_DECK="$HERE/decks/$deck.cxx" "$OUT/tree/src/main.cxx" "$OUT/tree/src/deck_wrapper.cxx" \
       "$OUT/hybrid/libvpic_ref_scalar.a" -lm -lpthread -o "$OUT/$deck.op"
 done
+# BASELINE configs[0] as a deck, on the reference as shipped (V4/SSE + pthreads hot path): the CPU arm of bench.py --deck-e2e
+ar rcs "$OUT/hybrid/libvpic_ref_sse.a" $(ls "$OUT"/obj_sse/*.o | grep -v ref_harness)
+g++ -std=gnu++98 $COMMON -DUSE_V4_SSE -DINPUT_DECK="$HERE/decks/thermal_c1.cxx" "$OUT/tree/src/main.cxx" "$OUT/tree/src/deck_wrapper.cxx" \
+    "$OUT/hybrid/libvpic_ref_sse.a" -lm -lpthread -o "$OUT/thermal_c1.op"
 # the reference's own trecon-part deck, as shipped (16x16x1 cells, topology 2x2x1): golden energies for the 4-rank run
 g++ -std=gnu++98 $COMMON -DINPUT_DECK="$REF/decks/trecon-part/turbulence.cxx" "$OUT/tree/src/main.cxx" "$OUT/tree/src/deck_wrapper.cxx" \
     "$OUT/hybrid/libvpic_ref_scalar.a" -lm -lpthread -o "$OUT/turbulence.op"

@@ -1,0 +1,58 @@
+// TEST/BENCH INFRASTRUCTURE -- an input deck written for this repository (not part of the reference): BASELINE.json
+// configs[0], the thermal e-/p+ plasma at 64^3 cells x 32 particles per cell per species, on the
+// reference's deck API.  Built like thermal_small.cxx by oracle/build_hybrid.sh, on the reference alone
+// (oracle/_ref/thermal_c1.op, the shipped V4/SSE + pthreads hot path) and on the reference's host objects + libvpic_b200.so
+// (oracle/_ref/hybrid/thermal_c1.b200.op); `bench.py --deck-e2e` times both: the same unmodified host program, the
+// hot path swapped at link time.  Size and length can be changed from the environment: VPB_DECK_CELLS, VPB_DECK_PPC,
+// VPB_DECK_STEPS.
+#include <stdlib.h>
+
+begin_globals {
+  int dummy;
+};
+
+static int env_int( const char * name, int dflt ) {
+  const char * e = getenv( name );
+  return e ? atoi( e ) : dflt;
+}
+
+begin_initialization {
+  const int n = env_int( "VPB_DECK_CELLS", 64 ), ppc = env_int( "VPB_DECK_PPC", 32 );
+  const double L = n;
+  const double Ne = double(n) * n * n * ppc;
+
+  num_step = env_int( "VPB_DECK_STEPS", 40 );
+  status_interval = 0;
+  sync_shared_interval = 0;
+  clean_div_e_interval = 0;
+  clean_div_b_interval = 0;
+
+  grid->dt = 0.95 * courant_length( L, L, L, n, n, n );
+  grid->cvac = 1;
+  grid->eps0 = 1;
+  grid->damp = 0;
+  define_periodic_grid( 0, 0, 0, L, L, L, n, n, n, int( nproc() ), 1, 1 );
+
+  define_material( "vacuum", 1 );
+  finalize_field_advance( standard_field_advance );
+
+  species_t * electron = define_species( "electron", -1, 1.25 * Ne / nproc(), -1, 20, 1 );
+  species_t * ion      = define_species( "ion",       1, 1.25 * Ne / nproc(), -1, 20, 1 );
+
+  seed_rand( 7 );
+  const double q = L * L * L / Ne;     // plasma frequency 1
+  for( double k = 0; k < Ne; k++ ) {
+    const double x = uniform_rand( 0, L ), y = uniform_rand( 0, L ), z = uniform_rand( 0, L );
+    inject_particle( electron, x, y, z, maxwellian_rand( 0.1 ), maxwellian_rand( 0.1 ), maxwellian_rand( 0.1 ), -q, 0, 0, 0 );
+    inject_particle( ion,      x, y, z, maxwellian_rand( 0.1 ), maxwellian_rand( 0.1 ), maxwellian_rand( 0.1 ),  q, 0, 0, 0 );
+  }
+}
+
+begin_diagnostics {
+  if( step == 0 || step == num_step ) dump_energies( "energies", step == 0 ? 0 : 1 );
+}
+
+begin_particle_injection { }
+begin_current_injection { }
+begin_field_injection { }
+begin_particle_collisions { }

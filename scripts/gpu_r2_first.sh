@@ -16,4 +16,9 @@ for v in 0 1 2 3; do
     > gpurun_out/r2_bench_variant$v.json 2> gpurun_out/r2_bench_variant$v.err
   echo "bench variant $v rc=$?" | tee -a gpurun_out/r2_summary.txt
 done
+# 3. BASELINE configs[0] as an unmodified reference host program: on the library, then on the reference alone
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline --field-cells 0 --deck-e2e > gpurun_out/r2_bench_deck.json 2> gpurun_out/r2_bench_deck.err
+echo "bench deck-e2e rc=$?" | tee -a gpurun_out/r2_summary.txt
+python bench.py --impl reference --steps 3 --warmup 1 --deck-e2e > gpurun_out/r2_bench_deck_ref.json 2> gpurun_out/r2_bench_deck_ref.err
+echo "bench deck-e2e reference rc=$?" | tee -a gpurun_out/r2_summary.txt
 tail -n 5 gpurun_out/r2_variants_pytest.log gpurun_out/r2_deck_pytest.log
