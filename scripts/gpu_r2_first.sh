@@ -8,6 +8,8 @@ mkdir -p gpurun_out
 export VPB_RUN_UNVALIDATED=1
 python -m pytest tests/test_gpu_particles.py -q -m gpu -k "variants" > gpurun_out/r2_variants_pytest.log 2>&1
 echo "variants pytest rc=$?" | tee -a gpurun_out/r2_summary.txt
+python -m pytest tests/test_gpu_aniso.py -q -m gpu > gpurun_out/r2_aniso_pytest.log 2>&1
+echo "aniso pytest rc=$?" | tee -a gpurun_out/r2_summary.txt
 timeout 1500 python -m pytest tests/test_gpu_deck.py -q -m gpu > gpurun_out/r2_deck_pytest.log 2>&1
 echo "deck pytest rc=$?" | tee -a gpurun_out/r2_summary.txt
 unset VPB_RUN_UNVALIDATED
@@ -21,4 +23,4 @@ python bench.py --steps 5 --warmup 3 --no-cpu-baseline --field-cells 0 --deck-e2
 echo "bench deck-e2e rc=$?" | tee -a gpurun_out/r2_summary.txt
 python bench.py --impl reference --steps 3 --warmup 1 --deck-e2e > gpurun_out/r2_bench_deck_ref.json 2> gpurun_out/r2_bench_deck_ref.err
 echo "bench deck-e2e reference rc=$?" | tee -a gpurun_out/r2_summary.txt
-tail -n 5 gpurun_out/r2_variants_pytest.log gpurun_out/r2_deck_pytest.log
+tail -n 5 gpurun_out/r2_aniso_pytest.log gpurun_out/r2_variants_pytest.log gpurun_out/r2_deck_pytest.log
