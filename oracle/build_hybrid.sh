@@ -40,7 +40,7 @@ link_hybrid "$HERE/decks/thermal_c1.cxx" thermal_c1
 # the same deck on the reference alone; hot path in its scalar flavour (what the library is bit-compatible with)
 rm -f "$OUT/hybrid/libvpic_ref_scalar.a" "$OUT/hybrid/libvpic_ref_sse.a"
 ar rcs "$OUT/hybrid/libvpic_ref_scalar.a" $(ls "$OUT"/obj_scalar/*.o | grep -v ref_harness)
-for deck in thermal_small sheet_small absorb_small; do
+for deck in thermal_small sheet_small absorb_small pin_history; do
   g++ -std=gnu++98 $COMMON -DINPUT_DECK="$HERE/decks/$deck.cxx" "$OUT/tree/src/main.cxx" "$OUT/tree/src/deck_wrapper.cxx" \
       "$OUT/hybrid/libvpic_ref_scalar.a" -lm -lpthread -o "$OUT/$deck.op"
 done
