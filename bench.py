@@ -45,7 +45,9 @@ def parse():
     ap.add_argument("--e2e-particles", type=int, default=64 * 1024 * 1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--field-cells", type=int, default=1024, help="cells per axis of the field-only leg (configs[1]); 0 = skip")
-    ap.add_argument("--workload", default="thermal", choices=["thermal", "fields"])
+    ap.add_argument("--workload", default="thermal", choices=["thermal", "fields", "harris"],
+                    help="thermal: BASELINE configs[3] (the headline, default); fields: configs[1] alone; harris: configs[2], the "
+                         "trecon-part shape 2048x1x1024 cells x 100 ppc on one GPU")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--deck-e2e", action="store_true",
                     help="also time BASELINE configs[0] as an unmodified reference host program (oracle/decks/thermal_c1.cxx): "
@@ -203,6 +205,15 @@ def deck_e2e(exe, steps, tpp, what):
 
 
 def workload_config(args):
+    if args.workload == "harris":
+        return {"workload": "BASELINE configs[2]: the trecon-part shape on one GPU -- 2048 x 1 x 1024 cells (0.488 x 1.95 x 0.488 c/wpe), "
+                            "%d ppc per species, pair plasma at vth=0.6c, wce/wpe=10 force-free sheet field, periodic x/y, conducting "
+                            "reflecting z walls, dt=0.99 Courant, sort every %d steps; thermal device load without the sheet's drift "
+                            "current" % (args.ppc, args.sort_interval),
+                "sort_key": "voxel 0.6 x interval steps ahead" if (args.sort_lookahead != 0 and args.driver == "native") else "current voxel",
+                "cells_per_gpu": [2048, 1, 1024], "ppc_per_species": args.ppc, "species": 2,
+                "l2_policy": "inputs (20 GB of particles) are far larger than the 126 MB L2; no flush needed",
+                "decomposition": "1 rank"}
     return {"workload": "BASELINE configs[3]: thermal e-/p+ plasma weak scaling, %d^3 cells and %d ppc per species per GPU, "
                         "periodic, dt=0.95 Courant, vth=%.1fc, sort every %d steps" % (args.cells, args.ppc, VTH, args.sort_interval),
             "sort_key": ("voxel %s steps ahead (a look-ahead grouping: same particles, same physics, different array order)" % ("0.6 x interval" if args.sort_lookahead < 0 else args.sort_lookahead)) if (args.sort_lookahead != 0 and args.driver == "native") else "current voxel",
@@ -243,15 +254,35 @@ def run_b200(args):
         L.vpb_comm_init(rank, world, ub)
 
     fields_c2 = None
-    if world == 1 and args.field_cells > 0:
+    if world == 1 and args.field_cells > 0 and args.workload != "harris":
         fields_c2 = fields_measure(L, args.field_cells, 5, 3)
         if args.workload == "fields":
             print(json.dumps(fields_c2), flush=True)
             return
 
     n = args.cells
-    topo = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
-    g = helpers.make_grid((n * topo[0], n * topo[1], n * topo[2]), "periodic", topo=topo, rank=rank)
+    harris = args.workload == "harris"
+    if harris:
+        # BASELINE configs[2]: the shape and plasma of decks/trecon-part/turbulence.cxx:86-160 -- 2048 x 1 x 1024 cells of
+        # 0.488 x 1.95 x 0.488 c/wpe, pair plasma (mi/me = 1) at vth = 0.6 c, wce/wpe = 10, force-free sheet of half
+        # thickness 6 c/wpe, conducting walls that reflect particles at z = 0, Lz, dt = 0.99 Courant, sort every 25.
+        # The device loader is thermal: the sheet's drift current is not loaded (the field near the sheet, 5 % of the
+        # box, is not in equilibrium; |B| = b0 everywhere, so the particle work is the deck's).
+        if world != 1 or args.driver != "native":
+            raise SystemExit("--workload harris is the one-GPU configuration, through the native driver")
+        if args.ppc == 64:
+            args.ppc = 100
+        if args.sort_interval == SORT_INTERVAL:
+            args.sort_interval = 25
+        hn = (2048, 1, 1024)
+        hL = (1000.0, 500.0 / 256, 500.0)
+        g = helpers.make_grid(hn, "periodic", L=hL, dt=helpers.courant_dt(hL[0] / hn[0], 0, hL[2] / hn[2], frac=0.99))
+        for sgn in (-1, 1):
+            g.set_fbc(abi.boundary(0, 0, sgn), abi.PEC_FIELDS)
+            g.set_pbc(abi.boundary(0, 0, sgn), abi.REFLECT_PARTICLES)
+    else:
+        topo = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
+        g = helpers.make_grid((n * topo[0], n * topo[1], n * topo[2]), "periodic", topo=topo, rank=rank)
     # the library's C++ time-step driver (csrc/vpb_step.cu); --driver python = the same call order issued from sim.py
     Driver = NativeSimulation if args.driver == "native" else Simulation
     sim = Driver(g, n_mat=1, L=L, planar=L.vpb_get_tuning(b"sim.aos_fields") == 0,
@@ -259,13 +290,24 @@ def run_b200(args):
                      particle_planes=L.vpb_get_tuning(b"sim.aos_particles") == 0)
     if args.driver == "native":
         sim.set_sort_lookahead(args.sort_lookahead)
-    np_ = n ** 3 * args.ppc
+    cells = g.n[0] * g.n[1] * g.n[2]
+    np_ = cells * args.ppc
     max_np = int(np_ * (1.0 if world == 1 else 1.02)) + 1024
+    vth = 0.6 if harris else VTH
+    cell_volume = g.struct.dx * g.struct.dy * g.struct.dz
+    if harris:
+        b0, half = 10.0, 6.0
+        f0 = abi.aligned_zeros(g.nv, abi.field_dtype)
+        zc = ((np.arange(g.nv) // ((g.n[0] + 2) * (g.n[1] + 2))) - 0.5) * g.struct.dz - 0.5 * hL[2]      # cell centres
+        f0["cbx"] = (b0 * np.tanh(zc / half)).astype(np.float32)
+        f0["cby"] = (b0 / np.cosh(zc / half)).astype(np.float32)
+        sim.set_fields(f0)
+        del f0, zc
     # macro-charge q = +-(cell volume)/ppc so that the plasma frequency is 1 (the reference's thermal recipe,
     # q = +-L^3/Ne); dt*wpe = 0.55
-    for name, q_m, q, seed in (("electron", -1.0, -1.0 / args.ppc, 7 + rank), ("ion", 1.0, 1.0 / args.ppc, 1007 + rank)):
+    for name, q_m, q, seed in (("electron", -1.0, -cell_volume / args.ppc, 7 + rank), ("ion", 1.0, cell_volume / args.ppc, 1007 + rank)):
         sp = sim.define_species(name, q_m, max_np, sort_interval=args.sort_interval)
-        sim.load_thermal(sp, args.ppc, VTH, q, seed, tag0=rank * (1 << 40))
+        sim.load_thermal(sp, args.ppc, vth, q, seed, tag0=rank * (1 << 40))
     L.vpb_sync()
 
     def barrier():
@@ -322,7 +364,6 @@ def run_b200(args):
     bytes_alg = 64.0 + 176.0 / args.ppc
     per_launch_particles = np_
     achieved = bytes_alg * per_launch_particles / (adv_ms / max(adv_n, 1) * 1e-3) / 1e9 if adv_n else None
-    cells = n ** 3
     line = {
         "metric": "particle-advances/s (push+deposit)", "value": value, "unit": "particle-advances/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
