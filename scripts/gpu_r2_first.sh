@@ -23,4 +23,7 @@ python bench.py --steps 5 --warmup 3 --no-cpu-baseline --field-cells 0 --deck-e2
 echo "bench deck-e2e rc=$?" | tee -a gpurun_out/r2_summary.txt
 python bench.py --impl reference --steps 3 --warmup 1 --deck-e2e > gpurun_out/r2_bench_deck_ref.json 2> gpurun_out/r2_bench_deck_ref.err
 echo "bench deck-e2e reference rc=$?" | tee -a gpurun_out/r2_summary.txt
+# 4. BASELINE configs[2] throughput (trecon-part shape)
+python bench.py --workload harris --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/r2_bench_harris.json 2> gpurun_out/r2_bench_harris.err
+echo "bench harris rc=$?" | tee -a gpurun_out/r2_summary.txt
 tail -n 5 gpurun_out/r2_aniso_pytest.log gpurun_out/r2_variants_pytest.log gpurun_out/r2_deck_pytest.log
