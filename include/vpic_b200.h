@@ -254,6 +254,14 @@ typedef struct vpb_species_state {
  * back-fill, exchange with the face neighbours over NCCL, inject and finish the arrivals.  np and nm
  * of every species are updated; the call synchronises.  advance.cxx:94-96 calls it 3 times a step. */
 void vpb_boundary_p(vpb_domain_t *dom, vpb_species_state_t *sp, int n_sp, vpb_field_t *d_f, vpb_accumulator_t *d_a);
+/* boundary_p.c:416-447: when the arrivals of a round do not fit, the reference grows the species' arrays by 31 % and
+ * warns.  vpb_boundary_p leaves that to the owner of the arrays through this hook (NULL, the default: overflow is an
+ * error).  The hook gets the index of the species in the list and the capacities needed; it must update p / max_np
+ * (the first np particles preserved) and/or pm / max_nm in *st with device-accessible arrays and return non-zero, or
+ * return 0 to refuse.  The reference-named boundary_p() installs one that does what the reference does, for arrays
+ * that came from util_malloc_aligned. */
+typedef int (*vpb_grow_hook_t)(void *user, int index, int need_np, int need_nm, vpb_species_state_t *st);
+void vpb_boundary_set_grow_hook(vpb_grow_hook_t hook, void *user);
 
 /* single mover / single particle, for the reference's host-side callers (inject_particle, handlers) */
 void vpb_move_p_one(vpb_domain_t *dom, vpb_particle_t *d_p, vpb_particle_mover_t *d_pm, vpb_accumulator_t *d_a, int *d_result);

@@ -339,6 +339,9 @@ static inline int blocks(long n, int tb) { return (int)((n + tb - 1) / tb); }
 
 using namespace vpb;
 
+static vpb_grow_hook_t g_grow_hook = nullptr;
+static void *g_grow_user = nullptr;
+
 extern "C" {
 
 void vpb_move_p_one(vpb_domain_t *dom, vpb_particle_t *d_p, vpb_particle_mover_t *d_pm, vpb_accumulator_t *d_a, int *d_result) {
@@ -507,10 +510,19 @@ void vpb_boundary_p(vpb_domain_t *dom, vpb_species_state_t *sp, int n_sp, vpb_fi
   int cnt[7];
   for (int s = 0; s < n_sp; s++) {
     cnt[s] = c.h_pinned_i[s];
-    if (sp[s].np + cnt[s] > sp[s].max_np)
-      VPB_ERROR("species %d: %d particles + %d arrivals exceed max_np=%d (the reference would grow the array by 31%%, "
-                "boundary_p.c:416-430; size max_np with head-room)", sp[s].id, sp[s].np, cnt[s], sp[s].max_np);
-    if (cnt[s] > sp[s].max_nm) VPB_ERROR("species %d: %d arrivals exceed max_nm=%d", sp[s].id, cnt[s], sp[s].max_nm);
+    if (sp[s].np + cnt[s] > sp[s].max_np || cnt[s] > sp[s].max_nm) {
+      // boundary_p.c:416-447 grows the arrays here; their owner does it through the hook
+      const bool grown = g_grow_hook && g.p_plane == 0 && g_grow_hook(g_grow_user, s, sp[s].np + cnt[s], cnt[s], &sp[s]) &&
+                         sp[s].np + cnt[s] <= sp[s].max_np && cnt[s] <= sp[s].max_nm;
+      if (!grown) {
+        if (sp[s].np + cnt[s] > sp[s].max_np)
+          VPB_ERROR("species %d: %d particles + %d arrivals exceed max_np=%d (the reference would grow the array by 31%%, "
+                    "boundary_p.c:416-430; size max_np with head-room)", sp[s].id, sp[s].np, cnt[s], sp[s].max_np);
+        VPB_ERROR("species %d: %d arrivals exceed max_nm=%d", sp[s].id, cnt[s], sp[s].max_nm);
+      }
+      T.p[s] = sp[s].p;
+      T.pm[s] = sp[s].pm;
+    }
   }
   inject_kernel<<<blocks(n, 128), 128, 0, st>>>(list, n, c1, r1, T, reinterpret_cast<float *>(d_a), g.nbr, c2);
   rank_bins(c2, n, 0, r2, dc + 24, st);
@@ -523,6 +535,11 @@ void vpb_boundary_p(vpb_domain_t *dom, vpb_species_state_t *sp, int n_sp, vpb_fi
     sp[s].nm = c.h_pinned_i[s];
   }
   VPB_CUDA(cudaGetLastError());
+}
+
+void vpb_boundary_set_grow_hook(vpb_grow_hook_t hook, void *user) {
+  g_grow_hook = hook;
+  g_grow_user = user;
 }
 
 }  // extern "C"

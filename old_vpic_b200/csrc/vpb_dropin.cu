@@ -454,6 +454,45 @@ void accumulate_rhob(vpb_field_t *f0, const vpb_particle_t *p, const vpb_grid_t 
   r.finish();
 }
 
+// boundary_p.c:416-447: "Resizing local %s particle storage": n + n/4 + n/16, copy, free the old array.  Only arrays that
+// came from util_malloc_aligned (managed memory) can be replaced this way; anything else keeps the overflow error.
+static bool is_managed(const void *p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeManaged;
+}
+
+static int grow_species(void *user, int index, int need_np, int need_nm, vpb_species_state_t *st) {
+  vpb_species_t *sp = (*(std::vector<vpb_species_t *> *)user)[index];
+  Context &c = ctx();
+  if (need_np > sp->max_np) {
+    if (!is_managed(sp->p)) return 0;
+    int n = need_np;
+    n = n + (n >> 2) + (n >> 4);
+    VPB_WARNING("Resizing local %s particle storage from %i to %i", sp->name, sp->max_np, n);
+    vpb_particle_t *new_p = nullptr;
+    util_malloc_aligned("MALLOC_ALIGNED( new_p, (%lu bytes), 128 (%lu bytes) ) failed", &new_p, (size_t)n * sizeof(*new_p), 128);
+    VPB_CUDA(cudaMemcpyAsync(new_p, st->p, (size_t)st->np * sizeof(*new_p), cudaMemcpyDefault, c.stream));
+    VPB_CUDA(cudaStreamSynchronize(c.stream));
+    g_part_hint.erase(sp->p);
+    util_free_aligned(&sp->p);
+    sp->p = new_p; sp->max_np = n;
+    st->p = new_p; st->max_np = n;
+  }
+  if (need_nm > sp->max_nm) {
+    if (!is_managed(sp->pm)) return 0;
+    int n = need_nm;
+    n = n + (n >> 2) + (n >> 4);
+    VPB_WARNING("Resizing local %s mover storage from %i to %i", sp->name, sp->max_nm, n);
+    vpb_particle_mover_t *new_pm = nullptr;
+    util_malloc_aligned("MALLOC_ALIGNED( new_pm, (%lu bytes), 128 (%lu bytes) ) failed", &new_pm, (size_t)n * sizeof(*new_pm), 128);
+    util_free_aligned(&sp->pm);      // no movers are pending at this point of the round (boundary_p.c:323-324)
+    sp->pm = new_pm; sp->max_nm = n;
+    st->pm = new_pm; st->max_nm = n;
+  }
+  return 1;
+}
+
 // boundary_p.c:77-505: one round over the species list.  rng is only used by custom boundary
 // handlers in the reference (host callbacks), which the device path does not run.
 void boundary_p(vpb_species_t *sp_list, vpb_field_t *f0, vpb_accumulator_t *a0, const vpb_grid_t *g, void *rng) {
@@ -474,7 +513,9 @@ void boundary_p(vpb_species_t *sp_list, vpb_field_t *f0, vpb_accumulator_t *a0, 
   }
   vpb_field_t *df = f0 ? (vpb_field_t *)r.get_field(dom, f0, nvox(g) * sizeof(*f0), RW) : nullptr;
   vpb_accumulator_t *da = a0 ? (vpb_accumulator_t *)r.get(a0, nvox(g) * sizeof(*a0), RW) : nullptr;
+  vpb_boundary_set_grow_hook(grow_species, &list);
   vpb_boundary_p(dom, st.data(), (int)st.size(), df, da);
+  vpb_boundary_set_grow_hook(nullptr, nullptr);
   for (size_t s = 0; s < list.size(); s++) { list[s]->np = st[s].np; list[s]->nm = st[s].nm; }
   r.finish();
 }

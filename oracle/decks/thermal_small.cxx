@@ -6,6 +6,8 @@
 //   * against the reference's host objects with the hot path taken from libvpic_b200.so
 //                                            -> oracle/_ref/hybrid/thermal_small.b200.op
 // and tests/test_gpu_deck.py compares the two "energies" files.
+#include <stdlib.h>
+
 begin_globals {
   int dummy;
 };
@@ -30,8 +32,12 @@ begin_initialization {
   define_material( "vacuum", 1 );
   finalize_field_advance( standard_field_advance );
 
-  species_t * electron = define_species( "electron", -1, 1.5 * Ne, -1, 5, 1 );
-  species_t * ion      = define_species( "ion",       1, 1.5 * Ne, -1, 5, 1 );
+  // VPB_DECK_MAXNP (particles per species per rank) makes the arrays tight on purpose: boundary_p then has to grow
+  // them when arrivals do not fit (boundary_p.c:416-447, "Resizing local ... particle storage")
+  const char * tight = getenv( "VPB_DECK_MAXNP" );
+  const double max_np = tight ? atof( tight ) : 1.5 * Ne;
+  species_t * electron = define_species( "electron", -1, max_np, -1, 5, 1 );
+  species_t * ion      = define_species( "ion",       1, max_np, -1, 5, 1 );
 
   seed_rand( 7 );
   const double q = L * L * L / Ne;     // plasma frequency 1

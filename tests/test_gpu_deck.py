@@ -96,7 +96,7 @@ unvalidated = pytest.mark.skipif(os.environ.get("VPB_RUN_UNVALIDATED") != "1",
                                  reason="not yet run on hardware (set VPB_RUN_UNVALIDATED=1)")
 
 
-def _run_ranks(exe, world, cwd):
+def _run_ranks(exe, world, cwd, **env):
     """`world` processes of an unmodified reference host program on the library.  The host side talks through the
     reference's mp layer (here over oracle/mpi_shim's shared-memory transport, which tests/test_ref_multirank.py
     exercises with the pure reference); the library finds that layer by itself (vpb_comm_autoboot: no line of host
@@ -104,7 +104,7 @@ def _run_ranks(exe, world, cwd):
     GPU of its own, or through the host program's message layer when ranks share one (tests/test_mp_transport.py
     drives that transport on CPU ranks) -- so this runs on a one-GPU box too."""
     from test_ref_multirank import run_ranks
-    return run_ranks(world, {"VPIC_SHIM_SLOT_MB": "8"}, timeout=900, argv=[exe, "-tpp=1"], cwd=str(cwd), marker=None)
+    return run_ranks(world, dict({"VPIC_SHIM_SLOT_MB": "8"}, **env), timeout=900, argv=[exe, "-tpp=1"], cwd=str(cwd), marker=None)
 
 
 @unvalidated
@@ -117,6 +117,20 @@ def test_reference_deck_on_ranks(world, tmp_path):
     outs = _run_ranks(EXE, world, tmp_path)
     got, want = read_energies(tmp_path / "energies"), read_energies(GOLD)
     assert got.shape == want.shape == (21, 9), outs[0][-2000:]
+    rel = np.abs(got[:, 1:] - want[:, 1:]) / np.abs(want[:, 1:]).max(axis=0)
+    assert rel.max() < 1e-4, rel.max(axis=0)
+
+
+@unvalidated
+def test_reference_deck_grows_tight_arrays(tmp_path):
+    """66 particles of head-room per rank: the arrivals of some round do not fit and boundary_p has to grow the species'
+    arrays the way boundary_p.c:416-447 does (n + n/4 + n/16, warning, copy, free).  The pure reference does so on this
+    input (tests/test_ref_multirank.py); the library must, and the energies must not notice."""
+    if not os.path.exists(EXE):
+        pytest.skip("oracle/_ref/hybrid/thermal_small.b200.op not built (needs /root/reference at build time)")
+    outs = _run_ranks(EXE, 2, tmp_path, VPB_DECK_MAXNP="16450")
+    assert sum(o.count("Resizing local") for o in outs) >= 1, outs[0][-2000:]
+    got, want = read_energies(tmp_path / "energies"), read_energies(GOLD)
     rel = np.abs(got[:, 1:] - want[:, 1:]) / np.abs(want[:, 1:]).max(axis=0)
     assert rel.max() < 1e-4, rel.max(axis=0)
 

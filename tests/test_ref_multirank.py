@@ -68,3 +68,18 @@ def test_reference_deck_on_ranks(world, tmp_path):
     assert got.shape == want.shape == (21, 9)
     rel = np.abs(got[:, 1:] - want[:, 1:]) / np.abs(want[:, 1:]).max(axis=0)
     assert rel.max() < 1e-5, rel.max(axis=0)
+
+
+def test_reference_deck_grows_tight_arrays(tmp_path):
+    """VPB_DECK_MAXNP=16450 leaves each rank 66 particles of head-room: boundary_p has to grow the arrays
+    (boundary_p.c:416-447).  Here the pure reference does it; tests/test_gpu_deck.py asks the same of the library."""
+    import numpy as np
+    exe = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "thermal_small.op")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/thermal_small.op not built")
+    outs = run_ranks(2, {"VPIC_SHIM_SLOT_MB": "2", "VPB_DECK_MAXNP": "16450"}, argv=[exe, "-tpp=1"], cwd=str(tmp_path), marker=None)
+    assert sum(o.count("Resizing local") for o in outs) >= 1
+    got = read_energies(tmp_path / "energies")
+    want = read_energies(os.path.join(HERE, "golden", "deck_thermal_small_energies.txt"))
+    rel = np.abs(got[:, 1:] - want[:, 1:]) / np.abs(want[:, 1:]).max(axis=0)
+    assert rel.max() < 1e-5, rel.max(axis=0)
