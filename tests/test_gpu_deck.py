@@ -104,7 +104,7 @@ def _run_ranks(exe, world, cwd, **env):
     GPU of its own, or through the host program's message layer when ranks share one (tests/test_mp_transport.py
     drives that transport on CPU ranks) -- so this runs on a one-GPU box too."""
     from test_ref_multirank import run_ranks
-    return run_ranks(world, dict({"VPIC_SHIM_SLOT_MB": "8"}, **env), timeout=900, argv=[exe, "-tpp=1"], cwd=str(cwd), marker=None)
+    return run_ranks(world, dict({"VPIC_SHIM_SLOT_MB": "2"}, **env), timeout=900, argv=[exe, "-tpp=1"], cwd=str(cwd), marker=None)
 
 
 @unvalidated
