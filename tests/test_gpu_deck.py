@@ -149,8 +149,13 @@ def test_trecon_part_deck_as_shipped(tmp_path):
     want = read_energies(GOLD.replace("thermal_small", "turbulence"))
     assert got.shape == want.shape, outs[0][-2000:]
     assert np.array_equal(got[:, 0], want[:, 0])
-    # 2500 steps of a chaotic system: field columns on the scale of the total field energy, species columns on their own
+    # 2500 steps of a chaotic system of 12 800 particles per species: trajectories decorrelate completely, the energies
+    # agree as statistics.  The yardstick is the reference against ITSELF: its shipped V4/SSE flavour and its scalar
+    # flavour, run here on the same four ranks, differ by up to 5.2e-3 in the species columns and 2.4e-5 of the total
+    # field energy in the field columns (ez and bx, noise-level quantities, by 30 % of their own size).
     scale = np.abs(want[:, 1:]).max(axis=0)
     scale[:6] = want[:, 1:7].sum(axis=1).max()
     rel = np.abs(got[:, 1:] - want[:, 1:]) / scale
-    assert rel.max() < 1e-3, rel.max(axis=0)
+    assert rel[:, :6].max() < 1e-4 and rel[:, 6:].max() < 2e-2, rel.max(axis=0)
+    # the first interval is still deterministic enough for a tight check
+    assert (np.abs(got[1, 1:] - want[1, 1:]) / scale).max() < 1e-3
