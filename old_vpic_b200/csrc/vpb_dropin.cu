@@ -135,6 +135,18 @@ static uint64_t neighbor_print(const vpb_grid_t *g) {
 }
 static std::unordered_map<const void *, uint64_t> g_domain_print;
 
+// A host program that is the reference itself never calls vpb_comm_init: bring the communicator up through its own
+// message layer the first time a grid with an mp handle shows up.  The bootstrap is collective, so it is also tried
+// from new_field_advance / new_interpolator / new_accumulators, which every rank calls from finalize_field_advance
+// (vpic.hxx:373-384) before any rank-dependent work such as inject_particle can reach a hot-path entry point.
+static void ensure_comm(const vpb_grid_t *g) {
+  static bool boot_tried = false;
+  if (boot_tried || !g || !g->mp || g_world_nproc != 1) return;
+  boot_tried = true;
+  const int n = vpb_comm_autoboot(g->mp);
+  if (n > 1) g_world_nproc = n;
+}
+
 static vpb_domain_t *domain_of(const vpb_grid_t *g) {
   if (!g) VPB_ERROR("Bad grid");
   auto it = g_domains.find(g);
@@ -152,15 +164,7 @@ static vpb_domain_t *domain_of(const vpb_grid_t *g) {
     vpb_domain_destroy(it->second);
     g_domains.erase(it);
   }
-  // A host program that is the reference itself never calls vpb_comm_init: bring the communicator up through its own
-  // message layer the first time a grid with an mp handle shows up (collective; every rank reaches its first hot-path
-  // call at the same point of advance()/initialize()).
-  static bool boot_tried = false;
-  if (!boot_tried && g->mp && g_world_nproc == 1) {
-    boot_tried = true;
-    const int n = vpb_comm_autoboot(g->mp);
-    if (n > 1) g_world_nproc = n;
-  }
+  ensure_comm(g);
   // the centre entry of bc[] is this rank (grid_structors.c:22, ops.c:47)
   vpb_domain_t *dom = vpb_domain_create(g, g->bc[VPB_BOUNDARY(0, 0, 0)], g_world_nproc);
   g_domains[g] = dom;
@@ -557,6 +561,7 @@ void sort_p(vpb_species_t *sp, const vpb_grid_t *g) {
 vpb_interpolator_t *new_interpolator(vpb_grid_t *g) {
   if (!g) VPB_ERROR("Invalid grid.");
   if (g->nx < 1 || g->ny < 1 || g->nz < 1) VPB_ERROR("Invalid grid resolution.");
+  ensure_comm(g);
   return (vpb_interpolator_t *)vpb_malloc_managed(nvox(g) * sizeof(vpb_interpolator_t));
 }
 void delete_interpolator(vpb_interpolator_t *fi) { util_free_aligned(&fi); }
@@ -565,6 +570,7 @@ void delete_interpolator(vpb_interpolator_t *fi) { util_free_aligned(&fi); }
 vpb_accumulator_t *new_accumulators(vpb_grid_t *g) {
   if (!g) VPB_ERROR("Bad grid.");
   if (g->nx < 1 || g->ny < 1 || g->nz < 1) VPB_ERROR("Bad resolution.");
+  ensure_comm(g);
   return (vpb_accumulator_t *)vpb_malloc_managed(((nvox(g) + 1) & ~(size_t)1) * sizeof(vpb_accumulator_t));
 }
 void delete_accumulators(vpb_accumulator_t *a) { util_free_aligned(&a); }
@@ -572,6 +578,7 @@ void delete_accumulators(vpb_accumulator_t *a) { util_free_aligned(&a); }
 // src/field_advance/field_advance.c:3-28: bind a grid, a material list and a method table
 vpb_field_advance_t *new_field_advance(vpb_grid_t *g, vpb_material_t *m_list, vpb_field_advance_methods_t *fam) {
   if (!g || !m_list || !fam) VPB_ERROR("Bad args");
+  ensure_comm(g);
   vpb_field_advance_t *fa = (vpb_field_advance_t *)calloc(1, sizeof(*fa));
   if (!fa) VPB_ERROR("Could not allocate field_advance_t");
   fa->method[0] = fam[0];
@@ -691,6 +698,7 @@ void unload_accumulator(vpb_field_t *f, const vpb_accumulator_t *a, const vpb_gr
 static vpb_field_t *fa_new_field(vpb_grid_t *g) {
   if (!g) VPB_ERROR("Bad grid.");
   if (g->nx < 1 || g->ny < 1 || g->nz < 1) VPB_ERROR("Bad resolution.");
+  ensure_comm(g);
   return (vpb_field_t *)vpb_malloc_managed(nvox(g) * sizeof(vpb_field_t));
 }
 static void fa_delete_field(vpb_field_t *f) { util_free_aligned(&f); }
