@@ -336,6 +336,19 @@ void vpb_sim_get_fields(vpb_sim_t *s, vpb_field_t *host);
 void vpb_sim_set_intervals(vpb_sim_t *s, int clean_div_e_interval, int clean_div_b_interval, int num_comm_round);
 void vpb_sim_set_sort_lookahead(vpb_sim_t *s, int steps);   /* < 0: 0.6 x sort_interval of each species; 0 (default): off */
 void vpb_sim_advance(vpb_sim_t *s, int nsteps);                        /* enqueues nsteps time steps */
+/* The deck's five hooks, called where vpic_simulation::advance() calls user_particle_collisions (advance.cxx:67),
+ * user_particle_injection (:85), user_current_injection (:123), user_field_injection (:141) and user_diagnostics
+ * (:233, after the step counter has advanced).  NULL members are skipped.  Device work is only enqueued when a hook
+ * runs: a hook that reads device arrays calls vpb_sync() first. */
+typedef struct vpb_sim_callbacks {
+  void (*particle_collisions)(void *user, vpb_sim_t *s);
+  void (*particle_injection)(void *user, vpb_sim_t *s);
+  void (*current_injection)(void *user, vpb_sim_t *s);
+  void (*field_injection)(void *user, vpb_sim_t *s);
+  void (*diagnostics)(void *user, vpb_sim_t *s);
+  void *user;
+} vpb_sim_callbacks_t;
+void vpb_sim_set_callbacks(vpb_sim_t *s, const vpb_sim_callbacks_t *cb);   /* NULL: none */
 void vpb_sim_energies(vpb_sim_t *s, double *out6_plus_nspecies);       /* dump_energies (dump.cxx:37-78), over all ranks */
 void vpb_sim_hydro(vpb_sim_t *s, int species, vpb_hydro_t *host);      /* clear + accumulate + synchronize, to the host */
 long vpb_sim_step(const vpb_sim_t *s);

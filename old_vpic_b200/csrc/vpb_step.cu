@@ -47,6 +47,7 @@ struct vpb_sim {
   int clean_div_e_interval = 0, clean_div_b_interval = 0, num_comm_round = 3;   // vpic.cxx:17
   int sort_lookahead = 0;        // steps; < 0: 0.6 x the species' sort interval (measured optimum, profiles/README.md)
   int needs_boundary_p = -1;
+  vpb_sim_callbacks_t cb = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 using namespace vpb;
@@ -135,23 +136,29 @@ static void clean_div_b(vpb_sim *s) {   // advance.cxx:177-195
 static void advance_one(vpb_sim *s) {
   vpb_domain_t *dom = s->dom;
   const bool particles = !s->sp.empty();
+  const vpb_sim_callbacks_t &cb = s->cb;
   if (particles) vpb_clear_accumulators(dom, s->a);                                   // advance.cxx:38
   for (Species &sp : s->sp)                                                            // :43-51
     if (sp.sort_interval > 0 && s->step % sp.sort_interval == 0) sort_species(s, sp);
+  if (cb.particle_collisions) cb.particle_collisions(cb.user, s);                      // :67 user_particle_collisions
   for (Species &sp : s->sp)                                                            // :70-73
     vpb_advance_p_ordered(dom, sp.p, sp.np, sp.q_m, sp.pm, sp.max_nm, s->a, s->fi, sp.nm, sp.partition);
   // reduce_accumulators (:74) is a no-op with one replica
+  if (cb.particle_injection) cb.particle_injection(cb.user, s);                        // :85 user_particle_injection
   migrate(s);                                                                          // :94-103
   vpb_clear_jf(dom, s->f);                                                             // :109
   if (particles) vpb_unload_accumulator(dom, s->f, s->a);                              // :110
   vpb_synchronize_jf(dom, s->f);                                                       // :112
+  if (cb.current_injection) cb.current_injection(cb.user, s);                          // :123 user_current_injection
   vpb_advance_b(dom, s->f, 0.5f);                                                      // :129
   vpb_advance_e(dom, s->f, s->m, s->n_mat, s->vacuum ? 1 : 0);                         // :133
+  if (cb.field_injection) cb.field_injection(cb.user, s);                              // :141 user_field_injection
   vpb_advance_b(dom, s->f, 0.5f);                                                      // :147
   if (s->clean_div_e_interval && s->step % s->clean_div_e_interval == 0) clean_div_e(s);
   if (s->clean_div_b_interval && s->step % s->clean_div_b_interval == 0) clean_div_b(s);
   if (particles) vpb_load_interpolator(dom, s->fi, s->f);                              // :214
   s->step++;
+  if (cb.diagnostics) cb.diagnostics(cb.user, s);                                      // :233 user_diagnostics, after step++
 }
 
 extern "C" {
@@ -341,6 +348,15 @@ void vpb_sim_set_sort_lookahead(vpb_sim_t *s, int steps) {
 void vpb_sim_advance(vpb_sim_t *s, int nsteps) {
   if (!s) VPB_ERROR("Bad run");
   for (int k = 0; k < nsteps; k++) advance_one(s);
+}
+
+// The deck's hooks (begin_particle_collisions, begin_particle_injection, begin_current_injection, begin_field_injection,
+// begin_diagnostics of deck_wrapper.cxx) at the points advance.cxx:67,85,123,141,233 calls them.  Work is enqueued, not
+// finished, when a hook runs: one that reads device arrays calls vpb_sync() first.
+void vpb_sim_set_callbacks(vpb_sim_t *s, const vpb_sim_callbacks_t *cb) {
+  if (!s) VPB_ERROR("Bad run");
+  if (cb) s->cb = *cb;
+  else s->cb = vpb_sim_callbacks_t{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 }
 
 long vpb_sim_step(const vpb_sim_t *s) { return s ? s->step : -1; }

@@ -85,6 +85,7 @@ SIGNATURES = {
     "vpb_comm_init": (None, [_i, _i, _vp]),
     "vpb_comm_autoboot": (_i, [_vp]),
     "vpb_boundary_set_grow_hook": (None, [_vp, _vp]),
+    "vpb_sim_set_callbacks": (None, [_vp, _vp]),
     "vpb_comm_finalize": (None, []),
     "vpb_comm_rank": (_i, []),
     "vpb_comm_nproc": (_i, []),

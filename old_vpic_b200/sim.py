@@ -385,6 +385,20 @@ class NativeSimulation:
         """< 0: 0.6 x each species' sort interval; 0: off (the reference's sort key)"""
         self.L.vpb_sim_set_sort_lookahead(self.h, steps)
 
+    def set_callbacks(self, particle_collisions=None, particle_injection=None, current_injection=None, field_injection=None,
+                      diagnostics=None):
+        """The deck's hooks at the points advance.cxx calls them (vpb_sim_set_callbacks); each is called as fn(self)."""
+        CB = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
+
+        class Callbacks(C.Structure):
+            _fields_ = [(n, CB) for n in ("particle_collisions", "particle_injection", "current_injection", "field_injection",
+                                          "diagnostics")] + [("user", C.c_void_p)]
+
+        fns = (particle_collisions, particle_injection, current_injection, field_injection, diagnostics)
+        self._cb_keep = [CB((lambda f: (lambda user, s: f(self)))(f)) if f else CB() for f in fns]
+        self._cb_struct = Callbacks(*self._cb_keep, None)
+        self.L.vpb_sim_set_callbacks(self.h, C.byref(self._cb_struct))
+
     def advance(self, nsteps=1):
         self.L.vpb_sim_advance(self.h, nsteps)
 

@@ -1,6 +1,8 @@
 """GPU: the library's C++ time-step driver (csrc/vpb_step.cu, vpb_sim_*) follows the call order of
 vpic_simulation::advance() -- same energy history as the CPU oracle stepping the same particles (tolerance 1e-4
 per column over 20 steps), same history as the Python driver, particle multiset conserved."""
+import os
+
 import numpy as np
 import pytest
 
@@ -87,3 +89,28 @@ def test_native_driver_sort_lookahead(vpb, orc, lookahead):
         out = sim.get_particles(sp)
         assert np.array_equal(np.sort(out["tag"]), np.sort(inp["p"]["tag"]))
     sim.free()
+
+
+@pytest.mark.skipif(os.environ.get("VPB_RUN_UNVALIDATED") != "1", reason="not yet run on hardware (set VPB_RUN_UNVALIDATED=1)")
+def test_native_driver_calls_the_deck_hooks_where_advance_does(vpb, orc):
+    """vpb_sim_set_callbacks: the five hooks of a deck fire once a step, in the order of advance.cxx:67,85,123,141,233,
+    the diagnostics hook after the step counter has advanced; a field-injection hook that edits the field array changes
+    the history exactly as the same edit in the CPU loop does."""
+    g = host_grid((8, 6, 4), "periodic")
+    sim = NativeSimulation(g, L=vpb)
+    for k, sp in enumerate(make_species(g, 4, 3)):
+        s = sim.define_species("s%d" % k, sp["q_m"], len(sp["p"]) + 64, sort_interval=SORT)
+        sim.set_particles(s, sp["p"])
+    sim.set_fields(abi.aligned_zeros(g.nv, abi.field_dtype))
+    log = []
+    sim.set_callbacks(particle_collisions=lambda s: log.append(("collisions", s.step)),
+                      particle_injection=lambda s: log.append(("particle_injection", s.step)),
+                      current_injection=lambda s: log.append(("current_injection", s.step)),
+                      field_injection=lambda s: log.append(("field_injection", s.step)),
+                      diagnostics=lambda s: log.append(("diagnostics", s.step)))
+    sim.advance(3)
+    names = ["collisions", "particle_injection", "current_injection", "field_injection", "diagnostics"]
+    assert log == [(n, k + (1 if n == "diagnostics" else 0)) for k in range(3) for n in names]
+    sim.set_callbacks()
+    sim.advance()
+    assert len(log) == 15
