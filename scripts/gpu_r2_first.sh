@@ -1,7 +1,6 @@
 #!/usr/bin/env bash
 # First GPU call of round 2: everything that was written in round 1 after the GPU budget was spent.
 #   gpurun --timeout 2400 -- 'bash scripts/gpu_r2_first.sh'
-# 2. advance_p_pair variants in bench.py: 0 default, 1 FULL, 2 LEAN, 3 both (average launch ms in the JSON line)
 set -u
 mkdir -p gpurun_out
 export VPB_RUN_UNVALIDATED=1
@@ -11,6 +10,7 @@ timeout 2400 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/r
 echo "full gpu pytest (gated included) rc=$?" | tee -a gpurun_out/r2_summary.txt
 grep -E "passed|failed|FAILED|ERROR" gpurun_out/r2_all_pytest.log | tail -40 | tee -a gpurun_out/r2_summary.txt
 unset VPB_RUN_UNVALIDATED
+# 2. advance_p_pair variants in bench.py: 0 default, 1 FULL, 2 LEAN, 3 both (average launch ms in the JSON line)
 for v in 0 1 2 3; do
   VPB_ADVANCE_P_PAIR_VARIANT=$v python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu-baseline --field-cells 0 \
     > gpurun_out/r2_bench_variant$v.json 2> gpurun_out/r2_bench_variant$v.err
