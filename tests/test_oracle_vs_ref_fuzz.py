@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from helpers import (RefGrid, abi, assert_bits_equal, loader, random_fields, random_interpolator, random_particles,
+from helpers import (RefGrid, abi, assert_bits_equal, host_grid, loader, random_fields, random_interpolator, random_particles,
                      vacuum_coefficients)
 from old_vpic_b200.abi import ptr
 from test_oracle_vs_ref import _accumulators
@@ -105,3 +105,28 @@ def test_random_configuration(orc, ref_scalar, seed):
     L.synchronize_hydro(ptr(h_r), g.ref())
     orc.orc_synchronize_hydro(ptr(h_o), g.ref(), 0, 1)
     assert_bits_equal(h_o, h_r, "synchronize_hydro")
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_host_grid_mirror_with_mixed_boundaries(ref_scalar, seed):
+    """old_vpic_b200.grid (what the GPU tests and bench.py build their grid_t with): set_fbc / set_pbc per face against
+    the reference's ops.c on the same random choices -- bc[] and neighbor[] identical."""
+    L = ref_scalar
+    rng = np.random.default_rng(3000 + seed)
+    n = tuple(int(v) for v in rng.choice([1, 2, 3, 5], size=3))
+    cell = rng.uniform(0.4, 1.6, 3)
+    Lbox = tuple(float(c * m) for c, m in zip(cell, n))
+    r = RefGrid(L, n, "periodic", Lbox=Lbox)
+    h = host_grid(n, "periodic", L=Lbox, dt=r.struct.dt)
+    for ax, (i, j, k) in enumerate(AXES):
+        if n[ax] == 1 or rng.random() < 0.3:
+            continue
+        for sgn in (-1, 1):
+            b = abi.boundary(sgn * i, sgn * j, sgn * k)
+            fbc, pbc = int(rng.choice(FBC)), int(rng.choice(PBC))
+            L.set_fbc(r.ref(), b, fbc); h.set_fbc(b, fbc)
+            L.set_pbc(r.ref(), b, pbc); h.set_pbc(b, pbc)
+    assert list(r.struct.bc) == list(h.struct.bc)
+    assert np.array_equal(r.neighbor, h.neighbor)
+    for name in ("dx", "dy", "dz", "rdx", "rdy", "rdz", "x0", "x1", "y1", "z1", "rangel", "rangeh"):
+        assert getattr(r.struct, name) == getattr(h.struct, name), name
