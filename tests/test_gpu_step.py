@@ -114,3 +114,36 @@ def test_native_driver_calls_the_deck_hooks_where_advance_does(vpb, orc):
     sim.set_callbacks()
     sim.advance()
     assert len(log) == 15
+
+
+@pytest.mark.skipif(os.environ.get("VPB_RUN_UNVALIDATED") != "1", reason="not yet run on hardware (set VPB_RUN_UNVALIDATED=1)")
+@pytest.mark.parametrize("lookahead", [0, -1])
+def test_native_driver_against_the_reference_main_loop(vpb, tmp_path, lookahead):
+    """The C++ driver against the reference's REAL main loop, not a restatement of it: oracle/decks/pin_history.cxx on
+    the reference alone (main.cxx, initialize(), advance(); run here on the host) writes the state advance() starts
+    from and the energies after every step; vpb_sim_* steps the same state on the GPU.  20 steps with sorts and both
+    divergence cleanings: every column within 1e-4 (the float sums are ordered differently), with and without the
+    look-ahead sort key.  (tests/test_history_vs_ref_deck.py: the CPU restatement reproduces that history bit for bit.)"""
+    import subprocess
+    from test_history_vs_ref_deck import EXE, read_state
+    if not os.path.exists(EXE):
+        pytest.skip("oracle/_ref/pin_history.op not built")
+    r = subprocess.run([EXE, "-tpp=1"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    want = np.fromfile(tmp_path / "hist.bin", np.float64).reshape(-1, 8)
+    f0, species = read_state(tmp_path / "state0.bin")
+    g = host_grid((12, 10, 8), "periodic")
+    sim = NativeSimulation(g, L=vpb)
+    sim.set_intervals(5, 5)
+    sim.set_sort_lookahead(lookahead)
+    for k, sp in enumerate(species):
+        s = sim.define_species("s%d" % k, sp["q_m"], len(sp["p"]) + 64, sort_interval=5)
+        sim.set_particles(s, sp["p"])
+    sim.set_fields(f0)
+    got = []
+    for _ in range(20):
+        sim.advance()
+        got.append(sim.energies())
+    got = np.array(got)
+    rel = np.abs(got - want[1:]) / np.abs(want[1:]).max(axis=0)
+    assert rel.max() < 1e-4, rel.max(axis=0)
