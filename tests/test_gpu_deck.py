@@ -90,28 +90,40 @@ def test_reference_deck_runs_on_the_library(tmp_path):
     assert want[-1, 1:7].sum() > 0 and got[-1, 7] > 0 and got[-1, 8] > 0
 
 
-# Written in round 1 after the GPU budget was spent: not yet run on hardware.  First thing to run next round:
-#   VPB_RUN_UNVALIDATED=1 python -m pytest tests/test_gpu_deck.py -m gpu -q      (one GPU is enough, see below)
+# Tests written in round 1 after most of the GPU budget was spent carry this mark until they have run on hardware:
+#   VPB_RUN_UNVALIDATED=1 python -m pytest tests/test_gpu_deck.py -m gpu -q
 unvalidated = pytest.mark.skipif(os.environ.get("VPB_RUN_UNVALIDATED") != "1",
                                  reason="not yet run on hardware (set VPB_RUN_UNVALIDATED=1)")
 
 
-def _run_ranks(exe, world, cwd, **env):
+def _run_ranks(exe, world, cwd, share_gpu=True, **env):
     """`world` processes of an unmodified reference host program on the library.  The host side talks through the
     reference's mp layer (here over oracle/mpi_shim's shared-memory transport, which tests/test_ref_multirank.py
     exercises with the pure reference); the library finds that layer by itself (vpb_comm_autoboot: no line of host
     code added), picks its GPU from the launcher's local rank and runs its exchanges over NCCL when every rank has a
     GPU of its own, or through the host program's message layer when ranks share one (tests/test_mp_transport.py
-    drives that transport on CPU ranks) -- so this runs on a one-GPU box too."""
+    drives that transport on CPU ranks).  share_gpu pins every rank to GPU 0, whatever the box has."""
     from test_ref_multirank import run_ranks
-    return run_ranks(world, dict({"VPIC_SHIM_SLOT_MB": "2"}, **env), timeout=900, argv=[exe, "-tpp=1"], cwd=str(cwd), marker=None)
+    extra = dict({"VPIC_SHIM_SLOT_MB": "2"}, **env)
+    if share_gpu:
+        extra["CUDA_VISIBLE_DEVICES"] = os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0]
+    return run_ranks(world, extra, timeout=900, argv=[exe, "-tpp=1"], cwd=str(cwd), marker=None)
 
 
-@unvalidated
+def _gpu_count():
+    try:
+        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=60).stdout
+    except (OSError, subprocess.TimeoutExpired):
+        return 0
+    return sum(1 for line in out.splitlines() if line.startswith("GPU "))
+
+
 @pytest.mark.parametrize("world", [2, 4])
 def test_reference_deck_on_ranks(world, tmp_path):
     """oracle/decks/thermal_small.cxx splits the box along x over the ranks of the job; every rank draws the same
-    particles and keeps its slab, so the energies must be those of the one-rank reference run."""
+    particles and keeps its slab, so the energies must be those of the one-rank reference run.  The ranks share one
+    GPU: bootstrap through the reference's mp layer, exchanges staged through it (ran on a B200 at the end of round 1:
+    gpurun_out/pytest_gpu52_ranks.log, pytest_gpu53_ranks4.log)."""
     if not os.path.exists(EXE):
         pytest.skip("oracle/_ref/hybrid/thermal_small.b200.op not built (needs /root/reference at build time)")
     outs = _run_ranks(EXE, world, tmp_path)
@@ -122,10 +134,24 @@ def test_reference_deck_on_ranks(world, tmp_path):
 
 
 @unvalidated
+def test_reference_deck_on_two_gpus_over_nccl(tmp_path):
+    """The same with one GPU per rank: the library brings NCCL up through the reference's mp layer."""
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    if not os.path.exists(EXE):
+        pytest.skip("oracle/_ref/hybrid/thermal_small.b200.op not built (needs /root/reference at build time)")
+    outs = _run_ranks(EXE, 2, tmp_path, share_gpu=False)
+    got, want = read_energies(tmp_path / "energies"), read_energies(GOLD)
+    assert got.shape == want.shape == (21, 9), outs[0][-2000:]
+    rel = np.abs(got[:, 1:] - want[:, 1:]) / np.abs(want[:, 1:]).max(axis=0)
+    assert rel.max() < 1e-4, rel.max(axis=0)
+
+
 def test_reference_deck_grows_tight_arrays(tmp_path):
     """66 particles of head-room per rank: the arrivals of some round do not fit and boundary_p has to grow the species'
     arrays the way boundary_p.c:416-447 does (n + n/4 + n/16, warning, copy, free).  The pure reference does so on this
-    input (tests/test_ref_multirank.py); the library must, and the energies must not notice."""
+    input (tests/test_ref_multirank.py); the library must, and the energies must not notice (ran on a B200 at the end
+    of round 1: gpurun_out/pytest_gpu53_grow.log)."""
     if not os.path.exists(EXE):
         pytest.skip("oracle/_ref/hybrid/thermal_small.b200.op not built (needs /root/reference at build time)")
     outs = _run_ranks(EXE, 2, tmp_path, VPB_DECK_MAXNP="16450")

@@ -412,9 +412,9 @@ def test_advance_p_pair_variants(vpb, orc, variant, kind, n, np_, sort, vth):
     assert not np.any(acc_floats(a_g)[untouched] != 0)
 
 
-@unvalidated
 @pytest.mark.parametrize("variant", [1, 2, 3])
 def test_advance_p_pair_variants_extreme_and_tails(vpb, orc, variant):
+    """(ran on a B200 at the end of round 1: gpurun_out/pytest_gpu51_variants.log)"""
     g = host_grid((5, 4, 3), "metal")
     rng = np.random.default_rng(32)
     fi = random_interpolator(rng, g, amp=0.3)
