@@ -16,6 +16,10 @@ for v in 0 1 2 3; do
     > gpurun_out/r2_bench_variant$v.json 2> gpurun_out/r2_bench_variant$v.err
   echo "bench variant $v rc=$?" | tee -a gpurun_out/r2_summary.txt
 done
+# the record-scatter variant of the look-ahead sort (breakdown_ms_per_step.sort_p in the JSON line)
+VPB_SORT_SCATTER=1 python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu-baseline --field-cells 0 \
+  > gpurun_out/r2_bench_sort_scatter.json 2> gpurun_out/r2_bench_sort_scatter.err
+echo "bench sort.scatter rc=$?" | tee -a gpurun_out/r2_summary.txt
 # 3. BASELINE configs[0] as an unmodified reference host program: on the library, then on the reference alone
 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --field-cells 0 --deck-e2e > gpurun_out/r2_bench_deck.json 2> gpurun_out/r2_bench_deck.err
 echo "bench deck-e2e rc=$?" | tee -a gpurun_out/r2_summary.txt

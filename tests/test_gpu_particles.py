@@ -487,8 +487,10 @@ def test_sort_p_planes(vpb, orc, n, np_):
     vpb.vpb_domain_destroy(dom)
 
 
-def test_sort_p_planes_lookahead(vpb):
-    """Look-ahead sort key (vpb_sort_p_planes_ahead): a grouping of the SAME particles by the voxel they reach `L`
+@pytest.mark.parametrize("scatter", [0, pytest.param(1, marks=unvalidated)])
+def test_sort_p_planes_lookahead(vpb, scatter):
+    """scatter = 1: the record-scatter variant of the sort (tuning sort.scatter; not yet run on hardware).
+    Look-ahead sort key (vpb_sort_p_planes_ahead): a grouping of the SAME particles by the voxel they reach `L`
     steps ahead at their present velocity; partition[] delimits the groups; L = 0 is the plain (stable) sort."""
     from old_vpic_b200.sim import DevArray, ParticleArray
     n, np_, L = (10, 9, 8), 60001, 7
@@ -500,7 +502,11 @@ def test_sort_p_planes_lookahead(vpb):
     d_p, d_tmp = ParticleArray(vpb, dom, np_), ParticleArray(vpb, dom, np_)
     d_part = DevArray(vpb, g.nv + 1, np.int32)
     d_p.upload(p)
-    vpb.vpb_sort_p_planes_ahead(dom, d_p.ptr, d_tmp.ptr, np_, d_part.ptr, L)
+    vpb.vpb_set_tuning(b"sort.scatter", scatter)
+    try:
+        vpb.vpb_sort_p_planes_ahead(dom, d_p.ptr, d_tmp.ptr, np_, d_part.ptr, L)
+    finally:
+        vpb.vpb_set_tuning(b"sort.scatter", 0)
     out, part = d_p.download(np_), d_part.download()
     # same particles
     order = np.argsort(out["tag"], kind="stable")
