@@ -331,17 +331,31 @@ int advance_p(vpb_particle_t *p0, int np, const float q_m, vpb_particle_mover_t 
     VPB_CUDA(cudaStreamWaitEvent(P.s_in, P.ev_aux, 0));    // buffers of a previous call are idle by now
     VPB_CUDA(cudaStreamWaitEvent(P.s_out, P.ev_aux, 0));
     const int npieces = (np + piece - 1) / piece;
+    // advance_p reads and writes only the 32 hot bytes of a 48-byte record (the tags are neither used nor changed): with
+    // dropin.hot_only the copies are 2-D, 32 bytes of every 48 (a third less over PCIe if the copy engine keeps its
+    // rate on 32-byte rows -- to be measured; default off)
+    const bool hot_only = tuning("dropin.hot_only", 0) != 0;
     for (int i = 0; i < npieces; i++) {
       const int b = i % 3, k0 = i * piece, k1 = (k0 + piece < np) ? k0 + piece : np;
-      const size_t bytes = (size_t)(k1 - k0) * sizeof(vpb_particle_t);
+      size_t bytes = (size_t)(k1 - k0) * sizeof(vpb_particle_t);
       if (i >= 3) VPB_CUDA(cudaStreamWaitEvent(P.s_in, P.ev_free[b], 0));
-      VPB_CUDA(cudaMemcpyAsync(P.buf[b], p0 + k0, bytes, cudaMemcpyHostToDevice, P.s_in));
+      if (hot_only)
+        VPB_CUDA(cudaMemcpy2DAsync(P.buf[b], sizeof(vpb_particle_t), p0 + k0, sizeof(vpb_particle_t), 32, (size_t)(k1 - k0),
+                                   cudaMemcpyHostToDevice, P.s_in));
+      else
+        VPB_CUDA(cudaMemcpyAsync(P.buf[b], p0 + k0, bytes, cudaMemcpyHostToDevice, P.s_in));
       VPB_CUDA(cudaEventRecord(P.ev_in[b], P.s_in));
       VPB_CUDA(cudaStreamWaitEvent(c.stream, P.ev_in[b], 0));
       advance_p_range(J, P.buf[b] - k0, k0, k1, nullptr, c.stream);
       VPB_CUDA(cudaEventRecord(P.ev_k[b], c.stream));
       VPB_CUDA(cudaStreamWaitEvent(P.s_out, P.ev_k[b], 0));
-      VPB_CUDA(cudaMemcpyAsync(p0 + k0, P.buf[b], bytes, cudaMemcpyDeviceToHost, P.s_out));
+      if (hot_only) {
+        VPB_CUDA(cudaMemcpy2DAsync(p0 + k0, sizeof(vpb_particle_t), P.buf[b], sizeof(vpb_particle_t), 32, (size_t)(k1 - k0),
+                                   cudaMemcpyDeviceToHost, P.s_out));
+        bytes = (size_t)(k1 - k0) * 32;
+      } else {
+        VPB_CUDA(cudaMemcpyAsync(p0 + k0, P.buf[b], bytes, cudaMemcpyDeviceToHost, P.s_out));
+      }
       VPB_CUDA(cudaEventRecord(P.ev_free[b], P.s_out));
       g_h2d_total += bytes; g_d2h_total += bytes;
     }

@@ -20,6 +20,10 @@ done
 VPB_SORT_SCATTER=1 python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu-baseline --field-cells 0 \
   > gpurun_out/r2_bench_sort_scatter.json 2> gpurun_out/r2_bench_sort_scatter.err
 echo "bench sort.scatter rc=$?" | tee -a gpurun_out/r2_summary.txt
+# the e2e leg with 2-D copies of the 32 hot bytes of every record (e2e.value / h2d_bytes_per_step in the JSON line)
+VPB_DROPIN_HOT_ONLY=1 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --field-cells 0 \
+  > gpurun_out/r2_bench_e2e_hot_only.json 2> gpurun_out/r2_bench_e2e_hot_only.err
+echo "bench e2e hot_only rc=$?" | tee -a gpurun_out/r2_summary.txt
 # 3. BASELINE configs[0] as an unmodified reference host program: on the library, then on the reference alone
 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --field-cells 0 --deck-e2e > gpurun_out/r2_bench_deck.json 2> gpurun_out/r2_bench_deck.err
 echo "bench deck-e2e rc=$?" | tee -a gpurun_out/r2_summary.txt

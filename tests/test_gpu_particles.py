@@ -21,6 +21,8 @@ from old_vpic_b200.abi import ptr
 pytestmark = pytest.mark.gpu
 
 ACC_TOL = 2e-5
+# tests of code that has not run on hardware yet
+unvalidated = pytest.mark.skipif(os.environ.get("VPB_RUN_UNVALIDATED") != "1", reason="not yet run on hardware (set VPB_RUN_UNVALIDATED=1)")
 
 
 def acc_floats(a):
@@ -115,16 +117,19 @@ def test_advance_p_managed_memory_in_place(vpb, orc):
     assert max_rel(acc_floats(a_m), acc_floats(a_o)) < ACC_TOL
 
 
+@pytest.mark.parametrize("hot_only", [0, pytest.param(1, marks=unvalidated)])
 @pytest.mark.parametrize("kind", ["periodic", "absorbing"])
-def test_advance_p_streamed_in_pieces(vpb, orc, kind):
+def test_advance_p_streamed_in_pieces(vpb, orc, kind, hot_only):
     """Large host arrays go through the device in pieces (H2D / kernel / D2H overlapped); same results,
-    movers still ordered by particle index across pieces."""
+    movers still ordered by particle index across pieces.  hot_only: 2-D copies of the 32 hot bytes of every record
+    (tuning dropin.hot_only); the tags on the host must come through untouched."""
     g = host_grid((10, 9, 8), kind)
     rng = np.random.default_rng(23)
     np_ = 20000 + 17
     p = random_particles(rng, g, np_, vth=0.6, edge_frac=0.02)
     fi = random_interpolator(rng, g, amp=0.3)
     vpb.vpb_set_tuning(b"dropin.piece", 2048)
+    vpb.vpb_set_tuning(b"dropin.hot_only", hot_only)
     try:
         p_o, p_g = p.copy(), p.copy()
         a_o = abi.aligned_zeros(g.nv, abi.accumulator_dtype)
@@ -135,6 +140,7 @@ def test_advance_p_streamed_in_pieces(vpb, orc, kind):
         nm_g = vpb.advance_p(ptr(p_g), np_, -1.0, ptr(pm_g), np_, ptr(a_g), ptr(fi), g.ref())
     finally:
         vpb.vpb_set_tuning(b"dropin.piece", 4 << 20)
+        vpb.vpb_set_tuning(b"dropin.hot_only", 0)
     assert nm_g == nm_o and (kind != "absorbing" or nm_o > 0)
     assert_bits_equal(p_g, p_o, "particles")
     assert_bits_equal(pm_g[:nm_g], pm_o[:nm_o], "movers")
@@ -381,7 +387,6 @@ def test_advance_p_pair_tails(vpb, orc):
 
 # Kernel variants written after round 1's GPU budget was spent (vpb_advance_p_pair.cu: FULL fast path for whole chunks,
 # LEAN index-only mover ring): same bar as the default kernel, not yet run on hardware.
-unvalidated = pytest.mark.skipif(os.environ.get("VPB_RUN_UNVALIDATED") != "1", reason="not yet run on hardware (set VPB_RUN_UNVALIDATED=1)")
 
 
 @unvalidated
