@@ -390,7 +390,7 @@ def run_b200(args):
         "host_wall_ms_per_step": 1e3 * wall / args.steps, "driver": args.driver,
         "l2_fetch_granularity_bytes": int(L.vpb_l2_fetch_granularity()),
         "advance_p_ms_by_launch": adv_list,
-        "tuning": {k: L.vpb_get_tuning(k.encode()) for k in ("advance_p.deposit", "advance_p.tma", "advance_p.stream_store", "advance_p.stream_cps", "sim.aos_fields", "sim.narrow_interpolator", "sim.aos_particles", "advance_p.pair_cps", "advance_p.pair_pipe", "advance_p.pair_merge", "advance_p.pair_variant",
+        "tuning": {k: L.vpb_get_tuning(k.encode()) for k in ("advance_p.deposit", "advance_p.tma", "advance_p.stream_store", "advance_p.stream_cps", "sim.aos_fields", "sim.narrow_interpolator", "sim.aos_particles", "advance_p.pair_cps", "advance_p.pair_pipe", "advance_p.pair_merge", "advance_p.pair_variant", "sort.scatter", "dropin.hot_only",
                                                              "advance_p.tma_ctas_per_sm", "advance_p.ctas_per_sm")},
     }
     if fields_c2 is not None:
