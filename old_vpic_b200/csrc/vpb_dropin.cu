@@ -492,7 +492,11 @@ static int grow_species(void *user, int index, int need_np, int need_nm, vpb_spe
     util_malloc_aligned("MALLOC_ALIGNED( new_p, (%lu bytes), 128 (%lu bytes) ) failed", &new_p, (size_t)n * sizeof(*new_p), 128);
     VPB_CUDA(cudaMemcpyAsync(new_p, st->p, (size_t)st->np * sizeof(*new_p), cudaMemcpyDefault, c.stream));
     VPB_CUDA(cudaStreamSynchronize(c.stream));
-    g_part_hint.erase(sp->p);
+    auto ph = g_part_hint.find(sp->p);          // the traversal hint belongs to the old array
+    if (ph != g_part_hint.end()) {
+      if (ph->second.dev) cudaFree(ph->second.dev);
+      g_part_hint.erase(ph);
+    }
     util_free_aligned(&sp->p);
     sp->p = new_p; sp->max_np = n;
     st->p = new_p; st->max_np = n;
