@@ -11,6 +11,8 @@ fields differ in the last bit -- and that particle deposits into the neighbourin
 "exactness hot spots"; seen here at step 5 of the second case, scripts/dbg_harris4.py).  It shifts the three small
 field-energy columns (ex, ez, cbz: 1e-2 of the field energy) by 1e-3 of THEIR size and nothing else.  Field columns are
 therefore compared on the scale of the total field energy, kinetic columns on their own: 1e-4 over 20 steps."""
+import os
+
 import numpy as np
 import pytest
 
@@ -86,4 +88,51 @@ def test_trecon_geometry_history(vpb, orc, nx, nz, clean):
     for plane in (1, nz + 1):
         assert not np.any(f["ex"][plane, 1, 1:nx + 1]) and not np.any(f["ey"][plane, 1, 1:nx + 1])
         assert not np.any(f["cbz"][plane, 1, 1:nx + 1])
+    sim.free()
+
+
+@pytest.mark.skipif(os.environ.get("VPB_RUN_UNVALIDATED") != "1", reason="not yet run on hardware (set VPB_RUN_UNVALIDATED=1)")
+def test_trecon_cells_and_field_strength_history(vpb, orc):
+    """The same geometry with the deck's OWN cell shape and field strength (turbulence.cxx:86-160): cells of 0.488 x 1.95 x
+    0.488 c/wpe, dt = 0.99 Courant, wce/wpe = 10 (b0 = 10), sheet half-thickness 6, vth = 0.6 c -- anisotropic cells and
+    a gyro-phase of 3.4 rad per step, which none of the unit-cube histories exercise."""
+    nx, nz, ppc = 32, 24, 16
+    cell = (1000.0 / 2048, 500.0 / 256, 500.0 / 1024)
+    g = host_grid((nx, 1, nz), "periodic", L=(cell[0] * nx, cell[1], cell[2] * nz))
+    for sgn in (-1, 1):
+        g.set_fbc(abi.boundary(0, 0, sgn), abi.PEC_FIELDS)
+        g.set_pbc(abi.boundary(0, 0, sgn), abi.REFLECT_PARTICLES)
+    g.set_units(0.99 / np.sqrt(1.0 / cell[0] ** 2 + 1.0 / cell[2] ** 2), 1.0, 1.0, 0.0)
+    f0 = abi.aligned_zeros(g.nv, abi.field_dtype)
+    zc = ((np.arange(g.nv) // ((nx + 2) * 3)) - 0.5 - 0.5 * nz) * cell[2]
+    f0["cbx"] = (10.0 * np.tanh(zc / 6.0)).astype(np.float32)
+    f0["cby"] = (10.0 / np.cosh(zc / 6.0)).astype(np.float32)
+
+    def species():
+        rng = np.random.default_rng(19)
+        n = nx * nz * ppc
+        vol = cell[0] * cell[1] * cell[2]
+        e = random_particles(rng, g, n, vth=0.6, sort=True, q=-vol / ppc)
+        i = random_particles(rng, g, n, vth=0.6, sort=True, q=+vol / ppc)
+        i["dx"], i["dy"], i["dz"], i["i"] = e["dx"], e["dy"], e["dz"], e["i"]
+        return [{"p": e, "q_m": -1.0}, {"p": i, "q_m": 1.0}]
+
+    h_cpu = cpu_history(oracle_kernels(orc), g, species(), STEPS, 5, 5, f_init=f0)
+    sim = NativeSimulation(g, L=vpb)
+    sim.set_intervals(5, 5)
+    inputs = species()
+    for k, sp in enumerate(inputs):
+        s = sim.define_species("s%d" % k, sp["q_m"], len(sp["p"]) + 64, sort_interval=SORT)
+        sim.set_particles(s, sp["p"])
+    sim.set_fields(f0)
+    h_gpu = []
+    for _ in range(STEPS):
+        sim.advance()
+        h_gpu.append(sim.energies())
+    h_gpu = np.array(h_gpu)
+    scale = np.abs(h_cpu).max(axis=0)
+    scale[:6] = h_cpu[:, :6].sum(axis=1).max()
+    assert (np.abs(h_gpu - h_cpu) / scale).max() < 1e-4, (np.abs(h_gpu - h_cpu) / scale).max(axis=0)
+    for sp, inp in zip(sim.species, inputs):
+        assert np.array_equal(np.sort(sim.get_particles(sp)["tag"]), np.sort(inp["p"]["tag"]))
     sim.free()
