@@ -23,7 +23,7 @@ begin_initialization {
   grid->cvac = 1;
   grid->eps0 = 1;
   grid->damp = 0;
-  define_absorbing_grid( 0, 0, 0, Lx, Ly, Lz, nx, ny, nz, 1, 1, 1, absorb_particles );
+  define_absorbing_grid( 0, 0, 0, Lx, Ly, Lz, nx, ny, nz, int( nproc() ), 1, 1, absorb_particles );   // split along x over the ranks of the job
 
   define_material( "vacuum", 1 );
   finalize_field_advance( standard_field_advance );
@@ -43,7 +43,10 @@ begin_initialization {
 begin_diagnostics {
   dump_energies( "energies", step == 0 ? 0 : 1 );
   if( step == num_step ) {
-    FILE * fp = fopen( "counts", "w" );
+    char name[64];
+    if( nproc() > 1 ) sprintf( name, "counts.%d", int( rank() ) );    // one file per rank; the test adds them up
+    else              sprintf( name, "counts" );
+    FILE * fp = fopen( name, "w" );
     for( species_t * sp = species_list; sp; sp = sp->next ) fprintf( fp, "%s %d\n", sp->name, sp->np );
     fclose( fp );
   }

@@ -24,7 +24,7 @@ begin_initialization {
   grid->cvac = 1;
   grid->eps0 = 1;
   grid->damp = 0;
-  define_periodic_grid( 0, -0.5 * Ly, -0.5 * Lz, Lx, 0.5 * Ly, 0.5 * Lz, nx, ny, nz, 1, 1, 1 );
+  define_periodic_grid( 0, -0.5 * Ly, -0.5 * Lz, Lx, 0.5 * Ly, 0.5 * Lz, nx, ny, nz, int( nproc() ), 1, 1 );   // split along x: every rank keeps both z walls
   set_domain_field_bc( BOUNDARY( 0, 0, -1 ), pec_fields );
   set_domain_field_bc( BOUNDARY( 0, 0,  1 ), pec_fields );
   set_domain_particle_bc( BOUNDARY( 0, 0, -1 ), reflect_particles );

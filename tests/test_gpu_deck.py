@@ -162,6 +162,33 @@ def test_reference_deck_grows_tight_arrays(tmp_path):
 
 
 @unvalidated
+@pytest.mark.parametrize("deck", ["absorb_small", "sheet_small"])
+def test_reference_wall_decks_on_two_ranks(deck, tmp_path):
+    """The wall decks split along x over two ranks sharing the GPU: migration together with absorbing faces (Higdon
+    fields, absorbed particles, rhob) and with conducting reflecting walls, sheet field and the hydro dump.  Against
+    the one-rank reference goldens (tests/test_ref_multirank.py: the pure reference on two ranks reproduces them to 8e-8)."""
+    exe = EXE.replace("thermal_small", deck)
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/hybrid/%s.b200.op not built (needs /root/reference at build time)" % deck)
+    outs = _run_ranks(exe, 2, tmp_path)
+    got, want = read_energies(tmp_path / "energies"), read_energies(GOLD.replace("thermal_small", deck))
+    assert got.shape == want.shape == (21, 9), outs[0][-2000:]
+    scale = np.abs(want[:, 1:]).max(axis=0)
+    scale[:6] = want[:, 1:7].sum(axis=1).max()
+    rel = np.abs(got[:, 1:] - want[:, 1:]) / scale
+    assert rel.max() < 5e-4, rel.max(axis=0)
+    if deck == "absorb_small":
+        tot = {}
+        for r in range(2):
+            for line in open(tmp_path / ("counts.%d" % r)):
+                k, v = line.split()
+                tot[k] = tot.get(k, 0) + int(v)
+        want_counts = dict(line.split() for line in open(GOLD.replace("thermal_small_energies", "absorb_small_counts")))
+        for name in want_counts:
+            assert abs(tot[name] - int(want_counts[name])) <= 2, (tot, want_counts)
+
+
+@unvalidated
 def test_trecon_part_deck_as_shipped(tmp_path):
     """The reference's own trecon-part deck (decks/trecon-part/turbulence.cxx with its config.h: 16x16x1 cells, 50 ppc,
     four species + tracers, topology 2x2x1, 2500 steps, field/hydro/particle/tracer dumps), not one character changed,

@@ -83,3 +83,28 @@ def test_reference_deck_grows_tight_arrays(tmp_path):
     want = read_energies(os.path.join(HERE, "golden", "deck_thermal_small_energies.txt"))
     rel = np.abs(got[:, 1:] - want[:, 1:]) / np.abs(want[:, 1:]).max(axis=0)
     assert rel.max() < 1e-5, rel.max(axis=0)
+
+
+@pytest.mark.parametrize("deck", ["absorb_small", "sheet_small"])
+def test_reference_wall_decks_on_two_ranks(deck, tmp_path):
+    """The decks with walls, split along x over two reference ranks: six absorbing faces with Higdon fields and
+    absorbed particles (absorb_small), and the trecon-part geometry with conducting reflecting z walls, a force-free
+    sheet and a hydro dump (sheet_small).  Energies of the one-rank run, particle counts exactly."""
+    import numpy as np
+    exe = os.path.join(os.path.dirname(HERE), "oracle", "_ref", deck + ".op")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/%s.op not built" % deck)
+    run_ranks(2, {"VPIC_SHIM_SLOT_MB": "2"}, argv=[exe, "-tpp=1"], cwd=str(tmp_path), marker=None)
+    got = read_energies(tmp_path / "energies")
+    want = read_energies(os.path.join(HERE, "golden", "deck_%s_energies.txt" % deck))
+    scale = np.abs(want[:, 1:]).max(axis=0)
+    scale[:6] = want[:, 1:7].sum(axis=1).max()
+    assert (np.abs(got[:, 1:] - want[:, 1:]) / scale).max() < 1e-5
+    if deck == "absorb_small":
+        tot = {}
+        for r in range(2):
+            for line in open(tmp_path / ("counts.%d" % r)):
+                k, v = line.split()
+                tot[k] = tot.get(k, 0) + int(v)
+        want_counts = {k: int(v) for k, v in (line.split() for line in open(os.path.join(HERE, "golden", "deck_absorb_small_counts.txt")))}
+        assert tot == want_counts
