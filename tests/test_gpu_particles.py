@@ -288,7 +288,7 @@ def test_layer_b_wide_interpolator(vpb, orc, kind, store):
 class particle_planes:
     """Layer-A calls inside this context stage their particle array as component planes on the device."""
 
-    def __init__(self, vpb, cps=4, pipe=1, merge=1, variant=0):
+    def __init__(self, vpb, cps=4, pipe=1, merge=1, variant=-1):
         self.vpb, self.cps, self.pipe, self.merge, self.variant = vpb, cps, pipe, merge, variant
 
     def __enter__(self):
@@ -299,7 +299,7 @@ class particle_planes:
         self.vpb.vpb_set_tuning(b"advance_p.pair_variant", self.variant)
 
     def __exit__(self, *a):
-        self.vpb.vpb_set_tuning(b"advance_p.pair_variant", 0)
+        self.vpb.vpb_set_tuning(b"advance_p.pair_variant", -1)      # back to the library's default
         self.vpb.vpb_set_tuning(b"dropin.particle_planes", 0)
         self.vpb.vpb_set_tuning(b"advance_p.pair_cps", 4)
         self.vpb.vpb_set_tuning(b"advance_p.pair_pipe", 1)
@@ -417,9 +417,11 @@ def test_advance_p_pair_variants(vpb, orc, variant, kind, n, np_, sort, vth):
     assert not np.any(acc_floats(a_g)[untouched] != 0)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_advance_p_pair_variants_extreme_and_tails(vpb, orc, variant):
-    """(ran on a B200 at the end of round 1: gpurun_out/pytest_gpu51_variants.log)"""
+    """Every kernel variant (0: validity tests in every chunk, the default until the end of round 1; 1: FULL, the
+    default now; 2: LEAN; 3: both) on extreme operands and every tail length.  Variants 1-3 ran on a B200 at the end of
+    round 1 (profiles/r1s_last_calls_pytest.txt); variant 0 is what all earlier runs measured."""
     g = host_grid((5, 4, 3), "metal")
     rng = np.random.default_rng(32)
     fi = random_interpolator(rng, g, amp=0.3)
