@@ -394,8 +394,11 @@ def run_b200(args):
         "host_wall_ms_per_step": 1e3 * wall / args.steps, "driver": args.driver,
         "l2_fetch_granularity_bytes": int(L.vpb_l2_fetch_granularity()),
         "advance_p_ms_by_launch": adv_list,
-        "tuning": {k: L.vpb_get_tuning(k.encode()) for k in ("advance_p.deposit", "advance_p.tma", "advance_p.stream_store", "advance_p.stream_cps", "sim.aos_fields", "sim.narrow_interpolator", "sim.aos_particles", "advance_p.pair_cps", "advance_p.pair_pipe", "advance_p.pair_merge", "advance_p.pair_variant", "sort.scatter", "dropin.hot_only",
-                                                             "advance_p.tma_ctas_per_sm", "advance_p.ctas_per_sm")},
+        # effective values: the environment override if there is one, else the library's default
+        "tuning": {k: int(os.environ.get("VPB_" + k.upper().replace(".", "_"), d)) for k, d in (
+            ("advance_p.pair_variant", 1), ("advance_p.pair_cps", 4), ("advance_p.pair_pipe", 1), ("advance_p.pair_merge", 1),
+            ("sort.scatter", 0), ("dropin.hot_only", 0), ("sim.aos_fields", 0), ("sim.narrow_interpolator", 0), ("sim.aos_particles", 0),
+            ("advance_p.tma", 2), ("advance_p.stream_cps", 5), ("advance_p.stream_store", 0), ("advance_p.deposit", 1))},
     }
     if fields_c2 is not None:
         line["fields_c2"] = fields_c2
