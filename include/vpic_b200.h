@@ -140,6 +140,12 @@ float vpb_timer_ms(int slot);                /* synchronises on the stop event *
 void vpb_prof_enable(int on);
 void vpb_prof_collect(int cls, double *total_ms, int *count, int reset);
 int vpb_prof_list(int cls, float *out_ms, int max);   /* per-launch durations in launch order */
+/* Host wall-clock accounting of the layer-A entry points (also switched on by VPB_TRACE=1 in the environment, which
+ * prints the table at exit to stderr or to the file VPB_TRACE_FILE names): calls and seconds per entry point. */
+void vpb_trace_enable(int on);
+void vpb_trace_reset(void);
+void vpb_trace_report(void);
+double vpb_trace_get(const char *label, long *calls);
 
 /* Count of kernel launches made by this library since the last reset. */
 long vpb_launch_count(int reset);

@@ -103,6 +103,19 @@ struct ProfScope {
   ~ProfScope() { prof_end(cls); }
 };
 
+// Host wall-clock accounting of the layer-A entry points (VPB_TRACE=1 or vpb_trace_enable): calls and seconds
+// per label, nested labels ("  prefetch", "  sync") counted inside their entry point.  Written to stderr (or to
+// the file VPB_TRACE_FILE names) at exit or by vpb_trace_report.  Costs two clock reads per scope when on.
+extern bool g_trace_on;
+void trace_add(const char *label, double seconds);
+double trace_now();
+struct TraceScope {
+  const char *label;
+  double t0;
+  explicit TraceScope(const char *l) : label(l), t0(g_trace_on ? trace_now() : 0.0) {}
+  ~TraceScope() { if (g_trace_on) trace_add(label, trace_now() - t0); }
+};
+
 }  // namespace vpb
 
 struct vpb_domain {

@@ -3,6 +3,7 @@
 #include <map>
 #include <string>
 #include <string.h>
+#include <time.h>
 #include <vector>
 #include "vpb_common.cuh"
 
@@ -40,6 +41,40 @@ int tuning(const char *name, int dflt) {
   return v;
 }
 
+// ---- host wall-clock trace of entry points (vpb_common.cuh: TraceScope) ----
+bool g_trace_on = false;
+struct TraceRec { long calls = 0; double seconds = 0, worst = 0; };
+static std::map<std::string, TraceRec> g_trace;
+static std::vector<std::string> g_trace_order;
+double trace_now() {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+void trace_add(const char *label, double s) {
+  auto it = g_trace.find(label);
+  if (it == g_trace.end()) { g_trace_order.push_back(label); it = g_trace.emplace(label, TraceRec()).first; }
+  it->second.calls++;
+  it->second.seconds += s;
+  if (s > it->second.worst) it->second.worst = s;
+}
+static void trace_report_to(FILE *fp) {
+  fprintf(fp, "vpb trace: %-34s %10s %12s %12s %12s\n", "label", "calls", "total ms", "us/call", "worst ms");
+  for (auto &name : g_trace_order) {
+    const TraceRec &r = g_trace[name];
+    fprintf(fp, "vpb trace: %-34s %10ld %12.3f %12.2f %12.3f\n", name.c_str(), r.calls, 1e3 * r.seconds,
+            r.calls ? 1e6 * r.seconds / (double)r.calls : 0.0, 1e3 * r.worst);
+  }
+  fflush(fp);
+}
+static void trace_atexit() {
+  if (!g_trace_on || g_trace.empty()) return;
+  const char *fn = getenv("VPB_TRACE_FILE");
+  FILE *fp = fn ? fopen(fn, "a") : nullptr;
+  trace_report_to(fp ? fp : stderr);
+  if (fp) fclose(fp);
+}
+
 struct ProfRec { cudaEvent_t a, b; int cls; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;       // pool of event pairs
@@ -74,6 +109,16 @@ extern "C" int vpb_prof_list(int cls, float *out_ms, int max) {
   for (size_t i = 0; i < g_prof_used && n < max; i++)
     if (g_prof[i].cls == cls) VPB_CUDA(cudaEventElapsedTime(&out_ms[n++], g_prof[i].a, g_prof[i].b));
   return n;
+}
+
+extern "C" void vpb_trace_enable(int on) { g_trace_on = on != 0; }
+extern "C" void vpb_trace_reset(void) { g_trace.clear(); g_trace_order.clear(); }
+extern "C" void vpb_trace_report(void) { trace_report_to(stderr); }
+// seconds and calls of one label since the last reset (0 when the label never ran)
+extern "C" double vpb_trace_get(const char *label, long *calls) {
+  auto it = g_trace.find(label);
+  if (calls) *calls = it == g_trace.end() ? 0 : it->second.calls;
+  return it == g_trace.end() ? 0.0 : it->second.seconds;
 }
 
 extern "C" void vpb_prof_enable(int on) { g_prof_on = on != 0; g_prof_used = 0; }
@@ -151,6 +196,7 @@ int vpb_init(int device_ordinal) {
   uint64_t thresh = UINT64_MAX;
   VPB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
   g_ready = true;
+  if (getenv("VPB_TRACE") && atoi(getenv("VPB_TRACE"))) { g_trace_on = true; atexit(trace_atexit); }
   return 0;
 }
 

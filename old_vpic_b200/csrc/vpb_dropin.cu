@@ -42,10 +42,12 @@ struct Residency {
     if (!host || bytes == 0) return const_cast<void *>(host);
     Context &c = ctx();
     cudaPointerAttributes at;
-    cudaError_t e = cudaPointerGetAttributes(&at, host);
+    cudaError_t e;
+    { TraceScope _t("  ptr_attributes"); e = cudaPointerGetAttributes(&at, host); }
     if (e != cudaSuccess) { cudaGetLastError(); at.type = cudaMemoryTypeUnregistered; }
     if (at.type == cudaMemoryTypeDevice) return const_cast<void *>(host);
     if (at.type == cudaMemoryTypeManaged) {
+      TraceScope _t("  prefetch");
       if (tuning("dropin.prefetch", 1)) cudaMemPrefetchAsync(host, bytes, c.device, c.stream);
       cudaGetLastError();
       return const_cast<void *>(host);
@@ -118,7 +120,7 @@ struct Residency {
     planar.clear();
     for (auto &a : staged)
       if (a.mode & WR) { VPB_CUDA(cudaMemcpyAsync(a.host, a.dev, a.bytes, cudaMemcpyDeviceToHost, c.stream)); d2h += a.bytes; }
-    VPB_CUDA(cudaStreamSynchronize(c.stream));
+    { TraceScope _t("  finish_sync"); VPB_CUDA(cudaStreamSynchronize(c.stream)); }
     staged.clear();
     g_h2d_total += h2d; g_d2h_total += d2h;
     h2d = d2h = 0;
@@ -149,6 +151,7 @@ static void ensure_comm(const vpb_grid_t *g) {
 
 static vpb_domain_t *domain_of(const vpb_grid_t *g) {
   if (!g) VPB_ERROR("Bad grid");
+  TraceScope _t("  domain_of");
   auto it = g_domains.find(g);
   if (it != g_domains.end() && g_domain_print[g] != neighbor_print(g)) {
     vpb_domain_destroy(it->second);
@@ -284,6 +287,7 @@ static bool is_plain_host(const void *p) {
 
 int advance_p(vpb_particle_t *p0, int np, const float q_m, vpb_particle_mover_t *pm, int max_nm, vpb_accumulator_t *a0,
               const vpb_interpolator_t *f0, const vpb_grid_t *g) {
+  TraceScope _ts("advance_p");
   if (!p0) VPB_ERROR("Bad particle array");
   if (np < 0) VPB_ERROR("Bad number of particles");
   if (!pm) VPB_ERROR("Bad particle mover");
@@ -377,6 +381,7 @@ int advance_p(vpb_particle_t *p0, int np, const float q_m, vpb_particle_mover_t 
 }
 
 void center_p(vpb_particle_t *p0, int np, const float q_m, const vpb_interpolator_t *f0, const vpb_grid_t *g) {
+  TraceScope _ts("center_p");
   if (np < 0) VPB_ERROR("Bad number of particles");
   if (!f0) VPB_ERROR("Bad interpolator");
   if (!g) VPB_ERROR("Bad grid");
@@ -389,6 +394,7 @@ void center_p(vpb_particle_t *p0, int np, const float q_m, const vpb_interpolato
 }
 
 void uncenter_p(vpb_particle_t *p0, int np, const float q_m, const vpb_interpolator_t *f0, const vpb_grid_t *g) {
+  TraceScope _ts("uncenter_p");
   if (np < 0) VPB_ERROR("Bad number of particles");
   if (!f0) VPB_ERROR("Bad interpolator");
   if (!g) VPB_ERROR("Bad grid");
@@ -401,6 +407,7 @@ void uncenter_p(vpb_particle_t *p0, int np, const float q_m, const vpb_interpola
 }
 
 double energy_p(const vpb_particle_t *p0, int np, float q_m, const vpb_interpolator_t *f0, const vpb_grid_t *g) {
+  TraceScope _ts("energy_p");
   if (np < 0) VPB_ERROR("Bad number of particles");
   if (!f0) VPB_ERROR("Bad interpolator");
   if (!g) VPB_ERROR("Bad grid");
@@ -420,6 +427,7 @@ double energy_p(const vpb_particle_t *p0, int np, float q_m, const vpb_interpola
 }
 
 void accumulate_rho_p(vpb_field_t *f, const vpb_particle_t *p0, int np, const vpb_grid_t *g) {
+  TraceScope _ts("accumulate_rho_p");
   if (!f) VPB_ERROR("Bad field");
   if (!p0) VPB_ERROR("Bad particle array");
   if (np < 0) VPB_ERROR("Bad number of particles");
@@ -435,6 +443,7 @@ void accumulate_rho_p(vpb_field_t *f, const vpb_particle_t *p0, int np, const vp
 // move_p.c:20-136 for ONE mover.  Host code of the reference calls this per injected particle
 // (misc.cxx:102); it costs a kernel launch here and is meant for set-up paths only.
 int move_p(vpb_particle_t *p0, vpb_particle_mover_t *m, vpb_accumulator_t *a0, const vpb_grid_t *g) {
+  TraceScope _ts("move_p");
   vpb_domain_t *dom = domain_of(g);
   Context &c = ctx();
   Residency r;
@@ -459,6 +468,7 @@ int move_p(vpb_particle_t *p0, vpb_particle_mover_t *m, vpb_accumulator_t *a0, c
 
 // boundary_p.c:9-71 for ONE particle
 void accumulate_rhob(vpb_field_t *f0, const vpb_particle_t *p, const vpb_grid_t *g) {
+  TraceScope _ts("accumulate_rhob");
   if (!f0 || !p) VPB_ERROR("Bad field or particle");
   vpb_domain_t *dom = domain_of(g);
   Context &c = ctx();
@@ -518,6 +528,7 @@ static int grow_species(void *user, int index, int need_np, int need_nm, vpb_spe
 // boundary_p.c:77-505: one round over the species list.  rng is only used by custom boundary
 // handlers in the reference (host callbacks), which the device path does not run.
 void boundary_p(vpb_species_t *sp_list, vpb_field_t *f0, vpb_accumulator_t *a0, const vpb_grid_t *g, void *rng) {
+  TraceScope _ts("boundary_p");
   (void)rng;
   if (!g) VPB_ERROR("Bad grid");
   vpb_domain_t *dom = domain_of(g);
@@ -543,6 +554,7 @@ void boundary_p(vpb_species_t *sp_list, vpb_field_t *f0, vpb_accumulator_t *a0, 
 }
 
 void sort_p(vpb_species_t *sp, const vpb_grid_t *g) {
+  TraceScope _ts("sort_p");
   if (!sp) VPB_ERROR("Bad species");
   if (!g) VPB_ERROR("Bad grid");
   vpb_domain_t *dom = domain_of(g);
@@ -622,6 +634,7 @@ vpb_hydro_t *new_hydro(vpb_grid_t *g) {
 void delete_hydro(vpb_hydro_t *h) { util_free_aligned(&h); }
 
 void clear_hydro(vpb_hydro_t *h, const vpb_grid_t *g) {
+  TraceScope _ts("clear_hydro");
   if (!h) VPB_ERROR("Bad hydro");
   if (!g) VPB_ERROR("Bad grid");
   vpb_domain_t *dom = domain_of(g);
@@ -634,6 +647,7 @@ void clear_hydro(vpb_hydro_t *h, const vpb_grid_t *g) {
 // hydro_p.c:24-161
 void accumulate_hydro_p(vpb_hydro_t *h0, const vpb_particle_t *p0, int n, float q_m, const vpb_interpolator_t *f0,
                         const vpb_grid_t *g) {
+  TraceScope _ts("accumulate_hydro_p");
   if (!h0) VPB_ERROR("Bad hydro");
   if (!p0) VPB_ERROR("Bad particle array");
   if (n < 0) VPB_ERROR("Bad number of particles");
@@ -650,6 +664,7 @@ void accumulate_hydro_p(vpb_hydro_t *h0, const vpb_particle_t *p0, int n, float 
 
 // sf_interface/hydro.c:30-141, :146-184
 void synchronize_hydro(vpb_hydro_t *h, const vpb_grid_t *g) {
+  TraceScope _ts("synchronize_hydro");
   if (!h) VPB_ERROR("Bad hydro");
   if (!g) VPB_ERROR("Bad grid");
   vpb_domain_t *dom = domain_of(g);
@@ -660,6 +675,7 @@ void synchronize_hydro(vpb_hydro_t *h, const vpb_grid_t *g) {
 }
 
 void local_adjust_hydro(vpb_hydro_t *h, const vpb_grid_t *g) {
+  TraceScope _ts("local_adjust_hydro");
   if (!h) VPB_ERROR("Bad hydro");
   if (!g) VPB_ERROR("Bad grid");
   vpb_domain_t *dom = domain_of(g);
@@ -670,6 +686,7 @@ void local_adjust_hydro(vpb_hydro_t *h, const vpb_grid_t *g) {
 }
 
 void load_interpolator(vpb_interpolator_t *fi, const vpb_field_t *f, const vpb_grid_t *g) {
+  TraceScope _ts("load_interpolator");
   if (!fi) VPB_ERROR("Bad interpolator");
   if (!f) VPB_ERROR("Bad field");
   if (!g) VPB_ERROR("Bad grid");
@@ -683,6 +700,7 @@ void load_interpolator(vpb_interpolator_t *fi, const vpb_field_t *f, const vpb_g
 }
 
 void clear_accumulators(vpb_accumulator_t *a, const vpb_grid_t *g) {
+  TraceScope _ts("clear_accumulators");
   if (!a) VPB_ERROR("Bad accumulator");
   if (!g) VPB_ERROR("Bad grid");
   vpb_domain_t *dom = domain_of(g);
@@ -699,6 +717,7 @@ void reduce_accumulators(vpb_accumulator_t *a, const vpb_grid_t *g) {
 }
 
 void unload_accumulator(vpb_field_t *f, const vpb_accumulator_t *a, const vpb_grid_t *g) {
+  TraceScope _ts("unload_accumulator");
   if (!f) VPB_ERROR("Bad field");
   if (!a) VPB_ERROR("Bad accumulator");
   if (!g) VPB_ERROR("Bad grid");
@@ -809,22 +828,26 @@ static double *dev_doubles(int n) {
 static void free_doubles(double *d) { VPB_CUDA(cudaFreeAsync(d, ctx().stream)); }
 
 static void fa_advance_b(vpb_field_t *f, const vpb_grid_t *g, float frac) {
+  TraceScope _ts("advance_b");
   FieldCall k(f, g, RW);
   vpb_advance_b(k.dom, k.df, frac);
   k.r.finish();
 }
 static void fa_advance_e(vpb_field_t *f, const vpb_material_coefficient_t *m, const vpb_grid_t *g) {
+  TraceScope _ts("advance_e");
   FieldCall k(f, g, RW, m, true);
   vpb_advance_e(k.dom, k.df, k.dm, k.n_mat, 0);
   k.r.finish();
 }
 static void vfa_advance_e(vpb_field_t *f, const vpb_material_coefficient_t *m, const vpb_grid_t *g) {
+  TraceScope _ts("vadvance_e");
   (void)m;
   FieldCall k(f, g, RW);
   vpb_advance_e(k.dom, k.df, nullptr, 1, 1);
   k.r.finish();
 }
 static void energy_common(double *en, const vpb_field_t *f, const vpb_material_coefficient_t *m, const vpb_grid_t *g, bool need_m) {
+  TraceScope _ts("energy");
   if (!en) VPB_ERROR("Bad energy");
   FieldCall k(const_cast<vpb_field_t *>(f), g, RD, m, need_m);
   double *d = dev_doubles(6);
@@ -844,23 +867,28 @@ static void vfa_energy_f(double *en, const vpb_field_t *f, const vpb_material_co
   (void)m;
   energy_common(en, f, nullptr, g, false);
 }
-static void fa_clear_jf(vpb_field_t *f, const vpb_grid_t *g) { FieldCall k(f, g, RW); vpb_clear_jf(k.dom, k.df); k.r.finish(); }
-static void fa_synchronize_jf(vpb_field_t *f, const vpb_grid_t *g) { FieldCall k(f, g, RW); vpb_synchronize_jf(k.dom, k.df); k.r.finish(); }
-static void fa_clear_rhof(vpb_field_t *f, const vpb_grid_t *g) { FieldCall k(f, g, RW); vpb_clear_rhof(k.dom, k.df); k.r.finish(); }
-static void fa_synchronize_rho(vpb_field_t *f, const vpb_grid_t *g) { FieldCall k(f, g, RW); vpb_synchronize_rho(k.dom, k.df); k.r.finish(); }
+static void fa_clear_jf(vpb_field_t *f, const vpb_grid_t *g) { TraceScope _ts("clear_jf"); FieldCall k(f, g, RW); vpb_clear_jf(k.dom, k.df); k.r.finish(); }
+static void fa_synchronize_jf(vpb_field_t *f, const vpb_grid_t *g) { TraceScope _ts("synchronize_jf"); FieldCall k(f, g, RW); vpb_synchronize_jf(k.dom, k.df); k.r.finish(); }
+static void fa_clear_rhof(vpb_field_t *f, const vpb_grid_t *g) { TraceScope _ts("clear_rhof"); FieldCall k(f, g, RW); vpb_clear_rhof(k.dom, k.df); k.r.finish(); }
+static void fa_synchronize_rho(vpb_field_t *f, const vpb_grid_t *g) { TraceScope _ts("synchronize_rho"); FieldCall k(f, g, RW); vpb_synchronize_rho(k.dom, k.df); k.r.finish(); }
 static void fa_compute_rhob(vpb_field_t *f, const vpb_material_coefficient_t *m, const vpb_grid_t *g) {
+  TraceScope _ts("compute_rhob");
   FieldCall k(f, g, RW, m, true); vpb_compute_rhob(k.dom, k.df, k.dm, k.n_mat); k.r.finish();
 }
 static void vfa_compute_rhob(vpb_field_t *f, const vpb_material_coefficient_t *m, const vpb_grid_t *g) {
+  TraceScope _ts("compute_rhob");
   (void)m; FieldCall k(f, g, RW); vpb_compute_rhob(k.dom, k.df, nullptr, 1); k.r.finish();
 }
 static void fa_compute_curl_b(vpb_field_t *f, const vpb_material_coefficient_t *m, const vpb_grid_t *g) {
+  TraceScope _ts("compute_curl_b");
   FieldCall k(f, g, RW, m, true); vpb_compute_curl_b(k.dom, k.df, k.dm, k.n_mat); k.r.finish();
 }
 static void vfa_compute_curl_b(vpb_field_t *f, const vpb_material_coefficient_t *m, const vpb_grid_t *g) {
+  TraceScope _ts("compute_curl_b");
   (void)m; FieldCall k(f, g, RW); vpb_compute_curl_b(k.dom, k.df, nullptr, 1); k.r.finish();
 }
 static double fa_synchronize_tang_e_norm_b(vpb_field_t *f, const vpb_grid_t *g) {
+  TraceScope _ts("synchronize_tang_e_norm_b");
   FieldCall k(f, g, RW);
   double *d = dev_doubles(1), out[1];
   vpb_synchronize_tang_e_norm_b(k.dom, k.df, d);
@@ -871,12 +899,15 @@ static double fa_synchronize_tang_e_norm_b(vpb_field_t *f, const vpb_grid_t *g) 
   return out[0];
 }
 static void fa_compute_div_e_err(vpb_field_t *f, const vpb_material_coefficient_t *m, const vpb_grid_t *g) {
+  TraceScope _ts("compute_div_e_err");
   FieldCall k(f, g, RW, m, true); vpb_compute_div_e_err(k.dom, k.df, k.dm, k.n_mat); k.r.finish();
 }
 static void vfa_compute_div_e_err(vpb_field_t *f, const vpb_material_coefficient_t *m, const vpb_grid_t *g) {
+  TraceScope _ts("compute_div_e_err");
   (void)m; FieldCall k(f, g, RW); vpb_compute_div_e_err(k.dom, k.df, nullptr, 1); k.r.finish();
 }
 static double rms_common(vpb_field_t *f, const vpb_grid_t *g, int which) {
+  TraceScope _ts("rms");
   FieldCall k(f, g, RD);
   double *d = dev_doubles(2), loc[2];
   if (which == 0) vpb_compute_rms_div_e_err(k.dom, k.df, d); else vpb_compute_rms_div_b_err(k.dom, k.df, d);
@@ -895,13 +926,15 @@ static double rms_common(vpb_field_t *f, const vpb_grid_t *g, int which) {
 static double fa_compute_rms_div_e_err(vpb_field_t *f, const vpb_grid_t *g) { return rms_common(f, g, 0); }
 static double fa_compute_rms_div_b_err(vpb_field_t *f, const vpb_grid_t *g) { return rms_common(f, g, 1); }
 static void fa_clean_div_e(vpb_field_t *f, const vpb_material_coefficient_t *m, const vpb_grid_t *g) {
+  TraceScope _ts("clean_div_e");
   FieldCall k(f, g, RW, m, true); vpb_clean_div_e(k.dom, k.df, k.dm, k.n_mat); k.r.finish();
 }
 static void vfa_clean_div_e(vpb_field_t *f, const vpb_material_coefficient_t *m, const vpb_grid_t *g) {
+  TraceScope _ts("clean_div_e");
   (void)m; FieldCall k(f, g, RW); vpb_clean_div_e(k.dom, k.df, nullptr, 1); k.r.finish();
 }
-static void fa_compute_div_b_err(vpb_field_t *f, const vpb_grid_t *g) { FieldCall k(f, g, RW); vpb_compute_div_b_err(k.dom, k.df); k.r.finish(); }
-static void fa_clean_div_b(vpb_field_t *f, const vpb_grid_t *g) { FieldCall k(f, g, RW); vpb_clean_div_b(k.dom, k.df); k.r.finish(); }
+static void fa_compute_div_b_err(vpb_field_t *f, const vpb_grid_t *g) { TraceScope _ts("compute_div_b_err"); FieldCall k(f, g, RW); vpb_compute_div_b_err(k.dom, k.df); k.r.finish(); }
+static void fa_clean_div_b(vpb_field_t *f, const vpb_grid_t *g) { TraceScope _ts("clean_div_b"); FieldCall k(f, g, RW); vpb_clean_div_b(k.dom, k.df); k.r.finish(); }
 
 #define VPB_STANDARD_TABLE                                                                                              \
   { { fa_new_field, fa_delete_field, fa_new_material_coefficients, fa_delete_material_coefficients, fa_advance_b,       \

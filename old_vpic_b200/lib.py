@@ -68,6 +68,10 @@ SIGNATURES = {
     "vpb_prof_enable": (None, [_i]),
     "vpb_prof_collect": (None, [_i, _vp, _vp, _i]),
     "vpb_prof_list": (_i, [_i, _vp, _i]),
+    "vpb_trace_enable": (None, [_i]),
+    "vpb_trace_reset": (None, []),
+    "vpb_trace_report": (None, []),
+    "vpb_trace_get": (C.c_double, [C.c_char_p, _vp]),
     "vpb_load_thermal": (None, [_vp, _vp, _i, _f, _f, C.c_ulonglong, _l]),
     "vpb_copy_positions": (None, [_vp, _vp, _l]),
     "vpb_load_plane_wave": (None, [_vp, _vp, _i, _f]),
