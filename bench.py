@@ -59,7 +59,7 @@ def parse():
     ap.add_argument("--deck-timeout", type=int, default=150)
     ap.add_argument("--sort-lookahead", type=int, default=-1,
                     help="sort key = voxel the particle reaches this many steps ahead (-1: 0.6 x the sort interval, 0: current voxel)")
-    ap.add_argument("--driver", default="native", choices=["native", "python"], help="time-step driver: csrc/vpb_step.cu or sim.py")
+    ap.add_argument("--driver", default="native", choices=["native"], help=argparse.SUPPRESS)   # one driver: csrc/vpb_step.cu
     ap.add_argument("--sort-interval", type=int, default=SORT_INTERVAL, help="species sort_interval (the reference recipe: 20)")
     return ap.parse_args()
 
@@ -234,7 +234,7 @@ def run_b200(args):
     import torch.distributed as dist
     from old_vpic_b200 import abi, lib
     from old_vpic_b200 import grid as helpers
-    from old_vpic_b200.sim import NativeSimulation, Simulation
+    from old_vpic_b200.sim import NativeSimulation
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -287,9 +287,8 @@ def run_b200(args):
     else:
         topo = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
         g = helpers.make_grid((n * topo[0], n * topo[1], n * topo[2]), "periodic", topo=topo, rank=rank)
-    # the library's C++ time-step driver (csrc/vpb_step.cu); --driver python = the same call order issued from sim.py
-    Driver = NativeSimulation if args.driver == "native" else Simulation
-    sim = Driver(g, n_mat=1, L=L, planar=L.vpb_get_tuning(b"sim.aos_fields") == 0,
+    # the library's C++ time-step driver (csrc/vpb_step.cu)
+    sim = NativeSimulation(g, n_mat=1, L=L, planar=L.vpb_get_tuning(b"sim.aos_fields") == 0,
                      wide_interpolator=L.vpb_get_tuning(b"sim.narrow_interpolator") == 0,
                      particle_planes=L.vpb_get_tuning(b"sim.aos_particles") == 0)
     if args.driver == "native":
@@ -420,7 +419,7 @@ def fields_measure(L, n, steps, warmup):
     Returns cell-update rates and the roofline fractions of the two stencil kernels, timed with CUDA events around
     each kernel launch (vpb_prof classes 2 and 3) over `steps` steps."""
     from old_vpic_b200 import grid as helpers
-    from old_vpic_b200.sim import NativeSimulation, Simulation
+    from old_vpic_b200.sim import NativeSimulation
     g = helpers.make_grid((n, n, n), "periodic", field_only=True)
     sim = NativeSimulation(g, n_mat=1, vacuum=True, L=L, planar=L.vpb_get_tuning(b"sim.aos_fields") == 0)
     L.vpb_load_plane_wave(sim.dom, sim.field_ptr, 8, 1.0)

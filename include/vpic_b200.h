@@ -340,6 +340,12 @@ long vpb_sim_get_particles(vpb_sim_t *s, int species, vpb_particle_t *host, long
 void vpb_sim_set_fields(vpb_sim_t *s, const vpb_field_t *host);       /* field_t[nvoxel], reference layout */
 void vpb_sim_get_fields(vpb_sim_t *s, vpb_field_t *host);
 void vpb_sim_set_intervals(vpb_sim_t *s, int clean_div_e_interval, int clean_div_b_interval, int num_comm_round);
+/* sync_shared_interval of vpic_simulation (vpic.cxx:14; advance.cxx:199-208): synchronize_tang_e_norm_b every that many
+ * steps, 0 = never.  vpb_sim_last_errors: the numbers advance.cxx:160,168,182,190,205 report, latest values --
+ * out[0..1] rms div E error before the first / second cleaning pass, out[2..3] the same for div B, out[4] the domain
+ * desynchronisation error.  The cleaning passes are skipped when their error is not > 0, as in the reference. */
+void vpb_sim_set_sync_shared_interval(vpb_sim_t *s, int interval);
+void vpb_sim_last_errors(const vpb_sim_t *s, double *out5);
 void vpb_sim_set_sort_lookahead(vpb_sim_t *s, int steps);   /* < 0: 0.6 x sort_interval of each species; 0 (default): off */
 void vpb_sim_advance(vpb_sim_t *s, int nsteps);                        /* enqueues nsteps time steps */
 /* The deck's five hooks, called where vpic_simulation::advance() calls user_particle_collisions (advance.cxx:67),

@@ -309,14 +309,24 @@ vpb_domain_t *vpb_domain_create(const vpb_grid_t *g, int rank, int nproc) {
   if (g->neighbor) {
     // compress: local ids to int32, everything else to a negative code
     std::vector<int32_t> nb((size_t)6 * nv);
+    size_t n_handler = 0;
     for (size_t k = 0; k < nb.size(); k++) {
       int64_t n = g->neighbor[k];
       if (n >= g->rangel && n <= g->rangeh) nb[k] = (int32_t)(n - g->rangel);
       else if (n == vpb_reflect_particles) nb[k] = -1;
       else if (n == vpb_absorb_particles) nb[k] = -2;
-      else if (n < 0) nb[k] = (n > -0x40000000L) ? (int32_t)n : -3;  // custom handler code
+      else if (n < 0) {
+        // boundary_p.c:271-277: -3-k selects the deck's k-th custom particle-boundary handler, a HOST callback with user
+        // parameters and the host RNG.  The device cannot run it, and absorbing such particles instead (with a rhob
+        // deposit the handler would not have made) silently changes the physics: refuse the grid.
+        if (-n - 3 < (int64_t)g->nb) n_handler++;
+        nb[k] = (n > -0x40000000L) ? (int32_t)n : -3;               // any other code: "unknown boundary interaction"
+      }
       else nb[k] = INT32_MIN;                                        // owned by another rank
     }
+    if (n_handler)
+      VPB_ERROR("grid has %zu cell faces bound to custom particle-boundary handlers (grid->nb = %d): host callbacks are not "
+                "supported by libvpic_b200 (no CPU fallback); use reflect_particles / absorb_particles faces", n_handler, g->nb);
     VPB_CUDA(cudaMalloc(&dom->nbr, nb.size() * sizeof(int32_t)));
     VPB_CUDA(cudaMemcpyAsync(dom->nbr, nb.data(), nb.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c.stream));
     VPB_CUDA(cudaMalloc(&dom->nbr64, nb.size() * sizeof(int64_t)));

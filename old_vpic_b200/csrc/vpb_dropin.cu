@@ -29,6 +29,13 @@ static int g_world_nproc = 1;
 struct PartHint { int *dev = nullptr; size_t n = 0; int np = 0; };
 static std::unordered_map<const void *, PartHint> g_part_hint;
 static size_t g_h2d_total = 0, g_d2h_total = 0;   // bytes moved by the staging path (bench.py e2e accounting)
+// Managed arrays already brought to the device once: allocation -> bytes prefetched so far.  Measured on a B200
+// (profiles/r2a_deck_trace.txt): cudaMemPrefetchAsync costs 140 us of host time per call even when every page is
+// already resident -- 1444 calls = 203 ms of a 248 ms run -- so an array is prefetched when it is first seen (one DMA
+// instead of a storm of GPU page faults: 3-9 ms instead of 36-41 ms for a 400 MB species) and never again; pages the
+// host program touches later come back through ordinary demand migration.  dropin.prefetch: 0 never, 1 first sight
+// (default), 2 every call.
+static std::unordered_map<const void *, size_t> g_prefetched;
 
 static size_t nvox(const vpb_grid_t *g) { return (size_t)(g->nx + 2) * (g->ny + 2) * (g->nz + 2); }
 
@@ -47,8 +54,15 @@ struct Residency {
     if (e != cudaSuccess) { cudaGetLastError(); at.type = cudaMemoryTypeUnregistered; }
     if (at.type == cudaMemoryTypeDevice) return const_cast<void *>(host);
     if (at.type == cudaMemoryTypeManaged) {
+      const int policy = tuning("dropin.prefetch", 1);
+      if (policy == 0) return const_cast<void *>(host);
+      if (policy == 1) {
+        size_t &done = g_prefetched[host];
+        if (done >= bytes) return const_cast<void *>(host);
+        done = bytes;
+      }
       TraceScope _t("  prefetch");
-      if (tuning("dropin.prefetch", 1)) cudaMemPrefetchAsync(host, bytes, c.device, c.stream);
+      cudaMemPrefetchAsync(host, bytes, c.device, c.stream);
       cudaGetLastError();
       return const_cast<void *>(host);
     }
@@ -127,13 +141,28 @@ struct Residency {
   }
 };
 
-// cheap fingerprint of the neighbor table (a grid_t may be edited, or its address reused)
+// Cheap fingerprint of the neighbor table (a grid_t may be edited -- set_domain_particle_bc rewrites the outward
+// entries of a whole face, grid/ops.c -- or its address reused).  It runs on every layer-A call and the table is
+// managed memory read by the host here, so it samples instead of walking: the outward entry of five interior cells
+// spread over each of the six faces, plus the two ends of the table (was: 4096 words, 26 us per call and 17 % of a
+// 64^3 step, profiles/r2a_deck_trace.txt).
 static uint64_t neighbor_print(const vpb_grid_t *g) {
   if (!g->neighbor) return 0;
-  const size_t n = 6 * nvox(g), step = n > 8192 ? n / 4096 : 1;
-  uint64_t h = 1469598103934665603ull;
-  for (size_t k = 0; k < n; k += step) h = (h ^ (uint64_t)g->neighbor[k]) * 1099511628211ull + k;
-  return h ^ (uint64_t)g->neighbor[n - 1];
+  const int n[3] = {g->nx, g->ny, g->nz};
+  const long sx = g->nx + 2, sxy = sx * (g->ny + 2);
+  uint64_t h = 1469598103934665603ull ^ (uint64_t)(uintptr_t)g->neighbor;
+  for (int face = 0; face < 6; face++) {
+    const int axis = face % 3, hi = face / 3;          // neighbor[6*v + face]: faces 0,1,2 = -x,-y,-z; 3,4,5 = +x,+y,+z
+    for (int k = 0; k < 5; k++) {
+      int c[3];
+      for (int a = 0; a < 3; a++) c[a] = 1 + (int)(((long)(n[a] - 1) * ((k * (a + 2)) % 5)) / 4);
+      c[axis] = hi ? n[axis] : 1;
+      const long v = c[0] + sx * c[1] + sxy * c[2];
+      h = (h ^ (uint64_t)g->neighbor[6 * v + face]) * 1099511628211ull + (uint64_t)v;
+    }
+  }
+  const size_t last = 6 * nvox(g) - 1;
+  return (h ^ (uint64_t)g->neighbor[0]) * 1099511628211ull ^ (uint64_t)g->neighbor[last];
 }
 static std::unordered_map<const void *, uint64_t> g_domain_print;
 
@@ -237,6 +266,7 @@ void util_free_aligned(void *mem_ref) {
   char **mem = (char **)mem_ref;
   if (!mem || !*mem) return;
   cudaStreamSynchronize(ctx().stream);
+  g_prefetched.erase(*mem);
   cudaFree(*mem);
   *mem = nullptr;
 }
@@ -553,6 +583,11 @@ void boundary_p(vpb_species_t *sp_list, vpb_field_t *f0, vpb_accumulator_t *a0, 
   r.finish();
 }
 
+// One spare particle array per capacity: what an out-of-place sort writes into.  The array it read from becomes the
+// next spare (the reference allocates a new array and frees the old one on every such sort, sort_p.c:69-77; managed
+// allocations and frees synchronise the device, so the pair is recycled instead).  Species of equal capacity share it.
+static std::unordered_map<size_t, vpb_particle_t *> g_sort_spare;
+
 void sort_p(vpb_species_t *sp, const vpb_grid_t *g) {
   TraceScope _ts("sort_p");
   if (!sp) VPB_ERROR("Bad species");
@@ -564,16 +599,36 @@ void sort_p(vpb_species_t *sp, const vpb_grid_t *g) {
                                           nv1 * sizeof(int), 128);   // sort_p.c:32
   if (sp->np == 0) return;   // sort_p.c:35
   Residency r;
-  vpb_particle_t *dp = (vpb_particle_t *)r.get(sp->p, (size_t)sp->np * sizeof(vpb_particle_t), RW);
   int *dpart = (int *)r.get(sp->partition, nv1 * sizeof(int), WR);
-  vpb_particle_t *tmp = nullptr;
-  VPB_CUDA(cudaMallocAsync(&tmp, (size_t)sp->np * sizeof(vpb_particle_t), c.stream));
-  // Both reference variants (out-of-place: stable; in-place: cycle sort) leave the particles grouped by
-  // voxel; the device sort is the stable one and writes back into the caller's array.
-  vpb_sort_p(dom, dp, tmp, sp->np, dpart);
-  VPB_CUDA(cudaMemcpyAsync(dp, tmp, (size_t)sp->np * sizeof(vpb_particle_t), cudaMemcpyDeviceToDevice, c.stream));
-  VPB_CUDA(cudaFreeAsync(tmp, c.stream));
+  const vpb_particle_t *old_p = sp->p;
+  if (sp->sort_out_of_place && is_managed(sp->p)) {
+    // sort_p.c:63-77: a new array of max_np records receives the particles in order and replaces sp->p
+    const size_t cap = (size_t)sp->max_np * sizeof(vpb_particle_t);
+    vpb_particle_t *new_p = nullptr;
+    auto sparep = g_sort_spare.find(cap);
+    if (sparep != g_sort_spare.end() && sparep->second) { new_p = sparep->second; sparep->second = nullptr; }
+    else util_malloc_aligned("MALLOC_ALIGNED( new_p, (%lu bytes), 128 (%lu bytes) ) failed", &new_p, cap, 128);
+    vpb_particle_t *dp = (vpb_particle_t *)r.get(sp->p, (size_t)sp->np * sizeof(vpb_particle_t), RD);
+    vpb_particle_t *dn = (vpb_particle_t *)r.get(new_p, (size_t)sp->np * sizeof(vpb_particle_t), WR);
+    vpb_sort_p(dom, dp, dn, sp->np, dpart);
+    g_sort_spare[cap] = sp->p;
+    sp->p = new_p;
+  } else {
+    // in place (the reference's cycle sort, sort_p.c:79-101, leaves the particles grouped by voxel in the SAME array; so
+    // does this: a copy goes to scratch and the stable sort writes back into the caller's array), or an array this
+    // library cannot replace (plain host memory: staged)
+    vpb_particle_t *dp = (vpb_particle_t *)r.get(sp->p, (size_t)sp->np * sizeof(vpb_particle_t), RW);
+    vpb_particle_t *tmp = nullptr;
+    VPB_CUDA(cudaMallocAsync(&tmp, (size_t)sp->np * sizeof(vpb_particle_t), c.stream));
+    VPB_CUDA(cudaMemcpyAsync(tmp, dp, (size_t)sp->np * sizeof(vpb_particle_t), cudaMemcpyDeviceToDevice, c.stream));
+    vpb_sort_p(dom, tmp, dp, sp->np, dpart);
+    VPB_CUDA(cudaFreeAsync(tmp, c.stream));
+  }
   // remember the layout for advance_p's traversal (keyed by the caller's array)
+  if (old_p != sp->p) {
+    auto stale = g_part_hint.find(old_p);
+    if (stale != g_part_hint.end()) { g_part_hint[sp->p] = stale->second; g_part_hint.erase(stale); }
+  }
   PartHint &h = g_part_hint[sp->p];
   if (h.n != nv1) {
     if (h.dev) cudaFree(h.dev);

@@ -8,6 +8,7 @@
 //
 // old_vpic_b200/sim.py is the same driver in Python (kept for tests that poke at the pieces);
 // tests/test_gpu_step.py runs both on the same input.
+#include <math.h>
 #include <string>
 #include <vector>
 #include "vpb_common.cuh"
@@ -45,6 +46,9 @@ struct vpb_sim {
   long sort_tmp_cap = 0;
   long step = 0;
   int clean_div_e_interval = 0, clean_div_b_interval = 0, num_comm_round = 3;   // vpic.cxx:17
+  int sync_shared_interval = 0;                                                 // vpic.cxx:14
+  // what the reference prints from advance.cxx:160,168,182,190,205 (last value of each, for callers and tests)
+  double div_e_err[2] = {0, 0}, div_b_err[2] = {0, 0}, desync_err = 0;
   int sort_lookahead = 0;        // steps; < 0: 0.6 x the species' sort interval (measured optimum, profiles/README.md)
   int needs_boundary_p = -1;
   vpb_sim_callbacks_t cb = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -116,21 +120,61 @@ static void migrate(vpb_sim *s) {
   }
 }
 
-static void clean_div_e(vpb_sim *s) {   // advance.cxx:151-173
+// compute_rms_div_{e,b}_err (compute_rms_div_e_err.c:150-160): local sum x dV and the cell volume total, summed over
+// ranks, eps0*sqrt(ratio).  The cleaning passes are conditional on this number (advance.cxx:164,169,186,191), so it is
+// read back: one small synchronising copy per pass on cleaning steps only.
+static double rms_err(vpb_sim *s, int which) {
+  const vpb_grid_t *g = s->g;
+  double loc[2];
+  if (which == 0) vpb_compute_rms_div_e_err(s->dom, s->f, s->scalars); else vpb_compute_rms_div_b_err(s->dom, s->f, s->scalars);
+  if (s->nproc > 1) {
+    vpb_d2h(loc, s->scalars, sizeof(double));
+    vpb_sync();
+    loc[0] *= (double)g->dx * g->dy * g->dz;
+    loc[1] = (double)(g->nx * g->ny * g->nz * g->dx * g->dy * g->dz);
+    vpb_h2d(s->scalars, loc, 2 * sizeof(double));
+    vpb_comm_allsum_d(s->scalars, 2);
+    vpb_d2h(loc, s->scalars, 2 * sizeof(double));
+    vpb_sync();
+  } else {
+    vpb_d2h(loc, s->scalars, sizeof(double));
+    vpb_sync();
+    loc[0] *= (double)g->dx * g->dy * g->dz;
+    loc[1] = (double)(g->nx * g->ny * g->nz * g->dx * g->dy * g->dz);
+  }
+  return g->eps0 * sqrt(loc[0] / loc[1]);
+}
+
+static void clean_div_e(vpb_sim *s) {   // advance.cxx:149-173
   vpb_clear_rhof(s->dom, s->f);
   for (Species &sp : s->sp) vpb_accumulate_rho_p(s->dom, s->f, sp.p, sp.np);
   vpb_synchronize_rho(s->dom, s->f);
-  for (int k = 0; k < 2; k++) {
-    vpb_compute_div_e_err(s->dom, s->f, s->m, s->n_mat);
+  vpb_compute_div_e_err(s->dom, s->f, s->m, s->n_mat);
+  double err = s->div_e_err[0] = rms_err(s, 0);
+  if (err > 0) {
     vpb_clean_div_e(s->dom, s->f, s->m, s->n_mat);
+    vpb_compute_div_e_err(s->dom, s->f, s->m, s->n_mat);
+    err = s->div_e_err[1] = rms_err(s, 0);
+    if (err > 0) vpb_clean_div_e(s->dom, s->f, s->m, s->n_mat);
   }
 }
 
 static void clean_div_b(vpb_sim *s) {   // advance.cxx:177-195
-  for (int k = 0; k < 2; k++) {
-    vpb_compute_div_b_err(s->dom, s->f);
+  vpb_compute_div_b_err(s->dom, s->f);
+  double err = s->div_b_err[0] = rms_err(s, 1);
+  if (err > 0) {
     vpb_clean_div_b(s->dom, s->f);
+    vpb_compute_div_b_err(s->dom, s->f);
+    err = s->div_b_err[1] = rms_err(s, 1);
+    if (err > 0) vpb_clean_div_b(s->dom, s->f);
   }
+}
+
+static void sync_shared(vpb_sim *s) {   // advance.cxx:199-208
+  vpb_synchronize_tang_e_norm_b(s->dom, s->f, s->scalars);
+  vpb_comm_allsum_d(s->scalars, 1);     // remote.c:412
+  vpb_d2h(&s->desync_err, s->scalars, sizeof(double));
+  vpb_sync();
 }
 
 static void advance_one(vpb_sim *s) {
@@ -154,8 +198,9 @@ static void advance_one(vpb_sim *s) {
   vpb_advance_e(dom, s->f, s->m, s->n_mat, s->vacuum ? 1 : 0);                         // :133
   if (cb.field_injection) cb.field_injection(cb.user, s);                              // :141 user_field_injection
   vpb_advance_b(dom, s->f, 0.5f);                                                      // :147
-  if (s->clean_div_e_interval && s->step % s->clean_div_e_interval == 0) clean_div_e(s);
-  if (s->clean_div_b_interval && s->step % s->clean_div_b_interval == 0) clean_div_b(s);
+  if (s->clean_div_e_interval > 0 && s->step % s->clean_div_e_interval == 0) clean_div_e(s);      // :151
+  if (s->clean_div_b_interval > 0 && s->step % s->clean_div_b_interval == 0) clean_div_b(s);      // :177
+  if (s->sync_shared_interval > 0 && s->step % s->sync_shared_interval == 0) sync_shared(s);      // :199
   if (particles) vpb_load_interpolator(dom, s->fi, s->f);                              // :214
   s->step++;
   if (cb.diagnostics) cb.diagnostics(cb.user, s);                                      // :233 user_diagnostics, after step++
@@ -337,6 +382,19 @@ void vpb_sim_set_intervals(vpb_sim_t *s, int clean_div_e_interval, int clean_div
   s->clean_div_e_interval = clean_div_e_interval;
   s->clean_div_b_interval = clean_div_b_interval;
   if (num_comm_round > 0) s->num_comm_round = num_comm_round;
+}
+
+// sync_shared_interval (vpic.cxx:14, advance.cxx:199-208): synchronize_tang_e_norm_b every that many steps; 0 = never
+void vpb_sim_set_sync_shared_interval(vpb_sim_t *s, int interval) {
+  if (!s) VPB_ERROR("Bad run");
+  s->sync_shared_interval = interval;
+}
+
+// The numbers advance.cxx reports on cleaning / synchronising steps, latest values: out[0..1] rms div E error before the
+// first and before the second cleaning pass, out[2..3] the same for div B, out[4] domain desynchronisation error.
+void vpb_sim_last_errors(const vpb_sim_t *s, double *out) {
+  if (!s || !out) VPB_ERROR("Bad args");
+  out[0] = s->div_e_err[0]; out[1] = s->div_e_err[1]; out[2] = s->div_b_err[0]; out[3] = s->div_b_err[1]; out[4] = s->desync_err;
 }
 
 void vpb_sim_set_sort_lookahead(vpb_sim_t *s, int steps) {

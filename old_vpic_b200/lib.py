@@ -154,6 +154,8 @@ SIGNATURES = {
     "vpb_sim_get_fields": (None, [_vp, _vp]),
     "vpb_sim_set_intervals": (None, [_vp, _i, _i, _i]),
     "vpb_sim_set_sort_lookahead": (None, [_vp, _i]),
+    "vpb_sim_set_sync_shared_interval": (None, [_vp, _i]),
+    "vpb_sim_last_errors": (None, [_vp, _vp]),
     "vpb_sim_advance": (None, [_vp, _i]),
     "vpb_sim_energies": (None, [_vp, _vp]),
     "vpb_sim_hydro": (None, [_vp, _i, _vp]),

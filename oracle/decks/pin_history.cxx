@@ -5,8 +5,10 @@
 // after every step the eight numbers dump_energies prints, as raw doubles.  tests/test_history_vs_ref_deck.py replays
 // the run from that state with the oracle kernels and compares.  12 x 10 x 8 cells, 8 particles per cell per species
 // (a multiple of 16 per species: every particle goes through pipeline 0, so float sums are in array order), periodic,
-// sort every 5 steps, both divergence cleanings every 5.
+// sort every 5 steps, both divergence cleanings every 5; VPB_PIN_SYNC in the environment sets sync_shared_interval
+// (default 0), VPB_PIN_CLEAN the two cleaning intervals (default 5).
 #include <stdio.h>
+#include <stdlib.h>
 
 begin_globals {
   int dummy;
@@ -18,9 +20,9 @@ begin_initialization {
 
   num_step = 20;
   status_interval = 0;
-  sync_shared_interval = 0;
-  clean_div_e_interval = 5;
-  clean_div_b_interval = 5;
+  sync_shared_interval = getenv( "VPB_PIN_SYNC" ) ? atoi( getenv( "VPB_PIN_SYNC" ) ) : 0;
+  clean_div_e_interval = getenv( "VPB_PIN_CLEAN" ) ? atoi( getenv( "VPB_PIN_CLEAN" ) ) : 5;
+  clean_div_b_interval = clean_div_e_interval;
 
   grid->dt = 0.95 * courant_length( nx, ny, nz, nx, ny, nz );
   grid->cvac = 1;

@@ -1,7 +1,8 @@
 """Multi-GPU worker (torchrun, one rank per GPU, NCCL): a thermal plasma on a periodic box split over the
-ranks (2x1x1, 2x2x1 or 2x2x2), stepped with the library's C++ driver (look-ahead sort key on); every rank checks global invariants and rank 0
-compares the energy history and the hydro moments with a single-domain run of the SAME particles (Python driver,
-plain sort key) on its own GPU.
+ranks (2x1x1, 2x2x1 or 2x2x2), stepped with the library's C++ driver (look-ahead sort key on); every rank checks global
+invariants, and the energy history and the hydro moments are compared with the CPU ORACLE stepping the SAME particles
+on one domain (tests/test_gpu_history.py::cpu_history, pinned to the reference's main loop by
+tests/test_history_vs_ref_deck.py) -- not with another run of the library.
     torchrun --nproc-per-node N tests/dist_gpu_worker.py
 """
 import ctypes as C
@@ -14,19 +15,18 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from old_vpic_b200 import abi, grid as G, lib  # noqa: E402
-from old_vpic_b200.sim import NativeSimulation, Simulation  # noqa: E402
+from old_vpic_b200.sim import NativeSimulation  # noqa: E402
 
 
 SPECIES = (("e", -1.0, 11), ("i", 1.0, 911))
 PER, PPC, STEPS, VTH = 12, 24, 12, 0.3
 
 
-def make_sim(L, gn, topo, rank, native=False):
-    """native: the library's C++ driver (vpb_sim_*) with the look-ahead sort key; else the Python driver."""
+def make_sim(L, gn, topo, rank):
+    """the library's C++ driver (vpb_sim_*) with the look-ahead sort key"""
     g = G.make_grid(gn, "periodic", topo=topo, rank=rank)
-    sim = (NativeSimulation if native else Simulation)(g, L=L)
-    if native:
-        sim.set_sort_lookahead(-1)
+    sim = NativeSimulation(g, L=L)
+    sim.set_sort_lookahead(-1)
     n = g.n[0] * g.n[1] * g.n[2] * PPC
     for name, q_m, _ in SPECIES:
         sim.define_species(name, q_m, int(n * 1.5) + 4096, max_nm=n // 2 + 4096, sort_interval=5)
@@ -64,7 +64,7 @@ def main():
 
     # 1. every rank loads its share; the shares are gathered so that rank 0 can run the SAME particles on one
     #    domain (done before vpb_comm_init: until then the library's reductions are rank-local)
-    sim = make_sim(L, gn, topo, rank, native=True)
+    sim = make_sim(L, gn, topo, rank)
     shares = []
     for sp, (_, q_m, seed) in zip(sim.species, SPECIES):
         sim.load_thermal(sp, PPC, VTH, (1.0 if q_m > 0 else -1.0) / PPC, seed + rank, tag0=rank << 32)
@@ -74,15 +74,27 @@ def main():
         shares.append([t.cpu().numpy().view(abi.particle_dtype) for t in parts])
     ref_hist = ref_hydro = None
     if rank == 0:
-        single = make_sim(L, gn, (1, 1, 1), 0)
-        for sp, per_rank in zip(single.species, shares):
+        # the oracle on ONE domain holding every rank's particles (CPU; test infrastructure)
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        import helpers
+        from oracle import loader
+        from test_gpu_history import cpu_history, oracle_kernels
+        O = loader.oracle()
+        og = helpers.host_grid(gn, "periodic")
+        ospecies = []
+        for (_, q_m, _), per_rank in zip(SPECIES, shares):
             allp = np.concatenate([to_global(p, G._rank_to_index(r, *topo), topo) for r, p in enumerate(per_rank)])
-            sp.np = len(allp)
-            sp.p.upload(allp)
-        ref_hist = run(single, STEPS)
-        assert sum(sp.np for sp in single.species) == total
-        ref_hydro = single.hydro(single.species[0])
-        single.free()
+            buf = abi.aligned_zeros(len(allp), abi.particle_dtype)
+            buf[:] = allp
+            ospecies.append({"p": buf, "q_m": q_m})
+        assert sum(len(sp["p"]) for sp in ospecies) == total
+        ostate = {}
+        ref_hist = cpu_history(oracle_kernels(O), og, ospecies, STEPS, 0, 0, state=ostate, sort=5)
+        ref_hydro = abi.aligned_zeros(og.nv, abi.hydro_dtype)
+        e = ospecies[0]
+        O.orc_clear_hydro(abi.ptr(ref_hydro), og.ref())
+        O.orc_accumulate_hydro_p(abi.ptr(ref_hydro), abi.ptr(e["p"]), len(e["p"]), e["q_m"], abi.ptr(ostate["fi"]), og.ref())
+        O.orc_synchronize_hydro(abi.ptr(ref_hydro), og.ref(), 0, 1)
 
     # 2. the decomposed run
     uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -128,15 +140,16 @@ def main():
     assert herr < 2e-2, herr
     assert float(np.mean(rel > 2e-3)) < 1e-3, float(np.mean(rel > 2e-3))       # and such nodes are isolated
     if rank == 0:
-        # decomposition parity: same particles, one domain vs `world` domains.  Only the order of float sums differs
-        # (deposit atomics, shared-face current sums, allreduce): every energy column within 1e-4 of its own scale
+        # parity with the oracle: same particles, the oracle on one domain vs the library on `world` domains.  Only the
+        # order of float sums differs (deposit atomics, shared-face current sums, allreduce, sort key): every energy
+        # column within 1e-4 of its own scale
         scale = np.abs(ref_hist).max(axis=0, keepdims=True)
         err = float(np.max(np.abs(hist - ref_hist) / scale))
         assert err < 1e-4, err
         tot = hist.sum(axis=1)
         drift = abs(tot[-1] - tot[0]) / abs(tot[0])
         assert drift < 5e-3, drift
-        print("DIST_GPU_OK world=%d particles=%d decomposition_err=%.2e energy_drift=%.2e field_energy_last=%.4e hydro_err=%.2e" % (
+        print("DIST_GPU_OK world=%d particles=%d oracle_err=%.2e energy_drift=%.2e field_energy_last=%.4e hydro_err=%.2e" % (
             world, total, err, drift, hist[-1, :6].sum(), herr))
     dist.barrier()
     L.vpb_comm_finalize()

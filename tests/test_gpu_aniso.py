@@ -3,7 +3,7 @@ eps0 = 1.7, damp = 0.02) -- the CUDA counterpart of tests/test_oracle_vs_ref_ani
 reference on the same grids).  Every other GPU parity test runs with dx = dy = dz = cvac = eps0 = 1, where a swapped
 rdx/rdy, a missing eps0 or a c/dt mix-up cannot show.  Same bars as the isotropic tests.
 
-Written after round 1's GPU budget was spent: skipped unless VPB_RUN_UNVALIDATED=1 until it has run on hardware."""
+First run on hardware in round 2 (profiles/r2a_gpu_pytest_all.txt)."""
 import os
 
 import numpy as np
@@ -14,8 +14,7 @@ from helpers import (abi, assert_bits_equal, host_grid, max_rel, random_fields, 
 from old_vpic_b200 import lib
 from old_vpic_b200.abi import ptr
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("VPB_RUN_UNVALIDATED") != "1",
-                                                  reason="not yet run on hardware (set VPB_RUN_UNVALIDATED=1)")]
+pytestmark = pytest.mark.gpu
 
 SHAPES = [(6, 5, 4), (8, 1, 6), (1, 1, 16), (20, 12, 9)]
 CELL = (0.7, 1.3, 0.45)

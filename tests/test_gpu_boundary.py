@@ -5,6 +5,7 @@ visiting order (boundary_p.c:243-247); the device back-fill is order-free (DESIG
 arrays are compared as multisets keyed by the particle tag; counts are exact; rhob within the float-sum
 tolerance."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -86,3 +87,34 @@ def test_move_p_and_accumulate_rhob_single(vpb, orc):
     orc.orc_accumulate_rhob(ptr(f_o), ptr(one), g.ref())
     vpb.accumulate_rhob(ptr(f_g), ptr(one), g.ref())
     assert max_rel(f_g["rhob"], f_o["rhob"]) < 1e-6
+
+
+def test_custom_boundary_handlers_are_refused():
+    """boundary_p.c:271-277: a cell face bound to the deck's k-th custom handler (neighbor = -3-k, k < grid->nb) calls a
+    host callback.  The library has no CPU fallback and must not absorb such particles silently: the grid is refused
+    with the reference's ERROR convention (message, exit 1) the first time the hot path sees it.  Codes beyond grid->nb
+    stay "unknown boundary interaction" (absorbed with a warning by boundary_p)."""
+    import subprocess
+    import sys
+    code = r"""
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np
+from helpers import abi, host_grid
+from old_vpic_b200 import lib
+from old_vpic_b200.abi import ptr
+L = lib.load(); L.vpb_init(0)
+g = host_grid((4, 4, 4), "metal")
+v = g.voxel(1, 2, 2)
+g.neighbor[6 * v + 0] = -3            # handler 0 on one -x face
+g.struct.nb = int(sys.argv[1])
+a = abi.aligned_zeros(g.nv, abi.accumulator_dtype)
+L.clear_accumulators(ptr(a), g.ref())
+print("ACCEPTED")
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = code % (root, os.path.join(root, "tests"))
+    r = subprocess.run([sys.executable, "-c", src, "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 1 and "custom particle-boundary handlers" in r.stderr and "ACCEPTED" not in r.stdout, (r.stdout, r.stderr[-2000:])
+    r = subprocess.run([sys.executable, "-c", src, "0"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ACCEPTED" in r.stdout, (r.stdout, r.stderr[-2000:])

@@ -90,10 +90,6 @@ def test_reference_deck_runs_on_the_library(tmp_path):
     assert want[-1, 1:7].sum() > 0 and got[-1, 7] > 0 and got[-1, 8] > 0
 
 
-# Tests written in round 1 after most of the GPU budget was spent carry this mark until they have run on hardware:
-#   VPB_RUN_UNVALIDATED=1 python -m pytest tests/test_gpu_deck.py -m gpu -q
-unvalidated = pytest.mark.skipif(os.environ.get("VPB_RUN_UNVALIDATED") != "1",
-                                 reason="not yet run on hardware (set VPB_RUN_UNVALIDATED=1)")
 
 
 def _run_ranks(exe, world, cwd, share_gpu=True, **env):
@@ -133,7 +129,6 @@ def test_reference_deck_on_ranks(world, tmp_path):
     assert rel.max() < 1e-4, rel.max(axis=0)
 
 
-@unvalidated
 def test_reference_deck_on_two_gpus_over_nccl(tmp_path):
     """The same with one GPU per rank: the library brings NCCL up through the reference's mp layer."""
     if _gpu_count() < 2:
@@ -161,7 +156,6 @@ def test_reference_deck_grows_tight_arrays(tmp_path):
     assert rel.max() < 1e-4, rel.max(axis=0)
 
 
-@unvalidated
 @pytest.mark.parametrize("deck", ["absorb_small", "sheet_small"])
 def test_reference_wall_decks_on_two_ranks(deck, tmp_path):
     """The wall decks split along x over two ranks sharing the GPU: migration together with absorbing faces (Higdon
@@ -188,7 +182,6 @@ def test_reference_wall_decks_on_two_ranks(deck, tmp_path):
             assert abs(tot[name] - int(want_counts[name])) <= 2, (tot, want_counts)
 
 
-@unvalidated
 def test_trecon_part_deck_as_shipped(tmp_path):
     """The reference's own trecon-part deck (decks/trecon-part/turbulence.cxx with its config.h: 16x16x1 cells, 50 ppc,
     four species + tracers, topology 2x2x1, 2500 steps, field/hydro/particle/tracer dumps), not one character changed,

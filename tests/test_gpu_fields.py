@@ -164,13 +164,13 @@ def test_field_only_grid_and_plane_wave_loader(vpb, orc):
     """A grid without a neighbor table (field-only, bench.py's configs[1] leg) runs the same kernels: the device
     plane-wave loader reproduces the host formula bit for bit and 10 device steps match the oracle's."""
     from old_vpic_b200 import grid as gridmod
-    from old_vpic_b200.sim import Simulation
+    from old_vpic_b200.sim import NativeSimulation
     n = (32, 6, 5)
     g = gridmod.make_grid(n, "periodic", field_only=True)
     assert g.neighbor is None and not g.struct.neighbor
-    sim = Simulation(g, n_mat=1, vacuum=True, L=vpb)
-    vpb.vpb_load_plane_wave(sim.dom, sim.f.ptr, 2, 0.5)
-    f_g = sim.f.download()
+    sim = NativeSimulation(g, n_mat=1, vacuum=True, L=vpb)
+    vpb.vpb_load_plane_wave(sim.dom, sim.field_ptr, 2, 0.5)
+    f_g = sim.get_fields()
     x = np.arange(g.shape[2], dtype=np.float64)
     k = 2 * np.pi * 2 / n[0]
     f_o = abi.aligned_zeros(g.nv, abi.field_dtype)
@@ -188,7 +188,7 @@ def test_field_only_grid_and_plane_wave_loader(vpb, orc):
         orc.orc_advance_b(ptr(f_o), go.ref(), 0.5, 1)
         orc.orc_advance_e(ptr(f_o), None, go.ref(), 1)
         orc.orc_advance_b(ptr(f_o), go.ref(), 0.5, 1)
-    assert_bits_equal(sim.f.download(), f_o, "field-only advance")
+    assert_bits_equal(sim.get_fields(), f_o, "field-only advance")
     assert abs(sum(sim.energies()[:6]) - en0) / en0 < 2e-3
     sim.free()
 

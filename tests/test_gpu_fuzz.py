@@ -2,7 +2,7 @@
 own field and particle boundary condition; CUDA through the C ABI against the oracle (which that file pins to the
 reference on the same kind of configurations).  Stencils, ghost fills and synchronisations bit-exact; float sums made
 with atomics within 2e-5; boundary_p survivors as a set.
-Written after round 1's GPU budget was spent: skipped unless VPB_RUN_UNVALIDATED=1 until it has run on hardware."""
+First run on hardware in round 2 (profiles/r2a_gpu_pytest_all.txt)."""
 import ctypes as C
 import os
 
@@ -14,8 +14,7 @@ from helpers import (abi, assert_bits_equal, host_grid, max_rel, random_fields, 
 from old_vpic_b200 import lib
 from old_vpic_b200.abi import ptr
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("VPB_RUN_UNVALIDATED") != "1",
-                                                  reason="not yet run on hardware (set VPB_RUN_UNVALIDATED=1)")]
+pytestmark = pytest.mark.gpu
 
 FBC = [abi.PEC_FIELDS, abi.PMC_FIELDS, abi.SYMMETRIC_FIELDS, abi.ABSORB_FIELDS]
 PBC = [abi.REFLECT_PARTICLES, abi.ABSORB_PARTICLES]

@@ -91,7 +91,6 @@ def test_trecon_geometry_history(vpb, orc, nx, nz, clean):
     sim.free()
 
 
-@pytest.mark.skipif(os.environ.get("VPB_RUN_UNVALIDATED") != "1", reason="not yet run on hardware (set VPB_RUN_UNVALIDATED=1)")
 def test_trecon_cells_and_field_strength_history(vpb, orc):
     """The same geometry with the deck's OWN cell shape and field strength (turbulence.cxx:86-160): cells of 0.488 x 1.95 x
     0.488 c/wpe, dt = 0.99 Courant, wce/wpe = 10 (b0 = 10), sheet half-thickness 6, vth = 0.6 c -- anisotropic cells and

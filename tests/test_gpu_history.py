@@ -1,4 +1,4 @@
-"""Per-run parity: the device time-step driver (old_vpic_b200/sim.py, the call order of advance.cxx) against
+"""Per-run parity: the device time-step driver (csrc/vpb_step.cu, the call order of advance.cxx) against
 the same loop run on the CPU with the oracle kernels -- and, where oracle/_ref is present, with the
 reference's own compiled kernels -- from identical particles.  Energy histories (6 field + 2 kinetic, the
 columns of dump_energies, dump.cxx:37-78) must agree within 1e-4 relative over the first 20 steps
@@ -11,15 +11,18 @@ import pytest
 
 from helpers import abi, host_grid, loader, random_particles
 from old_vpic_b200.abi import ptr
-from old_vpic_b200.sim import Simulation
+from old_vpic_b200.sim import NativeSimulation
 
 pytestmark = pytest.mark.gpu
 
 STEPS, SORT = 20, 5
 
 
-def cpu_history(K, g, species, steps, clean_e=0, clean_b=0, f_init=None):
-    """K: dict of kernels with the oracle's calling convention."""
+def cpu_history(K, g, species, steps, clean_e=0, clean_b=0, f_init=None, sync_shared=0, errors=None, state=None, sort=None):
+    """K: dict of kernels with the oracle's calling convention.  errors: a list that receives, per cleaning / synchronising
+    step, what advance.cxx:160,168,182,190,205 would print.  state: a dict that receives the final field and interpolator
+    arrays ("f", "fi"); the species' arrays are updated in place.  sort: sort interval (default SORT)."""
+    sort = SORT if sort is None else sort
     f = abi.aligned_zeros(g.nv, abi.field_dtype)
     if f_init is not None:
         f[:] = f_init
@@ -34,7 +37,7 @@ def cpu_history(K, g, species, steps, clean_e=0, clean_b=0, f_init=None):
     for step in range(steps):
         K["clear_accumulators"](a, g)
         for sp in species:
-            if step % SORT == 0:
+            if sort > 0 and step % sort == 0:
                 sp["p"] = K["sort"](sp["p"], g)
         for sp in species:
             pm = abi.aligned_zeros(len(sp["p"]), abi.mover_dtype)
@@ -47,26 +50,54 @@ def cpu_history(K, g, species, steps, clean_e=0, clean_b=0, f_init=None):
         K["advance_b"](f, g, 0.5)
         K["advance_e"](f, m, g)
         K["advance_b"](f, g, 0.5)
-        if clean_e and step % clean_e == 0:
+        rec = {"step": step}
+        if clean_e > 0 and step % clean_e == 0:                      # advance.cxx:151-173
             K["clear_rhof"](f, g)
             for sp in species:
                 K["accumulate_rho_p"](f, sp["p"], g)
             K["synchronize_rho"](f, g)
-            for _ in range(2):
-                K["compute_div_e_err"](f, m, g)
+            K["compute_div_e_err"](f, m, g)
+            err = K["rms_div_e_err"](f, g)
+            rec["div_e"] = [err]
+            if err > 0:
                 K["clean_div_e"](f, m, g)
-        if clean_b and step % clean_b == 0:
-            for _ in range(2):
-                K["compute_div_b_err"](f, g)
+                K["compute_div_e_err"](f, m, g)
+                err = K["rms_div_e_err"](f, g)
+                rec["div_e"].append(err)
+                if err > 0:
+                    K["clean_div_e"](f, m, g)
+        if clean_b > 0 and step % clean_b == 0:                      # :177-195
+            K["compute_div_b_err"](f, g)
+            err = K["rms_div_b_err"](f, g)
+            rec["div_b"] = [err]
+            if err > 0:
                 K["clean_div_b"](f, g)
+                K["compute_div_b_err"](f, g)
+                err = K["rms_div_b_err"](f, g)
+                rec["div_b"].append(err)
+                if err > 0:
+                    K["clean_div_b"](f, g)
+        if sync_shared > 0 and step % sync_shared == 0:              # :199-208
+            rec["desync"] = K["synchronize_tang_e_norm_b"](f, g)
+        if errors is not None and len(rec) > 1:
+            errors.append(rec)
         K["load_interpolator"](fi, f, g)
         en = np.zeros(6)
         K["energy_f"](en, f, m, g)
         hist.append(list(en) + [K["energy_p"](sp["p"], sp["q_m"], fi, g) for sp in species])
+    if state is not None:
+        state["f"], state["fi"] = f, fi
     return np.array(hist)
 
 
 def oracle_kernels(O):
+    def rms(fn):
+        def f_(f, g):
+            loc = np.zeros(2)
+            fn(ptr(loc), ptr(f), g.ref())            # one rank: {err^2 sum * dV, volume} (compute_rms_div_e_err.c:150-160)
+            return float(g.struct.eps0 * np.sqrt(loc[0] / loc[1]))
+        return f_
+
     def sort(p, g):
         out = abi.aligned_zeros(len(p), abi.particle_dtype)
         part = np.zeros(g.nv + 1, np.int32)
@@ -91,6 +122,9 @@ def oracle_kernels(O):
         "clean_div_e": lambda f, m, g: O.orc_clean_div_e(ptr(f), ptr(m), g.ref()),
         "compute_div_b_err": lambda f, g: O.orc_compute_div_b_err(ptr(f), g.ref()),
         "clean_div_b": lambda f, g: O.orc_clean_div_b(ptr(f), g.ref()),
+        "rms_div_e_err": rms(O.orc_rms_div_e_err_local),
+        "rms_div_b_err": rms(O.orc_rms_div_b_err_local),
+        "synchronize_tang_e_norm_b": lambda f, g: float(O.orc_synchronize_tang_e_norm_b(ptr(f), g.ref())),
         "energy_f": lambda en, f, m, g: O.orc_energy_f(ptr(en), ptr(f), ptr(m), g.ref()),
         "energy_p": lambda p, q_m, fi, g: O.orc_energy_p(ptr(p), len(p), q_m, ptr(fi), g.ref()),
     }
@@ -105,18 +139,19 @@ def make_species(g, ppc, seed):
     return [{"p": e, "q_m": -1.0}, {"p": i, "q_m": 1.0}]
 
 
-def gpu_history(vpb, g, species, steps, clean_e=0, clean_b=0):
-    sim = Simulation(g, L=vpb)
-    sim.clean_div_e_interval, sim.clean_div_b_interval = clean_e, clean_b
+def gpu_history(vpb, g, species, steps, clean_e=0, clean_b=0, sync_shared=0, f_init=None, lookahead=0, sort=SORT, **layouts):
+    """The same run through the library's time-step driver (csrc/vpb_step.cu)."""
+    sim = NativeSimulation(g, L=vpb, **layouts)
+    sim.set_intervals(clean_e, clean_b, sync_shared=sync_shared)
+    sim.set_sort_lookahead(lookahead)
     for k, sp in enumerate(species):
-        s = sim.define_species("s%d" % k, sp["q_m"], len(sp["p"]) + 64, sort_interval=SORT)
-        s.p.upload(sp["p"])
-        s.np = len(sp["p"])
-    vpb.vpb_load_interpolator(sim.dom, sim.fi.ptr, sim.f.ptr)
+        s = sim.define_species("s%d" % k, sp["q_m"], len(sp["p"]) + 64, sort_interval=sort)
+        sim.set_particles(s, sp["p"])
+    # also loads the interpolator (initialize.cxx:67)
+    sim.set_fields(abi.aligned_zeros(g.nv, abi.field_dtype) if f_init is None else f_init)
     hist = []
     for _ in range(steps):
         sim.advance()
-        assert sim.mover_counts() == [0] * len(species)
         hist.append(sim.energies())
     return np.array(hist), sim
 

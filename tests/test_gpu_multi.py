@@ -8,7 +8,6 @@ import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 pytestmark = pytest.mark.gpu
-unvalidated = pytest.mark.skipif(os.environ.get("VPB_RUN_UNVALIDATED") != "1", reason="not yet run on hardware (set VPB_RUN_UNVALIDATED=1)")
 
 
 def gpu_count():
@@ -39,7 +38,6 @@ def test_decomposed_run_matches_single_domain(world):
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
 
 
-@unvalidated
 @pytest.mark.parametrize("world", [2, 4])
 def test_decomposed_calls_match_oracle_cluster(world):
     """tests/dist_gpu_percall_worker.py: per-call, bit-level parity of halos and migration over NCCL."""

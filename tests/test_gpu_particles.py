@@ -22,7 +22,6 @@ pytestmark = pytest.mark.gpu
 
 ACC_TOL = 2e-5
 # tests of code that has not run on hardware yet
-unvalidated = pytest.mark.skipif(os.environ.get("VPB_RUN_UNVALIDATED") != "1", reason="not yet run on hardware (set VPB_RUN_UNVALIDATED=1)")
 
 
 def acc_floats(a):
@@ -117,7 +116,7 @@ def test_advance_p_managed_memory_in_place(vpb, orc):
     assert max_rel(acc_floats(a_m), acc_floats(a_o)) < ACC_TOL
 
 
-@pytest.mark.parametrize("hot_only", [0, pytest.param(1, marks=unvalidated)])
+@pytest.mark.parametrize("hot_only", [0, 1])
 @pytest.mark.parametrize("kind", ["periodic", "absorbing"])
 def test_advance_p_streamed_in_pieces(vpb, orc, kind, hot_only):
     """Large host arrays go through the device in pieces (H2D / kernel / D2H overlapped); same results,
@@ -389,7 +388,6 @@ def test_advance_p_pair_tails(vpb, orc):
 # LEAN index-only mover ring): same bar as the default kernel, not yet run on hardware.
 
 
-@unvalidated
 @pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("kind", ["periodic", "metal", "absorbing"])
 @pytest.mark.parametrize("n,np_,sort,vth", [((6, 5, 4), 5000, True, 0.6), ((8, 1, 6), 7001, False, 0.6), ((1, 1, 16), 300, True, 0.6),
@@ -494,7 +492,7 @@ def test_sort_p_planes(vpb, orc, n, np_):
     vpb.vpb_domain_destroy(dom)
 
 
-@pytest.mark.parametrize("scatter", [0, pytest.param(1, marks=unvalidated)])
+@pytest.mark.parametrize("scatter", [0, 1])
 def test_sort_p_planes_lookahead(vpb, scatter):
     """scatter = 1: the record-scatter variant of the sort (tuning sort.scatter; not yet run on hardware).
     Look-ahead sort key (vpb_sort_p_planes_ahead): a grouping of the SAME particles by the voxel they reach `L`

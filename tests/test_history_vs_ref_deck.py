@@ -42,16 +42,24 @@ def read_state(path):
     return f, species
 
 
-def test_cpu_history_is_the_reference_main_loop(orc, tmp_path):
+@pytest.mark.parametrize("clean,sync", [(5, 0), (5, 4), (0, 3)])
+def test_cpu_history_is_the_reference_main_loop(orc, tmp_path, clean, sync):
+    """clean: both divergence-cleaning intervals (with the err>0 guards of advance.cxx:164-172,185-193); sync:
+    sync_shared_interval (advance.cxx:199-208)."""
     assert (STEPS, SORT) == (20, 5)          # what the deck was written for
-    r = subprocess.run([EXE, "-tpp=1"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    env = dict(os.environ, VPB_PIN_SYNC=str(sync), VPB_PIN_CLEAN=str(clean))
+    r = subprocess.run([EXE, "-tpp=1"], cwd=tmp_path, capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
     want = np.fromfile(tmp_path / "hist.bin", np.float64).reshape(-1, 8)
     assert want.shape == (STEPS + 1, 8)
     f0, species = read_state(tmp_path / "state0.bin")
     assert [len(s["p"]) % 16 for s in species] == [0, 0] and [s["q_m"] for s in species] == [1.0, -1.0]   # ion first: list order
     g = host_grid((12, 10, 8), "periodic")
-    got = cpu_history(oracle_kernels(orc), g, species, STEPS, 5, 5, f_init=f0)
+    errors = []
+    got = cpu_history(oracle_kernels(orc), g, species, STEPS, clean, clean, f_init=f0, sync_shared=sync, errors=errors)
+    assert len(errors) == len([k for k in range(STEPS) if (clean and k % clean == 0) or (sync and k % sync == 0)])
+    if sync:     # one rank: both copies of a periodic face see the same arithmetic, the desynchronisation error is exactly 0
+        assert all(e["desync"] == 0 for e in errors if "desync" in e)
     assert got.shape == (STEPS, 8)
     rel = np.abs(got - want[1:]) / np.abs(want[1:]).max(axis=0)
     assert rel.max() < 1e-12, rel.max(axis=0)
