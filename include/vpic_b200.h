@@ -136,7 +136,8 @@ float vpb_timer_ms(int slot);                /* synchronises on the stop event *
 
 /* Per-kernel-class timing with CUDA events on the library stream (off by default).
  * Classes: 0 advance_p, 1 sort_p, 2 advance_b, 3 advance_e, 4 load_interpolator,
- * 5 unload_accumulator, 6 other. */
+ * 5 unload_accumulator, 6 other (compute_curl_b), 7 boundary_p (migration), 8 halo (synchronize_jf, ghost
+ * exchanges and local boundary conditions of advance_e), 9 divergence cleaning / shared-face synchronisation. */
 void vpb_prof_enable(int on);
 void vpb_prof_collect(int cls, double *total_ms, int *count, int reset);
 int vpb_prof_list(int cls, float *out_ms, int max);   /* per-launch durations in launch order */
@@ -287,6 +288,16 @@ void vpb_sort_p_planes(vpb_domain_t *dom, vpb_particle_t *d_p, vpb_particle_t *d
  * gathers and REDs pay for.  d_partition describes the groups, not the current voxels.  lookahead = 0 is
  * vpb_sort_p_planes. */
 void vpb_sort_p_planes_ahead(vpb_domain_t *dom, vpb_particle_t *d_p, vpb_particle_t *d_tmp, int np, int *d_partition, int lookahead);
+/* The device-resident driver's sort (csrc/vpb_sort_group.cu): d_out receives the particles of the component-plane array
+ * d_in GROUPED by the voxel they occupy (lookahead == 0) or reach `lookahead` steps from now; the groups follow a
+ * brick-Morton order of the voxels, key(x,y,z) = fx[x] + fy[y] + fz[z] (vpb_sort_group_order: tables of n+2 entries
+ * for coordinates 0..n+1, host code, returns the number of keys); d_partition (int[keys+1]) = first particle of every
+ * group; the order inside a group is arbitrary.  Same particles, same physics as sort_p (sort_p.c:16-77), whose only
+ * purpose is that particles of a voxel are neighbours in the array; the reference's ORDER and partition[] are what
+ * sort_p / vpb_sort_p / vpb_sort_p_planes deliver. */
+void vpb_sort_p_planes_grouped(vpb_domain_t *dom, const vpb_particle_t *d_in, vpb_particle_t *d_out, int np, int *d_partition, int lookahead);
+long vpb_sort_group_order(int nx, int ny, int nz, int *fx, int *fy, int *fz);
+long vpb_sort_group_keys(vpb_domain_t *dom);
 
 /* Hydro moments on device arrays (vpb_hydro_t[nvoxel], the reference layout; the particle array in the domain's
  * particle layout, the interpolator in the domain's interpolator layout). */

@@ -36,6 +36,8 @@
       VPB_ERROR("CUDA failure %s: %s (no CPU fallback exists)", #call, cudaGetErrorString(_e)); \
   } while (0)
 
+struct vpb_domain;
+
 namespace vpb {
 
 // Device mirror of the parts of grid_t the kernels read (grid.h:112-167).
@@ -91,16 +93,19 @@ void *scratch(size_t bytes);          // stream-ordered scratch of at least `byt
 int tuning(const char *name, int dflt);
 
 inline void count_launch(int n = 1) { ctx().launches += n; }
+void sort_group_forget(const vpb_domain *dom);   // vpb_sort_group.cu: drop the order tables cached for a domain
 
 // Optional per-kernel timing (CUDA events on the library stream around selected
 // launches); off unless vpb_prof_enable(1).  Classes: 0 advance_p, 1 sort_p,
-// 2 advance_b, 3 advance_e, 4 load_interpolator, 5 unload_accumulator, 6 other.
-void prof_begin(int cls);
-void prof_end(int cls);
+// 2 advance_b, 3 advance_e, 4 load_interpolator, 5 unload_accumulator, 6 other (compute_curl_b),
+// 7 boundary_p (particle migration), 8 halo (synchronize_jf and the ghost exchanges of advance_e),
+// 9 divergence cleaning and shared-face synchronisation.  Scopes may nest (7-9 are set by the step driver).
+int prof_begin(int cls);
+void prof_end(int idx);
 struct ProfScope {
-  int cls;
-  explicit ProfScope(int c) : cls(c) { prof_begin(c); }
-  ~ProfScope() { prof_end(cls); }
+  int idx;
+  explicit ProfScope(int c) : idx(prof_begin(c)) {}
+  ~ProfScope() { prof_end(idx); }
 };
 
 // Host wall-clock accounting of the layer-A entry points (VPB_TRACE=1 or vpb_trace_enable): calls and seconds

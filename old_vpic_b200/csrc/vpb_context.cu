@@ -80,22 +80,22 @@ static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;       // pool of event pairs
 static size_t g_prof_used = 0;
 
-void prof_begin(int cls) {
-  if (!g_prof_on) return;
+int prof_begin(int cls) {
+  if (!g_prof_on) return -1;
   if (g_prof_used == g_prof.size()) {
     ProfRec r;
     VPB_CUDA(cudaEventCreate(&r.a));
     VPB_CUDA(cudaEventCreate(&r.b));
     g_prof.push_back(r);
   }
-  g_prof[g_prof_used].cls = cls;
-  VPB_CUDA(cudaEventRecord(g_prof[g_prof_used].a, ctx().stream));
+  const int idx = (int)g_prof_used++;
+  g_prof[idx].cls = cls;
+  VPB_CUDA(cudaEventRecord(g_prof[idx].a, ctx().stream));
+  return idx;
 }
-void prof_end(int cls) {
-  if (!g_prof_on) return;
-  (void)cls;
-  VPB_CUDA(cudaEventRecord(g_prof[g_prof_used].b, ctx().stream));
-  g_prof_used++;
+void prof_end(int idx) {
+  if (idx < 0 || !g_prof_on || (size_t)idx >= g_prof_used) return;
+  VPB_CUDA(cudaEventRecord(g_prof[idx].b, ctx().stream));
 }
 
 }  // namespace vpb
@@ -341,6 +341,7 @@ vpb_domain_t *vpb_domain_create(const vpb_grid_t *g, int rank, int nproc) {
 void vpb_domain_destroy(vpb_domain_t *dom) {
   if (!dom) return;
   VPB_CUDA(cudaStreamSynchronize(ctx().stream));
+  sort_group_forget(dom);
   if (dom->nbr) cudaFree(dom->nbr);
   if (dom->nbr64) cudaFree(dom->nbr64);
   for (int f = 0; f < 6; f++) {

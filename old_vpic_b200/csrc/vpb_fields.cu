@@ -387,9 +387,9 @@ void vpb_advance_e(vpb_domain_t *dom, vpb_field_t *d_f, const vpb_material_coeff
     if (g.damp != 0) VPB_ERROR("Vacuum field advance does not support TCA radiation damping");   // vfa.c:66-67
     d_m = uniform_vacuum(); n_mat = 1;
   } else if (!d_m) VPB_ERROR("Bad material coefficients");
-  faces_ghost_exchange(dom, d_f, MSG_GHOST_TANG_B);   // begin/local/end_remote_ghost_tang_b (advance_e.c:114-115,197)
+  { ProfScope prof(8); faces_ghost_exchange(dom, d_f, MSG_GHOST_TANG_B); }   // begin/local/end_remote_ghost_tang_b (advance_e.c:114-115,197)
   launch_e(vacuum ? 1 : 0, dom, d_f, d_m, n_mat);
-  faces_local_adjust(dom, d_f, ADJ_TANG_E);
+  { ProfScope prof(8); faces_local_adjust(dom, d_f, ADJ_TANG_E); }
   VPB_CUDA(cudaGetLastError());
 }
 

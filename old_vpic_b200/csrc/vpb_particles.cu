@@ -299,77 +299,6 @@ __global__ void __launch_bounds__(256) sort_gather_records_to_planes_kernel(cons
   }
 }
 
-// ---- scatter variant of the look-ahead sort (tuning sort.scatter, default off; not yet measured) ------------------
-// The gather above reads 170 GB for 51 GB of payload: a source line is wanted again one z-plane (200 MB of records)
-// later, long after L2 dropped it.  Scattering has the opposite locality: consecutive SOURCE particles go to nearby
-// destinations, the lines being assembled stay in L2 until they are complete, and every pass streams its input.
-//   A  sort_hist_kernel            planes -> keys, counts                         (28 B read, 4 B written per particle)
-//   B  sort_scatter_records_kernel planes + keys -> 48-byte records at their slot (52 B read, 48 B written)
-//   C  records_to_planes_kernel    records -> planes, both sides coalesced        (48 B read, 48 B written)
-// The slot claim of pass B is that of sort_claim_kernel (tile-aggregated in shared memory).
-__global__ void __launch_bounds__(256) sort_scatter_records_kernel(const PView p, int np, int *__restrict__ cursor,
-                                                                   float4 *__restrict__ rec, const int *__restrict__ keys) {
-  __shared__ int hkey[kClaimHash], hcnt[kClaimHash];
-  const int ntiles = (np + kClaimTile - 1) / kClaimTile;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    for (int s = threadIdx.x; s < kClaimHash; s += 256) { hkey[s] = -1; hcnt[s] = 0; }
-    __syncthreads();
-    int slot[kClaimPer], rank[kClaimPer];
-#pragma unroll
-    for (int j = 0; j < kClaimPer; j++) {
-      const int k = tile * kClaimTile + j * 256 + threadIdx.x;
-      slot[j] = -1;
-      if (k < np) {
-        const int v = keys[k];
-        int s = (int)(((unsigned)v * 2654435761u) >> 21) & (kClaimHash - 1);
-        for (;;) {
-          const int old = atomicCAS(&hkey[s], -1, v);
-          if (old == -1 || old == v) break;
-          s = (s + 1) & (kClaimHash - 1);
-        }
-        slot[j] = s;
-        rank[j] = atomicAdd(&hcnt[s], 1);
-      }
-    }
-    __syncthreads();
-    for (int s = threadIdx.x; s < kClaimHash; s += 256)
-      if (hkey[s] >= 0) hcnt[s] = atomicAdd(cursor + hkey[s], hcnt[s]);
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < kClaimPer; j++)
-      if (slot[j] >= 0) {
-        const int k = tile * kClaimTile + j * 256 + threadIdx.x;
-        float4 *o = rec + 3 * (size_t)(hcnt[slot[j]] + rank[j]);
-        o[0] = p.pos(k);
-        o[1] = p.mom(k);
-        o[2] = p.tag(k);
-      }
-    __syncthreads();
-  }
-}
-
-// 48-byte records -> planes, both sides coalesced (the inverse of planes_to_records_kernel)
-__global__ void __launch_bounds__(256) records_to_planes_kernel(const float4 *__restrict__ rec, const PView out, int np) {
-  __shared__ float4 tile[8][96];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int nblk = (np + 31) >> 5;
-  for (int blk = blockIdx.x * 8 + w; blk < nblk; blk += gridDim.x * 8) {
-    const int nq = 3 * (np - blk * 32 < 32 ? np - blk * 32 : 32);
-    const float4 *in = rec + 96 * (size_t)blk;
-#pragma unroll
-    for (int j = 0; j < 3; j++)
-      if (lane + 32 * j < nq) tile[w][lane + 32 * j] = __ldcs(in + lane + 32 * j);
-    __syncwarp();
-    const int k = blk * 32 + lane;
-    if (k < np) {
-      out.set_pos(k, tile[w][3 * lane]);
-      out.set_mom(k, tile[w][3 * lane + 1]);
-      out.set_tag(k, tile[w][3 * lane + 2]);
-    }
-    __syncwarp();
-  }
-}
-
 // AoS <-> component planes (uploads, downloads, tests)
 __global__ void __launch_bounds__(256) particle_convert_kernel(const PView dst, const PView src, long np) {
   for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < np; k += (long)gridDim.x * blockDim.x) {
@@ -465,10 +394,8 @@ static void sort_particles(vpb_domain_t *dom, const vpb_particle_t *d_in, vpb_pa
   ahead.kx = 2.f * ahead.L * gd.cvac * gd.dt * gd.rdx;
   ahead.ky = 2.f * ahead.L * gd.cvac * gd.dt * gd.rdy;
   ahead.kz = 2.f * ahead.L * gd.cvac * gd.dt * gd.rdz;
-  // look-ahead grouping, in place: optionally scatter the records to their slots instead of gathering them
-  const bool scatter = in_place && np > 0 && ahead.L > 0 && tuning("sort.scatter", 0) != 0;
   // in place (planes): the transposition to records doubles as the histogram pass and always leaves the keys
-  const bool fused = in_place && np > 0 && !scatter;
+  const bool fused = in_place && np > 0;
   int *keys = (ahead.L || fused) ? perm2 : nullptr;
   VPB_CUDA(cudaMemsetAsync(cursor, 0, (size_t)nv1 * 4, c.stream));
   if (fused) {
@@ -483,14 +410,6 @@ static void sort_particles(vpb_domain_t *dom, const vpb_particle_t *d_in, vpb_pa
   if (np == 0) return;
   if (!d_in || !d_out) VPB_ERROR("Bad particle array");
   VPB_CUDA(cudaMemcpyAsync(cursor, d_partition, (size_t)nv1 * 4, cudaMemcpyDeviceToDevice, c.stream));
-  if (scatter) {
-    sort_scatter_records_kernel<<<grid_for(np, 256), 256, 0, c.stream>>>(PView(d_in, dom->d.p_plane), np, cursor,
-                                                                         reinterpret_cast<float4 *>(d_out), keys);
-    records_to_planes_kernel<<<grid_for(np, 256), 256, 0, c.stream>>>(reinterpret_cast<const float4 *>(d_out), PView(d_in, dom->d.p_plane), np);
-    count_launch(2);
-    VPB_CUDA(cudaGetLastError());
-    return;
-  }
   sort_claim_kernel<<<grid_for(np, 256), 256, 0, c.stream>>>(PView(d_in, dom->d.p_plane), np, cursor, perm, keys);
   // The reference's out-of-place sort is stable (sort_p.c:74): slots claimed by atomics are re-ranked by source index
   // within every voxel.  A look-ahead grouping is not the reference's order to begin with, so it keeps the claim order

@@ -1,0 +1,383 @@
+// vpb_sort_group.cu -- the device-resident driver's particle sort: component planes in, component planes out, in
+// THREE streaming passes (keys, scan, move), particles grouped by voxel in a brick-Morton order of the voxels.
+//
+// What sort_p is for (sort_p.c:16-77): particles that share a voxel sit next to each other, so that advance_p's
+// interpolator reads and accumulator updates of neighbouring particles hit the same lines.  The ORDER of the groups
+// in the array has no meaning to the physics or to advance_p (every particle carries its voxel index); only the
+// reference-named sort_p / vpb_sort_p (vpb_particles.cu) promise the reference's order and its partition[].
+//
+// Why not the voxel index as the key (round 1, vpb_sort_p_planes_ahead: 76 ms per 2^30 particles, 0.21 of the HBM
+// roofline).  The array is nearly sorted: since the last sort a particle has moved a cell or two.  With x-fastest
+// voxel indices a step of one cell in z is 258^2 voxels = 200 MB of particles away, far outside the 126 MB L2, so a
+// permutation pass -- gather or scatter -- touches every DRAM line several times (ncu: 170 GB read for 51 GB of
+// payload), and to keep the requests wide the planes had to be transposed to 48-byte records and back.
+//
+// Here the key of a voxel is  Morton(brick) * brick_volume + index inside the brick,  bricks of 8 x 4 x 4 voxels:
+// spatial neighbours are neighbours in the array (for all but a geometrically small share of brick faces), so
+//   * a chunk of 2048 consecutive source particles (a quarter of a brick) sends its particles to a few dozen
+//     destination groups, most of them in the same or an adjacent brick;
+//   * the chunk is bucketed in shared memory (hash table of its destination keys, one global atomic per distinct key
+//     claims the slots), its plane words are staged in shared memory with coalesced loads and leave in destination
+//     order: runs of a group's particles, i.e. mostly whole 32-byte sectors;
+//   * the lines a chunk only partly fills are completed by chunks that run at almost the same time, while they are
+//     still in L2.
+// Traffic per particle: keys pass 28 B read (4 B without look-ahead) + 4 B written; move pass 4 + 48 B read, 48 B
+// written: 132 B, against ~320 B before.  The key is separable, key = fx[x] + fy[y] + fz[z], three small tables built
+// on the host (vpb_sort_group_order; also what the tests use to check the grouping).
+#include <algorithm>
+#include <vector>
+#include "vpb_common.cuh"
+#include "vpb_pview.cuh"
+#include "vpb_scan.cuh"
+
+namespace vpb {
+
+// ---- host: the order tables ---------------------------------------------------------------------------------------
+struct GroupOrder {
+  std::vector<int> fx, fy, fz;   // per coordinate 0..n+1 (ghosts share the key of the nearest interior coordinate)
+  long nkeys = 0;
+  int b[3] = {1, 1, 1};
+};
+
+static int ceil_log2(long v) { int b = 0; while ((1L << b) < v) b++; return b; }
+
+static GroupOrder make_group_order(int nx, int ny, int nz) {
+  const int n[3] = {nx, ny, nz};
+  GroupOrder o;
+  // brick: 8 x 4 x 4 voxels, clipped to the grid; a clipped axis lets the others grow until the brick holds ~128 voxels
+  int b[3] = {std::min(8, nx), std::min(4, ny), std::min(4, nz)};
+  for (int pass = 0; pass < 8 && b[0] * b[1] * b[2] < 128; pass++)
+    for (int a = 2; a >= 0; a--)
+      if (b[0] * b[1] * b[2] < 128 && 2 * b[a] <= n[a]) b[a] *= 2;
+  long nb[3];
+  int w[3];
+  for (int a = 0; a < 3; a++) { nb[a] = (n[a] + b[a] - 1) / b[a]; w[a] = ceil_log2(nb[a]); }
+  const long bv = (long)b[0] * b[1] * b[2];
+  const long nv_real = (long)nx * ny * nz;
+  // Morton interleave of the brick coordinates (axes with fewer bits simply run out); when padding the brick counts to
+  // powers of two would inflate the key space beyond 2x (+ a little), bricks are ordered row-major instead
+  const bool morton = ((1L << (w[0] + w[1] + w[2])) * bv) <= 2 * nv_real + 4096;
+  std::vector<long> spread[3];
+  if (morton) {
+    int pos[3][32];
+    int out = 0;
+    for (int bit = 0; bit < 31; bit++)
+      for (int a = 0; a < 3; a++)
+        if (bit < w[a]) pos[a][bit] = out++;
+    for (int a = 0; a < 3; a++) {
+      spread[a].resize(nb[a]);
+      for (long v = 0; v < nb[a]; v++) {
+        long s = 0;
+        for (int bit = 0; bit < w[a]; bit++)
+          if ((v >> bit) & 1) s |= 1L << pos[a][bit];
+        spread[a][v] = s;
+      }
+    }
+    o.nkeys = (1L << (w[0] + w[1] + w[2])) * bv;
+  } else {
+    const long stride[3] = {1, nb[0], nb[0] * nb[1]};
+    for (int a = 0; a < 3; a++) {
+      spread[a].resize(nb[a]);
+      for (long v = 0; v < nb[a]; v++) spread[a][v] = v * stride[a];
+    }
+    o.nkeys = nb[0] * nb[1] * nb[2] * bv;
+  }
+  if (o.nkeys > 0x7fff0000L) VPB_ERROR("sort key space of %ld groups exceeds 2^31", o.nkeys);
+  const long in_stride[3] = {1, b[0], (long)b[0] * b[1]};
+  std::vector<int> *tab[3] = {&o.fx, &o.fy, &o.fz};
+  for (int a = 0; a < 3; a++) {
+    tab[a]->resize(n[a] + 2);
+    for (int c = 0; c <= n[a] + 1; c++) {
+      const int ci = std::min(std::max(c, 1), n[a]) - 1;       // 0-based interior coordinate
+      (*tab[a])[c] = (int)(spread[a][ci / b[a]] * bv + (ci % b[a]) * in_stride[a]);
+    }
+    o.b[a] = b[a];
+  }
+  return o;
+}
+
+// ---- device -------------------------------------------------------------------------------------------------------
+struct GroupKeyArgs {
+  int L, sx, sy, nx, ny, nz;
+  float kx, ky, kz;             // 2 * L * c dt / d{x,y,z} (vpb_particles.cu: SortAhead)
+  const int *fx, *fy, *fz;
+};
+
+// Key of particle k: the group of its voxel (L == 0) or of the voxel it reaches in L steps at its present velocity,
+// clamped to the interior (look-ahead grouping).
+__device__ __forceinline__ int group_key(const PView &p, int k, const GroupKeyArgs &A) {
+  const int v = p.voxel(k);
+  const int ix = v % A.sx, t = v / A.sx, iy = t % A.sy, iz = t / A.sy;
+  int cx = ix, cy = iy, cz = iz;
+  if (A.L > 0) {
+    const size_t pl = (size_t)p.plane;
+    const float *b = p.b + k;
+    const float dx = __ldcs(b), dy = __ldcs(b + pl), dz = __ldcs(b + 2 * pl);
+    const float ux = __ldcs(b + 4 * pl), uy = __ldcs(b + 5 * pl), uz = __ldcs(b + 6 * pl);
+    const float rg = rsqrtf(1.f + (ux * ux + (uy * uy + uz * uz)));
+    cx = ix + (int)floorf((dx + A.kx * ux * rg + 1.f) * 0.5f);
+    cy = iy + (int)floorf((dy + A.ky * uy * rg + 1.f) * 0.5f);
+    cz = iz + (int)floorf((dz + A.kz * uz * rg + 1.f) * 0.5f);
+    cx = min(max(cx, 1), A.nx); cy = min(max(cy, 1), A.ny); cz = min(max(cz, 1), A.nz);
+  }
+  return __ldg(A.fx + cx) + __ldg(A.fy + cy) + __ldg(A.fz + cz);
+}
+
+// pass 1: keys[k], count[key]++ (one global atomic per distinct key among 32 consecutive particles)
+__global__ void __launch_bounds__(256) group_keys_kernel(const PView p, int np, const GroupKeyArgs A, int *__restrict__ keys,
+                                                         int *__restrict__ count) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const long stride = (long)gridDim.x * blockDim.x;
+  const long n_round = ((long)np + 31) & ~31L;                 // whole warps enter the loop together
+  for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < n_round; k += stride) {
+    const bool valid = k < np;
+    const int key = valid ? group_key(p, (int)k, A) : -1 - lane;
+    if (valid) keys[k] = key;
+    const unsigned peers = __match_any_sync(full, key);
+    if (valid && lane == __ffs(peers) - 1) atomicAdd(count + key, __popc(peers));
+  }
+}
+
+constexpr int kGsThreads = 256, kGsPer = 8, kGsChunk = kGsThreads * kGsPer, kGsHash = 4096;
+
+struct GroupSmem {
+  int hkey[kGsHash];                 // key of the slot (-1 free); after the claim: first destination of the chunk's group
+  int hcnt[kGsHash];                 // particles of the chunk with that key; after the claim: their first local position
+  int ldst[kGsChunk];                // destination of the particle at local position l
+  unsigned short lsrc[kGsChunk];     // its index inside the chunk
+  union {
+    float w[4][kGsChunk];            // four word planes of the chunk
+    float4 t[kGsChunk];              // or its tag plane
+  } buf;
+  int wsum[kGsThreads / 32];
+};
+
+// pass 3: move.  cursor[] starts as a copy of partition[]; one atomicAdd per (chunk, distinct key) claims the slots.
+__global__ void __launch_bounds__(kGsThreads) group_move_kernel(const PView in, const PView out, int np, const int *__restrict__ keys,
+                                                                int *__restrict__ cursor) {
+  extern __shared__ __align__(16) unsigned char gs_raw[];
+  GroupSmem &S = *reinterpret_cast<GroupSmem *>(gs_raw);
+  const unsigned full = 0xffffffffu;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int s = tid; s < kGsHash; s += kGsThreads) { S.hkey[s] = -1; S.hcnt[s] = 0; }
+  __syncthreads();
+  const int nchunks = (np + kGsChunk - 1) / kGsChunk;
+  const size_t pli = (size_t)in.plane, plo = (size_t)out.plane;
+  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const int c0 = chunk * kGsChunk;
+    const int nvalid = np - c0 < kGsChunk ? np - c0 : kGsChunk;
+    // ---- bucket the chunk by key: (slot, rank inside the slot) per particle, one table insert per distinct key and warp
+    int slot[kGsPer], rank[kGsPer];
+#pragma unroll
+    for (int j = 0; j < kGsPer; j++) {
+      const int i = j * kGsThreads + tid;
+      const bool valid = i < nvalid;
+      const int key = valid ? __ldcs(keys + c0 + i) : -1 - lane;
+      const unsigned peers = __match_any_sync(full, key);
+      const int leader = __ffs(peers) - 1;
+      int s = 0, r0 = 0;
+      if (valid && lane == leader) {
+        s = (int)(((unsigned)key * 2654435761u) >> 20) & (kGsHash - 1);
+        for (;;) {   // linear probing; at most half of the table is ever in use
+          const int old = atomicCAS(&S.hkey[s], -1, key);
+          if (old == -1 || old == key) break;
+          s = (s + 1) & (kGsHash - 1);
+        }
+        r0 = atomicAdd(&S.hcnt[s], __popc(peers));
+      }
+      s = __shfl_sync(full, s, leader);
+      r0 = __shfl_sync(full, r0, leader);
+      slot[j] = valid ? s : -1;
+      rank[j] = r0 + __popc(peers & lt);
+    }
+    __syncthreads();
+    // ---- the particle of rank 0 speaks for its group: local offset by a block-wide exclusive scan of the group
+    //      sizes, destination by ONE global atomic
+    int gcnt[kGsPer], gkey[kGsPer], mine = 0;
+#pragma unroll
+    for (int j = 0; j < kGsPer; j++) {
+      const bool lead = slot[j] >= 0 && rank[j] == 0;
+      gcnt[j] = lead ? S.hcnt[slot[j]] : 0;
+      gkey[j] = lead ? S.hkey[slot[j]] : -1;
+      mine += gcnt[j];
+    }
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(full, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) S.wsum[w] = incl;
+    __syncthreads();                                   // every group size has been read; wsum is complete
+    int run = incl - mine;
+    for (int q = 0; q < w; q++) run += S.wsum[q];
+#pragma unroll
+    for (int j = 0; j < kGsPer; j++)
+      if (gkey[j] >= 0) {
+        S.hkey[slot[j]] = atomicAdd(cursor + gkey[j], gcnt[j]);
+        S.hcnt[slot[j]] = run;
+        run += gcnt[j];
+      }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kGsPer; j++)
+      if (slot[j] >= 0) {
+        const int l = S.hcnt[slot[j]] + rank[j];
+        S.lsrc[l] = (unsigned short)(j * kGsThreads + tid);
+        S.ldst[l] = S.hkey[slot[j]] + rank[j];
+      }
+    // ---- move the words: coalesced loads into shared memory, out in destination order
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const float *src = in.b + (size_t)(4 * half + c) * pli + c0;
+#pragma unroll
+        for (int j = 0; j < kGsPer; j++) {
+          const int i = j * kGsThreads + tid;
+          if (i < nvalid) S.buf.w[c][i] = __ldcs(src + i);
+        }
+      }
+      __syncthreads();                                 // (first half: also publishes lsrc / ldst)
+#pragma unroll
+      for (int j = 0; j < kGsPer; j++) {
+        const int l = j * kGsThreads + tid;
+        if (l < nvalid) {
+          const int sidx = S.lsrc[l];
+          float *dst = out.b + (size_t)(4 * half) * plo + S.ldst[l];
+#pragma unroll
+          for (int c = 0; c < 4; c++) dst[(size_t)c * plo] = S.buf.w[c][sidx];
+        }
+      }
+      __syncthreads();
+    }
+    {
+      const float4 *src = reinterpret_cast<const float4 *>(in.b + 8 * pli) + c0;
+#pragma unroll
+      for (int j = 0; j < kGsPer; j++) {
+        const int i = j * kGsThreads + tid;
+        if (i < nvalid) S.buf.t[i] = __ldcs(src + i);
+      }
+      __syncthreads();
+      float4 *dst = reinterpret_cast<float4 *>(out.b + 8 * plo);
+#pragma unroll
+      for (int j = 0; j < kGsPer; j++) {
+        const int l = j * kGsThreads + tid;
+        if (l < nvalid) dst[S.ldst[l]] = S.buf.t[S.lsrc[l]];
+      }
+      // leave the table empty for the next chunk
+#pragma unroll
+      for (int j = 0; j < kGsPer; j++)
+        if (slot[j] >= 0) { S.hkey[slot[j]] = -1; S.hcnt[slot[j]] = 0; }
+      __syncthreads();
+    }
+  }
+}
+
+struct GroupTables { int *dev = nullptr; long nkeys = 0; int nx = 0, ny = 0, nz = 0; };
+static std::vector<std::pair<const vpb_domain_t *, GroupTables>> g_group_tables;
+
+static const GroupTables &tables_of(vpb_domain_t *dom) {
+  const DomainDev &g = dom->d;
+  for (auto &e : g_group_tables)
+    if (e.first == dom && e.second.nx == g.nx && e.second.ny == g.ny && e.second.nz == g.nz) return e.second;
+  const GroupOrder o = make_group_order(g.nx, g.ny, g.nz);
+  GroupTables t;
+  t.nkeys = o.nkeys; t.nx = g.nx; t.ny = g.ny; t.nz = g.nz;
+  std::vector<int> all;
+  all.insert(all.end(), o.fx.begin(), o.fx.end());
+  all.insert(all.end(), o.fy.begin(), o.fy.end());
+  all.insert(all.end(), o.fz.begin(), o.fz.end());
+  VPB_CUDA(cudaMalloc(&t.dev, all.size() * sizeof(int)));
+  VPB_CUDA(cudaMemcpyAsync(t.dev, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, ctx().stream));
+  VPB_CUDA(cudaStreamSynchronize(ctx().stream));
+  for (auto &e : g_group_tables)
+    if (e.first == dom) { cudaFree(e.second.dev); e.second = t; return e.second; }
+  g_group_tables.push_back({dom, t});
+  return g_group_tables.back().second;
+}
+
+void sort_group_forget(const vpb_domain_t *dom) {
+  for (size_t i = 0; i < g_group_tables.size(); i++)
+    if (g_group_tables[i].first == dom) {
+      cudaFree(g_group_tables[i].second.dev);
+      g_group_tables.erase(g_group_tables.begin() + i);
+      return;
+    }
+}
+
+}  // namespace vpb
+
+using namespace vpb;
+
+extern "C" {
+
+// The order of the groups: key(voxel x,y,z) = fx[x] + fy[y] + fz[z] for interior coordinates 1..n (tables of n+2
+// entries; NULL = only the size is wanted).  Returns the number of keys; the partition of a grouped sort has one
+// entry more.  Pure host code (no device needed).
+long vpb_sort_group_order(int nx, int ny, int nz, int *fx, int *fy, int *fz) {
+  if (nx < 1 || ny < 1 || nz < 1) VPB_ERROR("Bad grid size");
+  const GroupOrder o = make_group_order(nx, ny, nz);
+  if (fx) std::copy(o.fx.begin(), o.fx.end(), fx);
+  if (fy) std::copy(o.fy.begin(), o.fy.end(), fy);
+  if (fz) std::copy(o.fz.begin(), o.fz.end(), fz);
+  return o.nkeys;
+}
+
+long vpb_sort_group_keys(vpb_domain_t *dom) {
+  if (!dom) VPB_ERROR("Bad grid");
+  return make_group_order(dom->d.nx, dom->d.ny, dom->d.nz).nkeys;
+}
+
+// Grouping sort of a component-plane array: d_out receives the particles of d_in grouped by the voxel they occupy
+// (lookahead == 0) or will occupy `lookahead` steps from now, groups in the order of vpb_sort_group_order;
+// d_partition (int[keys+1]) the first particle of every group.  The order inside a group is arbitrary.
+void vpb_sort_p_planes_grouped(vpb_domain_t *dom, const vpb_particle_t *d_in, vpb_particle_t *d_out, int np, int *d_partition,
+                               int lookahead) {
+  if (!dom) VPB_ERROR("Bad grid");
+  if (dom->d.p_plane <= 0) VPB_ERROR("the domain keeps its particles in the reference layout: use vpb_sort_p");
+  if (!d_partition) VPB_ERROR("Bad partition");
+  if (np < 0) VPB_ERROR("Bad number of particles");
+  if (lookahead < 0) VPB_ERROR("Bad look-ahead");
+  if (np > 0 && (!d_in || !d_out || d_in == d_out)) VPB_ERROR("Bad particle array");
+  Context &c = ctx();
+  ProfScope prof(1);
+  const DomainDev &gd = dom->d;
+  const GroupTables &T = tables_of(dom);
+  const int nk1 = (int)T.nkeys + 1;
+  auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t off_keys = al((size_t)nk1 * 4), off_scan = off_keys + al((size_t)np * 4 + 4);
+  char *s = (char *)scratch(off_scan + scan_scratch_bytes(nk1));
+  int *cursor = (int *)s, *keys = (int *)(s + off_keys);
+  GroupKeyArgs A;
+  A.L = lookahead; A.sx = gd.sx; A.sy = gd.sy; A.nx = gd.nx; A.ny = gd.ny; A.nz = gd.nz;
+  A.kx = 2.f * lookahead * gd.cvac * gd.dt * gd.rdx;
+  A.ky = 2.f * lookahead * gd.cvac * gd.dt * gd.rdy;
+  A.kz = 2.f * lookahead * gd.cvac * gd.dt * gd.rdz;
+  A.fx = T.dev; A.fy = T.dev + gd.sx; A.fz = T.dev + gd.sx + gd.sy;
+  const PView in(d_in, gd.p_plane), out(d_out, gd.p_plane);
+  VPB_CUDA(cudaMemsetAsync(cursor, 0, (size_t)nk1 * 4, c.stream));
+  if (np > 0) {
+    const long blocks = ((long)np + 255) / 256, cap = (long)c.sm_count * 16;
+    group_keys_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, c.stream>>>(in, np, A, keys, cursor);
+  }
+  exclusive_scan_i32(cursor, d_partition, nk1, s + off_scan, c.stream);   // partition[keys] = np
+  count_launch(1 + scan_launches(nk1));
+  if (np == 0) return;
+  VPB_CUDA(cudaMemcpyAsync(cursor, d_partition, (size_t)nk1 * 4, cudaMemcpyDeviceToDevice, c.stream));
+  static int ctas_per_sm = 0;
+  if (!ctas_per_sm) {
+    VPB_CUDA(cudaFuncSetAttribute(group_move_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem)));
+    VPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, group_move_kernel, kGsThreads, sizeof(GroupSmem)));
+    if (ctas_per_sm < 1) VPB_ERROR("group_move_kernel does not fit on this device");
+  }
+  const int nchunks = (np + kGsChunk - 1) / kGsChunk;
+  const int grid = nchunks < ctas_per_sm * c.sm_count ? nchunks : ctas_per_sm * c.sm_count;
+  group_move_kernel<<<grid, kGsThreads, sizeof(GroupSmem), c.stream>>>(in, out, np, keys, cursor);
+  count_launch(2);
+  VPB_CUDA(cudaGetLastError());
+}
+
+}  // extern "C"

@@ -87,10 +87,20 @@ static void sort_species(vpb_sim *s, Species &sp) {
     s->sort_tmp = (vpb_particle_t *)vpb_dev_alloc(particle_bytes(s, sp.max_np));
     s->sort_tmp_cap = sp.max_np;
   }
-  if (!sp.partition) sp.partition = (int *)vpb_dev_alloc((size_t)(s->nv + 1) * sizeof(int));
-  if (vpb_domain_particle_layout(s->dom) > 0) {
+  const bool planes = vpb_domain_particle_layout(s->dom) > 0;
+  const bool grouped = planes && tuning("sort.grouped", 1) != 0;
+  if (!sp.partition) {
+    const long groups = grouped ? vpb_sort_group_keys(s->dom) : 0;
+    sp.partition = (int *)vpb_dev_alloc((size_t)((groups > s->nv ? groups : s->nv) + 1) * sizeof(int));
+  }
+  if (planes) {
     const int ahead = s->sort_lookahead < 0 ? (3 * sp.sort_interval + 2) / 5 : s->sort_lookahead;
-    vpb_sort_p_planes_ahead(s->dom, sp.p, s->sort_tmp, sp.np, sp.partition, ahead);   // sorted planes return to sp.p
+    if (grouped) {   // same particles grouped by voxel, groups in brick-Morton order (vpb_sort_group.cu); out of place
+      vpb_sort_p_planes_grouped(s->dom, sp.p, s->sort_tmp, sp.np, sp.partition, ahead);
+      std::swap(sp.p, s->sort_tmp);
+    } else {
+      vpb_sort_p_planes_ahead(s->dom, sp.p, s->sort_tmp, sp.np, sp.partition, ahead);   // sorted planes return to sp.p
+    }
   } else {
     vpb_sort_p(s->dom, sp.p, s->sort_tmp, sp.np, sp.partition);
     std::swap(sp.p, s->sort_tmp);                                           // out of place: swap (sort_p.c:76-77)
@@ -189,18 +199,18 @@ static void advance_one(vpb_sim *s) {
     vpb_advance_p_ordered(dom, sp.p, sp.np, sp.q_m, sp.pm, sp.max_nm, s->a, s->fi, sp.nm, sp.partition);
   // reduce_accumulators (:74) is a no-op with one replica
   if (cb.particle_injection) cb.particle_injection(cb.user, s);                        // :85 user_particle_injection
-  migrate(s);                                                                          // :94-103
+  { ProfScope prof(7); migrate(s); }                                                   // :94-103
   vpb_clear_jf(dom, s->f);                                                             // :109
   if (particles) vpb_unload_accumulator(dom, s->f, s->a);                              // :110
-  vpb_synchronize_jf(dom, s->f);                                                       // :112
+  { ProfScope prof(8); vpb_synchronize_jf(dom, s->f); }                                // :112
   if (cb.current_injection) cb.current_injection(cb.user, s);                          // :123 user_current_injection
   vpb_advance_b(dom, s->f, 0.5f);                                                      // :129
   vpb_advance_e(dom, s->f, s->m, s->n_mat, s->vacuum ? 1 : 0);                         // :133
   if (cb.field_injection) cb.field_injection(cb.user, s);                              // :141 user_field_injection
   vpb_advance_b(dom, s->f, 0.5f);                                                      // :147
-  if (s->clean_div_e_interval > 0 && s->step % s->clean_div_e_interval == 0) clean_div_e(s);      // :151
-  if (s->clean_div_b_interval > 0 && s->step % s->clean_div_b_interval == 0) clean_div_b(s);      // :177
-  if (s->sync_shared_interval > 0 && s->step % s->sync_shared_interval == 0) sync_shared(s);      // :199
+  if (s->clean_div_e_interval > 0 && s->step % s->clean_div_e_interval == 0) { ProfScope prof(9); clean_div_e(s); }   // :151
+  if (s->clean_div_b_interval > 0 && s->step % s->clean_div_b_interval == 0) { ProfScope prof(9); clean_div_b(s); }   // :177
+  if (s->sync_shared_interval > 0 && s->step % s->sync_shared_interval == 0) { ProfScope prof(9); sync_shared(s); }   // :199
   if (particles) vpb_load_interpolator(dom, s->fi, s->f);                              // :214
   s->step++;
   if (cb.diagnostics) cb.diagnostics(cb.user, s);                                      // :233 user_diagnostics, after step++

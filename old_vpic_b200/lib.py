@@ -119,6 +119,9 @@ SIGNATURES = {
     "vpb_sort_p": (None, [_vp, _vp, _vp, _i, _vp]),
     "vpb_sort_p_planes": (None, [_vp, _vp, _vp, _i, _vp]),
     "vpb_sort_p_planes_ahead": (None, [_vp, _vp, _vp, _i, _vp, _i]),
+    "vpb_sort_p_planes_grouped": (None, [_vp, _vp, _vp, _i, _vp, _i]),
+    "vpb_sort_group_order": (_l, [_i, _i, _i, _vp, _vp, _vp]),
+    "vpb_sort_group_keys": (_l, [_vp]),
     "vpb_clear_hydro": (None, [_vp, _vp]),
     "vpb_accumulate_hydro_p": (None, [_vp, _vp, _vp, _i, _f, _vp]),
     "vpb_local_adjust_hydro": (None, [_vp, _vp]),

@@ -4,8 +4,12 @@
 // (oracle/_ref/thermal_c1.op, the shipped V4/SSE + pthreads hot path) and on the reference's host objects + libvpic_b200.so
 // (oracle/_ref/hybrid/thermal_c1.b200.op); `bench.py --deck-e2e` times both: the same unmodified host program, the
 // hot path swapped at link time.  Size and length can be changed from the environment: VPB_DECK_CELLS, VPB_DECK_PPC,
-// VPB_DECK_STEPS.
+// VPB_DECK_STEPS.  Every step the diagnostics hook reads the step's result back on the host -- dump_energies (6 field
+// energies + one kinetic energy per species, appended to `energies`) unless VPB_DECK_ENERGIES=0 -- and appends the wall
+// clock to `steps.txt`, so that a caller can time steps W..W+K of the run.
 #include <stdlib.h>
+#include <stdio.h>
+#include <time.h>
 
 begin_globals {
   int dummy;
@@ -49,7 +53,14 @@ begin_initialization {
 }
 
 begin_diagnostics {
-  if( step == 0 || step == num_step ) dump_energies( "energies", step == 0 ? 0 : 1 );
+  const int every = env_int( "VPB_DECK_ENERGIES", 1 );
+  if( step == 0 || step == num_step || ( every > 0 && step % every == 0 ) ) dump_energies( "energies", step == 0 ? 0 : 1 );
+  if( rank() == 0 ) {
+    struct timespec ts;
+    clock_gettime( CLOCK_MONOTONIC, &ts );
+    FILE * fp = fopen( "steps.txt", step == 0 ? "w" : "a" );
+    if( fp ) { fprintf( fp, "%d %.9f\n", int(step), double(ts.tv_sec) + 1e-9 * double(ts.tv_nsec) ); fclose( fp ); }
+  }
 }
 
 begin_particle_injection { }

@@ -492,10 +492,8 @@ def test_sort_p_planes(vpb, orc, n, np_):
     vpb.vpb_domain_destroy(dom)
 
 
-@pytest.mark.parametrize("scatter", [0, 1])
-def test_sort_p_planes_lookahead(vpb, scatter):
-    """scatter = 1: the record-scatter variant of the sort (tuning sort.scatter; not yet run on hardware).
-    Look-ahead sort key (vpb_sort_p_planes_ahead): a grouping of the SAME particles by the voxel they reach `L`
+def test_sort_p_planes_lookahead(vpb):
+    """Look-ahead sort key (vpb_sort_p_planes_ahead): a grouping of the SAME particles by the voxel they reach `L`
     steps ahead at their present velocity; partition[] delimits the groups; L = 0 is the plain (stable) sort."""
     from old_vpic_b200.sim import DevArray, ParticleArray
     n, np_, L = (10, 9, 8), 60001, 7
@@ -507,11 +505,7 @@ def test_sort_p_planes_lookahead(vpb, scatter):
     d_p, d_tmp = ParticleArray(vpb, dom, np_), ParticleArray(vpb, dom, np_)
     d_part = DevArray(vpb, g.nv + 1, np.int32)
     d_p.upload(p)
-    vpb.vpb_set_tuning(b"sort.scatter", scatter)
-    try:
-        vpb.vpb_sort_p_planes_ahead(dom, d_p.ptr, d_tmp.ptr, np_, d_part.ptr, L)
-    finally:
-        vpb.vpb_set_tuning(b"sort.scatter", 0)
+    vpb.vpb_sort_p_planes_ahead(dom, d_p.ptr, d_tmp.ptr, np_, d_part.ptr, L)
     out, part = d_p.download(np_), d_part.download()
     # same particles
     order = np.argsort(out["tag"], kind="stable")
@@ -548,5 +542,65 @@ def test_sort_p_planes_lookahead(vpb, scatter):
     vpb.vpb_sort_p_planes(dom, d_p.ptr, d_tmp.ptr, np_, d_part.ptr)
     assert_bits_equal(ref, d_p.download(np_), "lookahead 0")
     for arr in (d_p, d_tmp, d_part):
+        arr.free()
+    vpb.vpb_domain_destroy(dom)
+
+
+def group_tables(vpb, n):
+    """key(x,y,z) = fx[x] + fy[y] + fz[z] of the grouped sort (host code of the library, csrc/vpb_sort_group.cu)"""
+    fx, fy, fz = (np.zeros(m + 2, np.int32) for m in n)
+    nkeys = vpb.vpb_sort_group_order(n[0], n[1], n[2], fx.ctypes.data, fy.ctypes.data, fz.ctypes.data)
+    return fx, fy, fz, int(nkeys)
+
+
+@pytest.mark.parametrize("n,np_,L,vth", [((10, 9, 8), 60001, 0, 0.5), ((10, 9, 8), 60001, 7, 0.5), ((33, 1, 17), 150000, 0, 0.3),
+                                          ((16, 16, 16), 300000, 4, 0.2), ((5, 4, 3), 63, 0, 0.1), ((40, 36, 20), 2048 * 37 + 5, 3, 0.4)])
+def test_sort_p_planes_grouped(vpb, n, np_, L, vth):
+    """The device-resident driver's sort (vpb_sort_p_planes_grouped): the same particles, bit for bit, grouped by the
+    voxel they occupy (L = 0) or reach L steps ahead, groups in the brick-Morton order of vpb_sort_group_order,
+    partition[] = first particle of every group.  Several sizes: ragged last chunk, fewer particles than a warp, more
+    chunks than resident CTAs' worth of keys, a 2-D grid."""
+    from old_vpic_b200.sim import DevArray, ParticleArray
+    g = host_grid(n)
+    rng = np.random.default_rng(41)
+    p = random_particles(rng, g, np_, vth=vth, sort=False)
+    p["tag"] = np.arange(np_)
+    fx, fy, fz, nkeys = group_tables(vpb, n)
+    dom = vpb.vpb_domain_create(g.ref(), 0, 1)
+    assert vpb.vpb_sort_group_keys(dom) == nkeys
+    vpb.vpb_domain_set_particle_layout(dom, (np_ + 63) // 64 * 64)
+    d_p, d_out = ParticleArray(vpb, dom, np_), ParticleArray(vpb, dom, np_)
+    d_part = DevArray(vpb, nkeys + 1, np.int32)
+    d_p.upload(p)
+    vpb.vpb_sort_p_planes_grouped(dom, d_p.ptr, d_out.ptr, np_, d_part.ptr, L)
+    out, part = d_out.download(np_), d_part.download()
+    assert_bits_equal(d_p.download(np_), p, "the input is left alone")
+    # same particles, every record intact
+    assert_bits_equal(out[np.argsort(out["tag"], kind="stable")], p, "multiset")
+    assert part[0] == 0 and part[-1] == np_ and np.all(np.diff(part) >= 0)
+    sx, sy = n[0] + 2, n[1] + 2
+    s = g.struct
+
+    def keys(q):
+        v = q["i"].astype(np.int64)
+        c = [v % sx, (v // sx) % sy, v // (sx * sy)]
+        if L:
+            u2 = (q["ux"] * q["ux"] + (q["uy"] * q["uy"] + q["uz"] * q["uz"])).astype(np.float32)
+            rg = (np.float32(1) / np.sqrt(np.float32(1) + u2)).astype(np.float32)
+            for a, (d, u, rd) in enumerate(((q["dx"], q["ux"], s.rdx), (q["dy"], q["uy"], s.rdy), (q["dz"], q["uz"], s.rdz))):
+                k = np.float32(2.0 * L * s.cvac * s.dt * rd)
+                pos = (d + k * u * rg + np.float32(1)) * np.float32(0.5)
+                c[a] = np.clip(c[a] + np.floor(pos).astype(np.int64), 1, n[a])
+        return fx[c[0]].astype(np.int64) + fy[c[1]] + fz[c[2]]
+
+    dev_key = np.repeat(np.arange(nkeys), np.diff(part))        # the key the device gave every output slot
+    assert len(dev_key) == np_
+    k_out = keys(out)
+    if L == 0:
+        assert np.array_equal(dev_key, k_out)                   # integer arithmetic: exact
+    else:
+        # rsqrt on the device is approximate: a key may differ where the predicted position sits on a cell face
+        assert np.mean(dev_key != k_out) < 1e-3
+    for arr in (d_p, d_out, d_part):
         arr.free()
     vpb.vpb_domain_destroy(dom)
