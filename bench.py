@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--workload", default="thermal", choices=["thermal", "fields", "harris"],
                     help="thermal: BASELINE configs[3] (the headline, default); fields: configs[1] alone; harris: configs[2], the "
                          "trecon-part shape 2048x1x1024 cells x 100 ppc on one GPU")
+    ap.add_argument("--trecon-deck", action="store_true",
+                    help="with --workload harris: also run the reference's trecon-part deck itself (unmodified turbulence.cxx, "
+                         "config.h knobs 2048 x 1 x 1024, one rank) on libvpic_b200.so -- minutes of host-side load and I/O")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-deck-e2e", dest="deck_e2e", action="store_false",
                     help="skip the deck_e2e key: BASELINE configs[0] as an unmodified reference host program "
@@ -230,6 +233,35 @@ def deck_e2e(exe, steps, warmup, tpp, what, timeout=240, cells=64, ppc=32):
             "sample": "%s: BASELINE configs[0], thermal %d^3 cells x %d ppc x 2 species (%d particles), %d timed steps of "
                       "vpic_simulation::advance() after %d warm-up steps (sort every 20, energies read back every step), "
                       "unmodified reference host program, -tpp=%d" % (what, n, ppc, 2 * n ** 3 * ppc, steps, warmup, tpp)}
+
+
+def trecon_deck(exe, cells, steps, tpp, what, timeout):
+    """decks/trecon-part/turbulence.cxx with other config.h knobs (oracle/build_hybrid.sh: symlinked deck sources + a
+    generated config.h), as a whole program: the deck loads nppc = 50 particles per cell per species on the host (four
+    species + two tracer species that copy them), pushes the tracers itself from its particle-injection hook, dumps
+    fields and hydro moments every 20 steps.  Rate = particle pushes (tracers included) over the `simulation time` the
+    reference's main loop prints."""
+    import re
+    import tempfile
+    if not os.path.exists(exe):
+        return {"unavailable": "%s not built" % os.path.relpath(exe, ROOT)}
+    try:
+        with tempfile.TemporaryDirectory() as t:
+            t0 = time.perf_counter()
+            r = subprocess.run([exe, "-tpp=%d" % tpp], cwd=t, capture_output=True, text=True, timeout=timeout)
+            wall = time.perf_counter() - t0
+            m = re.search(r"simulation time: ([0-9.eE+-]+)", r.stdout + r.stderr)
+            if r.returncode != 0 or not m:
+                return {"unavailable": "deck exited %d: %s" % (r.returncode, (r.stdout + r.stderr)[-300:])}
+            sec = float(m.group(1))
+    except Exception as e:          # noqa: BLE001
+        return {"unavailable": repr(e)[:300]}
+    pushed = 4 * 50 * cells          # e + i, each also copied into a tracer species (particle_select = 1)
+    return {"value": pushed * steps / sec, "unit": "particle-advances/s", "ms_per_step": 1e3 * sec / steps, "steps": steps,
+            "particles_pushed_per_step": pushed, "process_wall_s": wall,
+            "sample": "%s: decks/trecon-part/turbulence.cxx, config.h knobs %s cells, topology 1x1x1, %d steps; nppc 50 as shipped "
+                      "(BASELINE asks 100: a constant in the deck body, not a knob), tracer copies pushed by the deck, field + hydro "
+                      "dumps every 20 steps; -tpp=%d" % (what, cells, steps, tpp)}
 
 
 def workload_config(args):
@@ -448,6 +480,16 @@ def run_b200(args):
         line["fields_c2"] = fields_c2
     # release the big run before the other legs
     sim.free()
+    if harris and args.trecon_deck:
+        hyb = os.path.join(ROOT, "oracle", "_ref", "hybrid")
+        line["trecon_deck"] = trecon_deck(os.path.join(hyb, "turbulence_c2.b200.op"), 2048 * 1024, 60, 1,
+                                          "reference host objects + libvpic_b200.so", 1500)
+        # the same deck at a shape the CPU finishes in seconds, both ways, for a like-for-like ratio
+        tpp = max(1, min(os.cpu_count() or 1, 16))
+        line["trecon_deck_scaled"] = {
+            "b200": trecon_deck(os.path.join(hyb, "turbulence_c2s.b200.op"), 128 * 64, 200, 1, "reference host objects + libvpic_b200.so", 600),
+            "reference": trecon_deck(os.path.join(ROOT, "oracle", "_ref", "turbulence_c2s_sse.op"), 128 * 64, 200, tpp,
+                                     "reference alone (V4/SSE + pthreads)", 600)}
     if args.deck_e2e and not args.no_e2e:
         # e2e: the reference-facing path.  An unmodified reference host program (HOST-allocated arrays, HOST particle
         # load) on libvpic_b200.so; at N > 1 this is still rank 0's GPU alone (said in the key)

@@ -295,6 +295,21 @@ void vpb_sort_p_planes_ahead(vpb_domain_t *dom, vpb_particle_t *d_p, vpb_particl
  * group; the order inside a group is arbitrary.  Same particles, same physics as sort_p (sort_p.c:16-77), whose only
  * purpose is that particles of a voxel are neighbours in the array; the reference's ORDER and partition[] are what
  * sort_p / vpb_sort_p / vpb_sort_p_planes deliver. */
+/* Deck-side particle diagnostics on the device (csrc/vpb_diag.cu).  vpb_energy_spectrum =
+ * decks/trecon-part/energy.cxx:90-176: dist[k*nvoxel + voxel] counts the particles of a voxel in nex kinetic-energy bands
+ * of width dke (the last band open-ended), normalised per cell, ghost cells copied from their interior neighbour exactly
+ * as that loop does; edist[nbin] is the global spectrum over log-spaced bins between eminp and emaxp.  Either output may
+ * be NULL.  vpb_tracer_records = dump_tracers of tracer.cxx:125-160: thirteen floats per particle (q, global x y z,
+ * ux uy uz, ex ey ez, cbx cby cbz); field_of_first != 0 reproduces the macro's `field[p->i]` (the voxel of the FIRST
+ * particle for every record), 0 uses each particle's own voxel.  Device pointers; the vpb_deck_* forms take the deck's
+ * own (host or managed) arrays and return with the results on the host. */
+void vpb_energy_spectrum(vpb_domain_t *dom, const vpb_particle_t *d_p, int np, double dke, int nex, float *d_dist, double eminp,
+                         double emaxp, int nbin, float *d_edist);
+void vpb_tracer_records(vpb_domain_t *dom, const vpb_particle_t *d_p, int np, const vpb_field_t *d_f, float x0, float y0, float z0,
+                        int field_of_first, float *d_out);
+void vpb_deck_energy_spectrum(const vpb_particle_t *p0, int np, double dke, int nex, float *dist, double eminp, double emaxp, int nbin,
+                              float *edist, const vpb_grid_t *g);
+void vpb_deck_tracer_records(const vpb_particle_t *p0, int np, const vpb_field_t *f, float *out13, int field_of_first, const vpb_grid_t *g);
 void vpb_sort_p_planes_grouped(vpb_domain_t *dom, const vpb_particle_t *d_in, vpb_particle_t *d_out, int np, int *d_partition, int lookahead);
 long vpb_sort_group_order(int nx, int ny, int nz, int *fx, int *fy, int *fz);
 long vpb_sort_group_keys(vpb_domain_t *dom);

@@ -166,6 +166,9 @@ __global__ void __launch_bounds__(256) classify_kernel(const PView p, const vpb_
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= nm) return;
   const int pi = pm[k].i;
+  // the hole filling below (and the reference's, boundary_p.c:168-176,243-247) needs the movers in ascending particle
+  // order; advance_p and inject_particle produce them that way, a list built by other host code might not
+  if (k + 1 < nm && pm[k + 1].i <= pi) atomicAdd(n_unknown + 1, 1);
   const float4 r0 = p.pos(pi);
   const float4 r1 = p.mom(pi);
   const int vi = __float_as_int(r0.w);
@@ -433,6 +436,9 @@ void vpb_boundary_p(vpb_domain_t *dom, vpb_species_state_t *sp, int n_sp, vpb_fi
   for (int f = 0; f < 6; f++) { ns[f] = c.h_pinned_i[f]; nr[f] = remote[f] ? c.h_pinned_i[8 + f] : 0; }
   if (c.h_pinned_i[33])
     VPB_WARNING("Unknown boundary interaction ... using absorption (%d particles, rank=%d)", c.h_pinned_i[33], g.rank);
+  if (c.h_pinned_i[34])
+    VPB_ERROR("boundary_p: a mover list is not in ascending particle order (%d inversions); removing its particles would "
+              "overwrite live ones (boundary_p.c:168-176 relies on the same order)", c.h_pinned_i[34]);
   for (int f = 0; f < 6; f++) {
     if (ns[f] && !remote[f]) VPB_ERROR("movers classified for face %d which is not shared with another rank", f);
     const int need = ns[f] > nr[f] ? ns[f] : nr[f];

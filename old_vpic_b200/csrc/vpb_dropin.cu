@@ -1020,6 +1020,36 @@ vpb_field_advance_methods_t *vpb_field_advance_table(int which) {
   return nullptr;
 }
 
+// ---------------------------------------------------------------------------
+// Deck-side particle diagnostics on the device (vpb_diag.cu), for host / managed arrays: what a deck calls INSTEAD of
+// its host loops over sp->p (decks/trecon-part/energy.cxx:90-176, tracer.cxx:125-160).  Only the results cross PCIe.
+// ---------------------------------------------------------------------------
+void vpb_deck_energy_spectrum(const vpb_particle_t *p0, int np, double dke, int nex, float *dist, double eminp, double emaxp, int nbin,
+                              float *edist, const vpb_grid_t *g) {
+  TraceScope _ts("deck_energy_spectrum");
+  if (!g) VPB_ERROR("Bad grid");
+  vpb_domain_t *dom = domain_of(g);
+  Residency r;
+  const vpb_particle_t *dp = (const vpb_particle_t *)r.get(p0, (size_t)np * sizeof(*p0), RD);
+  float *dd = dist ? (float *)r.get(dist, (size_t)nex * nvox(g) * sizeof(float), WR) : nullptr;
+  float *de = edist ? (float *)r.get(edist, (size_t)nbin * sizeof(float), WR) : nullptr;
+  vpb_energy_spectrum(dom, dp, np, dke, nex, dd, eminp, emaxp, nbin, de);
+  r.finish();
+}
+
+void vpb_deck_tracer_records(const vpb_particle_t *p0, int np, const vpb_field_t *f, float *out13, int field_of_first, const vpb_grid_t *g) {
+  TraceScope _ts("deck_tracer_records");
+  if (!g) VPB_ERROR("Bad grid");
+  if (np <= 0) return;
+  vpb_domain_t *dom = domain_of(g);
+  Residency r;
+  const vpb_particle_t *dp = (const vpb_particle_t *)r.get(p0, (size_t)np * sizeof(*p0), RD);
+  const vpb_field_t *df = (const vpb_field_t *)r.get(f, nvox(g) * sizeof(*f), RD);
+  float *dout = (float *)r.get(out13, (size_t)np * 13 * sizeof(float), WR);
+  vpb_tracer_records(dom, dp, np, df, g->x0, g->y0, g->z0, field_of_first, dout);
+  r.finish();
+}
+
 // bytes moved by the staging path since the last call (bench.py e2e accounting)
 void vpb_staging_bytes(size_t *h2d, size_t *d2h) { *h2d = g_h2d_total; *d2h = g_d2h_total; g_h2d_total = g_d2h_total = 0; }
 

@@ -119,6 +119,10 @@ SIGNATURES = {
     "vpb_sort_p": (None, [_vp, _vp, _vp, _i, _vp]),
     "vpb_sort_p_planes": (None, [_vp, _vp, _vp, _i, _vp]),
     "vpb_sort_p_planes_ahead": (None, [_vp, _vp, _vp, _i, _vp, _i]),
+    "vpb_energy_spectrum": (None, [_vp, _vp, _i, C.c_double, _i, _vp, C.c_double, C.c_double, _i, _vp]),
+    "vpb_tracer_records": (None, [_vp, _vp, _i, _vp, _f, _f, _f, _i, _vp]),
+    "vpb_deck_energy_spectrum": (None, [_vp, _i, C.c_double, _i, _vp, C.c_double, C.c_double, _i, _vp, _vp]),
+    "vpb_deck_tracer_records": (None, [_vp, _i, _vp, _vp, _i, _vp]),
     "vpb_sort_p_planes_grouped": (None, [_vp, _vp, _vp, _i, _vp, _i]),
     "vpb_sort_group_order": (_l, [_i, _i, _i, _vp, _vp, _vp]),
     "vpb_sort_group_keys": (_l, [_vp]),

@@ -7,6 +7,10 @@ oracle/build_ref.sh + oracle/build_hybrid.sh have compiled /root/reference into 
   deck_turbulence_energies.txt              decks/trecon-part/turbulence.cxx AS SHIPPED (config.h: 16x16x1 cells,
                                             topology 2x2x1, 2500 steps) on oracle/_ref/turbulence.op, four ranks over
                                             oracle/mpi_shim's shared-memory transport
+  deck_turbulence_c2s_energies.txt          the same deck source with the config.h knobs of a scaled-down BASELINE
+                                            configs[2] (128 x 1 x 64 cells, one rank, 200 steps; the directory of
+                                            symlinks + generated config.h that oracle/build_hybrid.sh makes) on
+                                            oracle/_ref/turbulence_c2s.op
 
 The hot path of these executables is the reference's scalar flavour, the one libvpic_b200 reproduces bit for bit per
 call.  usage: python tests/golden/make_deck_golden.py [--check]   (--check: compare instead of overwrite)"""
@@ -74,6 +78,10 @@ def main():
         os.mkdir(w)
         run_ranks(os.path.join(REF, "turbulence.op"), 4, w)
         ok &= emit(os.path.join(w, "rundata", "energies"), "deck_turbulence_energies.txt", check)
+        w = os.path.join(t, "turbulence_c2s")
+        os.mkdir(w)
+        run_one("turbulence_c2s", w)
+        ok &= emit(os.path.join(w, "rundata", "energies"), "deck_turbulence_c2s_energies.txt", check)
     sys.exit(0 if ok else 1)
 
 

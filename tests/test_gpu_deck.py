@@ -205,3 +205,30 @@ def test_trecon_part_deck_as_shipped(tmp_path):
     assert rel[:, :6].max() < 1e-4 and rel[:, 6:].max() < 2e-2, rel.max(axis=0)
     # the first interval is still deterministic enough for a tight check
     assert (np.abs(got[1, 1:] - want[1, 1:]) / scale).max() < 1e-3
+
+
+def test_trecon_part_deck_at_a_scaled_configs2_shape(tmp_path):
+    """BASELINE configs[2] is "decks/trecon-part, 2D 2048 x 1 x 1024 cells on one B200": the reference's deck source with
+    other config.h knobs.  oracle/build_hybrid.sh builds it -- a directory of symlinks to the
+    reference's turbulence.cxx / tracer.cxx / energy.cxx plus a generated config.h -- at 128 x 1 x 64 cells, one rank,
+    200 steps, on libvpic_b200.so; here it runs on the GPU (four species, two tracer species pushed by the deck's own
+    advance_p / boundary_p / sort_p calls against a private accumulator, field / hydro / particle dumps) and its energies
+    are compared with the pure reference's.  Yardstick: the reference's V4/SSE and scalar flavours differ by 3.3e-6 of
+    the total field energy in the field columns and 3.2e-4 in the species columns at step 200 on this shape."""
+    exe = EXE.replace("thermal_small", "turbulence_c2s")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/hybrid/turbulence_c2s.b200.op not built (needs /root/reference at build time)")
+    r = subprocess.run([exe, "-tpp=1"], cwd=tmp_path, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    got = read_energies(tmp_path / "rundata" / "energies")
+    want = read_energies(GOLD.replace("thermal_small", "turbulence_c2s"))
+    assert got.shape == want.shape == (3, 11)
+    assert np.array_equal(got[:, 0], want[:, 0])
+    scale = np.abs(want[:, 1:]).max(axis=0)
+    scale[:6] = want[:, 1:7].sum(axis=1).max()
+    rel = np.abs(got[:, 1:] - want[:, 1:]) / scale
+    assert rel[:, :6].max() < 1e-4 and rel[:, 6:].max() < 2e-3, rel.max(axis=0)
+    # the dumps the deck makes through the library's arrays exist and have the reference's sizes
+    for name in ("fields", "hydro", "particle", "tracer", "names"):
+        assert (tmp_path / name).is_dir()
+    assert (tmp_path / "particle" / "T.200").is_dir()
