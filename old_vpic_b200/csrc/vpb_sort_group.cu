@@ -14,11 +14,11 @@
 //
 // Here the key of a voxel is  Morton(brick) * brick_volume + index inside the brick,  bricks of 8 x 4 x 4 voxels:
 // spatial neighbours are neighbours in the array (for all but a geometrically small share of brick faces), so
-//   * a chunk of 2048 consecutive source particles (a quarter of a brick) sends its particles to a few dozen
+//   * a chunk of 1024 consecutive source particles (an eighth of a brick) sends its particles to a few dozen
 //     destination groups, most of them in the same or an adjacent brick;
 //   * the chunk is bucketed in shared memory (hash table of its destination keys, one global atomic per distinct key
-//     claims the slots), its plane words are staged in shared memory with coalesced loads and leave in destination
-//     order: runs of a group's particles, i.e. mostly whole 32-byte sectors;
+//     claims the slots) while its plane words arrive in shared memory by bulk async copies (cp.async.bulk), and they
+//     leave in destination order: runs of a group's particles, i.e. mostly whole 32-byte sectors;
 //   * the lines a chunk only partly fills are completed by chunks that run at almost the same time, while they are
 //     still in L2.
 // Traffic per particle: keys pass 28 B read (4 B without look-ahead) + 4 B written; move pass 4 + 48 B read, 48 B
@@ -139,47 +139,92 @@ __global__ void __launch_bounds__(256) group_keys_kernel(const PView p, int np, 
   }
 }
 
-constexpr int kGsThreads = 256, kGsPer = 8, kGsChunk = kGsThreads * kGsPer, kGsHash = 4096;
+constexpr int kGsThreads = 256, kGsPer = 4, kGsChunk = kGsThreads * kGsPer, kGsHash = 2 * kGsChunk;
 
 struct GroupSmem {
+  union {
+    float w[8][kGsChunk];            // the eight word planes of the chunk ...
+    float4 pad_[2 * kGsChunk];
+  } data;
+  float4 tag[kGsChunk];              // ... and its tag plane, filled by bulk async copies (cp.async.bulk, SASS UBLKCP)
   int hkey[kGsHash];                 // key of the slot (-1 free); after the claim: first destination of the chunk's group
   int hcnt[kGsHash];                 // particles of the chunk with that key; after the claim: their first local position
   int ldst[kGsChunk];                // destination of the particle at local position l
   unsigned short lsrc[kGsChunk];     // its index inside the chunk
-  union {
-    float w[4][kGsChunk];            // four word planes of the chunk
-    float4 t[kGsChunk];              // or its tag plane
-  } buf;
   int wsum[kGsThreads / 32];
+  unsigned long long full;           // mbarrier: the chunk's 48 bytes per particle have landed
 };
 
+__device__ __forceinline__ uint32_t gs_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void gs_bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void gs_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+
 // pass 3: move.  cursor[] starts as a copy of partition[]; one atomicAdd per (chunk, distinct key) claims the slots.
-__global__ void __launch_bounds__(kGsThreads) group_move_kernel(const PView in, const PView out, int np, const int *__restrict__ keys,
-                                                                int *__restrict__ cursor) {
-  extern __shared__ __align__(16) unsigned char gs_raw[];
+// A CTA works on chunks of 1024 consecutive source particles.  Per chunk: one thread starts the bulk copies of the
+// chunk's nine planes into shared memory; meanwhile all threads bucket the chunk by key (its keys were requested one
+// chunk earlier), claim the destination ranges and lay out the local order; then the words leave shared memory in
+// destination order.  Three CTAs per SM are in different phases at any time.
+template <int EVICT_LAST>
+__global__ void __launch_bounds__(kGsThreads, 3) group_move_kernel(const PView in, const PView out, int np, const int *__restrict__ keys,
+                                                                   int *__restrict__ cursor) {
+  extern __shared__ __align__(128) unsigned char gs_raw[];
   GroupSmem &S = *reinterpret_cast<GroupSmem *>(gs_raw);
   const unsigned full = 0xffffffffu;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const unsigned lt = (1u << lane) - 1u;
+  const uint32_t bar = gs_smem_u32(&S.full);
   for (int s = tid; s < kGsHash; s += kGsThreads) { S.hkey[s] = -1; S.hcnt[s] = 0; }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
+  const uint64_t pol_in = l2_policy_evict_first(), pol_out = l2_policy_evict_last();
   const int nchunks = (np + kGsChunk - 1) / kGsChunk;
   const size_t pli = (size_t)in.plane, plo = (size_t)out.plane;
-  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+  // keys of a chunk, requested a whole chunk ahead
+  int key_next[kGsPer];
+  auto load_keys = [&](int chunk) {
+    const int c0 = chunk * kGsChunk;
+#pragma unroll
+    for (int j = 0; j < kGsPer; j++) {
+      const int i = c0 + j * kGsThreads + tid;
+      key_next[j] = (chunk < nchunks && i < np) ? __ldcs(keys + i) : -1;
+    }
+  };
+  load_keys(blockIdx.x);
+  uint32_t parity = 0;
+  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, parity ^= 1u) {
     const int c0 = chunk * kGsChunk;
     const int nvalid = np - c0 < kGsChunk ? np - c0 : kGsChunk;
+    if (tid == 0) {
+      // word planes: a multiple of 16 bytes (the plane stride is a multiple of 64 particles, so rounding the count up to
+      // 4 stays inside the allocation); tags: 16 bytes each
+      const uint32_t wbytes = (uint32_t)((nvalid + 3) & ~3) * 4u, tbytes = (uint32_t)nvalid * 16u;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(8u * wbytes + tbytes) : "memory");
+#pragma unroll
+      for (int c = 0; c < 8; c++) gs_bulk_load(gs_smem_u32(&S.data.w[c][0]), in.b + (size_t)c * pli + c0, wbytes, bar, pol_in);
+      gs_bulk_load(gs_smem_u32(&S.tag[0]), reinterpret_cast<const float4 *>(in.b + 8 * pli) + c0, tbytes, bar, pol_in);
+    }
     // ---- bucket the chunk by key: (slot, rank inside the slot) per particle, one table insert per distinct key and warp
     int slot[kGsPer], rank[kGsPer];
 #pragma unroll
     for (int j = 0; j < kGsPer; j++) {
-      const int i = j * kGsThreads + tid;
-      const bool valid = i < nvalid;
-      const int key = valid ? __ldcs(keys + c0 + i) : -1 - lane;
+      const bool valid = j * kGsThreads + tid < nvalid;
+      const int key = valid ? key_next[j] : -1 - lane;
       const unsigned peers = __match_any_sync(full, key);
       const int leader = __ffs(peers) - 1;
       int s = 0, r0 = 0;
       if (valid && lane == leader) {
-        s = (int)(((unsigned)key * 2654435761u) >> 20) & (kGsHash - 1);
+        s = (int)(((unsigned)key * 2654435761u) >> 19) & (kGsHash - 1);
         for (;;) {   // linear probing; at most half of the table is ever in use
           const int old = atomicCAS(&S.hkey[s], -1, key);
           if (old == -1 || old == key) break;
@@ -192,6 +237,7 @@ __global__ void __launch_bounds__(kGsThreads) group_move_kernel(const PView in, 
       slot[j] = valid ? s : -1;
       rank[j] = r0 + __popc(peers & lt);
     }
+    load_keys(chunk + gridDim.x);                      // in flight until the next iteration
     __syncthreads();
     // ---- the particle of rank 0 speaks for its group: local offset by a block-wide exclusive scan of the group
     //      sizes, destination by ONE global atomic
@@ -203,6 +249,9 @@ __global__ void __launch_bounds__(kGsThreads) group_move_kernel(const PView in, 
       gkey[j] = lead ? S.hkey[slot[j]] : -1;
       mine += gcnt[j];
     }
+    int base[kGsPer];
+#pragma unroll
+    for (int j = 0; j < kGsPer; j++) base[j] = gkey[j] >= 0 ? atomicAdd(cursor + gkey[j], gcnt[j]) : 0;   // issued together
     int incl = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -216,7 +265,7 @@ __global__ void __launch_bounds__(kGsThreads) group_move_kernel(const PView in, 
 #pragma unroll
     for (int j = 0; j < kGsPer; j++)
       if (gkey[j] >= 0) {
-        S.hkey[slot[j]] = atomicAdd(cursor + gkey[j], gcnt[j]);
+        S.hkey[slot[j]] = base[j];
         S.hcnt[slot[j]] = run;
         run += gcnt[j];
       }
@@ -228,51 +277,34 @@ __global__ void __launch_bounds__(kGsThreads) group_move_kernel(const PView in, 
         S.lsrc[l] = (unsigned short)(j * kGsThreads + tid);
         S.ldst[l] = S.hkey[slot[j]] + rank[j];
       }
-    // ---- move the words: coalesced loads into shared memory, out in destination order
+    __syncthreads();
+    // leave the table empty for the next chunk (nobody reads it any more)
 #pragma unroll
-    for (int half = 0; half < 2; half++) {
+    for (int j = 0; j < kGsPer; j++)
+      if (slot[j] >= 0) { S.hkey[slot[j]] = -1; S.hcnt[slot[j]] = 0; }
+    // ---- the chunk's words have landed: out they go, in destination order
+    gs_mbar_wait(bar, parity);
+    float4 *tdst = reinterpret_cast<float4 *>(out.b + 8 * plo);
 #pragma unroll
-      for (int c = 0; c < 4; c++) {
-        const float *src = in.b + (size_t)(4 * half + c) * pli + c0;
+    for (int j = 0; j < kGsPer; j++) {
+      const int l = j * kGsThreads + tid;
+      if (l < nvalid) {
+        const int sidx = S.lsrc[l];
+        const int d = S.ldst[l];
+        float *dst = out.b + d;
+        if (EVICT_LAST) {
 #pragma unroll
-        for (int j = 0; j < kGsPer; j++) {
-          const int i = j * kGsThreads + tid;
-          if (i < nvalid) S.buf.w[c][i] = __ldcs(src + i);
+          for (int c = 0; c < 8; c++)
+            asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(dst + (size_t)c * plo), "f"(S.data.w[c][sidx]), "l"(pol_out) : "memory");
+          st_hint4(tdst + d, S.tag[sidx], pol_out);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; c++) dst[(size_t)c * plo] = S.data.w[c][sidx];
+          tdst[d] = S.tag[sidx];
         }
       }
-      __syncthreads();                                 // (first half: also publishes lsrc / ldst)
-#pragma unroll
-      for (int j = 0; j < kGsPer; j++) {
-        const int l = j * kGsThreads + tid;
-        if (l < nvalid) {
-          const int sidx = S.lsrc[l];
-          float *dst = out.b + (size_t)(4 * half) * plo + S.ldst[l];
-#pragma unroll
-          for (int c = 0; c < 4; c++) dst[(size_t)c * plo] = S.buf.w[c][sidx];
-        }
-      }
-      __syncthreads();
     }
-    {
-      const float4 *src = reinterpret_cast<const float4 *>(in.b + 8 * pli) + c0;
-#pragma unroll
-      for (int j = 0; j < kGsPer; j++) {
-        const int i = j * kGsThreads + tid;
-        if (i < nvalid) S.buf.t[i] = __ldcs(src + i);
-      }
-      __syncthreads();
-      float4 *dst = reinterpret_cast<float4 *>(out.b + 8 * plo);
-#pragma unroll
-      for (int j = 0; j < kGsPer; j++) {
-        const int l = j * kGsThreads + tid;
-        if (l < nvalid) dst[S.ldst[l]] = S.buf.t[S.lsrc[l]];
-      }
-      // leave the table empty for the next chunk
-#pragma unroll
-      for (int j = 0; j < kGsPer; j++)
-        if (slot[j] >= 0) { S.hkey[slot[j]] = -1; S.hcnt[slot[j]] = 0; }
-      __syncthreads();
-    }
+    __syncthreads();                                   // the data buffer and the table are free again
   }
 }
 
@@ -367,15 +399,18 @@ void vpb_sort_p_planes_grouped(vpb_domain_t *dom, const vpb_particle_t *d_in, vp
   count_launch(1 + scan_launches(nk1));
   if (np == 0) return;
   VPB_CUDA(cudaMemcpyAsync(cursor, d_partition, (size_t)nk1 * 4, cudaMemcpyDeviceToDevice, c.stream));
-  static int ctas_per_sm = 0;
-  if (!ctas_per_sm) {
-    VPB_CUDA(cudaFuncSetAttribute(group_move_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem)));
-    VPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, group_move_kernel, kGsThreads, sizeof(GroupSmem)));
-    if (ctas_per_sm < 1) VPB_ERROR("group_move_kernel does not fit on this device");
+  static int ctas_per_sm[2] = {0, 0};
+  const int ev = tuning("sort.evict_last", 0) ? 1 : 0;
+  auto kern = ev ? group_move_kernel<1> : group_move_kernel<0>;
+  if (!ctas_per_sm[ev]) {
+    VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem)));
+    VPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[ev], kern, kGsThreads, sizeof(GroupSmem)));
+    if (ctas_per_sm[ev] < 1) VPB_ERROR("group_move_kernel does not fit on this device");
   }
   const int nchunks = (np + kGsChunk - 1) / kGsChunk;
-  const int grid = nchunks < ctas_per_sm * c.sm_count ? nchunks : ctas_per_sm * c.sm_count;
-  group_move_kernel<<<grid, kGsThreads, sizeof(GroupSmem), c.stream>>>(in, out, np, keys, cursor);
+  const int want = ctas_per_sm[ev] * c.sm_count;
+  const int grid = nchunks < want ? nchunks : want;
+  kern<<<grid, kGsThreads, sizeof(GroupSmem), c.stream>>>(in, out, np, keys, cursor);
   count_launch(2);
   VPB_CUDA(cudaGetLastError());
 }
