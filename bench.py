@@ -459,7 +459,9 @@ def run_b200(args):
         "sort_p": {"ms_per_sort": (sum(sort_list) / len(sort_list)) if sort_list else None, "sorts_timed": len(sort_list),
                    "particles_per_sort": np_, "algorithmic_bytes_per_particle": 100.0,
                    "frac": (100.0 * np_ / (sum(sort_list) / len(sort_list) * 1e-3) / 1e9 / peak) if sort_list else None,
-                   "kernel": "group_keys_kernel + group_move_kernel (csrc/vpb_sort_group.cu)"
+                   "kernel": ({2: "group_keys_kernel + group_invert_kernel + group_gather_kernel", 1: "group_keys_kernel + group_scatter_kernel",
+                               0: "group_keys_kernel + group_move_kernel"}[int(os.environ.get("VPB_SORT_GROUP_VARIANT", "2"))]
+                              + " (csrc/vpb_sort_group.cu)")
                              if int(os.environ.get("VPB_SORT_GROUPED", "1")) else "round-1 pipeline (csrc/vpb_particles.cu)"},
         "div_clean": {"ms_per_cleaning_step": clean_ms, "interval": args.clean_div_interval,
                       "amortised_ms_per_step": clean_ms / args.clean_div_interval if args.clean_div_interval > 0 else 0.0,
@@ -473,7 +475,7 @@ def run_b200(args):
         # effective values: the environment override if there is one, else the library's default
         "tuning": {k: int(os.environ.get("VPB_" + k.upper().replace(".", "_"), d)) for k, d in (
             ("advance_p.pair_variant", 1), ("advance_p.pair_cps", 4), ("advance_p.pair_pipe", 1), ("advance_p.pair_merge", 1),
-            ("sort.grouped", 1), ("sim.aos_fields", 0), ("sim.narrow_interpolator", 0), ("sim.aos_particles", 0),
+            ("sort.grouped", 1), ("sort.group_variant", 2), ("sim.aos_fields", 0), ("sim.narrow_interpolator", 0), ("sim.aos_particles", 0),
             ("advance_p.tma", 2), ("advance_p.stream_cps", 5), ("advance_p.stream_store", 0), ("advance_p.deposit", 1))},
     }
     if fields_c2 is not None:

@@ -99,6 +99,7 @@ static GroupOrder make_group_order(int nx, int ny, int nz) {
 // ---- device -------------------------------------------------------------------------------------------------------
 struct GroupKeyArgs {
   int L, sx, sy, nx, ny, nz;
+  unsigned long long msx, msy;  // ceil(2^64 / sx), ceil(2^64 / sy): v / sx == umul64hi(v, msx) for every 32-bit v
   float kx, ky, kz;             // 2 * L * c dt / d{x,y,z} (vpb_particles.cu: SortAhead)
   const int *fx, *fy, *fz;
 };
@@ -107,7 +108,8 @@ struct GroupKeyArgs {
 // clamped to the interior (look-ahead grouping).
 __device__ __forceinline__ int group_key(const PView &p, int k, const GroupKeyArgs &A) {
   const int v = p.voxel(k);
-  const int ix = v % A.sx, t = v / A.sx, iy = t % A.sy, iz = t / A.sy;
+  const int t = (int)__umul64hi((unsigned long long)(unsigned)v, A.msx), ix = v - t * A.sx;
+  const int iz = (int)__umul64hi((unsigned long long)(unsigned)t, A.msy), iy = t - iz * A.sy;
   int cx = ix, cy = iy, cz = iz;
   if (A.L > 0) {
     const size_t pl = (size_t)p.plane;
@@ -308,6 +310,82 @@ __global__ void __launch_bounds__(kGsThreads, 3) group_move_kernel(const PView i
   }
 }
 
+
+// ---- pass 3, destination-driven (the default) -----------------------------------------------------------------------
+// The chunk kernel above scatters 4-byte words: a destination sector (eight particles of one plane) is assembled from
+// the partial writes of several CTAs, and whatever part of it has left L2 before the last writer arrives costs a
+// partial DRAM write now and a read-modify-write later (ncu, 2^30 particles ten steps after a sort: 2.0 G write misses
+// for 1.6 G distinct sectors, 87 GB read + 73 GB written for 56 + 52 GB of payload).  Reads have no such penalty, so
+// the move is turned around: group_invert_kernel claims a slot per particle (one atomic per distinct key and warp) and
+// records src[slot]; group_gather_kernel walks the DESTINATION in order -- src[] and every output plane are coalesced,
+// full-line streaming stores -- and gathers the nine source words of a slot.  Blocks are dispatched in destination
+// order, i.e. (the array being nearly sorted) in source order too, so the source sectors a warp touches are the ones
+// its neighbours in time touch: they are fetched from DRAM once and served from L2/L1 afterwards.
+__global__ void __launch_bounds__(256) group_invert_kernel(int np, const int *__restrict__ keys, int *__restrict__ cursor,
+                                                           int *__restrict__ src) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const long stride = (long)gridDim.x * blockDim.x;
+  const long n_round = ((long)np + 31) & ~31L;
+  for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < n_round; k += stride) {
+    const bool valid = k < np;
+    const int key = valid ? __ldcs(keys + k) : -1 - lane;
+    const unsigned peers = __match_any_sync(full, key);
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (valid && lane == leader) base = atomicAdd(cursor + key, __popc(peers));
+    base = __shfl_sync(full, base, leader);
+    if (valid) src[base + __popc(peers & lt)] = (int)k;
+  }
+}
+
+__global__ void __launch_bounds__(256) group_gather_kernel(const PView in, const PView out, int np, const int *__restrict__ src) {
+  const int d = blockIdx.x * 256 + threadIdx.x;
+  if (d >= np) return;
+  const int s = __ldcs(src + d);
+  const size_t pli = (size_t)in.plane, plo = (size_t)out.plane;
+  const float *b = in.b + s;
+  float w[8];
+#pragma unroll
+  for (int c = 0; c < 8; c++) w[c] = __ldg(b + (size_t)c * pli);
+  const float4 t = __ldg(reinterpret_cast<const float4 *>(in.b + 8 * pli) + s);
+  float *o = out.b + d;
+#pragma unroll
+  for (int c = 0; c < 8; c++) __stcs(o + (size_t)c * plo, w[c]);
+  __stcs(reinterpret_cast<float4 *>(out.b + 8 * plo) + d, t);
+}
+
+// ---- pass 3, source-driven without staging (sort.group_variant = 1, for A/B runs) -----------------------------------
+// Thread per source particle: claim the slot, stream the nine words in, scatter them.  Per warp the stores touch the
+// same sectors the chunk kernel's do (a warp's 32 consecutive particles go to about ten groups either way).
+__global__ void __launch_bounds__(256) group_scatter_kernel(const PView in, const PView out, int np, const int *__restrict__ keys,
+                                                            int *__restrict__ cursor) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const long k = (long)blockIdx.x * 256 + threadIdx.x;      // whole warps stay together: np is rounded up by the grid
+  const bool valid = k < np;
+  const int key = valid ? __ldcs(keys + k) : -1 - lane;
+  const unsigned peers = __match_any_sync(full, key);
+  const int leader = __ffs(peers) - 1;
+  int base = 0;
+  if (valid && lane == leader) base = atomicAdd(cursor + key, __popc(peers));
+  base = __shfl_sync(full, base, leader);
+  if (!valid) return;
+  const int d = base + __popc(peers & lt);
+  const size_t pli = (size_t)in.plane, plo = (size_t)out.plane;
+  const float *b = in.b + k;
+  float w[8];
+#pragma unroll
+  for (int c = 0; c < 8; c++) w[c] = __ldcs(b + (size_t)c * pli);
+  const float4 t = __ldcs(reinterpret_cast<const float4 *>(in.b + 8 * pli) + k);
+  float *o = out.b + d;
+#pragma unroll
+  for (int c = 0; c < 8; c++) o[(size_t)c * plo] = w[c];
+  reinterpret_cast<float4 *>(out.b + 8 * plo)[d] = t;
+}
+
 struct GroupTables { int *dev = nullptr; long nkeys = 0; int nx = 0, ny = 0, nz = 0; };
 static std::vector<std::pair<const vpb_domain_t *, GroupTables>> g_group_tables;
 
@@ -380,38 +458,51 @@ void vpb_sort_p_planes_grouped(vpb_domain_t *dom, const vpb_particle_t *d_in, vp
   const GroupTables &T = tables_of(dom);
   const int nk1 = (int)T.nkeys + 1;
   auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-  const size_t off_keys = al((size_t)nk1 * 4), off_scan = off_keys + al((size_t)np * 4 + 4);
+  // 0: chunks of 1024 staged in shared memory, scattered; 1: thread per source particle, scattered; 2: inverse
+  // permutation, then a destination-ordered gather (default)
+  const int variant = tuning("sort.group_variant", 2);
+  const size_t off_keys = al((size_t)nk1 * 4), off_src = off_keys + al((size_t)np * 4 + 4);
+  const size_t off_scan = off_src + (variant == 2 ? al((size_t)np * 4 + 4) : 0);
   char *s = (char *)scratch(off_scan + scan_scratch_bytes(nk1));
-  int *cursor = (int *)s, *keys = (int *)(s + off_keys);
+  int *cursor = (int *)s, *keys = (int *)(s + off_keys), *src = (int *)(s + off_src);
   GroupKeyArgs A;
   A.L = lookahead; A.sx = gd.sx; A.sy = gd.sy; A.nx = gd.nx; A.ny = gd.ny; A.nz = gd.nz;
   A.kx = 2.f * lookahead * gd.cvac * gd.dt * gd.rdx;
   A.ky = 2.f * lookahead * gd.cvac * gd.dt * gd.rdy;
   A.kz = 2.f * lookahead * gd.cvac * gd.dt * gd.rdz;
   A.fx = T.dev; A.fy = T.dev + gd.sx; A.fz = T.dev + gd.sx + gd.sy;
+  A.msx = ~0ULL / (unsigned long long)gd.sx + 1ULL;
+  A.msy = ~0ULL / (unsigned long long)gd.sy + 1ULL;
   const PView in(d_in, gd.p_plane), out(d_out, gd.p_plane);
   VPB_CUDA(cudaMemsetAsync(cursor, 0, (size_t)nk1 * 4, c.stream));
-  if (np > 0) {
-    const long blocks = ((long)np + 255) / 256, cap = (long)c.sm_count * 16;
-    group_keys_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, c.stream>>>(in, np, A, keys, cursor);
-  }
+  const long blocks = ((long)np + 255) / 256, cap = (long)c.sm_count * 16;
+  if (np > 0) group_keys_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, c.stream>>>(in, np, A, keys, cursor);
   exclusive_scan_i32(cursor, d_partition, nk1, s + off_scan, c.stream);   // partition[keys] = np
   count_launch(1 + scan_launches(nk1));
   if (np == 0) return;
   VPB_CUDA(cudaMemcpyAsync(cursor, d_partition, (size_t)nk1 * 4, cudaMemcpyDeviceToDevice, c.stream));
-  static int ctas_per_sm[2] = {0, 0};
-  const int ev = tuning("sort.evict_last", 0) ? 1 : 0;
-  auto kern = ev ? group_move_kernel<1> : group_move_kernel<0>;
-  if (!ctas_per_sm[ev]) {
-    VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem)));
-    VPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[ev], kern, kGsThreads, sizeof(GroupSmem)));
-    if (ctas_per_sm[ev] < 1) VPB_ERROR("group_move_kernel does not fit on this device");
+  if (variant == 2) {
+    group_invert_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, c.stream>>>(np, keys, cursor, src);
+    group_gather_kernel<<<(int)blocks, 256, 0, c.stream>>>(in, out, np, src);
+    count_launch(3);
+  } else if (variant == 1) {
+    group_scatter_kernel<<<(int)blocks, 256, 0, c.stream>>>(in, out, np, keys, cursor);
+    count_launch(2);
+  } else {
+    static int ctas_per_sm[2] = {0, 0};
+    const int ev = tuning("sort.evict_last", 0) ? 1 : 0;
+    auto kern = ev ? group_move_kernel<1> : group_move_kernel<0>;
+    if (!ctas_per_sm[ev]) {
+      VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem)));
+      VPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[ev], kern, kGsThreads, sizeof(GroupSmem)));
+      if (ctas_per_sm[ev] < 1) VPB_ERROR("group_move_kernel does not fit on this device");
+    }
+    const int nchunks = (np + kGsChunk - 1) / kGsChunk;
+    const int want = ctas_per_sm[ev] * c.sm_count;
+    const int grid = nchunks < want ? nchunks : want;
+    kern<<<grid, kGsThreads, sizeof(GroupSmem), c.stream>>>(in, out, np, keys, cursor);
+    count_launch(2);
   }
-  const int nchunks = (np + kGsChunk - 1) / kGsChunk;
-  const int want = ctas_per_sm[ev] * c.sm_count;
-  const int grid = nchunks < want ? nchunks : want;
-  kern<<<grid, kGsThreads, sizeof(GroupSmem), c.stream>>>(in, out, np, keys, cursor);
-  count_launch(2);
   VPB_CUDA(cudaGetLastError());
 }
 

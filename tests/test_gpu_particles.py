@@ -555,11 +555,13 @@ def group_tables(vpb, n):
 
 @pytest.mark.parametrize("n,np_,L,vth", [((10, 9, 8), 60001, 0, 0.5), ((10, 9, 8), 60001, 7, 0.5), ((33, 1, 17), 150000, 0, 0.3),
                                           ((16, 16, 16), 300000, 4, 0.2), ((5, 4, 3), 63, 0, 0.1), ((40, 36, 20), 2048 * 37 + 5, 3, 0.4)])
-def test_sort_p_planes_grouped(vpb, n, np_, L, vth):
+@pytest.mark.parametrize("variant", [2, 1, 0])
+def test_sort_p_planes_grouped(vpb, n, np_, L, vth, variant):
     """The device-resident driver's sort (vpb_sort_p_planes_grouped): the same particles, bit for bit, grouped by the
     voxel they occupy (L = 0) or reach L steps ahead, groups in the brick-Morton order of vpb_sort_group_order,
     partition[] = first particle of every group.  Several sizes: ragged last chunk, fewer particles than a warp, more
-    chunks than resident CTAs' worth of keys, a 2-D grid."""
+    chunks than resident CTAs' worth of keys, a 2-D grid.  All three forms of the move pass (sort.group_variant: 2 =
+    inverse permutation + destination-ordered gather, the default; 1 = direct scatter; 0 = chunks staged in shared memory)."""
     from old_vpic_b200.sim import DevArray, ParticleArray
     g = host_grid(n)
     rng = np.random.default_rng(41)
@@ -572,7 +574,11 @@ def test_sort_p_planes_grouped(vpb, n, np_, L, vth):
     d_p, d_out = ParticleArray(vpb, dom, np_), ParticleArray(vpb, dom, np_)
     d_part = DevArray(vpb, nkeys + 1, np.int32)
     d_p.upload(p)
-    vpb.vpb_sort_p_planes_grouped(dom, d_p.ptr, d_out.ptr, np_, d_part.ptr, L)
+    vpb.vpb_set_tuning(b"sort.group_variant", variant)
+    try:
+        vpb.vpb_sort_p_planes_grouped(dom, d_p.ptr, d_out.ptr, np_, d_part.ptr, L)
+    finally:
+        vpb.vpb_set_tuning(b"sort.group_variant", 2)
     out, part = d_out.download(np_), d_part.download()
     assert_bits_equal(d_p.download(np_), p, "the input is left alone")
     # same particles, every record intact
