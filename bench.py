@@ -51,9 +51,12 @@ def parse():
     ap.add_argument("--e2e-particles", type=int, default=64 * 1024 * 1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--field-cells", type=int, default=1024, help="cells per axis of the field-only leg (configs[1]); 0 = skip")
-    ap.add_argument("--workload", default="thermal", choices=["thermal", "fields", "harris"],
+    ap.add_argument("--workload", default="thermal", choices=["thermal", "fields", "harris", "harris3d"],
                     help="thermal: BASELINE configs[3] (the headline, default); fields: configs[1] alone; harris: configs[2], the "
-                         "trecon-part shape 2048x1x1024 cells x 100 ppc on one GPU")
+                         "trecon-part shape 2048x1x1024 cells x 100 ppc on one GPU; harris3d: configs[4], the trecon-part plasma "
+                         "in 3D, 1024x512x512 cells x 64 ppc (32 per species) decomposed 2x2x2 over 8 GPUs")
+    ap.add_argument("--harris3d-cells", default="", help="global cells X,Y,Z of --workload harris3d at other GPU counts "
+                                                          "(default 1024,512,512 at 8 GPUs; 512,256,256 per GPU otherwise)")
     ap.add_argument("--trecon-deck", action="store_true",
                     help="with --workload harris: also run the reference's trecon-part deck itself (unmodified turbulence.cxx, "
                          "config.h knobs 2048 x 1 x 1024, one rank) on libvpic_b200.so -- minutes of host-side load and I/O")
@@ -264,7 +267,32 @@ def trecon_deck(exe, cells, steps, tpp, what, timeout):
                       "dumps every 20 steps; -tpp=%d" % (what, cells, steps, tpp)}
 
 
+H3D_TOPO = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}
+
+
+def harris3d_shape(args, world):
+    if args.harris3d_cells:
+        return tuple(int(v) for v in args.harris3d_cells.split(","))
+    t = H3D_TOPO[world]
+    return (512 * t[0], 256 * t[1], 256 * t[2])
+
+
 def workload_config(args):
+    if args.workload == "harris3d":
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        hn, t = harris3d_shape(args, world), H3D_TOPO[world]
+        return {"workload": "BASELINE configs[4]: the trecon-part plasma in 3D -- %d x %d x %d cells of 0.488 c/wpe, %d ppc per species "
+                            "(%d per cell; tracer copies off), pair plasma at vth=0.6c, wce/wpe=10 force-free sheet field, periodic "
+                            "x/y, conducting reflecting z walls, dt=0.99 Courant, sort every %d steps; decomposed %dx%dx%d, one rank per "
+                            "GPU; thermal device load without the sheet's drift current"
+                            % (hn + (args.ppc, 2 * args.ppc, args.sort_interval) + t),
+                "sort_key": "voxel 0.6 x interval steps ahead" if args.sort_lookahead != 0 else "current voxel",
+                "cells_global": list(hn), "cells_per_gpu": [hn[0] // t[0], hn[1] // t[1], hn[2] // t[2]], "ppc_per_species": args.ppc,
+                "species": 2, "l2_policy": "inputs (100 GB of particles per GPU) are far larger than the 126 MB L2; no flush needed",
+                "decomposition": "%dx%dx%d, 1 rank per GPU" % t,
+                "capacity": "48 B per particle in the plane layout, 2 species x 1.07 G particles per GPU + one sort buffer of one "
+                            "species = 155 GB of 180; the deck's 64 ppc PER SPECIES plus tracer copies (1.65 TB, SURVEY.md 8d) does "
+                            "not fit 8 x 180 GB at any layout that keeps the 16-byte tags"}
     if args.workload == "harris":
         return {"workload": "BASELINE configs[2]: the trecon-part shape on one GPU -- 2048 x 1 x 1024 cells (0.488 x 1.95 x 0.488 c/wpe), "
                             "%d ppc per species, pair plasma at vth=0.6c, wce/wpe=10 force-free sheet field, periodic x/y, conducting "
@@ -314,15 +342,33 @@ def run_b200(args):
         L.vpb_comm_init(rank, world, ub)
 
     fields_c2 = None
-    if world == 1 and args.field_cells > 0 and args.workload != "harris":
+    if world == 1 and args.field_cells > 0 and args.workload not in ("harris", "harris3d"):
         fields_c2 = fields_measure(L, args.field_cells, 5, 3)
         if args.workload == "fields":
             print(json.dumps(fields_c2), flush=True)
             return
 
     n = args.cells
-    harris = args.workload == "harris"
-    if harris:
+    harris = args.workload in ("harris", "harris3d")
+    if args.workload == "harris3d":
+        args.no_e2e = args.no_cpu_baseline = True      # those legs belong to the headline workload
+        # BASELINE configs[4]: the same plasma and field as configs[2] (turbulence.cxx:86-160) in a 3-D box of cubic
+        # 0.488 c/wpe cells, decomposed over the GPUs; 32 ppc per species = 64 particles per cell
+        if args.ppc == 64:
+            args.ppc = 32
+        if args.sort_interval == SORT_INTERVAL:
+            args.sort_interval = 25
+        hn, topo = harris3d_shape(args, world), H3D_TOPO[world]
+        d = 1000.0 / 2048
+        hL = (hn[0] * d, hn[1] * d, hn[2] * d)
+        g = helpers.make_grid(hn, "periodic", topo=topo, rank=rank, L=hL, dt=helpers.courant_dt(d, d, d, frac=0.99))
+        if g.coords[2] == 0:
+            g.set_fbc(abi.boundary(0, 0, -1), abi.PEC_FIELDS)
+            g.set_pbc(abi.boundary(0, 0, -1), abi.REFLECT_PARTICLES)
+        if g.coords[2] == topo[2] - 1:
+            g.set_fbc(abi.boundary(0, 0, 1), abi.PEC_FIELDS)
+            g.set_pbc(abi.boundary(0, 0, 1), abi.REFLECT_PARTICLES)
+    elif harris:
         # BASELINE configs[2]: the shape and plasma of decks/trecon-part/turbulence.cxx:86-160 -- 2048 x 1 x 1024 cells of
         # 0.488 x 1.95 x 0.488 c/wpe, pair plasma (mi/me = 1) at vth = 0.6 c, wce/wpe = 10, force-free sheet of half
         # thickness 6 c/wpe, conducting walls that reflect particles at z = 0, Lz, dt = 0.99 Courant, sort every 25.
@@ -359,7 +405,7 @@ def run_b200(args):
     if harris:
         b0, half = 10.0, 6.0
         f0 = abi.aligned_zeros(g.nv, abi.field_dtype)
-        zc = ((np.arange(g.nv) // ((g.n[0] + 2) * (g.n[1] + 2))) - 0.5) * g.struct.dz - 0.5 * hL[2]      # cell centres
+        zc = ((np.arange(g.nv) // ((g.n[0] + 2) * (g.n[1] + 2))) - 0.5) * g.struct.dz + g.struct.z0 - 0.5 * hL[2]   # cell centres
         f0["cbx"] = (b0 * np.tanh(zc / half)).astype(np.float32)
         f0["cby"] = (b0 / np.cosh(zc / half)).astype(np.float32)
         sim.set_fields(f0)

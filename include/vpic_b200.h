@@ -390,6 +390,10 @@ void vpb_sim_set_callbacks(vpb_sim_t *s, const vpb_sim_callbacks_t *cb);   /* NU
 void vpb_sim_energies(vpb_sim_t *s, double *out6_plus_nspecies);       /* dump_energies (dump.cxx:37-78), over all ranks */
 void vpb_sim_hydro(vpb_sim_t *s, int species, vpb_hydro_t *host);      /* clear + accumulate + synchronize, to the host */
 long vpb_sim_step(const vpb_sim_t *s);
+/* The field part of a step (advance.cxx:109-147, and :214 on steps without cleaning) is captured once into a CUDA graph
+ * and replayed (tuning sim.graph, default 1; off while per-kernel timing is on, with deck hooks inside the segment, or
+ * over the host-staged transport).  Returns how many steps replayed it. */
+long vpb_sim_graph_replays(const vpb_sim_t *s);
 int vpb_sim_num_species(const vpb_sim_t *s);
 long vpb_sim_np(vpb_sim_t *s, int species);
 vpb_domain_t *vpb_sim_domain(vpb_sim_t *s);

@@ -76,6 +76,7 @@ static void load_nccl() {
 int comm_rank() { return g_rank; }
 int comm_nproc() { return g_nproc; }
 bool comm_is_multi() { return g_comm != nullptr || g_use_mp; }
+bool comm_capturable() { return !g_use_mp; }
 
 void comm_exchange(const Xfer *x, int n) {
   cudaStream_t st = ctx().stream;

@@ -12,6 +12,7 @@ namespace vpb {
 int comm_rank();
 int comm_nproc();
 bool comm_is_multi();
+bool comm_capturable();   // exchanges are stream work only (NCCL or none): a CUDA graph may hold them
 
 // Posts every send and receive of `x[0..n)` as one NCCL group on the library
 // stream (or, for jobs whose ranks share a GPU, through the host program's message layer: vpb_mp_transport.hpp).  Messages between the same pair of ranks are matched in posting order,

@@ -102,6 +102,7 @@ void sort_group_forget(const vpb_domain *dom);   // vpb_sort_group.cu: drop the 
 // 9 divergence cleaning and shared-face synchronisation.  Scopes may nest (7-9 are set by the step driver).
 int prof_begin(int cls);
 void prof_end(int idx);
+bool prof_enabled();
 struct ProfScope {
   int idx;
   explicit ProfScope(int c) : idx(prof_begin(c)) {}

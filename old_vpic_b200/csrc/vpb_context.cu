@@ -80,6 +80,8 @@ static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;       // pool of event pairs
 static size_t g_prof_used = 0;
 
+bool prof_enabled() { return g_prof_on; }
+
 int prof_begin(int cls) {
   if (!g_prof_on) return -1;
   if (g_prof_used == g_prof.size()) {

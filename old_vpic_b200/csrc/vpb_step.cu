@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 #include "vpb_common.cuh"
+#include "vpb_comm.cuh"
 
 namespace {
 
@@ -52,6 +53,13 @@ struct vpb_sim {
   int sort_lookahead = 0;        // steps; < 0: 0.6 x the species' sort interval (measured optimum, profiles/README.md)
   int needs_boundary_p = -1;
   vpb_sim_callbacks_t cb = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // The field part of a step (clear_jf ... second advance_b [, load_interpolator]) as an instantiated CUDA graph:
+  // [0] without, [1] with load_interpolator.  Captured the second time the segment runs (the first run makes the lazy
+  // allocations); every pointer in it belongs to the run, so it is replayed unchanged until the materials change.
+  cudaGraphExec_t field_graph[2] = {nullptr, nullptr};
+  long field_graph_launches[2] = {0, 0};
+  int field_segment_runs = 0;
+  long graph_replays = 0;
 };
 
 using namespace vpb;
@@ -187,6 +195,57 @@ static void sync_shared(vpb_sim *s) {   // advance.cxx:199-208
   vpb_sync();
 }
 
+// advance.cxx:109-147 (+ :214): everything between particle migration and the divergence cleaning
+static void field_segment_launch(vpb_sim *s, bool with_load) {
+  vpb_domain_t *dom = s->dom;
+  const vpb_sim_callbacks_t &cb = s->cb;
+  vpb_clear_jf(dom, s->f);                                                             // :109
+  if (!s->sp.empty()) vpb_unload_accumulator(dom, s->f, s->a);                         // :110
+  { ProfScope prof(8); vpb_synchronize_jf(dom, s->f); }                                // :112
+  if (cb.current_injection) cb.current_injection(cb.user, s);                          // :123 user_current_injection
+  vpb_advance_b(dom, s->f, 0.5f);                                                      // :129
+  vpb_advance_e(dom, s->f, s->m, s->n_mat, s->vacuum ? 1 : 0);                         // :133
+  if (cb.field_injection) cb.field_injection(cb.user, s);                              // :141 user_field_injection
+  vpb_advance_b(dom, s->f, 0.5f);                                                      // :147
+  if (with_load) vpb_load_interpolator(dom, s->fi, s->f);                              // :214
+}
+
+static void drop_field_graphs(vpb_sim *s) {
+  for (int k = 0; k < 2; k++)
+    if (s->field_graph[k]) { cudaGraphExecDestroy(s->field_graph[k]); s->field_graph[k] = nullptr; }
+  s->field_segment_runs = 0;
+}
+
+// The segment is ~20 small launches (local boundary conditions, face packs and unpacks, the stencils) whose arguments
+// never change: one graph launch instead.  Not while per-kernel timing is on (its events would sit inside the graph),
+// not with deck hooks inside the segment, not over the host-staged transport (it synchronises).
+static void field_segment(vpb_sim *s, bool with_load) {
+  const vpb_sim_callbacks_t &cb = s->cb;
+  const bool can = tuning("sim.graph", 1) != 0 && !prof_enabled() && !cb.current_injection && !cb.field_injection &&
+                   comm_capturable();
+  if (!can || s->field_segment_runs < 1) {
+    field_segment_launch(s, with_load);
+    if (can) s->field_segment_runs++;
+    return;
+  }
+  Context &c = ctx();
+  const int k = with_load ? 1 : 0;
+  if (!s->field_graph[k]) {
+    cudaGraph_t graph = nullptr;
+    const long before = c.launches;
+    VPB_CUDA(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
+    field_segment_launch(s, with_load);
+    VPB_CUDA(cudaStreamEndCapture(c.stream, &graph));
+    s->field_graph_launches[k] = c.launches - before;
+    c.launches = before;
+    VPB_CUDA(cudaGraphInstantiate(&s->field_graph[k], graph, 0));
+    VPB_CUDA(cudaGraphDestroy(graph));
+  }
+  VPB_CUDA(cudaGraphLaunch(s->field_graph[k], c.stream));
+  c.launches += s->field_graph_launches[k];
+  s->graph_replays++;
+}
+
 static void advance_one(vpb_sim *s) {
   vpb_domain_t *dom = s->dom;
   const bool particles = !s->sp.empty();
@@ -200,18 +259,14 @@ static void advance_one(vpb_sim *s) {
   // reduce_accumulators (:74) is a no-op with one replica
   if (cb.particle_injection) cb.particle_injection(cb.user, s);                        // :85 user_particle_injection
   { ProfScope prof(7); migrate(s); }                                                   // :94-103
-  vpb_clear_jf(dom, s->f);                                                             // :109
-  if (particles) vpb_unload_accumulator(dom, s->f, s->a);                              // :110
-  { ProfScope prof(8); vpb_synchronize_jf(dom, s->f); }                                // :112
-  if (cb.current_injection) cb.current_injection(cb.user, s);                          // :123 user_current_injection
-  vpb_advance_b(dom, s->f, 0.5f);                                                      // :129
-  vpb_advance_e(dom, s->f, s->m, s->n_mat, s->vacuum ? 1 : 0);                         // :133
-  if (cb.field_injection) cb.field_injection(cb.user, s);                              // :141 user_field_injection
-  vpb_advance_b(dom, s->f, 0.5f);                                                      // :147
+  const bool cleaning = (s->clean_div_e_interval > 0 && s->step % s->clean_div_e_interval == 0) ||
+                        (s->clean_div_b_interval > 0 && s->step % s->clean_div_b_interval == 0) ||
+                        (s->sync_shared_interval > 0 && s->step % s->sync_shared_interval == 0);
+  field_segment(s, particles && !cleaning);                                            // :109-147 (+ :214 on plain steps)
   if (s->clean_div_e_interval > 0 && s->step % s->clean_div_e_interval == 0) { ProfScope prof(9); clean_div_e(s); }   // :151
   if (s->clean_div_b_interval > 0 && s->step % s->clean_div_b_interval == 0) { ProfScope prof(9); clean_div_b(s); }   // :177
   if (s->sync_shared_interval > 0 && s->step % s->sync_shared_interval == 0) { ProfScope prof(9); sync_shared(s); }   // :199
-  if (particles) vpb_load_interpolator(dom, s->fi, s->f);                              // :214
+  if (particles && cleaning) vpb_load_interpolator(dom, s->fi, s->f);                  // :214
   s->step++;
   if (cb.diagnostics) cb.diagnostics(cb.user, s);                                      // :233 user_diagnostics, after step++
 }
@@ -258,6 +313,7 @@ vpb_sim_t *vpb_sim_create(const vpb_grid_t *g, int rank, int nproc, int n_mat, i
 
 void vpb_sim_set_materials(vpb_sim_t *s, const vpb_material_coefficient_t *m, int n_mat) {
   if (!s || !m || n_mat < 1) VPB_ERROR("Bad args");
+  drop_field_graphs(s);
   if (s->m) vpb_dev_free(s->m);
   s->m = (vpb_material_coefficient_t *)vpb_dev_alloc((size_t)n_mat * sizeof(*m));
   vpb_h2d(s->m, m, (size_t)n_mat * sizeof(*m));
@@ -269,6 +325,7 @@ void vpb_sim_set_materials(vpb_sim_t *s, const vpb_material_coefficient_t *m, in
 void vpb_sim_destroy(vpb_sim_t *s) {
   if (!s) return;
   vpb_sync();
+  drop_field_graphs(s);
   for (Species &sp : s->sp) {
     vpb_dev_free(sp.p); vpb_dev_free(sp.pm); vpb_dev_free(sp.nm);
     if (sp.partition) vpb_dev_free(sp.partition);
@@ -425,7 +482,11 @@ void vpb_sim_set_callbacks(vpb_sim_t *s, const vpb_sim_callbacks_t *cb) {
   if (!s) VPB_ERROR("Bad run");
   if (cb) s->cb = *cb;
   else s->cb = vpb_sim_callbacks_t{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  drop_field_graphs(s);
 }
+
+// how many steps replayed the captured field segment (0: sim.graph off, per-kernel timing on, hooks inside it, ...)
+long vpb_sim_graph_replays(const vpb_sim_t *s) { return s ? s->graph_replays : 0; }
 
 long vpb_sim_step(const vpb_sim_t *s) { return s ? s->step : -1; }
 int vpb_sim_num_species(const vpb_sim_t *s) { return s ? (int)s->sp.size() : 0; }

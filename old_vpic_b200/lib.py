@@ -167,6 +167,7 @@ SIGNATURES = {
     "vpb_sim_energies": (None, [_vp, _vp]),
     "vpb_sim_hydro": (None, [_vp, _i, _vp]),
     "vpb_sim_step": (_l, [_vp]),
+    "vpb_sim_graph_replays": (_l, [_vp]),
     "vpb_sim_num_species": (_i, [_vp]),
     "vpb_sim_np": (_l, [_vp, _i]),
     "vpb_sim_domain": (_vp, [_vp]),

@@ -20,11 +20,48 @@ from old_vpic_b200.sim import NativeSimulation  # noqa: E402
 
 SPECIES = (("e", -1.0, 11), ("i", 1.0, 911))
 PER, PPC, STEPS, VTH = 12, 24, 12, 0.3
+# VPB_DIST_KIND=harris: BASELINE configs[4] scaled down -- the trecon-part plasma (pair plasma at vth = 0.6 c in a
+# force-free current-sheet field of wce/wpe = 10, cubic cells of 0.488 c/wpe, dt = 0.99 Courant, periodic x/y, conducting
+# walls that reflect particles at z = 0, Lz; turbulence.cxx:86-160) split 1x1x2 / 1x2x2 / 2x2x2 as bench.py
+# --workload harris3d splits it
+HARRIS = os.environ.get("VPB_DIST_KIND", "thermal") == "harris"
+CELL = 1000.0 / 2048
+if HARRIS:
+    VTH = 0.6
+
+
+def walls(g, topo):
+    if g.coords[2] == 0:
+        g.set_fbc(abi.boundary(0, 0, -1), abi.PEC_FIELDS)
+        g.set_pbc(abi.boundary(0, 0, -1), abi.REFLECT_PARTICLES)
+    if g.coords[2] == topo[2] - 1:
+        g.set_fbc(abi.boundary(0, 0, 1), abi.PEC_FIELDS)
+        g.set_pbc(abi.boundary(0, 0, 1), abi.REFLECT_PARTICLES)
+
+
+def make_grid(gn, topo, rank):
+    if not HARRIS:
+        return G.make_grid(gn, "periodic", topo=topo, rank=rank)
+    g = G.make_grid(gn, "periodic", topo=topo, rank=rank, L=tuple(n * CELL for n in gn), dt=G.courant_dt(CELL, CELL, CELL, frac=0.99))
+    walls(g, topo)
+    return g
+
+
+def sheet_field(g, gn, cz):
+    """cbx = b0 tanh(z/l), cby = b0 / cosh(z/l) about the mid-plane, from the GLOBAL z index of every voxel (so that a
+    rank's slab and the single-domain array hold the same floats)"""
+    f = abi.aligned_zeros(g.nv, abi.field_dtype)
+    iz = np.arange(g.nv) // ((g.n[0] + 2) * (g.n[1] + 2)) + cz * PER
+    z = (iz - 0.5 - 0.5 * gn[2]) * CELL
+    half = gn[2] * CELL / 8
+    f["cbx"] = (10.0 * np.tanh(z / half)).astype(np.float32)
+    f["cby"] = (10.0 / np.cosh(z / half)).astype(np.float32)
+    return f
 
 
 def make_sim(L, gn, topo, rank):
     """the library's C++ driver (vpb_sim_*) with the look-ahead sort key"""
-    g = G.make_grid(gn, "periodic", topo=topo, rank=rank)
+    g = make_grid(gn, topo, rank)
     sim = NativeSimulation(g, L=L)
     sim.set_sort_lookahead(-1)
     n = g.n[0] * g.n[1] * g.n[2] * PPC
@@ -58,7 +95,7 @@ def main():
     L.vpb_init(local)
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    topo = {2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
+    topo = ({2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)} if HARRIS else {2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)})[world]
     gn = (PER * topo[0], PER * topo[1], PER * topo[2])
     total = 2 * gn[0] * gn[1] * gn[2] * PPC
 
@@ -67,7 +104,8 @@ def main():
     sim = make_sim(L, gn, topo, rank)
     shares = []
     for sp, (_, q_m, seed) in zip(sim.species, SPECIES):
-        sim.load_thermal(sp, PPC, VTH, (1.0 if q_m > 0 else -1.0) / PPC, seed + rank, tag0=rank << 32)
+        cell_volume = CELL ** 3 if HARRIS else 1.0
+        sim.load_thermal(sp, PPC, VTH, (1.0 if q_m > 0 else -1.0) * cell_volume / PPC, seed + rank, tag0=rank << 32)
         mine = torch.from_numpy(sim.get_particles(sp).view(np.uint8).copy()).cuda()
         parts = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(parts, mine)
@@ -80,7 +118,7 @@ def main():
         from oracle import loader
         from test_gpu_history import cpu_history, oracle_kernels
         O = loader.oracle()
-        og = helpers.host_grid(gn, "periodic")
+        og = make_grid(gn, (1, 1, 1), 0)
         ospecies = []
         for (_, q_m, _), per_rank in zip(SPECIES, shares):
             allp = np.concatenate([to_global(p, G._rank_to_index(r, *topo), topo) for r, p in enumerate(per_rank)])
@@ -89,7 +127,8 @@ def main():
             ospecies.append({"p": buf, "q_m": q_m})
         assert sum(len(sp["p"]) for sp in ospecies) == total
         ostate = {}
-        ref_hist = cpu_history(oracle_kernels(O), og, ospecies, STEPS, 0, 0, state=ostate, sort=5)
+        ref_hist = cpu_history(oracle_kernels(O), og, ospecies, STEPS, 0, 0, state=ostate, sort=5,
+                               f_init=sheet_field(og, gn, 0) if HARRIS else None)
         ref_hydro = abi.aligned_zeros(og.nv, abi.hydro_dtype)
         e = ospecies[0]
         O.orc_clear_hydro(abi.ptr(ref_hydro), og.ref())
@@ -104,6 +143,8 @@ def main():
         uid = torch.tensor(list(buf), dtype=torch.uint8, device="cuda")
     dist.broadcast(uid, 0)
     L.vpb_comm_init(rank, world, (C.c_uint8 * 128)(*uid.cpu().tolist()))
+    if HARRIS:
+        sim.set_fields(sheet_field(sim.grid, gn, G._rank_to_index(rank, *topo)[2]))
     hist = run(sim, STEPS)
     # invariants: particle count is conserved globally; particles did migrate
     cnt = torch.tensor([sum(sp.np for sp in sim.species)], device="cuda")
@@ -149,8 +190,8 @@ def main():
         tot = hist.sum(axis=1)
         drift = abs(tot[-1] - tot[0]) / abs(tot[0])
         assert drift < 5e-3, drift
-        print("DIST_GPU_OK world=%d particles=%d oracle_err=%.2e energy_drift=%.2e field_energy_last=%.4e hydro_err=%.2e" % (
-            world, total, err, drift, hist[-1, :6].sum(), herr))
+        print("DIST_GPU_OK kind=%s world=%d particles=%d oracle_err=%.2e energy_drift=%.2e field_energy_last=%.4e hydro_err=%.2e" % (
+            "harris" if HARRIS else "thermal", world, total, err, drift, hist[-1, :6].sum(), herr))
     dist.barrier()
     L.vpb_comm_finalize()
     dist.destroy_process_group()

@@ -18,14 +18,14 @@ def gpu_count():
     return sum(1 for line in out.splitlines() if line.startswith("GPU "))
 
 
-def torchrun(world, worker, timeout=900):
+def torchrun(world, worker, timeout=900, env=None):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(HERE, worker)]
-    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=dict(os.environ, **(env or {})))
 
 
 @pytest.mark.parametrize("world", [2])
@@ -36,6 +36,17 @@ def test_decomposed_run_matches_single_domain(world):
         pytest.skip("needs %d GPUs" % world)
     r = torchrun(world, "dist_gpu_worker.py")
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_decomposed_harris_sheet_matches_single_domain(world):
+    """BASELINE configs[4] scaled down (VPB_DIST_KIND=harris in tests/dist_gpu_worker.py): the trecon-part plasma and
+    sheet field with conducting, particle-reflecting z walls, split 1x1x2 (2x2x2 at 8 GPUs) like bench.py --workload
+    harris3d, against the CPU oracle stepping the same particles on one domain."""
+    if gpu_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    r = torchrun(world, "dist_gpu_worker.py", env={"VPB_DIST_KIND": "harris"})
+    assert r.returncode == 0 and "DIST_GPU_OK kind=harris" in r.stdout, (r.stdout + r.stderr)[-3000:]
 
 
 @pytest.mark.parametrize("world", [2, 4])

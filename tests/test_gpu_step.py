@@ -194,3 +194,45 @@ def test_native_driver_against_the_reference_main_loop(vpb, tmp_path, lookahead,
     got = np.array(got)
     rel = np.abs(got - want[1:]) / np.abs(want[1:]).max(axis=0)
     assert rel.max() < 1e-4, rel.max(axis=0)
+
+
+@pytest.mark.parametrize("kind,n,clean", [("periodic", (12, 10, 8), 0), ("metal", (14, 1, 12), 4)])
+def test_native_driver_field_graph(vpb, kind, n, clean):
+    """The field part of a step as a captured CUDA graph (vpb_step.cu field_segment): a field-only run (no float
+    atomics anywhere) ends with the same bits whether the segment is replayed from the graph or launched kernel by
+    kernel; with particles the graph is replayed on every step after the first two and the histories agree to
+    rounding of the deposit order."""
+    from old_vpic_b200 import grid as G
+    from helpers import random_fields
+    g = G.make_grid(n, kind, field_only=True)
+    f0 = random_fields(np.random.default_rng(5), g)
+    out = []
+    for graph in (1, 0):
+        vpb.vpb_set_tuning(b"sim.graph", graph)
+        try:
+            sim = NativeSimulation(g, L=vpb, vacuum=False)
+            sim.set_intervals(0, clean)
+            sim.set_fields(f0)
+            sim.advance(11)
+            out.append(sim.get_fields())
+            replays = int(vpb.vpb_sim_graph_replays(sim.h))
+            assert replays == (10 if graph else 0)        # the first step launches kernel by kernel (lazy allocations)
+            sim.free()
+        finally:
+            vpb.vpb_set_tuning(b"sim.graph", 1)
+    for name in out[0].dtype.names:
+        assert np.array_equal(out[0][name].view(np.uint8), out[1][name].view(np.uint8)), name
+    # with particles
+    g = host_grid(n, kind)
+    hist = []
+    for graph in (1, 0):
+        vpb.vpb_set_tuning(b"sim.graph", graph)
+        try:
+            h, sim = native_history(vpb, g, make_species(g, 8, 3), 12, clean, clean)
+            hist.append(h)
+            assert (int(vpb.vpb_sim_graph_replays(sim.h)) > 0) == bool(graph)
+            sim.free()
+        finally:
+            vpb.vpb_set_tuning(b"sim.graph", 1)
+    scale = np.maximum(np.abs(hist[1]).max(axis=0), 1e-300)
+    assert (np.abs(hist[0] - hist[1]) / scale).max() < 1e-5
