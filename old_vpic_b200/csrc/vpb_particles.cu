@@ -191,9 +191,13 @@ __global__ void __launch_bounds__(256) sort_claim_kernel(const PView p, int np, 
 }
 
 // INV = 0: perm_sorted[destination] = source (for a gather); INV = 1: perm_sorted[source] = destination (for a scatter)
+// Segments of more than kRankBig particles (a voxel holding thousands: localised loads, targets, sheets) are not ranked
+// here -- counting the smaller sources of each element is quadratic -- but listed in big[] (big[0] = how many,
+// big[1..cap] = the voxels) for sort_rank_big_kernel; when the list is full the quadratic loop does run.
+constexpr int kRankBig = 1024, kRankBigCap = 8191;
 template <int INV>
 __global__ void __launch_bounds__(256) sort_rank_kernel(const int *__restrict__ partition, int nv, const int *__restrict__ perm,
-                                                        int *__restrict__ perm_sorted) {
+                                                        int *__restrict__ perm_sorted, int *__restrict__ big) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int v = blockIdx.x * wpb + (threadIdx.x >> 5); v < nv; v += gridDim.x * wpb) {
@@ -205,6 +209,15 @@ __global__ void __launch_bounds__(256) sort_rank_kernel(const int *__restrict__ 
       for (int j = 0; j < n; j++) r += (__shfl_sync(0xffffffffu, mine, j) < mine);
       if (lane < n) perm_sorted[INV ? mine : b + r] = INV ? b + r : mine;
     } else {
+      if (n > kRankBig) {
+        int slot = 0;
+        if (lane == 0) slot = atomicAdd(big, 1);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot < kRankBigCap) {
+          if (lane == 0) big[1 + slot] = v;
+          continue;
+        }
+      }
       for (int i = lane; i < n; i += 32) {
         const int mine = perm[b + i];
         int r = 0;
@@ -212,6 +225,38 @@ __global__ void __launch_bounds__(256) sort_rank_kernel(const int *__restrict__ 
         perm_sorted[INV ? mine : b + r] = INV ? b + r : mine;
       }
     }
+  }
+}
+
+// The listed segments, one block at a time: bitonic sort of perm[b .. b+n) in place (it is scratch), n log^2 n / 256
+// steps per thread.  All compare-exchanges ascend (the first step of every merge mirrors the upper half), so the
+// virtual +infinity padding beyond n never moves and is never touched.
+template <int INV>
+__global__ void __launch_bounds__(256) sort_rank_big_kernel(const int *__restrict__ partition, int *__restrict__ perm,
+                                                            int *__restrict__ perm_sorted, const int *__restrict__ big) {
+  const int nbig = big[0] < kRankBigCap ? big[0] : kRankBigCap;
+  for (int s = blockIdx.x; s < nbig; s += gridDim.x) {
+    const int v = big[1 + s];
+    const int b = partition[v], n = partition[v + 1] - b;
+    int *a = perm + b;
+    int n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    for (int k = 2; k <= n2; k <<= 1) {
+      for (int j = k >> 1; j >= 1; j >>= 1) {
+        const bool flip = j == (k >> 1);
+        for (int t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
+          const int lo = (t / j) * 2 * j + (t % j);
+          const int hi = flip ? (t / j) * 2 * j + (2 * j - 1 - (t % j)) : lo + j;
+          if (hi < n) {
+            const int x = a[lo], y = a[hi];
+            if (y < x) { a[lo] = y; a[hi] = x; }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) perm_sorted[INV ? a[i] : b + i] = INV ? b + i : a[i];
+    __syncthreads();
   }
 }
 
@@ -384,9 +429,9 @@ static void sort_particles(vpb_domain_t *dom, const vpb_particle_t *d_in, vpb_pa
   // scratch: cursor[nv1] | perm[np] | perm_sorted[np] (also the look-ahead keys until the rank pass) | scan scratch
   auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
   const size_t off_perm = al((size_t)nv1 * 4), off_perm2 = off_perm + al((size_t)np * 4 + 4),
-               off_scan = off_perm2 + al((size_t)np * 4 + 4);
+               off_big = off_perm2 + al((size_t)np * 4 + 4), off_scan = off_big + al((size_t)(kRankBigCap + 1) * 4);
   char *s = (char *)scratch(off_scan + scan_scratch_bytes(nv1));
-  int *cursor = (int *)s, *perm = (int *)(s + off_perm), *perm2 = (int *)(s + off_perm2);
+  int *cursor = (int *)s, *perm = (int *)(s + off_perm), *perm2 = (int *)(s + off_perm2), *big = (int *)(s + off_big);
   const DomainDev &gd = dom->d;
   SortAhead ahead;
   ahead.L = lookahead > 0 ? lookahead : 0;
@@ -415,7 +460,12 @@ static void sort_particles(vpb_domain_t *dom, const vpb_particle_t *d_in, vpb_pa
   // within every voxel.  A look-ahead grouping is not the reference's order to begin with, so it keeps the claim order
   // (the particles of a group in arbitrary order; 15 ms less per 2^30 particles).
   if (ahead.L) perm2 = perm;
-  else sort_rank_kernel<0><<<grid_for((long)nv * 32, 256), 256, 0, c.stream>>>(d_partition, nv, perm, perm2);
+  else {
+    VPB_CUDA(cudaMemsetAsync(big, 0, sizeof(int), c.stream));
+    sort_rank_kernel<0><<<grid_for((long)nv * 32, 256), 256, 0, c.stream>>>(d_partition, nv, perm, perm2, big);
+    sort_rank_big_kernel<0><<<c.sm_count, 256, 0, c.stream>>>(d_partition, perm, perm2, big);   // returns at once when nothing is listed
+    count_launch();
+  }
   if (in_place) {   // vpb_sort_p_planes: d_out is scratch, the sorted planes return to d_in
     sort_gather_records_to_planes_kernel<<<grid_for(np, 256), 256, 0, c.stream>>>(reinterpret_cast<const float4 *>(d_out),
                                                                                   PView(d_in, dom->d.p_plane), np, perm2);

@@ -125,11 +125,15 @@ __device__ __forceinline__ int group_key(const PView &p, int k, const GroupKeyAr
   return __ldg(A.fx + cx) + __ldg(A.fy + cy) + __ldg(A.fz + cz);
 }
 
-// pass 1: keys[k], count[key]++ (one global atomic per distinct key among 32 consecutive particles)
+// pass 1: keys[k], count[key] += 1 (one global atomic per distinct key among 32 consecutive particles).  RANKS: the
+// atomic returns the count before it, which makes rank[k] = how many particles of the same key claimed a slot earlier --
+// the particle's place inside its group, known before the partition is.
+template <int RANKS>
 __global__ void __launch_bounds__(256) group_keys_kernel(const PView p, int np, const GroupKeyArgs A, int *__restrict__ keys,
-                                                         int *__restrict__ count) {
+                                                         int *__restrict__ ranks, int *__restrict__ count) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
   const long stride = (long)gridDim.x * blockDim.x;
   const long n_round = ((long)np + 31) & ~31L;                 // whole warps enter the loop together
   for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < n_round; k += stride) {
@@ -137,7 +141,15 @@ __global__ void __launch_bounds__(256) group_keys_kernel(const PView p, int np, 
     const int key = valid ? group_key(p, (int)k, A) : -1 - lane;
     if (valid) keys[k] = key;
     const unsigned peers = __match_any_sync(full, key);
-    if (valid && lane == __ffs(peers) - 1) atomicAdd(count + key, __popc(peers));
+    const int leader = __ffs(peers) - 1;
+    if (RANKS) {
+      int base = 0;
+      if (valid && lane == leader) base = atomicAdd(count + key, __popc(peers));
+      base = __shfl_sync(full, base, leader);
+      if (valid) ranks[k] = base + __popc(peers & lt);
+    } else {
+      if (valid && lane == leader) atomicAdd(count + key, __popc(peers));
+    }
   }
 }
 
@@ -316,45 +328,16 @@ __global__ void __launch_bounds__(kGsThreads, 3) group_move_kernel(const PView i
 // the partial writes of several CTAs, and whatever part of it has left L2 before the last writer arrives costs a
 // partial DRAM write now and a read-modify-write later (ncu, 2^30 particles ten steps after a sort: 2.0 G write misses
 // for 1.6 G distinct sectors, 87 GB read + 73 GB written for 56 + 52 GB of payload).  Reads have no such penalty, so
-// the move is turned around: group_invert_kernel claims a slot per particle (one atomic per distinct key and warp) and
-// records src[slot]; group_gather_kernel walks the DESTINATION in order -- src[] and every output plane are coalesced,
+// the move is turned around: the key pass also returns every particle's rank inside its group, group_invert_kernel
+// records src[partition[key] + rank] = particle; group_gather_kernel walks the DESTINATION in order -- src[] and every output plane are coalesced,
 // full-line streaming stores -- and gathers the nine source words of a slot.  Blocks are dispatched in destination
 // order, i.e. (the array being nearly sorted) in source order too, so the source sectors a warp touches are the ones
 // its neighbours in time touch: they are fetched from DRAM once and served from L2/L1 afterwards.
-// Four warp-rows of keys per thread and iteration: the four loads, then the four claims, are in flight together (the
-// claim is an atomic WITH a result; one per iteration left the kernel waiting on its latency: 11.2 ms per 2^30
-// particles at 21 % of the DRAM bandwidth, profiles/r2e).
-constexpr int kInvPer = 4;
-__global__ void __launch_bounds__(256) group_invert_kernel(int np, const int *__restrict__ keys, int *__restrict__ cursor,
-                                                           int *__restrict__ src) {
-  const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const unsigned lt = (1u << lane) - 1u;
-  const long tile = (long)blockDim.x * kInvPer;
-  const long ntiles = ((long)np + tile - 1) / tile;
-  for (long t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const long k0 = t * tile + threadIdx.x;
-    int key[kInvPer], base[kInvPer], leader[kInvPer];
-    unsigned peers[kInvPer];
-#pragma unroll
-    for (int j = 0; j < kInvPer; j++) {
-      const long k = k0 + (long)j * blockDim.x;
-      key[j] = k < np ? __ldcs(keys + k) : -1 - lane;
-    }
-#pragma unroll
-    for (int j = 0; j < kInvPer; j++) {
-      peers[j] = __match_any_sync(full, key[j]);
-      leader[j] = __ffs(peers[j]) - 1;
-      base[j] = 0;
-      if (key[j] >= 0 && lane == leader[j]) base[j] = atomicAdd(cursor + key[j], __popc(peers[j]));
-    }
-#pragma unroll
-    for (int j = 0; j < kInvPer; j++) {
-      const long k = k0 + (long)j * blockDim.x;
-      const int b = __shfl_sync(full, base[j], leader[j]);
-      if (key[j] >= 0) src[b + __popc(peers[j] & lt)] = (int)k;
-    }
-  }
+__global__ void __launch_bounds__(256) group_invert_kernel(int np, const int *__restrict__ keys, const int *__restrict__ ranks,
+                                                           const int *__restrict__ partition, int *__restrict__ src) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < np; k += stride)
+    src[__ldg(partition + __ldcs(keys + k)) + __ldcs(ranks + k)] = (int)k;
 }
 
 __global__ void __launch_bounds__(256) group_gather_kernel(const PView in, const PView out, int np, const int *__restrict__ src) {
@@ -478,10 +461,15 @@ void vpb_sort_p_planes_grouped(vpb_domain_t *dom, const vpb_particle_t *d_in, vp
   // 0: chunks of 1024 staged in shared memory, scattered; 1: thread per source particle, scattered; 2: inverse
   // permutation, then a destination-ordered gather (default)
   const int variant = tuning("sort.group_variant", 2);
-  const size_t off_keys = al((size_t)nk1 * 4), off_src = off_keys + al((size_t)np * 4 + 4);
-  const size_t off_scan = off_src + (variant == 2 ? al((size_t)np * 4 + 4) : 0);
+  const PView in(d_in, gd.p_plane), out(d_out, gd.p_plane);
+  // scratch: cursor[keys+1] | (variant 2) src[np] | (variants 0, 1) keys[np] | scan.  Variant 2 keeps keys[] and ranks[]
+  // in the first two planes of d_out: both are dead when the gather starts to write there.
+  const size_t off_arr = al((size_t)nk1 * 4), off_scan = off_arr + al((size_t)np * 4 + 4);
   char *s = (char *)scratch(off_scan + scan_scratch_bytes(nk1));
-  int *cursor = (int *)s, *keys = (int *)(s + off_keys), *src = (int *)(s + off_src);
+  int *cursor = (int *)s, *arr = (int *)(s + off_arr);
+  int *keys = variant == 2 ? reinterpret_cast<int *>(out.b) : arr;
+  int *ranks = variant == 2 ? reinterpret_cast<int *>(out.b) + gd.p_plane : nullptr;
+  int *src = arr;
   GroupKeyArgs A;
   A.L = lookahead; A.sx = gd.sx; A.sy = gd.sy; A.nx = gd.nx; A.ny = gd.ny; A.nz = gd.nz;
   A.kx = 2.f * lookahead * gd.cvac * gd.dt * gd.rdx;
@@ -490,23 +478,26 @@ void vpb_sort_p_planes_grouped(vpb_domain_t *dom, const vpb_particle_t *d_in, vp
   A.fx = T.dev; A.fy = T.dev + gd.sx; A.fz = T.dev + gd.sx + gd.sy;
   A.msx = ~0ULL / (unsigned long long)gd.sx + 1ULL;
   A.msy = ~0ULL / (unsigned long long)gd.sy + 1ULL;
-  const PView in(d_in, gd.p_plane), out(d_out, gd.p_plane);
   VPB_CUDA(cudaMemsetAsync(cursor, 0, (size_t)nk1 * 4, c.stream));
   const long blocks = ((long)np + 255) / 256, cap = (long)c.sm_count * 16;
-  if (np > 0) group_keys_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, c.stream>>>(in, np, A, keys, cursor);
+  const int grid = (int)(blocks < cap ? blocks : cap);
+  if (np > 0) {
+    if (variant == 2) group_keys_kernel<1><<<grid, 256, 0, c.stream>>>(in, np, A, keys, ranks, cursor);
+    else group_keys_kernel<0><<<grid, 256, 0, c.stream>>>(in, np, A, keys, ranks, cursor);
+  }
   exclusive_scan_i32(cursor, d_partition, nk1, s + off_scan, c.stream);   // partition[keys] = np
   count_launch(1 + scan_launches(nk1));
   if (np == 0) return;
-  VPB_CUDA(cudaMemcpyAsync(cursor, d_partition, (size_t)nk1 * 4, cudaMemcpyDeviceToDevice, c.stream));
   if (variant == 2) {
-    const long iblocks = ((long)np + 256 * kInvPer - 1) / (256 * kInvPer);
-    group_invert_kernel<<<(int)(iblocks < cap ? iblocks : cap), 256, 0, c.stream>>>(np, keys, cursor, src);
+    group_invert_kernel<<<grid, 256, 0, c.stream>>>(np, keys, ranks, d_partition, src);
     group_gather_kernel<<<(int)blocks, 256, 0, c.stream>>>(in, out, np, src);
-    count_launch(3);
+    count_launch(2);
   } else if (variant == 1) {
+    VPB_CUDA(cudaMemcpyAsync(cursor, d_partition, (size_t)nk1 * 4, cudaMemcpyDeviceToDevice, c.stream));
     group_scatter_kernel<<<(int)blocks, 256, 0, c.stream>>>(in, out, np, keys, cursor);
     count_launch(2);
   } else {
+    VPB_CUDA(cudaMemcpyAsync(cursor, d_partition, (size_t)nk1 * 4, cudaMemcpyDeviceToDevice, c.stream));
     static int ctas_per_sm[2] = {0, 0};
     const int ev = tuning("sort.evict_last", 0) ? 1 : 0;
     auto kern = ev ? group_move_kernel<1> : group_move_kernel<0>;
@@ -517,8 +508,7 @@ void vpb_sort_p_planes_grouped(vpb_domain_t *dom, const vpb_particle_t *d_in, vp
     }
     const int nchunks = (np + kGsChunk - 1) / kGsChunk;
     const int want = ctas_per_sm[ev] * c.sm_count;
-    const int grid = nchunks < want ? nchunks : want;
-    kern<<<grid, kGsThreads, sizeof(GroupSmem), c.stream>>>(in, out, np, keys, cursor);
+    kern<<<nchunks < want ? nchunks : want, kGsThreads, sizeof(GroupSmem), c.stream>>>(in, out, np, keys, cursor);
     count_launch(2);
   }
   VPB_CUDA(cudaGetLastError());

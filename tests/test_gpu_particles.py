@@ -219,6 +219,35 @@ def test_sort_p(vpb, orc, n, np_):
     assert part_g[-1] == np_
 
 
+@pytest.mark.parametrize("np_,dense", [(40000, (5000, 1025, 33)), (3000, (3000,)), (70000, (20000, 20000, 1500))])
+def test_sort_p_dense_voxels(vpb, orc, np_, dense):
+    """Voxels that hold thousands of particles (localised loads, sheets): the stable rank of a segment above 1024 goes
+    through the block-wide bitonic path (vpb_particles.cu sort_rank_big_kernel) instead of the quadratic count; still
+    the reference's out-of-place order, bit for bit."""
+    g = host_grid((6, 5, 4))
+    rng = np.random.default_rng(17)
+    p = random_particles(rng, g, np_, sort=False)
+    vox = rng.choice(np.unique(p["i"]), len(dense), replace=False)
+    at = 0
+    idx = rng.permutation(np_)
+    for v, n in zip(vox, dense):
+        p["i"][idx[at:at + n]] = v
+        at += n
+    p["tag"] = np.arange(np_)
+    sp = abi.SpeciesStruct()
+    sp.np, sp.max_np, sp.p = np_, np_, p.ctypes.data
+    sp.sort_interval, sp.sort_out_of_place = 20, 1
+    part_g = np.full(g.nv + 1, -1, np.int32)
+    sp.partition = part_g.ctypes.data
+    p_in = p.copy()
+    vpb.sort_p(C.byref(sp), g.ref())
+    p_o = abi.aligned_zeros(np_, abi.particle_dtype)
+    part_o = np.zeros(g.nv + 1, np.int32)
+    orc.orc_sort_p(ptr(p_in), ptr(p_o), np_, ptr(part_o), g.ref())
+    assert np.array_equal(part_g, part_o)
+    assert_bits_equal(p[:np_], p_o, "sorted particles (tags included)")
+
+
 @pytest.mark.parametrize("store", [0, 1])
 @pytest.mark.parametrize("kind", ["periodic", "metal"])
 def test_layer_b_wide_interpolator(vpb, orc, kind, store):
