@@ -307,7 +307,12 @@ def workload_config(args):
             "sort_key": ("voxel %s steps ahead (a look-ahead grouping: same particles, same physics, different array order)" % ("0.6 x interval" if args.sort_lookahead < 0 else args.sort_lookahead)) if args.sort_lookahead != 0 else "current voxel",
             "cells_per_gpu": [args.cells] * 3, "ppc_per_species": args.ppc, "species": 2,
             "l2_policy": "inputs (>=100 GB of particles per GPU) are far larger than the 126 MB L2; no flush needed",
-            "decomposition": "1 rank per GPU"}
+            "decomposition": "1 rank per GPU",
+            # both arms print this config; what the CPU can step within minutes is a bounded sample of it
+            "e2e_and_reference_arm_sample": "BASELINE configs[0] (64^3 cells x 32 ppc x 2 species, the same thermal plasma) as an "
+                                            "unmodified reference host program: `e2e` of this arm and every number of the "
+                                            "--impl reference arm are measured on that sample, `value` and `roofline` on the "
+                                            "workload above"}
 
 
 # ----------------------------------------------------------------------------

@@ -104,51 +104,87 @@ struct GroupKeyArgs {
   const int *fx, *fy, *fz;
 };
 
-// Key of particle k: the group of its voxel (L == 0) or of the voxel it reaches in L steps at its present velocity,
-// clamped to the interior (look-ahead grouping).
-__device__ __forceinline__ int group_key(const PView &p, int k, const GroupKeyArgs &A) {
-  const int v = p.voxel(k);
+// Key of particle k: the group of its voxel (AHEAD = 0) or of the voxel it reaches in L steps at its present velocity,
+// clamped to the interior (look-ahead grouping).  In two halves so that a thread can have the loads of
+// several particles in flight before it uses any of them.
+struct GroupRaw { int v; float dx, dy, dz, ux, uy, uz; };
+
+template <int AHEAD>
+__device__ __forceinline__ GroupRaw group_load(const PView &p, long k) {
+  GroupRaw r;
+  const size_t pl = (size_t)p.plane;
+  const float *b = p.b + k;
+  r.v = __float_as_int(__ldcs(b + 3 * pl));
+  if (AHEAD) {
+    r.dx = __ldcs(b); r.dy = __ldcs(b + pl); r.dz = __ldcs(b + 2 * pl);
+    r.ux = __ldcs(b + 4 * pl); r.uy = __ldcs(b + 5 * pl); r.uz = __ldcs(b + 6 * pl);
+  } else {
+    r.dx = r.dy = r.dz = r.ux = r.uy = r.uz = 0.f;
+  }
+  return r;
+}
+
+template <int AHEAD>
+__device__ __forceinline__ int group_key(const GroupRaw &r, const GroupKeyArgs &A) {
+  const int v = r.v;
   const int t = (int)__umul64hi((unsigned long long)(unsigned)v, A.msx), ix = v - t * A.sx;
   const int iz = (int)__umul64hi((unsigned long long)(unsigned)t, A.msy), iy = t - iz * A.sy;
   int cx = ix, cy = iy, cz = iz;
-  if (A.L > 0) {
-    const size_t pl = (size_t)p.plane;
-    const float *b = p.b + k;
-    const float dx = __ldcs(b), dy = __ldcs(b + pl), dz = __ldcs(b + 2 * pl);
-    const float ux = __ldcs(b + 4 * pl), uy = __ldcs(b + 5 * pl), uz = __ldcs(b + 6 * pl);
-    const float rg = rsqrtf(1.f + (ux * ux + (uy * uy + uz * uz)));
-    cx = ix + (int)floorf((dx + A.kx * ux * rg + 1.f) * 0.5f);
-    cy = iy + (int)floorf((dy + A.ky * uy * rg + 1.f) * 0.5f);
-    cz = iz + (int)floorf((dz + A.kz * uz * rg + 1.f) * 0.5f);
+  if (AHEAD) {
+    const float rg = rsqrtf(1.f + (r.ux * r.ux + (r.uy * r.uy + r.uz * r.uz)));
+    cx = ix + (int)floorf((r.dx + A.kx * r.ux * rg + 1.f) * 0.5f);
+    cy = iy + (int)floorf((r.dy + A.ky * r.uy * rg + 1.f) * 0.5f);
+    cz = iz + (int)floorf((r.dz + A.kz * r.uz * rg + 1.f) * 0.5f);
     cx = min(max(cx, 1), A.nx); cy = min(max(cy, 1), A.ny); cz = min(max(cz, 1), A.nz);
   }
   return __ldg(A.fx + cx) + __ldg(A.fy + cy) + __ldg(A.fz + cz);
 }
 
-// pass 1: keys[k], count[key] += 1 (one global atomic per distinct key among 32 consecutive particles).  RANKS: the
-// atomic returns the count before it, which makes rank[k] = how many particles of the same key claimed a slot earlier --
-// the particle's place inside its group, known before the partition is.
-template <int RANKS>
+// Both passes below are chains of dependent memory round trips (stream in -> table look-up -> atomic -> store): with one
+// row per thread in flight they ran at the latency of that chain (2.2 us per warp and row, a third of the DRAM
+// bandwidth; profiles/r2h), so every thread carries kKeyRows / kInvRows independent rows.
+constexpr int kKeyRows = 4, kInvRows = 8;
+template <int RANKS, int AHEAD>
 __global__ void __launch_bounds__(256) group_keys_kernel(const PView p, int np, const GroupKeyArgs A, int *__restrict__ keys,
                                                          int *__restrict__ ranks, int *__restrict__ count) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
-  const long stride = (long)gridDim.x * blockDim.x;
-  const long n_round = ((long)np + 31) & ~31L;                 // whole warps enter the loop together
-  for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < n_round; k += stride) {
-    const bool valid = k < np;
-    const int key = valid ? group_key(p, (int)k, A) : -1 - lane;
-    if (valid) keys[k] = key;
-    const unsigned peers = __match_any_sync(full, key);
-    const int leader = __ffs(peers) - 1;
-    if (RANKS) {
-      int base = 0;
-      if (valid && lane == leader) base = atomicAdd(count + key, __popc(peers));
-      base = __shfl_sync(full, base, leader);
-      if (valid) ranks[k] = base + __popc(peers & lt);
-    } else {
-      if (valid && lane == leader) atomicAdd(count + key, __popc(peers));
+  const long tile = (long)blockDim.x * kKeyRows;
+  const long ntiles = ((long)np + tile - 1) / tile;
+  for (long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const long k0 = t * tile + threadIdx.x;
+    GroupRaw raw[kKeyRows];
+#pragma unroll
+    for (int j = 0; j < kKeyRows; j++) {          // every load of the tile first (rows past the end re-read the last particle)
+      const long k = k0 + (long)j * blockDim.x;
+      raw[j] = group_load<AHEAD>(p, k < np ? k : (long)np - 1);
+    }
+    int key[kKeyRows];
+#pragma unroll
+    for (int j = 0; j < kKeyRows; j++) {
+      const long k = k0 + (long)j * blockDim.x;
+      key[j] = k < np ? group_key<AHEAD>(raw[j], A) : -1 - lane;
+    }
+    unsigned peers[kKeyRows];
+    int base[kKeyRows];
+#pragma unroll
+    for (int j = 0; j < kKeyRows; j++) {
+      peers[j] = __match_any_sync(full, key[j]);
+      base[j] = 0;
+      if (key[j] >= 0 && lane == __ffs(peers[j]) - 1) {
+        if (RANKS) base[j] = atomicAdd(count + key[j], __popc(peers[j]));
+        else atomicAdd(count + key[j], __popc(peers[j]));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kKeyRows; j++) {
+      const long k = k0 + (long)j * blockDim.x;
+      if (RANKS) base[j] = __shfl_sync(full, base[j], __ffs(peers[j]) - 1);
+      if (k < np) {
+        keys[k] = key[j];
+        if (RANKS) ranks[k] = base[j] + __popc(peers[j] & lt);
+      }
     }
   }
 }
@@ -335,9 +371,24 @@ __global__ void __launch_bounds__(kGsThreads, 3) group_move_kernel(const PView i
 // its neighbours in time touch: they are fetched from DRAM once and served from L2/L1 afterwards.
 __global__ void __launch_bounds__(256) group_invert_kernel(int np, const int *__restrict__ keys, const int *__restrict__ ranks,
                                                            const int *__restrict__ partition, int *__restrict__ src) {
-  const long stride = (long)gridDim.x * blockDim.x;
-  for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < np; k += stride)
-    src[__ldg(partition + __ldcs(keys + k)) + __ldcs(ranks + k)] = (int)k;
+  const long tile = (long)blockDim.x * kInvRows;
+  const long ntiles = ((long)np + tile - 1) / tile;
+  for (long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const long k0 = t * tile + threadIdx.x;
+    int key[kInvRows], d[kInvRows];
+#pragma unroll
+    for (int j = 0; j < kInvRows; j++) {
+      const long k = k0 + (long)j * blockDim.x;
+      key[j] = k < np ? __ldcs(keys + k) : -1;
+      d[j] = k < np ? __ldcs(ranks + k) : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < kInvRows; j++)
+      if (key[j] >= 0) d[j] += __ldg(partition + key[j]);
+#pragma unroll
+    for (int j = 0; j < kInvRows; j++)
+      if (key[j] >= 0) src[d[j]] = (int)(k0 + (long)j * blockDim.x);
+  }
 }
 
 __global__ void __launch_bounds__(256) group_gather_kernel(const PView in, const PView out, int np, const int *__restrict__ src) {
@@ -480,16 +531,17 @@ void vpb_sort_p_planes_grouped(vpb_domain_t *dom, const vpb_particle_t *d_in, vp
   A.msy = ~0ULL / (unsigned long long)gd.sy + 1ULL;
   VPB_CUDA(cudaMemsetAsync(cursor, 0, (size_t)nk1 * 4, c.stream));
   const long blocks = ((long)np + 255) / 256, cap = (long)c.sm_count * 16;
-  const int grid = (int)(blocks < cap ? blocks : cap);
+  auto grid_of = [&](int rows) { const long b = (blocks + rows - 1) / rows; return (int)(b < cap ? b : cap); };
   if (np > 0) {
-    if (variant == 2) group_keys_kernel<1><<<grid, 256, 0, c.stream>>>(in, np, A, keys, ranks, cursor);
-    else group_keys_kernel<0><<<grid, 256, 0, c.stream>>>(in, np, A, keys, ranks, cursor);
+    auto kern = variant == 2 ? (lookahead ? group_keys_kernel<1, 1> : group_keys_kernel<1, 0>)
+                             : (lookahead ? group_keys_kernel<0, 1> : group_keys_kernel<0, 0>);
+    kern<<<grid_of(kKeyRows), 256, 0, c.stream>>>(in, np, A, keys, ranks, cursor);
   }
   exclusive_scan_i32(cursor, d_partition, nk1, s + off_scan, c.stream);   // partition[keys] = np
   count_launch(1 + scan_launches(nk1));
   if (np == 0) return;
   if (variant == 2) {
-    group_invert_kernel<<<grid, 256, 0, c.stream>>>(np, keys, ranks, d_partition, src);
+    group_invert_kernel<<<grid_of(kInvRows), 256, 0, c.stream>>>(np, keys, ranks, d_partition, src);
     group_gather_kernel<<<(int)blocks, 256, 0, c.stream>>>(in, out, np, src);
     count_launch(2);
   } else if (variant == 1) {

@@ -22,15 +22,35 @@ from orc_cluster import OracleCluster  # noqa: E402
 def ref_grid(L, gn, kind, topo, dt, damp):
     p = L.new_grid()
     a = (p, 0.0, 0.0, 0.0, float(gn[0]), float(gn[1]), float(gn[2]), gn[0], gn[1], gn[2], topo[0], topo[1], topo[2])
-    if kind == "periodic":
+    if kind in ("periodic", "sheet"):
         L.partition_periodic_box(*a)
     elif kind == "metal":
         L.partition_metal_box(*a)
     else:
         L.partition_absorbing_box(*a, abi.ABSORB_PARTICLES)
+    if kind == "sheet":
+        # the trecon-part box (turbulence.cxx:283-290): periodic in x and y, conducting walls that reflect particles on the
+        # ranks that own the bottom and the top of the box -- BASELINE configs[4]'s 2x2x2 decomposition, scaled down
+        rank = int(os.environ["VPIC_SHIM_RANK"])
+        pz = rank // (topo[0] * topo[1])
+        for sgn, edge in ((-1, 0), (1, topo[2] - 1)):
+            if pz == edge:
+                L.set_fbc(p, abi.boundary(0, 0, sgn), abi.PEC_FIELDS)
+                L.set_pbc(p, abi.boundary(0, 0, sgn), abi.REFLECT_PARTICLES)
     s = abi.GridStruct.from_address(p)
     s.dt, s.cvac, s.eps0, s.damp = dt, 1.0, 1.0, damp
     return p, s
+
+
+def mirror_grid(gn, kind, topo, rank, dt, damp):
+    if kind != "sheet":
+        return host_grid(gn, kind, topo=topo, rank=rank, dt=dt, damp=damp)
+    g = host_grid(gn, "periodic", topo=topo, rank=rank, dt=dt, damp=damp)
+    for sgn, edge in ((-1, 0), (1, topo[2] - 1)):
+        if g.coords[2] == edge:
+            g.set_fbc(abi.boundary(0, 0, sgn), abi.PEC_FIELDS)
+            g.set_pbc(abi.boundary(0, 0, sgn), abi.REFLECT_PARTICLES)
+    return g
 
 
 def make_particles(seed, g, n, cap, q):
@@ -58,7 +78,7 @@ def main():
     dt = courant_dt(1.0, 1.0, 1.0)
     gp, gs = ref_grid(L, gn, kind, topo, dt, 0.01)
     gref = C.c_void_p(gp)
-    grids = [host_grid(gn, kind, topo=topo, rank=k, dt=dt, damp=0.01) for k in range(W)]
+    grids = [mirror_grid(gn, kind, topo, k, dt, 0.01) for k in range(W)]
     g = grids[rank]
 
     # 0. the host mirror's grid_t for this rank is the reference's (partition.c, ops.c:join_grid)

@@ -42,7 +42,8 @@ def run_ranks(world, env_extra, timeout=240, argv=None, cwd=None, marker="REF_MP
 
 
 @pytest.mark.parametrize("topo,kind,gn", [((2, 1, 1), "periodic", (8, 6, 4)), ((1, 1, 2), "absorbing", (5, 4, 6)),
-                                           ((1, 2, 1), "metal", (4, 8, 1)), ((2, 2, 1), "periodic", (8, 6, 3))])
+                                           ((1, 2, 1), "metal", (4, 8, 1)), ((2, 2, 1), "periodic", (8, 6, 3)),
+                                           ((2, 2, 2), "sheet", (8, 6, 6))])
 def test_reference_on_ranks_matches_oracle(topo, kind, gn):
     run_ranks(topo[0] * topo[1] * topo[2],
               {"REFW_TOPO": ",".join(map(str, topo)), "REFW_KIND": kind, "REFW_GN": ",".join(map(str, gn))})
