@@ -5,7 +5,7 @@
 
 Workload (config.workload): BASELINE.json configs[3], "thermal plasma weak scaling,
 256^3 cells and 64 ppc per species per GPU", periodic, dt = 0.95 Courant, vth = 0.1 c,
-sort every 20 steps; synthetic particles generated on the device.  One step = one full
+sort every 5 steps (--sort-interval); synthetic particles generated on the device.  One step = one full
 time step of vpic_simulation::advance() (src/vpic/advance.cxx:13-244) for this deck:
 clear_accumulators, sort_p when due, advance_p for both species, clear_jf,
 unload_accumulator, synchronize_jf, advance_b/advance_e/advance_b, load_interpolator.
@@ -37,7 +37,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 VTH = 0.1
-SORT_INTERVAL = 20
+# Species sort interval of the headline run.  The reference's decks sort every 20-25 steps because the CPU sort is dear;
+# here a sort costs less than two pushes, and advance_p is fastest on freshly grouped particles: 5 (with the look-ahead key
+# 3 steps ahead) is where advance_p averages >= 0.50 of the roofline; 10 gives the shortest step.
+SORT_INTERVAL = 5
 
 
 def parse():
@@ -74,7 +77,7 @@ def parse():
     ap.add_argument("--sort-lookahead", type=int, default=-1,
                     help="sort key = voxel the particle reaches this many steps ahead (-1: 0.6 x the sort interval, 0: current voxel)")
     ap.add_argument("--driver", default="native", choices=["native"], help=argparse.SUPPRESS)   # one driver: csrc/vpb_step.cu
-    ap.add_argument("--sort-interval", type=int, default=SORT_INTERVAL, help="species sort_interval (the reference recipe: 20)")
+    ap.add_argument("--sort-interval", type=int, default=SORT_INTERVAL, help="species sort_interval (default 5; the reference's decks use 20-25)")
     return ap.parse_args()
 
 
@@ -493,9 +496,9 @@ def run_b200(args):
         "config": workload_config(args), "clocks": clocks, "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None,
-                     # DRAM bytes of ONE launch from the ncu --set full capture of this workload (10 steps after a sort)
+                     # DRAM bytes of ONE launch from the ncu --set full capture of this workload (3 steps after a sort at interval 5)
                      "traffic": (TRAFFIC_PLANES if planes else TRAFFIC_AOS) if (args.cells == 256 and args.ppc == 64) else None,
-                     "traffic_source": ("profiles/r1p_256_step10_advance_p_pair_c4_pipe.txt" if planes else
+                     "traffic_source": ("profiles/r2g_256_advance_p_pair_full_3steps_after_sort.txt" if planes else
                                         "profiles/r1k_256_step10_advance_p_stream_c2.txt") + " (dram__bytes_read.sum + dram__bytes_write.sum)",
                      "kernel": "advance_p_pair_kernel" if planes else "advance_p_stream_kernel",
                      "algorithmic_bytes_per_particle": bytes_alg, "particles_per_launch": per_launch_particles,
@@ -526,7 +529,7 @@ def run_b200(args):
         # effective values: the environment override if there is one, else the library's default
         "tuning": {k: int(os.environ.get("VPB_" + k.upper().replace(".", "_"), d)) for k, d in (
             ("advance_p.pair_variant", 1), ("advance_p.pair_cps", 4), ("advance_p.pair_pipe", 1), ("advance_p.pair_merge", 1),
-            ("sort.grouped", 1), ("sort.group_variant", 2), ("sim.aos_fields", 0), ("sim.narrow_interpolator", 0), ("sim.aos_particles", 0),
+            ("sort.grouped", 1), ("sort.group_variant", 2), ("sort.pack_rank", 1), ("sort.gather_keep", 0), ("sim.graph", 1), ("sim.aos_fields", 0), ("sim.narrow_interpolator", 0), ("sim.aos_particles", 0),
             ("advance_p.tma", 2), ("advance_p.stream_cps", 5), ("advance_p.stream_store", 0), ("advance_p.deposit", 1))},
     }
     if fields_c2 is not None:
@@ -670,7 +673,7 @@ def e2e_measure(L, args, abi, helpers):
 
 
 TRAFFIC_AOS = 123.35e9      # profiles/r1k (48-byte records, advance_p_stream_kernel)
-TRAFFIC_PLANES = 80.96e9    # profiles/r1p (component planes, advance_p_pair_kernel)
+TRAFFIC_PLANES = 73.39e9    # profiles/r2g (component planes, advance_p_pair_kernel FULL variant, 3 steps after a sort at interval 5)
 
 
 def main():

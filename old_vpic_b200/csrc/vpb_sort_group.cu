@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(256) group_keys_kernel(const PView p, int np, 
       base[j] = 0;
       if (key[j] >= 0 && lane == __ffs(peers[j]) - 1) {
         if (RANKS) base[j] = atomicAdd(count + key[j], __popc(peers[j]));
-        else atomicAdd(count + key[j], __popc(peers[j]));
+        else atomicAdd(count + key[j], __popc(peers[j]));   // (ptxas turns an unused result into a RED)
       }
     }
 #pragma unroll
@@ -182,8 +182,14 @@ __global__ void __launch_bounds__(256) group_keys_kernel(const PView p, int np, 
       const long k = k0 + (long)j * blockDim.x;
       if (RANKS) base[j] = __shfl_sync(full, base[j], __ffs(peers[j]) - 1);
       if (k < np) {
-        keys[k] = key[j];
-        if (RANKS) ranks[k] = base[j] + __popc(peers[j] & lt);
+        const int rank = base[j] + __popc(peers[j] & lt);
+        if (RANKS == 2) {   // one word: key in the low 24 bits, rank in the high 8; the rare rank >= 255 goes to ranks[] as well
+          keys[k] = key[j] | ((rank < 255 ? rank : 255) << 24);
+          if (rank >= 255) ranks[k] = rank;
+        } else {
+          keys[k] = key[j];
+          if (RANKS) ranks[k] = rank;
+        }
       }
     }
   }
@@ -369,6 +375,7 @@ __global__ void __launch_bounds__(kGsThreads, 3) group_move_kernel(const PView i
 // full-line streaming stores -- and gathers the nine source words of a slot.  Blocks are dispatched in destination
 // order, i.e. (the array being nearly sorted) in source order too, so the source sectors a warp touches are the ones
 // its neighbours in time touch: they are fetched from DRAM once and served from L2/L1 afterwards.
+template <int PACKED>
 __global__ void __launch_bounds__(256) group_invert_kernel(int np, const int *__restrict__ keys, const int *__restrict__ ranks,
                                                            const int *__restrict__ partition, int *__restrict__ src) {
   const long tile = (long)blockDim.x * kInvRows;
@@ -379,8 +386,15 @@ __global__ void __launch_bounds__(256) group_invert_kernel(int np, const int *__
 #pragma unroll
     for (int j = 0; j < kInvRows; j++) {
       const long k = k0 + (long)j * blockDim.x;
-      key[j] = k < np ? __ldcs(keys + k) : -1;
-      d[j] = k < np ? __ldcs(ranks + k) : 0;
+      if (PACKED) {
+        const unsigned w = k < np ? (unsigned)__ldcs(keys + k) : 0xffffffffu;
+        key[j] = k < np ? (int)(w & 0xffffffu) : -1;
+        d[j] = (int)(w >> 24);
+        if (k < np && d[j] == 255) d[j] = __ldcs(ranks + k);
+      } else {
+        key[j] = k < np ? __ldcs(keys + k) : -1;
+        d[j] = k < np ? __ldcs(ranks + k) : 0;
+      }
     }
 #pragma unroll
     for (int j = 0; j < kInvRows; j++)
@@ -391,6 +405,7 @@ __global__ void __launch_bounds__(256) group_invert_kernel(int np, const int *__
   }
 }
 
+template <int KEEP>
 __global__ void __launch_bounds__(256) group_gather_kernel(const PView in, const PView out, int np, const int *__restrict__ src) {
   const int d = blockIdx.x * 256 + threadIdx.x;
   if (d >= np) return;
@@ -398,9 +413,18 @@ __global__ void __launch_bounds__(256) group_gather_kernel(const PView in, const
   const size_t pli = (size_t)in.plane, plo = (size_t)out.plane;
   const float *b = in.b + s;
   float w[8];
+  float4 t;
+  if (KEEP) {   // sort.gather_keep: ask L2 to hold on to the source sectors (their other words are wanted soon)
+    const uint64_t pol = l2_policy_evict_last();
 #pragma unroll
-  for (int c = 0; c < 8; c++) w[c] = __ldg(b + (size_t)c * pli);
-  const float4 t = __ldg(reinterpret_cast<const float4 *>(in.b + 8 * pli) + s);
+    for (int c = 0; c < 8; c++)
+      asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(w[c]) : "l"(b + (size_t)c * pli), "l"(pol));
+    t = ldg_hint4(reinterpret_cast<const float4 *>(in.b + 8 * pli) + s, pol);
+  } else {
+#pragma unroll
+    for (int c = 0; c < 8; c++) w[c] = __ldg(b + (size_t)c * pli);
+    t = __ldg(reinterpret_cast<const float4 *>(in.b + 8 * pli) + s);
+  }
   float *o = out.b + d;
 #pragma unroll
   for (int c = 0; c < 8; c++) __stcs(o + (size_t)c * plo, w[c]);
@@ -521,6 +545,7 @@ void vpb_sort_p_planes_grouped(vpb_domain_t *dom, const vpb_particle_t *d_in, vp
   int *keys = variant == 2 ? reinterpret_cast<int *>(out.b) : arr;
   int *ranks = variant == 2 ? reinterpret_cast<int *>(out.b) + gd.p_plane : nullptr;
   int *src = arr;
+  const bool packed = variant == 2 && T.nkeys <= (1L << 24) && tuning("sort.pack_rank", 1) != 0;
   GroupKeyArgs A;
   A.L = lookahead; A.sx = gd.sx; A.sy = gd.sy; A.nx = gd.nx; A.ny = gd.ny; A.nz = gd.nz;
   A.kx = 2.f * lookahead * gd.cvac * gd.dt * gd.rdx;
@@ -533,16 +558,19 @@ void vpb_sort_p_planes_grouped(vpb_domain_t *dom, const vpb_particle_t *d_in, vp
   const long blocks = ((long)np + 255) / 256, cap = (long)c.sm_count * 16;
   auto grid_of = [&](int rows) { const long b = (blocks + rows - 1) / rows; return (int)(b < cap ? b : cap); };
   if (np > 0) {
-    auto kern = variant == 2 ? (lookahead ? group_keys_kernel<1, 1> : group_keys_kernel<1, 0>)
-                             : (lookahead ? group_keys_kernel<0, 1> : group_keys_kernel<0, 0>);
+    auto kern = variant != 2 ? (lookahead ? group_keys_kernel<0, 1> : group_keys_kernel<0, 0>)
+                : packed     ? (lookahead ? group_keys_kernel<2, 1> : group_keys_kernel<2, 0>)
+                             : (lookahead ? group_keys_kernel<1, 1> : group_keys_kernel<1, 0>);
     kern<<<grid_of(kKeyRows), 256, 0, c.stream>>>(in, np, A, keys, ranks, cursor);
   }
   exclusive_scan_i32(cursor, d_partition, nk1, s + off_scan, c.stream);   // partition[keys] = np
   count_launch(1 + scan_launches(nk1));
   if (np == 0) return;
   if (variant == 2) {
-    group_invert_kernel<<<grid_of(kInvRows), 256, 0, c.stream>>>(np, keys, ranks, d_partition, src);
-    group_gather_kernel<<<(int)blocks, 256, 0, c.stream>>>(in, out, np, src);
+    if (packed) group_invert_kernel<1><<<grid_of(kInvRows), 256, 0, c.stream>>>(np, keys, ranks, d_partition, src);
+    else group_invert_kernel<0><<<grid_of(kInvRows), 256, 0, c.stream>>>(np, keys, ranks, d_partition, src);
+    if (tuning("sort.gather_keep", 0)) group_gather_kernel<1><<<(int)blocks, 256, 0, c.stream>>>(in, out, np, src);
+    else group_gather_kernel<0><<<(int)blocks, 256, 0, c.stream>>>(in, out, np, src);
     count_launch(2);
   } else if (variant == 1) {
     VPB_CUDA(cudaMemcpyAsync(cursor, d_partition, (size_t)nk1 * 4, cudaMemcpyDeviceToDevice, c.stream));

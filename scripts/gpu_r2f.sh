@@ -16,6 +16,8 @@ echo "bench N=2 rc=$?" | tee -a $S
 timeout 400 python bench.py --gpus 1 --steps 20 --warmup 3 $B > gpurun_out/r2f_bench_n1.json 2> gpurun_out/r2f_bench_n1.err
 echo "bench N=1 rc=$?" | tee -a $S
 timeout 600 $T bench.py --gpus 2 --workload harris3d --steps 25 --warmup 3 $B > gpurun_out/r2f_bench_h3d_n2.json 2> gpurun_out/r2f_bench_h3d_n2.err
+echo "bench harris3d N=2 (sort 25) rc=$?" | tee -a $S
+timeout 600 $T bench.py --gpus 2 --workload harris3d --steps 20 --warmup 3 --sort-interval 4 $B > gpurun_out/r2f_bench_h3d_n2_i4.json 2> gpurun_out/r2f_bench_h3d_n2_i4.err
 echo "bench harris3d N=2 rc=$?" | tee -a $S
 python - <<'PY' | tee -a $S
 import glob, json

@@ -583,8 +583,9 @@ def group_tables(vpb, n):
 
 
 @pytest.mark.parametrize("n,np_,L,vth", [((10, 9, 8), 60001, 0, 0.5), ((10, 9, 8), 60001, 7, 0.5), ((33, 1, 17), 150000, 0, 0.3),
-                                          ((16, 16, 16), 300000, 4, 0.2), ((5, 4, 3), 63, 0, 0.1), ((40, 36, 20), 2048 * 37 + 5, 3, 0.4)])
-@pytest.mark.parametrize("variant", [2, 1, 0])
+                                          ((16, 16, 16), 300000, 4, 0.2), ((5, 4, 3), 63, 0, 0.1), ((40, 36, 20), 2048 * 37 + 5, 3, 0.4),
+                                          ((5, 4, 3), 40000, 2, 0.3)])      # ~670 per group: ranks beyond the packed 8 bits
+@pytest.mark.parametrize("variant", [2, 3, 1, 0])
 def test_sort_p_planes_grouped(vpb, n, np_, L, vth, variant):
     """The device-resident driver's sort (vpb_sort_p_planes_grouped): the same particles, bit for bit, grouped by the
     voxel they occupy (L = 0) or reach L steps ahead, groups in the brick-Morton order of vpb_sort_group_order,
@@ -603,11 +604,13 @@ def test_sort_p_planes_grouped(vpb, n, np_, L, vth, variant):
     d_p, d_out = ParticleArray(vpb, dom, np_), ParticleArray(vpb, dom, np_)
     d_part = DevArray(vpb, nkeys + 1, np.int32)
     d_p.upload(p)
-    vpb.vpb_set_tuning(b"sort.group_variant", variant)
+    vpb.vpb_set_tuning(b"sort.group_variant", min(variant, 2))   # 3: the gather form with separate key and rank arrays
+    vpb.vpb_set_tuning(b"sort.pack_rank", int(variant == 2))
     try:
         vpb.vpb_sort_p_planes_grouped(dom, d_p.ptr, d_out.ptr, np_, d_part.ptr, L)
     finally:
         vpb.vpb_set_tuning(b"sort.group_variant", 2)
+        vpb.vpb_set_tuning(b"sort.pack_rank", 1)
     out, part = d_out.download(np_), d_part.download()
     assert_bits_equal(d_p.download(np_), p, "the input is left alone")
     # same particles, every record intact
