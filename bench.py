@@ -364,8 +364,6 @@ def run_b200(args):
         # 0.488 c/wpe cells, decomposed over the GPUs; 32 ppc per species = 64 particles per cell
         if args.ppc == 64:
             args.ppc = 32
-        if args.sort_interval == SORT_INTERVAL:
-            args.sort_interval = 25
         hn, topo = harris3d_shape(args, world), H3D_TOPO[world]
         d = 1000.0 / 2048
         hL = (hn[0] * d, hn[1] * d, hn[2] * d)
@@ -379,15 +377,14 @@ def run_b200(args):
     elif harris:
         # BASELINE configs[2]: the shape and plasma of decks/trecon-part/turbulence.cxx:86-160 -- 2048 x 1 x 1024 cells of
         # 0.488 x 1.95 x 0.488 c/wpe, pair plasma (mi/me = 1) at vth = 0.6 c, wce/wpe = 10, force-free sheet of half
-        # thickness 6 c/wpe, conducting walls that reflect particles at z = 0, Lz, dt = 0.99 Courant, sort every 25.
+        # thickness 6 c/wpe, conducting walls that reflect particles at z = 0, Lz, dt = 0.99 Courant (the deck sorts every 25 steps; here
+        # --sort-interval, default 5: at vth = 0.6 c a particle crosses a cell every other step).
         # The device loader is thermal: the sheet's drift current is not loaded (the field near the sheet, 5 % of the
         # box, is not in equilibrium; |B| = b0 everywhere, so the particle work is the deck's).
         if world != 1:
             raise SystemExit("--workload harris is the one-GPU configuration")
         if args.ppc == 64:
             args.ppc = 100
-        if args.sort_interval == SORT_INTERVAL:
-            args.sort_interval = 25
         hn = (2048, 1, 1024)
         hL = (1000.0, 500.0 / 256, 500.0)
         g = helpers.make_grid(hn, "periodic", L=hL, dt=helpers.courant_dt(hL[0] / hn[0], 0, hL[2] / hn[2], frac=0.99))
@@ -536,6 +533,8 @@ def run_b200(args):
         line["fields_c2"] = fields_c2
     # release the big run before the other legs
     sim.free()
+    if world == 1 and args.workload == "thermal" and not args.no_e2e:
+        line["small_step"] = small_step_measure(L)
     if harris and args.trecon_deck:
         hyb = os.path.join(ROOT, "oracle", "_ref", "hybrid")
         line["trecon_deck"] = trecon_deck(os.path.join(hyb, "turbulence_c2.b200.op"), 2048 * 1024, 60, 1,
@@ -569,6 +568,37 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def small_step_measure(L, n=64, ppc=32, steps=200):
+    """BASELINE configs[0]'s shape (64^3 cells x 32 ppc x 2 species) device-resident through the C++ driver: a step of
+    about half a millisecond, where the ~20 small launches of the field part matter.  Timed with the field part replayed
+    from its captured CUDA graph (the default) and launched kernel by kernel."""
+    from old_vpic_b200 import grid as helpers
+    from old_vpic_b200.sim import NativeSimulation
+    out = {"workload": "thermal %d^3 cells x %d ppc x 2 species, device-resident, %d steps, sort every 5" % (n, ppc, steps)}
+    for graph in (1, 0):
+        L.vpb_set_tuning(b"sim.graph", graph)
+        try:
+            g = helpers.make_grid((n, n, n), "periodic")
+            sim = NativeSimulation(g, L=L)
+            sim.set_sort_lookahead(-1)
+            for name, q_m, q, seed in (("electron", -1.0, -1.0 / ppc, 7), ("ion", 1.0, 1.0 / ppc, 1007)):
+                sp = sim.define_species(name, q_m, n ** 3 * ppc + 1024, sort_interval=5)
+                sim.load_thermal(sp, ppc, VTH, q, seed)
+            sim.advance(10)
+            L.vpb_sync()
+            L.vpb_timer_start(2)
+            sim.advance(steps)
+            L.vpb_timer_stop(2)
+            ms = L.vpb_timer_ms(2)
+            key = "graph" if graph else "kernel_by_kernel"
+            out[key] = {"ms_per_step": ms / steps, "particle_advances_per_s": 2.0 * n ** 3 * ppc * steps / (ms * 1e-3),
+                        "graph_replays": int(L.vpb_sim_graph_replays(sim.h))}
+            sim.free()
+        finally:
+            L.vpb_set_tuning(b"sim.graph", 1)
+    return out
 
 
 def fields_measure(L, n, steps, warmup):

@@ -391,8 +391,9 @@ void vpb_sim_energies(vpb_sim_t *s, double *out6_plus_nspecies);       /* dump_e
 void vpb_sim_hydro(vpb_sim_t *s, int species, vpb_hydro_t *host);      /* clear + accumulate + synchronize, to the host */
 long vpb_sim_step(const vpb_sim_t *s);
 /* The field part of a step (advance.cxx:109-147, and :214 on steps without cleaning) is captured once into a CUDA graph
- * and replayed (tuning sim.graph, default 1; off while per-kernel timing is on, with deck hooks inside the segment, or
- * over the host-staged transport).  Returns how many steps replayed it. */
+ * and replayed (tuning sim.graph, default 1: runs on one rank; 2: also runs split over ranks, whose segment holds NCCL
+ * groups -- untested; off while per-kernel timing is on, with deck hooks inside the segment, or over the host-staged
+ * transport).  Returns how many steps replayed it. */
 long vpb_sim_graph_replays(const vpb_sim_t *s);
 int vpb_sim_num_species(const vpb_sim_t *s);
 long vpb_sim_np(vpb_sim_t *s, int species);

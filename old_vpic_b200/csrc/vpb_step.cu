@@ -221,8 +221,12 @@ static void drop_field_graphs(vpb_sim *s) {
 // not with deck hooks inside the segment, not over the host-staged transport (it synchronises).
 static void field_segment(vpb_sim *s, bool with_load) {
   const vpb_sim_callbacks_t &cb = s->cb;
-  const bool can = tuning("sim.graph", 1) != 0 && !prof_enabled() && !cb.current_injection && !cb.field_injection &&
-                   comm_capturable();
+  // Runs split over ranks keep launching kernel by kernel unless sim.graph = 2: the segment then holds NCCL groups, and
+  // the first 2-GPU attempt at capturing those did not come back (round 2, call F) -- not pursued, the segment is 1 %
+  // of a step at the sizes ranks are split for.
+  const int mode = tuning("sim.graph", 1);
+  const bool can = mode != 0 && (s->nproc == 1 || mode == 2) && !prof_enabled() && !cb.current_injection &&
+                   !cb.field_injection && comm_capturable();
   if (!can || s->field_segment_runs < 1) {
     field_segment_launch(s, with_load);
     if (can) s->field_segment_runs++;

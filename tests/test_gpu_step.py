@@ -233,5 +233,7 @@ def test_native_driver_field_graph(vpb, kind, n, clean):
             sim.free()
         finally:
             vpb.vpb_set_tuning(b"sim.graph", 1)
+    # two runs of the same particles differ by the order of the deposit atomics, and from the first in-cell test that
+    # falls the other way by ~1e-4: the tolerance of every multi-step comparison
     scale = np.maximum(np.abs(hist[1]).max(axis=0), 1e-300)
-    assert (np.abs(hist[0] - hist[1]) / scale).max() < 1e-5
+    assert (np.abs(hist[0] - hist[1]) / scale).max() < 1e-4
