@@ -254,17 +254,35 @@ def trecon_deck(exe, cells, steps, tpp, what, timeout):
     try:
         with tempfile.TemporaryDirectory() as t:
             t0 = time.perf_counter()
-            r = subprocess.run([exe, "-tpp=%d" % tpp], cwd=t, capture_output=True, text=True, timeout=timeout)
+            # the library's host wall-clock account of its entry points (VPB_TRACE; ignored by the reference alone)
+            env = dict(os.environ, VPB_TRACE="1", VPB_TRACE_FILE=os.path.join(t, "vpb_trace.txt"))
+            r = subprocess.run([exe, "-tpp=%d" % tpp], cwd=t, env=env, capture_output=True, text=True, timeout=timeout)
             wall = time.perf_counter() - t0
             m = re.search(r"simulation time: ([0-9.eE+-]+)", r.stdout + r.stderr)
             if r.returncode != 0 or not m:
                 return {"unavailable": "deck exited %d: %s" % (r.returncode, (r.stdout + r.stderr)[-300:])}
             sec = float(m.group(1))
+            hot = {}
+            if os.path.exists(env["VPB_TRACE_FILE"]):
+                for ln in open(env["VPB_TRACE_FILE"]):
+                    f = ln[len("vpb trace: "):].split()
+                    # entry points start right after the prefix; labels nested inside one are indented
+                    if ln.startswith("vpb trace: ") and not ln.startswith("vpb trace:  ") and len(f) == 5 and f[0] != "label":
+                        hot[f[0]] = float(f[2]) * 1e-3
     except Exception as e:          # noqa: BLE001
         return {"unavailable": repr(e)[:300]}
     pushed = 4 * 50 * cells          # e + i, each also copied into a tracer species (particle_select = 1)
+    out_hot = {}
+    if hot:
+        # Whole run (initialisation included): seconds the program spent inside the library's entry points, i.e. the hot
+        # path; the rest of `simulation time` is the deck's own host code (turbulence.cxx / energy.cxx / tracer.cxx loop
+        # over every particle on the host for their diagnostics, which also pulls the managed arrays off the device)
+        tot = sum(hot.values())
+        out_hot = {"hot_path_s": tot, "hot_path_share_of_simulation_time": tot / sec if sec else None,
+                   "value_hot_path": pushed * steps / tot if tot else None,
+                   "hot_path_top": dict(sorted(hot.items(), key=lambda kv: -kv[1])[:6])}
     return {"value": pushed * steps / sec, "unit": "particle-advances/s", "ms_per_step": 1e3 * sec / steps, "steps": steps,
-            "particles_pushed_per_step": pushed, "process_wall_s": wall,
+            "particles_pushed_per_step": pushed, "process_wall_s": wall, **out_hot,
             "sample": "%s: decks/trecon-part/turbulence.cxx, config.h knobs %s cells, topology 1x1x1, %d steps; nppc 50 as shipped "
                       "(BASELINE asks 100: a constant in the deck body, not a knob), tracer copies pushed by the deck, field + hydro "
                       "dumps every 20 steps; -tpp=%d" % (what, cells, steps, tpp)}

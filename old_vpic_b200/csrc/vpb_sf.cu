@@ -57,7 +57,14 @@ __global__ void __launch_bounds__(256) load_interpolator_kernel(vpb_interpolator
   o4.x = half * (w1 + w0); o4.y = half * (w1 - w0);
   float4 *o = reinterpret_cast<float4 *>(reinterpret_cast<char *>(fi) + v * (size_t)g.fi_bytes);
   o[0] = o0; o[1] = o1; o[2] = o2; o[3] = o3;
-  *reinterpret_cast<float2 *>(o + 4) = o4;   // _pad[2] is left untouched, like the reference
+  if (g.fi_bytes == 96) {
+    // the padded device record: its last sector is written whole (a lone 8-byte store would make DRAM read the other
+    // 24 bytes first); bytes 72..95 belong to nobody
+    o[4] = make_float4(o4.x, o4.y, 0.f, 0.f);
+    o[5] = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    *reinterpret_cast<float2 *>(o + 4) = o4;   // _pad[2] is left untouched, like the reference
+  }
 }
 
 // One thread per voxel of (1..nx+1, 1..ny+1, 1..nz+1); jf += c*(4 quadrants).

@@ -8,7 +8,7 @@ migration over NCCL -- to match the oracle's state of its own rank:
     boundary_p.c:488-491), pending movers exact as a set, rhob and the accumulator within the float-sum tolerance;
   * synchronize_hydro: bit-exact.
     torchrun --nproc-per-node 2 tests/dist_gpu_percall_worker.py     (also 4: 2x2x1)
-Written after round 1's GPU budget was spent; not yet run on hardware."""
+Green on 2 B200s (profiles/r2b_summary_2gpu.txt, r2k_summary_2gpu_dist.txt)."""
 import ctypes as C
 import os
 import sys

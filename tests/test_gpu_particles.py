@@ -413,8 +413,8 @@ def test_advance_p_pair_tails(vpb, orc):
             assert max_rel(acc_floats(a_g), acc_floats(a_o)) < ACC_TOL
 
 
-# Kernel variants written after round 1's GPU budget was spent (vpb_advance_p_pair.cu: FULL fast path for whole chunks,
-# LEAN index-only mover ring): same bar as the default kernel, not yet run on hardware.
+# Kernel variants (vpb_advance_p_pair.cu: FULL fast path for whole chunks -- the default --, LEAN index-only mover ring):
+# same bar as the kernel they replace.
 
 
 @pytest.mark.parametrize("variant", [1, 2, 3])
