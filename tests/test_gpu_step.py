@@ -90,8 +90,11 @@ def test_native_driver_cleaning_guards_and_sync_shared(vpb, orc):
         w = want[step]
         assert len(w["div_e"]) == 2 and len(w["div_b"]) == 2            # both passes ran on the CPU: errors were > 0
         # the scheme conserves charge: the div E error is the accumulated rounding of the deposits (1e-7 of the charge
-        # density), so it depends on the order of the float sums -- same magnitude, not same digits (measured: 5 %)
-        assert np.allclose(got[0:2], w["div_e"], rtol=0.25), (step, got, w)
+        # density), so it depends on the order of the float sums -- same magnitude, not same digits.  rho_p adds the
+        # weights of a warp's particles that share a voxel in registers before they reach memory (a tree instead of the
+        # CPU's serial sum), which makes that rounding SMALLER: measured 0.59 of the CPU's number (5 % apart before).
+        ratio = np.asarray(got[0:2]) / np.asarray(w["div_e"])
+        assert np.all(ratio > 0.2) and np.all(ratio < 1.5), (step, got, w)
         # div B error is rounding noise of the Yee update (1e-8 of |B|/dx): same order of magnitude
         assert np.all(got[2:4] > 0) and np.all(got[2:4] < 10 * np.array(w["div_b"]) + 1e-30), (step, got, w)
         assert got[1] < got[0]                                           # the pass reduced the error
