@@ -261,6 +261,14 @@ typedef struct vpb_species_state {
  * back-fill, exchange with the face neighbours over NCCL, inject and finish the arrivals.  np and nm
  * of every species are updated; the call synchronises.  advance.cxx:94-96 calls it 3 times a step. */
 void vpb_boundary_p(vpb_domain_t *dom, vpb_species_state_t *sp, int n_sp, vpb_field_t *d_f, vpb_accumulator_t *d_a);
+/* The same round for callers that number the rounds of a step (0, 1, 2: advance.cxx:94-96), identically on every rank.
+ * After one exact round per number, which tells both sides of every face what passes through it, a round costs ONE
+ * message per face (fixed capacity, a header record carrying the count) and ONE read-back of all counters:
+ * the arrivals are appended, moved and turned into next round's movers with sizes the device reads from the headers.
+ * A face that outgrows its capacity sends the rest in a second message and the capacity is raised.  Arrays cannot
+ * grow on this path (no hook): arrivals beyond max_np / max_nm are an error.  round < 0 = vpb_boundary_p.
+ * Tuning boundary.fused: 1 (default) as described, 0 always the exact protocol. */
+void vpb_boundary_p_round(vpb_domain_t *dom, vpb_species_state_t *sp, int n_sp, vpb_field_t *d_f, vpb_accumulator_t *d_a, int round);
 /* boundary_p.c:416-447: when the arrivals of a round do not fit, the reference grows the species' arrays by 31 % and
  * warns.  vpb_boundary_p leaves that to the owner of the arrays through this hook (NULL, the default: overflow is an
  * error).  The hook gets the index of the species in the list and the capacities needed; it must update p / max_np

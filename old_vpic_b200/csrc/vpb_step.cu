@@ -130,7 +130,7 @@ static void migrate(vpb_sim *s) {
     st[k].p = sp.p; st[k].pm = sp.pm; st[k].np = sp.np; st[k].max_np = sp.max_np;
     st[k].nm = c.h_pinned_i[k]; st[k].max_nm = sp.max_nm; st[k].id = sp.id;
   }
-  for (int r = 0; r < s->num_comm_round; r++) vpb_boundary_p(s->dom, st.data(), n, s->f, s->a);
+  for (int r = 0; r < s->num_comm_round; r++) vpb_boundary_p_round(s->dom, st.data(), n, s->f, s->a, r);
   for (int k = 0; k < n; k++) {
     s->sp[k].np = st[k].np;
     if (st[k].nm)   // advance.cxx:98-102

@@ -116,6 +116,7 @@ SIGNATURES = {
     "vpb_move_p_one": (None, [_vp, _vp, _vp, _vp, _vp]),
     "vpb_accumulate_rhob_one": (None, [_vp, _vp, _vp]),
     "vpb_boundary_p": (None, [_vp, _vp, _i, _vp, _vp]),
+    "vpb_boundary_p_round": (None, [_vp, _vp, _i, _vp, _vp, _i]),
     "vpb_sort_p": (None, [_vp, _vp, _vp, _i, _vp]),
     "vpb_sort_p_planes": (None, [_vp, _vp, _vp, _i, _vp]),
     "vpb_sort_p_planes_ahead": (None, [_vp, _vp, _vp, _i, _vp, _i]),

@@ -8,7 +8,9 @@ migration over NCCL -- to match the oracle's state of its own rank:
     boundary_p.c:488-491), pending movers exact as a set, rhob and the accumulator within the float-sum tolerance;
   * synchronize_hydro: bit-exact.
     torchrun --nproc-per-node 2 tests/dist_gpu_percall_worker.py     (also 4: 2x2x1)
-Green on 2 B200s (profiles/r2b_summary_2gpu.txt, r2k_summary_2gpu_dist.txt)."""
+Green on 2 B200s (profiles/r2b_summary_2gpu.txt, r2k_summary_2gpu_dist.txt).
+VPB_BOUNDARY_FUSED=2 sends the reference-named boundary_p() through the driver's fused migration rounds
+(vpb_boundary_p_round) so that the same oracle comparison covers them."""
 import ctypes as C
 import os
 import sys
@@ -94,50 +96,53 @@ def main():
         M.energy_f(ptr(en_g), ptr(f_g), ptr(m), g.ref())
         np.testing.assert_allclose(en_g, cl.energy_f(fs, m), rtol=1e-12)
 
-        # particle migration
-        npk, cap = 16 * 188, 6000
-        species, accs, fis = [], [], []
-        for k in range(W):
-            gk = grids[k]
-            fi = random_interpolator(np.random.default_rng(200 + k), gk, amp=0.2)
-            acc = abi.aligned_zeros(gk.nv, abi.accumulator_dtype)
-            sl = []
-            for sid, q in ((0, -1.0), (1, 0.5)):
-                p = make_particles(10 * k + sid + 1, gk, npk, cap, q)
-                pm = abi.aligned_zeros(cap, abi.mover_dtype)
-                nm = O.orc_advance_p(ptr(p), npk, q, ptr(pm), cap, ptr(acc), ptr(fi), gk.ref())
-                sl.append({"id": sid, "p": p, "np": npk, "pm": pm, "nm": nm})
-            species.append(sl); accs.append(acc); fis.append(fi)
-        p_g = [s["p"].copy() for s in species[rank]]
-        pm_g = [s["pm"].copy() for s in species[rank]]
-        a_g = accs[rank].copy()
-        sps = [abi.SpeciesStruct() for _ in species[rank]]
-        for j, (sp, s) in enumerate(zip(sps, species[rank])):
-            sp.id, sp.np, sp.max_np, sp.p = s["id"], s["np"], cap, p_g[j].ctypes.data
-            sp.nm, sp.max_nm, sp.pm = s["nm"], cap, pm_g[j].ctypes.data
-            sp.q_m = 1.0
-        sps[0].next = C.pointer(sps[1])
-        rhob_scale = None
-        for rnd in range(3):
-            L.boundary_p(C.byref(sps[0]), ptr(f_g), ptr(a_g), g.ref(), None)
-            cl.boundary_p(species, fs, accs)
+        # particle migration, two waves of fresh particles on the same grid: with VPB_BOUNDARY_FUSED=2 the first wave's three
+        # rounds run the reference's exact protocol (and tell both sides of every face what passes through it), the second
+        # wave's run the fused fixed-capacity messages (VPB_BOUNDARY_CAP_MAX=16 forces their second message as well)
+        for wave in range(2):
+            npk, cap = 16 * 188, 6000
+            species, accs, fis = [], [], []
+            for k in range(W):
+                gk = grids[k]
+                fi = random_interpolator(np.random.default_rng(200 + k + 50 * wave), gk, amp=0.2)
+                acc = abi.aligned_zeros(gk.nv, abi.accumulator_dtype)
+                sl = []
+                for sid, q in ((0, -1.0), (1, 0.5)):
+                    p = make_particles(1000 * wave + 10 * k + sid + 1, gk, npk, cap, q)
+                    pm = abi.aligned_zeros(cap, abi.mover_dtype)
+                    nm = O.orc_advance_p(ptr(p), npk, q, ptr(pm), cap, ptr(acc), ptr(fi), gk.ref())
+                    sl.append({"id": sid, "p": p, "np": npk, "pm": pm, "nm": nm})
+                species.append(sl); accs.append(acc); fis.append(fi)
+            p_g = [s["p"].copy() for s in species[rank]]
+            pm_g = [s["pm"].copy() for s in species[rank]]
+            a_g = accs[rank].copy()
+            sps = [abi.SpeciesStruct() for _ in species[rank]]
             for j, (sp, s) in enumerate(zip(sps, species[rank])):
-                assert (sp.np, sp.nm) == (s["np"], s["nm"]), ("counts", kind, rank, rnd, j, sp.np, sp.nm, s["np"], s["nm"])
-                assert np.array_equal(hot_rows(p_g[j], sp.np), hot_rows(s["p"], s["np"])), ("particle set", kind, rank, rnd, j)
-                # a pending mover names its particle by index, and the order of the array is the device's: compare what it
-                # points at together with its displacement
-                def movers(pm, p, n):
-                    rows = np.concatenate([np.ascontiguousarray(pm[:n]).view(np.uint32).reshape(n, 4)[:, :3],
-                                           np.ascontiguousarray(p[pm["i"][:n]]).view(np.uint8).reshape(n, 48)[:, :32].copy().view(np.uint32).reshape(n, 8)], axis=1) if n else np.zeros((0, 11), np.uint32)
-                    return rows[np.lexsort(rows.T[::-1])] if n else rows
-                assert np.array_equal(movers(pm_g[j], p_g[j], sp.nm), movers(s["pm"], s["p"], s["nm"])), ("movers", kind, rank, rnd, j)
-            others = [n for n in abi.FIELD_FLOATS if n != "rhob"]
-            for n in others:
-                assert np.array_equal(f_g[n].view(np.uint32), fs[rank][n].view(np.uint32)), n
-            rhob_scale = max(float(np.abs(fs[rank]["rhob"]).max()), 1e-30)
-            assert float(np.abs(f_g["rhob"] - fs[rank]["rhob"]).max()) <= TOL * rhob_scale
-            f_g["rhob"] = fs[rank]["rhob"]          # keep the later bit-exact field checks independent of the float-sum order
-            assert max_rel(a_g.view(np.float32).reshape(-1, 12), accs[rank].view(np.float32).reshape(-1, 12)) < TOL
+                sp.id, sp.np, sp.max_np, sp.p = s["id"], s["np"], cap, p_g[j].ctypes.data
+                sp.nm, sp.max_nm, sp.pm = s["nm"], cap, pm_g[j].ctypes.data
+                sp.q_m = 1.0
+            sps[0].next = C.pointer(sps[1])
+            rhob_scale = None
+            for rnd in range(3):
+                L.boundary_p(C.byref(sps[0]), ptr(f_g), ptr(a_g), g.ref(), None)
+                cl.boundary_p(species, fs, accs)
+                for j, (sp, s) in enumerate(zip(sps, species[rank])):
+                    assert (sp.np, sp.nm) == (s["np"], s["nm"]), ("counts", kind, rank, rnd, j, sp.np, sp.nm, s["np"], s["nm"])
+                    assert np.array_equal(hot_rows(p_g[j], sp.np), hot_rows(s["p"], s["np"])), ("particle set", kind, rank, rnd, j)
+                    # a pending mover names its particle by index, and the order of the array is the device's: compare what it
+                    # points at together with its displacement
+                    def movers(pm, p, n):
+                        rows = np.concatenate([np.ascontiguousarray(pm[:n]).view(np.uint32).reshape(n, 4)[:, :3],
+                                               np.ascontiguousarray(p[pm["i"][:n]]).view(np.uint8).reshape(n, 48)[:, :32].copy().view(np.uint32).reshape(n, 8)], axis=1) if n else np.zeros((0, 11), np.uint32)
+                        return rows[np.lexsort(rows.T[::-1])] if n else rows
+                    assert np.array_equal(movers(pm_g[j], p_g[j], sp.nm), movers(s["pm"], s["p"], s["nm"])), ("movers", kind, rank, rnd, j)
+                others = [n for n in abi.FIELD_FLOATS if n != "rhob"]
+                for n in others:
+                    assert np.array_equal(f_g[n].view(np.uint32), fs[rank][n].view(np.uint32)), n
+                rhob_scale = max(float(np.abs(fs[rank]["rhob"]).max()), 1e-30)
+                assert float(np.abs(f_g["rhob"] - fs[rank]["rhob"]).max()) <= TOL * rhob_scale
+                f_g["rhob"] = fs[rank]["rhob"]          # keep the later bit-exact field checks independent of the float-sum order
+                assert max_rel(a_g.view(np.float32).reshape(-1, 12), accs[rank].view(np.float32).reshape(-1, 12)) < TOL
         # hydro
         hs = []
         for k in range(W):

@@ -96,76 +96,140 @@ def main():
     O.orc_advance_e_update(ptr(f), ptr(m), g.ref(), 0)
     O.orc_local_adjust_tang_e(ptr(f), g.ref(), world)
     compare(f, fg, "advance_e", (1, nx + 1), ("ex", "ey", "ez", "tcax", "tcay", "tcaz"))
-    # 3. particle migration
-    npg = 2000
-    rngp = np.random.default_rng(9)
-    P = abi.aligned_zeros(npg, abi.particle_dtype)
+    # 3. particle migration: three waves of fresh particles.  Wave 0 through the reference's protocol (counts, then
+    #    payloads of exactly that size); it also tells both sides of every face what passes through it per round, from
+    #    which the capacities of the FUSED rounds follow (vpb_boundary.cu: one fixed-capacity message per face whose
+    #    record 0 is a header {count, capacity, round, magic}; a face over its capacity sends the rest in a second,
+    #    exactly sized message).  Wave 1 runs the fused rounds, wave 2 the same with capacities clamped to 4 injectors
+    #    so that the second message is exercised.  Same checks for every wave.
     from old_vpic_b200.grid import interior_voxels
-    P["i"] = np.sort(rngp.choice(interior_voxels(gg), npg))
-    for k in ("dx", "dy", "dz"):
-        P[k] = rngp.uniform(-1, 1, npg).astype(np.float32)
-    for k in ("ux", "uy", "uz"):
-        P[k] = (0.8 * rngp.standard_normal(npg)).astype(np.float32)
-    P["q"] = 1.0
-    P["tag"] = np.arange(npg)
+    MAGIC = 0x76706221
     fi_g = abi.aligned_zeros(gg.nv, abi.interpolator_dtype)
     fi_l = abi.aligned_zeros(g.nv, abi.interpolator_dtype)
-    # global run
-    Pg = P.copy()
-    ag = abi.aligned_zeros(gg.nv, abi.accumulator_dtype)
-    pmg = abi.aligned_zeros(npg, abi.mover_dtype)
-    assert O.orc_advance_p(ptr(Pg), npg, 1.0, ptr(pmg), npg, ptr(ag), ptr(fi_g), gg.ref()) == 0
-    # local run: my particles are those whose voxel x lies in my slab
-    gx = P["i"] % (gn[0] + 2)
-    mine = (gx > x0) & (gx <= x0 + nx)
-    cap = npg
-    Pl = abi.aligned_zeros(cap, abi.particle_dtype)
-    nl = int(mine.sum())
-    Pl[:nl] = P[mine]
-    gy = (P["i"][mine] // (gn[0] + 2)) % (gn[1] + 2)
-    gz = P["i"][mine] // ((gn[0] + 2) * (gn[1] + 2))
-    Pl["i"][:nl] = (gx[mine] - x0) + (nx + 2) * (gy + (gn[1] + 2) * gz)
-    al_ = abi.aligned_zeros(g.nv, abi.accumulator_dtype)
-    pml = abi.aligned_zeros(cap, abi.mover_dtype)
-    nm = O.orc_advance_p(ptr(Pl), nl, 1.0, ptr(pml), cap, ptr(al_), ptr(fi_l), g.ref())
-    fl = abi.aligned_zeros(g.nv, abi.field_dtype)
-    for rnd in range(3):                       # num_comm_round (vpic.cxx:17)
+    gsx = gn[0] + 2
+    remote = [f_ for f_ in range(6) if peers[f_] != rank]
+
+    def capacity_for(ns, nr, cap_max):
+        m = max(ns, nr)
+        cap = m + m // 2 + 64
+        return min(cap, cap_max) if cap_max else cap
+
+    def inject(got, counts, Pl, nl, pml, nm, al_):
+        for face in RORDER:
+            if face in got and counts[face]:
+                inj = np.ascontiguousarray(got[face]).view(abi.injector_dtype)[:counts[face]]
+                npc = C.c_int(nl)
+                nm += O.orc_boundary_p_inject(ptr(Pl), C.byref(npc), ptr(pml), nm, ptr(np.ascontiguousarray(inj)), len(inj), 0, ptr(al_), g.ref())
+                nl = npc.value
+        return nl, nm
+
+    def exact_round(Pl, nl, pml, nm, al_, fl):
         outs = [abi.aligned_zeros(max(nm, 1), abi.injector_dtype) for _ in range(6)]
         outp = (C.c_void_p * 6)(*[o.ctypes.data for o in outs])
         n_out = (C.c_int * 6)()
         nl = O.orc_boundary_p_pack(ptr(Pl), nl, ptr(pml), nm, 0, ptr(fl), g.ref(), rank, world, outp, n_out)
-        counts = {f_: np.array([n_out[f_]], np.int32) for f_ in range(6) if peers[f_] != rank}
+        counts = {f_: np.array([n_out[f_]], np.int32) for f_ in remote}
         got_n = exchange(counts, peers, rank, {f_: 1 for f_ in counts}, np.int32)
         pay = {f_: outs[f_][:n_out[f_]].view(np.uint8).reshape(-1).copy() if n_out[f_] else np.zeros(0, np.uint8) for f_ in counts}
         got = exchange(pay, peers, rank, {f_: int(got_n[f_][0]) * 48 for f_ in counts}, np.uint8)
-        nm = 0
-        for face in RORDER:
-            if face in got and len(got[face]):
-                inj = np.ascontiguousarray(got[face]).view(abi.injector_dtype)
-                npc = C.c_int(nl)
-                nm += O.orc_boundary_p_inject(ptr(Pl), C.byref(npc), ptr(pml), nm, ptr(inj), len(inj), 0, ptr(al_), g.ref())
-                nl = npc.value
-    assert nm == 0
-    # global particle count is conserved and every particle I hold equals the global run's, bit for bit
-    tot = torch.tensor([nl])
-    dist.all_reduce(tot)
-    assert int(tot) == npg, (int(tot), npg)
-    ref = {int(t): k for k, t in enumerate(Pg["tag"])}
-    gsx, gsy = gn[0] + 2, gn[1] + 2
-    for k in range(nl):
-        r = Pg[ref[int(Pl["tag"][k])]] if False else None
-    # tags are not carried by injectors (boundary_p.c:488-491), so match on the hot state instead
-    def key(p, xoff, sx):
-        lx = p["i"] % sx
-        rest = p["i"] // sx
-        gi = (lx + xoff) + gsx * rest
-        return np.stack([gi.astype(np.int64)] + [p[c].view(np.uint32).astype(np.int64) for c in ("dx", "dy", "dz", "ux", "uy", "uz")], 1)
-    kg = {tuple(r) for r in key(Pg, 0, gsx)}
-    for r in key(Pl[:nl], x0, nx + 2):
-        assert tuple(r) in kg, ("particle not in the single-domain result", rank, r)
-    # accumulators of my interior voxels agree with the global run (same per-particle contributions)
-    a3, b3 = al_.view(np.float32).reshape(g.shape + (12,)), ag.view(np.float32).reshape(gg.shape + (12,))
-    np.testing.assert_allclose(a3[1:-1, 1:-1, 1:nx + 1], b3[1:-1, 1:-1, x0 + 1:x0 + nx + 1], rtol=0, atol=2e-5 * np.abs(b3).max())
+        nr = {f_: int(got_n[f_][0]) for f_ in counts}
+        nl, nm = inject(got, nr, Pl, nl, pml, 0, al_)
+        return nl, nm, {f_: int(n_out[f_]) for f_ in remote}, nr
+
+    def fused_round(Pl, nl, pml, nm, al_, fl, slot, cap, cap_max):
+        outs = [abi.aligned_zeros(max(nm, 1), abi.injector_dtype) for _ in range(6)]
+        outp = (C.c_void_p * 6)(*[o.ctypes.data for o in outs])
+        n_out = (C.c_int * 6)()
+        nl = O.orc_boundary_p_pack(ptr(Pl), nl, ptr(pml), nm, 0, ptr(fl), g.ref(), rank, world, outp, n_out)
+        msg = {}
+        for f_ in remote:
+            m_ = np.full((cap[f_] + 1) * 48, 0xAB, np.uint8)           # the unused part of a message is never read
+            m_[:16] = np.array([n_out[f_], cap[f_], slot, MAGIC], np.int32).view(np.uint8)
+            k = min(int(n_out[f_]), cap[f_])
+            m_[48:48 + 48 * k] = outs[f_][:k].view(np.uint8).reshape(-1)
+            msg[f_] = m_
+        got = exchange(msg, peers, rank, {f_: (cap[f_] + 1) * 48 for f_ in msg}, np.uint8)
+        ns, nr, first = {}, {}, {}
+        for f_ in remote:
+            h = np.ascontiguousarray(got[f_][:16]).view(np.int32)
+            assert (int(h[1]), int(h[2]), int(h[3])) == (cap[f_], slot, MAGIC), ("header", rank, f_, h, cap[f_], slot)
+            ns[f_], nr[f_] = int(n_out[f_]), int(h[0])
+            first[f_] = np.ascontiguousarray(got[f_][48:48 + 48 * min(nr[f_], cap[f_])])
+        nl, nm = inject(first, {f_: min(nr[f_], cap[f_]) for f_ in remote}, Pl, nl, pml, 0, al_)
+        seconds = 0
+        if any(ns[f_] > cap[f_] or nr[f_] > cap[f_] for f_ in remote):
+            more = {f_: (outs[f_][cap[f_]:ns[f_]].view(np.uint8).reshape(-1).copy() if ns[f_] > cap[f_] else np.zeros(0, np.uint8)) for f_ in remote}
+            rest = exchange(more, peers, rank, {f_: max(nr[f_] - cap[f_], 0) * 48 for f_ in remote}, np.uint8)
+            nl, nm = inject(rest, {f_: max(nr[f_] - cap[f_], 0) for f_ in remote}, Pl, nl, pml, nm, al_)
+            seconds = 1
+        for f_ in remote:
+            m_ = max(ns[f_], nr[f_])
+            if m_ + m_ // 4 > cap[f_]:
+                cap[f_] = capacity_for(ns[f_], nr[f_], cap_max)
+        return nl, nm, seconds
+
+    caps = [None, None, None]
+    for wave, cap_max in ((0, 0), (1, 0), (2, 4)):
+        npg = 2000
+        rngp = np.random.default_rng(9 + wave)
+        P = abi.aligned_zeros(npg, abi.particle_dtype)
+        P["i"] = np.sort(rngp.choice(interior_voxels(gg), npg))
+        for k in ("dx", "dy", "dz"):
+            P[k] = rngp.uniform(-1, 1, npg).astype(np.float32)
+        for k in ("ux", "uy", "uz"):
+            P[k] = (0.8 * rngp.standard_normal(npg)).astype(np.float32)
+        P["q"] = 1.0
+        P["tag"] = np.arange(npg)
+        # global run
+        Pg = P.copy()
+        ag = abi.aligned_zeros(gg.nv, abi.accumulator_dtype)
+        pmg = abi.aligned_zeros(npg, abi.mover_dtype)
+        assert O.orc_advance_p(ptr(Pg), npg, 1.0, ptr(pmg), npg, ptr(ag), ptr(fi_g), gg.ref()) == 0
+        # local run: my particles are those whose voxel x lies in my slab
+        gx = P["i"] % gsx
+        mine = (gx > x0) & (gx <= x0 + nx)
+        cap_p = npg
+        Pl = abi.aligned_zeros(cap_p, abi.particle_dtype)
+        nl = int(mine.sum())
+        Pl[:nl] = P[mine]
+        gy = (P["i"][mine] // gsx) % (gn[1] + 2)
+        gz = P["i"][mine] // (gsx * (gn[1] + 2))
+        Pl["i"][:nl] = (gx[mine] - x0) + (nx + 2) * (gy + (gn[1] + 2) * gz)
+        al_ = abi.aligned_zeros(g.nv, abi.accumulator_dtype)
+        pml = abi.aligned_zeros(cap_p, abi.mover_dtype)
+        nm = O.orc_advance_p(ptr(Pl), nl, 1.0, ptr(pml), cap_p, ptr(al_), ptr(fi_l), g.ref())
+        fl = abi.aligned_zeros(g.nv, abi.field_dtype)
+        seconds = 0
+        for rnd in range(3):                       # num_comm_round (vpic.cxx:17)
+            if wave == 0:
+                nl, nm, ns, nr = exact_round(Pl, nl, pml, nm, al_, fl)
+                caps[rnd] = {f_: capacity_for(ns[f_], nr[f_], 0) for f_ in remote}
+            else:
+                if cap_max:
+                    caps[rnd] = {f_: min(c_, cap_max) for f_, c_ in caps[rnd].items()}
+                nl, nm, sec = fused_round(Pl, nl, pml, nm, al_, fl, rnd, caps[rnd], cap_max)
+                seconds += sec
+        assert nm == 0
+        if wave == 2:
+            flag = torch.tensor([seconds])
+            dist.all_reduce(flag)
+            assert int(flag) > 0, "the clamped capacities never forced a second message"
+        # global particle count is conserved and every particle I hold equals the global run's, bit for bit
+        tot = torch.tensor([nl])
+        dist.all_reduce(tot)
+        assert int(tot) == npg, (int(tot), npg)
+        # tags are not carried by injectors (boundary_p.c:488-491), so match on the hot state instead
+        def key(p, xoff, sx):
+            lx = p["i"] % sx
+            rest = p["i"] // sx
+            gi = (lx + xoff) + gsx * rest
+            return np.stack([gi.astype(np.int64)] + [p[c].view(np.uint32).astype(np.int64) for c in ("dx", "dy", "dz", "ux", "uy", "uz")], 1)
+        kg = {tuple(r) for r in key(Pg, 0, gsx)}
+        for r in key(Pl[:nl], x0, nx + 2):
+            assert tuple(r) in kg, ("particle not in the single-domain result", rank, wave, r)
+        # accumulators of my interior voxels agree with the global run (same per-particle contributions)
+        a3, b3 = al_.view(np.float32).reshape(g.shape + (12,)), ag.view(np.float32).reshape(gg.shape + (12,))
+        np.testing.assert_allclose(a3[1:-1, 1:-1, 1:nx + 1], b3[1:-1, 1:-1, x0 + 1:x0 + nx + 1], rtol=0, atol=2e-5 * np.abs(b3).max())
     # 3. currents: unload_accumulator + synchronize_jf (x, y, z passes).  Each rank only holds its own
     #    particles' share of the plane it shares with its neighbour; after the exchange both copies must be
     #    identical and equal to the single-domain result up to float summation order.

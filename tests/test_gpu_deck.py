@@ -114,15 +114,19 @@ def _gpu_count():
     return sum(1 for line in out.splitlines() if line.startswith("GPU "))
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_reference_deck_on_ranks(world, tmp_path):
+@pytest.mark.parametrize("world,migration", [(2, "exact"), (4, "exact"), (2, "fused"), (4, "fused"), (2, "fused_overflow")])
+def test_reference_deck_on_ranks(world, migration, tmp_path):
     """oracle/decks/thermal_small.cxx splits the box along x over the ranks of the job; every rank draws the same
     particles and keeps its slab, so the energies must be those of the one-rank reference run.  The ranks share one
     GPU: bootstrap through the reference's mp layer, exchanges staged through it (ran on a B200 at the end of round 1:
-    gpurun_out/pytest_gpu52_ranks.log, pytest_gpu53_ranks4.log)."""
+    gpurun_out/pytest_gpu52_ranks.log, pytest_gpu53_ranks4.log).  `fused`: boundary_p() goes through the device-resident
+    driver's migration rounds (vpb_boundary_p_round: one fixed-capacity message per face with the count in its header,
+    one read-back per round) from the second step on; `fused_overflow` caps a message at 8 injectors, so nearly every
+    face also sends the exactly sized second message."""
     if not os.path.exists(EXE):
         pytest.skip("oracle/_ref/hybrid/thermal_small.b200.op not built (needs /root/reference at build time)")
-    outs = _run_ranks(EXE, world, tmp_path)
+    env = {"exact": {}, "fused": {"VPB_BOUNDARY_FUSED": "2"}, "fused_overflow": {"VPB_BOUNDARY_FUSED": "2", "VPB_BOUNDARY_CAP_MAX": "8"}}[migration]
+    outs = _run_ranks(EXE, world, tmp_path, **env)
     got, want = read_energies(tmp_path / "energies"), read_energies(GOLD)
     assert got.shape == want.shape == (21, 9), outs[0][-2000:]
     rel = np.abs(got[:, 1:] - want[:, 1:]) / np.abs(want[:, 1:]).max(axis=0)

@@ -49,10 +49,12 @@ def test_decomposed_harris_sheet_matches_single_domain(world):
     assert r.returncode == 0 and "DIST_GPU_OK kind=harris" in r.stdout, (r.stdout + r.stderr)[-3000:]
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_decomposed_calls_match_oracle_cluster(world):
-    """tests/dist_gpu_percall_worker.py: per-call, bit-level parity of halos and migration over NCCL."""
+@pytest.mark.parametrize("world,migration", [(2, "exact"), (4, "exact"), (2, "fused"), (2, "fused_overflow")])
+def test_decomposed_calls_match_oracle_cluster(world, migration):
+    """tests/dist_gpu_percall_worker.py: per-call, bit-level parity of halos and migration over NCCL; `fused*`: the
+    second wave of movers through the fused fixed-capacity rounds (and their second message)."""
     if gpu_count() < world:
         pytest.skip("needs %d GPUs" % world)
-    r = torchrun(world, "dist_gpu_percall_worker.py")
+    env = {"exact": {}, "fused": {"VPB_BOUNDARY_FUSED": "2"}, "fused_overflow": {"VPB_BOUNDARY_FUSED": "2", "VPB_BOUNDARY_CAP_MAX": "16"}}[migration]
+    r = torchrun(world, "dist_gpu_percall_worker.py", env=env)
     assert r.returncode == 0 and "PERCALL_OK world=%d" % world in r.stdout, (r.stdout + r.stderr)[-3000:]
