@@ -482,6 +482,15 @@ def run_b200(args):
     nl = L.vpb_prof_list(1, lst, 4096)
     sort_list = [round(float(lst[i]), 3) for i in range(nl)]
     L.vpb_prof_collect(0, None, None, 1)
+    # every rank's own class times: the ranks meet at the first exchange after advance_p (the count message of boundary_p),
+    # so whatever one rank's push and sort took less than the slowest rank's shows up as ITS boundary_p time
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([prof[nm][0] / args.steps for nm in names], dtype=torch.float64, device="cuda")
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        tab = torch.stack(every).cpu().numpy()
+        per_rank = {nm: [round(float(x), 3) for x in tab[:, k]] for k, nm in enumerate(names) if nm in ("advance_p", "sort_p", "boundary_p", "halo")}
     # one step with divergence cleaning (E and B) and shared-face synchronisation forced on, timed on its own: what the
     # interval-100 steps of a long run cost beyond an ordinary step (collective: every rank takes it)
     sim.set_intervals(1, 1, sync_shared=1)
@@ -525,6 +534,8 @@ def run_b200(args):
                      "min_launch_ms": min(adv_list) if adv_list else None, "max_launch_ms": max(adv_list) if adv_list else None},
         "breakdown_ms_per_step": dict({k: v[0] / args.steps for k, v in prof.items()},
                                       other=ms_max / args.steps - sum(v[0] for v in prof.values()) / args.steps),
+        # N > 1: the same classes on every rank (ms per step)
+        "ranks_ms_per_step": per_rank,
         "sort_p": {"ms_per_sort": (sum(sort_list) / len(sort_list)) if sort_list else None, "sorts_timed": len(sort_list),
                    "particles_per_sort": np_, "algorithmic_bytes_per_particle": 100.0,
                    "frac": (100.0 * np_ / (sum(sort_list) / len(sort_list) * 1e-3) / 1e9 / peak) if sort_list else None,

@@ -267,7 +267,8 @@ void vpb_boundary_p(vpb_domain_t *dom, vpb_species_state_t *sp, int n_sp, vpb_fi
  * the arrivals are appended, moved and turned into next round's movers with sizes the device reads from the headers.
  * A face that outgrows its capacity sends the rest in a second message and the capacity is raised.  Arrays cannot
  * grow on this path (no hook): arrivals beyond max_np / max_nm are an error.  round < 0 = vpb_boundary_p.
- * Tuning boundary.fused: 1 (default) as described, 0 always the exact protocol. */
+ * Tuning boundary.fused: 0 (default) always the exact protocol, 1 as described (measured on 2 and 4 GPUs: same step time,
+ * DESIGN.md section 6). */
 void vpb_boundary_p_round(vpb_domain_t *dom, vpb_species_state_t *sp, int n_sp, vpb_field_t *d_f, vpb_accumulator_t *d_a, int round);
 /* boundary_p.c:416-447: when the arrivals of a round do not fit, the reference grows the species' arrays by 31 % and
  * warns.  vpb_boundary_p leaves that to the owner of the arrays through this hook (NULL, the default: overflow is an

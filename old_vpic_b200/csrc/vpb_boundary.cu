@@ -842,14 +842,17 @@ void vpb_accumulate_rhob_one(vpb_domain_t *dom, vpb_field_t *d_f, const vpb_part
 
 // One round of boundary_p over n_sp species (at most 7).  sp[s].nm is the number of movers in
 // sp[s].pm (ascending particle index); on return np/nm are updated.  Synchronises the stream.
-// round >= 0 (the caller's rounds of one step, advance.cxx:94-96, numbered from 0): fixed-capacity fused messages
-// once a first exact round has told both sides of every face what passes through it; every rank of the job must
-// use the same numbering.  round < 0: always the reference's exact two-message protocol.
+// round >= 0 (the caller's rounds of one step, advance.cxx:94-96, numbered from 0) and tuning boundary.fused != 0:
+// fixed-capacity fused messages once a first exact round has told both sides of every face what passes through it;
+// every rank of the job must use the same numbering.  Otherwise the reference's exact two-message protocol, which
+// is the default: measured on 2 and 4 B200s the two cost the same (60.84 / 60.72 and 60.95 / 60.96 ms per step,
+// profiles/r2r, r2s) -- what a rank spends in here is mostly the wait for the slowest rank's advance_p at the first
+// message, not read-backs or message count.
 void vpb_boundary_p_round(vpb_domain_t *dom, vpb_species_state_t *sp, int n_sp, vpb_field_t *d_f, vpb_accumulator_t *d_a, int round) {
   if (!dom) VPB_ERROR("Bad grid");
   if (n_sp < 0 || n_sp > 7) VPB_ERROR("boundary_p handles at most 7 species per call (got %d)", n_sp);
   if (n_sp && !sp) VPB_ERROR("Bad species");
-  const int mode = tuning("boundary.fused", 1);
+  const int mode = tuning("boundary.fused", 0);
   bool any_remote = false;
   for (int f = 0; f < 6; f++) {
     const int b = dom->d.bc[kFaceBound[f]];
@@ -872,7 +875,7 @@ void vpb_boundary_p(vpb_domain_t *dom, vpb_species_state_t *sp, int n_sp, vpb_fi
   // boundary.fused = 2 (tests): the reference-named entry point through the fused rounds as well, the round taken
   // from the call count (advance.cxx makes three calls a step); arrays cannot grow on that path
   static long calls = 0;
-  const int round = tuning("boundary.fused", 1) == 2 ? (int)(calls++ % 3) : -1;
+  const int round = tuning("boundary.fused", 0) == 2 ? (int)(calls++ % 3) : -1;
   vpb_boundary_p_round(dom, sp, n_sp, d_f, d_a, round);
 }
 

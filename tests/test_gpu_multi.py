@@ -28,13 +28,14 @@ def torchrun(world, worker, timeout=900, env=None):
     return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=dict(os.environ, **(env or {})))
 
 
-@pytest.mark.parametrize("world", [2])
-def test_decomposed_run_matches_single_domain(world):
+@pytest.mark.parametrize("world,migration", [(2, "exact"), (2, "fused")])
+def test_decomposed_run_matches_single_domain(world, migration):
     """tests/dist_gpu_worker.py: thermal plasma split over the ranks, C++ driver, against a single-domain run of the same
-    particles (ran at 2 and 8 GPUs in round 1 from scripts/gpu_call47_2gpu.sh / gpu_call43_8gpu.sh)."""
+    particles (ran at 2 and 8 GPUs in round 1 from scripts/gpu_call47_2gpu.sh / gpu_call43_8gpu.sh); `fused`: the
+    driver's migration rounds as fixed-capacity messages (boundary.fused = 1)."""
     if gpu_count() < world:
         pytest.skip("needs %d GPUs" % world)
-    r = torchrun(world, "dist_gpu_worker.py")
+    r = torchrun(world, "dist_gpu_worker.py", env={"VPB_BOUNDARY_FUSED": "1"} if migration == "fused" else None)
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
 
 
@@ -49,7 +50,7 @@ def test_decomposed_harris_sheet_matches_single_domain(world):
     assert r.returncode == 0 and "DIST_GPU_OK kind=harris" in r.stdout, (r.stdout + r.stderr)[-3000:]
 
 
-@pytest.mark.parametrize("world,migration", [(2, "exact"), (4, "exact"), (2, "fused"), (2, "fused_overflow")])
+@pytest.mark.parametrize("world,migration", [(2, "exact"), (4, "exact"), (2, "fused"), (2, "fused_overflow"), (4, "fused")])
 def test_decomposed_calls_match_oracle_cluster(world, migration):
     """tests/dist_gpu_percall_worker.py: per-call, bit-level parity of halos and migration over NCCL; `fused*`: the
     second wave of movers through the fused fixed-capacity rounds (and their second message)."""
