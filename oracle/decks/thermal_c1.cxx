@@ -50,6 +50,19 @@ begin_initialization {
     inject_particle( electron, x, y, z, maxwellian_rand( 0.1 ), maxwellian_rand( 0.1 ), maxwellian_rand( 0.1 ), -q, 0, 0, 0 );
     inject_particle( ion,      x, y, z, maxwellian_rand( 0.1 ), maxwellian_rand( 0.1 ), maxwellian_rand( 0.1 ),  q, 0, 0, 0 );
   }
+
+  // VPB_DECK_DUMP_LOAD=<file>: the two particle arrays exactly as this loop left them (tests/test_oracle_mt.py pins the
+  // oracle's restatement of the Mersenne-Twister stream and of inject_particle against them)
+  const char * dump = getenv( "VPB_DECK_DUMP_LOAD" );
+  if( dump ) {
+    FILE * fp = fopen( dump, "wb" );
+    if( !fp ) ERROR(( "cannot write %s", dump ));
+    const int cnt[2] = { electron->np, ion->np };
+    fwrite( cnt, sizeof(int), 2, fp );
+    fwrite( electron->p, sizeof(particle_t), electron->np, fp );
+    fwrite( ion->p,      sizeof(particle_t), ion->np,      fp );
+    fclose( fp );
+  }
 }
 
 begin_diagnostics {
