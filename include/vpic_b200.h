@@ -213,6 +213,40 @@ void vpb_accumulate_rho_p(vpb_domain_t *dom, vpb_field_t *d_f, const vpb_particl
 void vpb_load_thermal(vpb_domain_t *dom, vpb_particle_t *d_p, int ppc, float vth, float q,
                       unsigned long long seed, long tag0);
 void vpb_copy_positions(vpb_particle_t *d_dst, const vpb_particle_t *d_src, long np);
+
+/* The deck's particle load, batched on the device from the reference's own random-number stream (SURVEY.md 8f-4;
+ * csrc/vpb_mt.cu).  Replaces, for a load loop of the usual shape, the serial host loop
+ *     seed_rand(s); for(...) inject_particle( sp, uniform_rand(..), .., maxwellian_rand(..), .., q, tag, 0, 0 );
+ * (src/vpic/vpic.hxx:491-505, src/vpic/misc.cxx:16-105, src/util/mtrand/mtrand.c) and leaves the same particles. */
+typedef struct vpb_mt vpb_mt_t;
+/* new_mt_rng(seed) / seed_mt_rng (mtrand.c:39-62) */
+vpb_mt_t *vpb_mt_create(unsigned int seed);
+void vpb_mt_destroy(vpb_mt_t *rng);
+/* the generator state in the byte format of get_mt_rng_state / set_mt_rng_state (mtrand.c:64-124, 4*(624+1) = 2500
+ * bytes): a host program hands its generator over with set and takes the stream back where the load left it with get */
+void vpb_mt_set_state(vpb_mt_t *rng, const void *state2500);
+void vpb_mt_get_state(vpb_mt_t *rng, void *state2500);
+/* n words of mt_urand to a device array */
+void vpb_mt_words(vpb_mt_t *rng, unsigned int *d_out, long n);
+/* n records of the token string prog ('U' = mt_drand, mtrand.c:240; 'N' = mt_drandn, mtrand.c:395-438; at most 32 tokens)
+ * in stream order to the device array d_out[n*strlen(prog)]: the doubles the n*strlen(prog) host calls would return,
+ * and the generator left where they would leave it. */
+void vpb_mt_draw(vpb_mt_t *rng, const char *prog, long n, double *d_out);
+/* the ziggurat layer table the device uses, x[257], y[257], *r (host computation: make_zig.c's construction) */
+void vpb_mt_ziggurat_table(double *x, double *y, double *r);
+/* n calls of inject_particle(sp, x, y, z, ux, uy, uz, q, tag, 0, 0) in order, arguments from row k of the deviate table
+ * d_table[n*stride]: x = lo[0]*(1-t[col[0]]) + hi[0]*t[col[0]] (uniform_rand), y, z alike from col[1], col[2];
+ * ux = dev[0]*t[col[3]] (maxwellian_rand), uy, uz from col[4], col[5].  Particles the reference would not inject on this
+ * rank (outside the local box, or on a far wall shared with a neighbour; misc.cxx:37-39) are skipped, the others appended
+ * at d_p[np...] in order (d_p in the domain's particle layout).  Returns the new np; more than max_np is an error. */
+int vpb_inject_from_draws(vpb_domain_t *dom, vpb_particle_t *d_p, int np, int max_np, const double *d_table, int stride, long n,
+                          const int col[6], const double lo[3], const double hi[3], const double dev[3], double q, long tag);
+/* The load loop of a thermal deck (BASELINE configs[0]/[3] recipe): n iterations of one position from three
+ * uniform_rand(lo, hi) and two co-located particles (charges q_a, q_b) with three maxwellian_rand(vth) each, the deviates
+ * written as arguments of inject_particle -- evaluated right to left by g++ (args_right_to_left = 1: the first deviate
+ * is uz) or left to right (0).  np[2]: particle counts of the two arrays, in and out. */
+long vpb_load_pairs_mt(vpb_domain_t *dom, vpb_mt_t *rng, long n, const double lo[3], const double hi[3], double vth_a, double vth_b, double q_a,
+                       double q_b, vpb_particle_t *d_a, int max_a, vpb_particle_t *d_b, int max_b, int np[2], int args_right_to_left);
 /* Device field layout.  A domain starts out with the reference's 80-byte AoS field_t (what every layer-A entry
  * point uses).  A caller that keeps the field array resident on the device can switch the domain to the PLANAR
  * layout: five planes (e|div_e, cb|div_b, tca|rhob, jf|rhof, material ids) of one 16-byte quad per voxel, so a

@@ -74,6 +74,15 @@ SIGNATURES = {
     "vpb_trace_get": (C.c_double, [C.c_char_p, _vp]),
     "vpb_load_thermal": (None, [_vp, _vp, _i, _f, _f, C.c_ulonglong, _l]),
     "vpb_copy_positions": (None, [_vp, _vp, _l]),
+    "vpb_mt_create": (_vp, [C.c_uint]),
+    "vpb_mt_destroy": (None, [_vp]),
+    "vpb_mt_set_state": (None, [_vp, _vp]),
+    "vpb_mt_get_state": (None, [_vp, _vp]),
+    "vpb_mt_words": (None, [_vp, _vp, _l]),
+    "vpb_mt_draw": (None, [_vp, C.c_char_p, _l, _vp]),
+    "vpb_mt_ziggurat_table": (None, [_vp, _vp, _vp]),
+    "vpb_inject_from_draws": (_i, [_vp, _vp, _i, _i, _vp, _i, _l, _vp, _vp, _vp, _vp, C.c_double, _l]),
+    "vpb_load_pairs_mt": (_l, [_vp, _vp, _l, _vp, _vp, C.c_double, C.c_double, C.c_double, C.c_double, _vp, _i, _vp, _i, _vp, _i]),
     "vpb_load_plane_wave": (None, [_vp, _vp, _i, _f]),
     "vpb_domain_set_particle_layout": (None, [_vp, _l]),
     "vpb_domain_particle_layout": (_l, [_vp]),

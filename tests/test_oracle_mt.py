@@ -137,3 +137,15 @@ def test_deck_load_matches_the_reference_initialize(cells, ppc, tmp_path):
                               want_e[name].view(np.uint32 if pe[name].dtype.itemsize == 4 else np.uint64)), ("electron", name)
         assert np.array_equal(pi[name][:n].view(np.uint32 if pi[name].dtype.itemsize == 4 else np.uint64),
                               want_i[name].view(np.uint32 if pi[name].dtype.itemsize == 4 else np.uint64)), ("ion", name)
+
+
+def test_library_builds_the_same_layer_table():
+    """csrc/vpb_mt.cu rebuilds the ziggurat table on the host at start-up (no GPU involved): the same doubles as the
+    oracle's, which test_normal_deviates_including_rejections_and_tail pins to the reference's"""
+    from old_vpic_b200 import lib
+    L, O = lib.load(), oracle_mt()
+    a, b = [np.zeros(257), np.zeros(257), np.zeros(1)], [np.zeros(257), np.zeros(257), np.zeros(1)]
+    L.vpb_mt_ziggurat_table(*[ptr(v) for v in a])
+    O.orc_mt_zig_table(*[ptr(v) for v in b])
+    for u, v in zip(a, b):
+        assert np.array_equal(u.view(np.uint64), v.view(np.uint64))
