@@ -564,6 +564,8 @@ def run_b200(args):
     sim.free()
     if world == 1 and args.workload == "thermal" and not args.no_e2e:
         line["small_step"] = small_step_measure(L)
+    if world == 1 and args.workload == "thermal" and not args.no_e2e:
+        line["load_mt"] = load_mt_measure(L, not args.no_cpu_baseline)
     if harris and args.trecon_deck:
         hyb = os.path.join(ROOT, "oracle", "_ref", "hybrid")
         line["trecon_deck"] = trecon_deck(os.path.join(hyb, "turbulence_c2.b200.op"), 2048 * 1024, 60, 1,
@@ -597,6 +599,59 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def load_mt_measure(L, with_cpu, n=64, ppc=32):
+    """The particle load of BASELINE configs[0]: seed_rand(7), then 64^3 x 32 iterations of three
+    uniform_rand, six maxwellian_rand and two inject_particle.  On the device from the reference's own Mersenne-Twister
+    stream (csrc/vpb_mt.cu: same particles, bit for bit -- tests/test_gpu_mt.py), wall clock of the whole call; beside it
+    the serial host loop (cpu_baseline leg: the oracle's restatement of the deck's loop on a bounded sample)."""
+    import ctypes as C
+    from old_vpic_b200 import grid as helpers
+    from old_vpic_b200.sim import NativeSimulation
+    g = helpers.make_grid((n, n, n), "periodic")
+    pairs = n ** 3 * ppc
+    sim = NativeSimulation(g, L=L)
+    e = sim.define_species("electron", -1.0, pairs + 1024, sort_interval=20)
+    i = sim.define_species("ion", 1.0, pairs + 1024, sort_interval=20)
+    q = float(n) ** 3 / pairs
+    out = {"workload": "BASELINE configs[0] load: %d iterations of {3 uniform_rand, 6 maxwellian_rand, 2 inject_particle}, seed 7" % pairs}
+    for rep in range(2):                      # the second call is the timed one (buffers allocated, kernels loaded)
+        if rep == 1:
+            sim.free()
+            sim = NativeSimulation(g, L=L)
+            e = sim.define_species("electron", -1.0, pairs + 1024, sort_interval=20)
+            i = sim.define_species("ion", 1.0, pairs + 1024, sort_interval=20)
+        L.vpb_sync()
+        t0 = time.perf_counter()
+        sim.load_pairs_mt(e, i, pairs, [0, 0, 0], [n, n, n], 0.1, 0.1, -q, q, seed=7)
+        L.vpb_sync()
+        dt = time.perf_counter() - t0
+    out["device"] = {"seconds": dt, "pairs_per_s": pairs / dt, "particles": 2 * pairs}
+    sim.free()
+    if with_cpu:
+        from oracle import loader
+        O = loader.oracle()
+        O.orc_mt_sizeof.restype = C.c_int
+        O.orc_load_thermal_pairs.restype = C.c_long
+        O.orc_load_thermal_pairs.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p,
+                                             C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        O.orc_mt_seed.argtypes = [C.c_void_p, C.c_uint]
+        rng = np.zeros(O.orc_mt_sizeof(), np.uint8)
+        O.orc_mt_seed(rng.ctypes.data, 7)
+        sample = 1 << 21
+        from old_vpic_b200 import abi
+        pe, pi = abi.aligned_zeros(sample, abi.particle_dtype), abi.aligned_zeros(sample, abi.particle_dtype)
+        npe, npi = C.c_int(0), C.c_int(0)
+        lo, hi = np.zeros(3), np.full(3, float(n))
+        t0 = time.perf_counter()
+        O.orc_load_thermal_pairs(rng.ctypes.data, sample, lo.ctypes.data, hi.ctypes.data, 0.1, 0.1, q, pe.ctypes.data, C.byref(npe), sample,
+                                 pi.ctypes.data, C.byref(npi), sample, g.ref())
+        ht = time.perf_counter() - t0
+        out["host_serial_loop"] = {"seconds_per_sample": ht, "pairs_per_s": sample / ht, "kind": "port", "cores": 1,
+                                   "sample": "%d iterations of the same loop (oracle/oracle_mt.c: mt_drand, mt_drandn, inject_particle)" % sample}
+        out["speedup"] = out["device"]["pairs_per_s"] / out["host_serial_loop"]["pairs_per_s"]
+    return out
 
 
 def small_step_measure(L, n=64, ppc=32, steps=200):

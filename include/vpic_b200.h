@@ -404,10 +404,18 @@ void vpb_sim_set_materials(vpb_sim_t *s, const vpb_material_coefficient_t *m, in
 /* species in definition order (= species_t.id); max_nm <= 0: the reference's 2*max_np/25 (vpic.hxx:416-420) */
 int vpb_sim_define_species(vpb_sim_t *s, const char *name, float q_m, long max_np, long max_nm, int sort_interval);
 void vpb_sim_load_thermal(vpb_sim_t *s, int species, int ppc, float vth, float q, unsigned long long seed, long tag0);
+/* vpb_load_pairs_mt (the deck's load loop from the reference's random-number stream) into two species of the run */
+long vpb_sim_load_pairs_mt(vpb_sim_t *s, vpb_mt_t *rng, int species_a, int species_b, long n, const double lo[3], const double hi[3],
+                           double vth_a, double vth_b, double q_a, double q_b, int args_right_to_left);
 void vpb_sim_set_particles(vpb_sim_t *s, int species, const vpb_particle_t *host, long np);
 long vpb_sim_get_particles(vpb_sim_t *s, int species, vpb_particle_t *host, long max);
 void vpb_sim_set_fields(vpb_sim_t *s, const vpb_field_t *host);       /* field_t[nvoxel], reference layout */
 void vpb_sim_get_fields(vpb_sim_t *s, vpb_field_t *host);
+/* vpic_simulation::initialize() after the deck's user_initialization (initialize.cxx:27-95): shared-face synchronisation,
+ * one div B clean, curl B, the bound charge density that makes the loaded plasma divergence-consistent (compute_rhob),
+ * one div E clean if an error is left, load_interpolator, uncenter_p.  out3 (or NULL): synchronisation error, rms div B
+ * error, rms div E error as the reference prints them. */
+void vpb_sim_initialize(vpb_sim_t *s, double *out3);
 void vpb_sim_set_intervals(vpb_sim_t *s, int clean_div_e_interval, int clean_div_b_interval, int num_comm_round);
 /* sync_shared_interval of vpic_simulation (vpic.cxx:14; advance.cxx:199-208): synchronize_tang_e_norm_b every that many
  * steps, 0 = never.  vpb_sim_last_errors: the numbers advance.cxx:160,168,182,190,205 report, latest values --

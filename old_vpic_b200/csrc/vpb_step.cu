@@ -381,6 +381,17 @@ void vpb_sim_load_thermal(vpb_sim_t *s, int id, int ppc, float vth, float q, uns
   vpb_load_thermal(s->dom, sp.p, ppc, vth, q, seed, tag0);
 }
 
+// The thermal deck's load loop from the reference's random-number stream (vpb_mt.cu), appended to two species of the run
+long vpb_sim_load_pairs_mt(vpb_sim_t *s, vpb_mt_t *rng, int id_a, int id_b, long n, const double lo[3], const double hi[3], double vth_a,
+                           double vth_b, double q_a, double q_b, int args_right_to_left) {
+  Species &a = species_of(s, id_a), &b = species_of(s, id_b);
+  int np[2] = {a.np, b.np};
+  const long done = vpb_load_pairs_mt(s->dom, rng, n, lo, hi, vth_a, vth_b, q_a, q_b, a.p, a.max_np, b.p, b.max_np, np, args_right_to_left);
+  a.np = np[0];
+  b.np = np[1];
+  return done;
+}
+
 // host particle_t[np] -> the species' device array (converted to the domain's layout on the device)
 void vpb_sim_set_particles(vpb_sim_t *s, int id, const vpb_particle_t *host, long np) {
   Species &sp = species_of(s, id);
@@ -431,6 +442,38 @@ void vpb_sim_set_fields(vpb_sim_t *s, const vpb_field_t *host) {
     vpb_sync();
   }
   if (s->fi) vpb_load_interpolator(s->dom, s->fi, s->f);   // initialize.cxx:67
+}
+
+// What vpic_simulation::initialize() does between the deck's user_initialization and the first step
+// (initialize.cxx:27-95): shared faces made consistent, div B cleaned once, the curl B the damping needs, the BOUND
+// charge density chosen so that the loaded plasma is divergence-consistent (rhob = div(eps E) - rhof), one div E clean
+// if that left an error, the interpolator, and the momenta moved back half a step (uncenter_p).  Call it after the
+// fields and particles of the initial condition are in place.  out3 (may be null): the three numbers the reference
+// prints there -- synchronisation error, rms div B error, rms div E error.
+void vpb_sim_initialize(vpb_sim_t *s, double *out3) {
+  if (!s) VPB_ERROR("Bad args");
+  double sync0, div_b, div_e = 0;
+  sync_shared(s);                                                                      // :32
+  sync0 = s->desync_err;
+  vpb_compute_div_b_err(s->dom, s->f);                                                 // :40
+  div_b = rms_err(s, 1);                                                               // :41
+  vpb_clean_div_b(s->dom, s->f);                                                       // :46 (unconditional there)
+  vpb_compute_curl_b(s->dom, s->f, s->m, s->n_mat);                                    // :54
+  if (!s->field_only) {
+    vpb_clear_rhof(s->dom, s->f);                                                      // :59
+    for (Species &sp : s->sp) vpb_accumulate_rho_p(s->dom, s->f, sp.p, sp.np);         // :60-61
+    vpb_synchronize_rho(s->dom, s->f);                                                 // :62
+    vpb_compute_rhob(s->dom, s->f, s->m, s->n_mat);                                    // :63
+    vpb_compute_div_e_err(s->dom, s->f, s->m, s->n_mat);                               // :70
+    div_e = rms_err(s, 0);                                                             // :71
+    if (div_e > 0) vpb_clean_div_e(s->dom, s->f, s->m, s->n_mat);                      // :75
+  }
+  sync_shared(s);                                                                      // :80
+  if (!s->sp.empty()) {
+    vpb_load_interpolator(s->dom, s->fi, s->f);                                        // :90
+    for (Species &sp : s->sp) vpb_uncenter_p(s->dom, sp.p, sp.np, sp.q_m, s->fi);      // :92-93
+  }
+  if (out3) { out3[0] = sync0; out3[1] = div_b; out3[2] = div_e; }
 }
 
 void vpb_sim_get_fields(vpb_sim_t *s, vpb_field_t *host) {

@@ -165,6 +165,8 @@ SIGNATURES = {
     "vpb_sim_set_materials": (None, [_vp, _vp, _i]),
     "vpb_sim_define_species": (_i, [_vp, C.c_char_p, _f, _l, _l, _i]),
     "vpb_sim_load_thermal": (None, [_vp, _i, _i, _f, _f, C.c_ulonglong, _l]),
+    "vpb_sim_initialize": (None, [_vp, _vp]),
+    "vpb_sim_load_pairs_mt": (_l, [_vp, _vp, _i, _i, _l, _vp, _vp, C.c_double, C.c_double, C.c_double, C.c_double, _i]),
     "vpb_sim_set_particles": (None, [_vp, _i, _vp, _l]),
     "vpb_sim_get_particles": (_l, [_vp, _i, _vp, _l]),
     "vpb_sim_set_fields": (None, [_vp, _vp]),

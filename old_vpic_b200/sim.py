@@ -157,6 +157,26 @@ class NativeSimulation:
     def load_thermal(self, sp, ppc, vth, q, seed, tag0=0):
         self.L.vpb_sim_load_thermal(self.h, sp.id, ppc, vth, q, seed, tag0)
 
+    def load_pairs_mt(self, sp_a, sp_b, n, lo, hi, vth_a, vth_b, q_a, q_b, seed=None, rng=None, args_right_to_left=1):
+        """The thermal deck's load loop (seed_rand(seed); n x {3 uniform_rand, 2 x 3 maxwellian_rand -> inject_particle})
+        from the reference's own random-number stream, on the device (include/vpic_b200.h vpb_load_pairs_mt)."""
+        own = rng is None
+        if own:
+            rng = self.L.vpb_mt_create(int(seed))
+        lo, hi = np.ascontiguousarray(lo, np.float64), np.ascontiguousarray(hi, np.float64)
+        done = self.L.vpb_sim_load_pairs_mt(self.h, rng, sp_a.id, sp_b.id, int(n), lo.ctypes.data, hi.ctypes.data, vth_a, vth_b, q_a, q_b,
+                                            int(args_right_to_left))
+        if own:
+            self.L.vpb_mt_destroy(rng)
+        return done
+
+    def initialize(self):
+        """vpic_simulation::initialize() after the deck's own part (initialize.cxx:27-95); returns the synchronisation,
+        div B and div E errors the reference prints there."""
+        out = np.zeros(3)
+        self.L.vpb_sim_initialize(self.h, out.ctypes.data)
+        return out
+
     def set_particles(self, sp, host):
         host = np.ascontiguousarray(host, dtype=abi.particle_dtype)
         self.L.vpb_sim_set_particles(self.h, sp.id, host.ctypes.data, len(host))

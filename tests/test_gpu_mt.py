@@ -126,3 +126,38 @@ def test_thermal_load_matches_the_serial_loop(vpb, n_cells, ppc, topo, rank, pla
         a.free()
     vpb.vpb_mt_destroy(rng)
     vpb.vpb_domain_destroy(dom)
+
+
+def test_device_run_from_the_seed_alone_reproduces_the_reference_deck(vpb):
+    """oracle/decks/thermal_small.cxx on the reference alone (tests/golden/deck_thermal_small_energies.txt: seed_rand(7),
+    the serial load loop, vpic_simulation::initialize(), 20 steps of advance() with both cleanings at step 10 and 20)
+    against a run in which NOTHING comes from the host but the seed: the load from the reference's random-number stream on
+    the device, vpb_sim_initialize (initialize.cxx:27-95: bound charge, uncenter_p) and the C++ step driver."""
+    from old_vpic_b200.sim import NativeSimulation
+    from test_gpu_deck import GOLD, read_energies
+    want = read_energies(GOLD)
+    n, ppc = 16, 8
+    ne = n ** 3 * ppc
+    g = host_grid((n, n, n), "periodic")
+    sim = NativeSimulation(g, L=vpb)
+    sim.set_intervals(10, 10)
+    # the reference walks its species list from the species defined last (the energies file has "ion" before "electron")
+    i = sim.define_species("ion", 1.0, int(1.5 * ne), sort_interval=5)
+    e = sim.define_species("electron", -1.0, int(1.5 * ne), sort_interval=5)
+    q = float(n) ** 3 / ne
+    assert sim.load_pairs_mt(e, i, ne, [0, 0, 0], [n, n, n], 0.1, 0.1, -q, q, seed=7) == ne
+    assert (e.np, i.np) == (ne, ne)
+    sim.set_fields(abi.aligned_zeros(g.nv, abi.field_dtype))
+    errs = sim.initialize()
+    assert errs[0] == 0 and errs[1] == 0          # no fields yet: nothing to synchronise, no div B
+    got = [sim.energies()]
+    for _ in range(20):
+        sim.advance()
+        got.append(sim.energies())
+    got = np.array(got)
+    assert want.shape == (21, 9) and got.shape == (21, 8)
+    rel = np.abs(got - want[:, 1:]) / np.abs(want[:, 1:]).max(axis=0)
+    assert rel.max() < 1e-4, rel.max(axis=0)
+    # the kinetic energies of the freshly loaded plasma are sums over the very same particles: tighter
+    assert np.all(rel[0, 6:] < 1e-6), rel[0]
+    sim.free()
