@@ -53,9 +53,20 @@ def test_load_interpolator_unload_accumulator(vpb, orc, n):
     assert not np.any(a_g.view(np.uint8))
 
 
+@pytest.mark.parametrize("march", [1, 0, 2])
 @pytest.mark.parametrize("fbc", FBCS)
 @pytest.mark.parametrize("n", SHAPES)
-def test_field_advance(vpb, orc, fbc, n):
+def test_field_advance(vpb, orc, fbc, n, march):
+    """march = tuning fields.march_z: advance_e with every thread marching up z (1, the default: the material-table
+    kernel; 2: also the one-material and vacuum kernels) or one voxel per thread (0) -- the same bits either way"""
+    vpb.vpb_set_tuning(b"fields.march_z", march)
+    try:
+        _field_advance(vpb, orc, fbc, n)
+    finally:
+        vpb.vpb_set_tuning(b"fields.march_z", 1)
+
+
+def _field_advance(vpb, orc, fbc, n):
     g = _grid(n, fbc, damp=0.01)
     M = lib.field_methods(vpb, 0)
     rng = np.random.default_rng(10)
