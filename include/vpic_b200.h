@@ -310,6 +310,11 @@ void vpb_boundary_p_round(vpb_domain_t *dom, vpb_species_state_t *sp, int n_sp, 
  * (the first np particles preserved) and/or pm / max_nm in *st with device-accessible arrays and return non-zero, or
  * return 0 to refuse.  The reference-named boundary_p() installs one that does what the reference does, for arrays
  * that came from util_malloc_aligned. */
+/* boundary_p.c:271-277: a mover that ends on a face bound to one of the deck's custom handlers (neighbor code -3-k) is given
+ * to that HOST callback, then destroyed; injectors the callbacks make are injected last (boundary_p.c's cmlist).  The
+ * reference-named boundary_p() runs the callbacks and brackets its vpb_boundary_p call with this: inj[0..n) = their
+ * injectors (n >= 0 opens the bracket, n < 0 closes it).  Outside such a bracket a mover on a handler face is an error. */
+void vpb_boundary_set_local_injectors(const vpb_particle_injector_t *inj, int n);
 typedef int (*vpb_grow_hook_t)(void *user, int index, int need_np, int need_nm, vpb_species_state_t *st);
 void vpb_boundary_set_grow_hook(vpb_grow_hook_t hook, void *user);
 

@@ -156,6 +156,17 @@ VPB_STATIC_ASSERT(offsetof(vpb_grid_t, dt) == 8 && offsetof(vpb_grid_t, x0) == 2
                   offsetof(vpb_grid_t, rangel) == 208 && offsetof(vpb_grid_t, nb) == 224 &&
                   offsetof(vpb_grid_t, boundary) == 232, "grid_t layout");
 
+/* src/grid/grid.h:32-53: the deck's custom particle-boundary handlers, grid_t.boundary[0..nb).  Host callbacks: the
+ * reference-named boundary_p() calls them on the host exactly where boundary_p.c:271-277 does. */
+struct vpb_species;
+typedef void (*vpb_boundary_handler_t)(void *params, vpb_particle_t *r, vpb_particle_mover_t *pm, vpb_field_t *f, vpb_accumulator_t *a,
+                                       const vpb_grid_t *g, struct vpb_species *s, vpb_particle_injector_t **ppi, void *rng, int face);
+typedef struct vpb_boundary {
+  vpb_boundary_handler_t handler;
+  char params[1024];     /* MAX_BOUNDARY_DATA_SIZE */
+} vpb_boundary_t;
+VPB_STATIC_ASSERT(sizeof(vpb_boundary_t) == 1032, "boundary_t is 1032 B");
+
 /* src/species_advance/species_advance.h:61-93 */
 typedef struct vpb_species {
   int32_t               id;

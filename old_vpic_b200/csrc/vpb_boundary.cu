@@ -170,6 +170,8 @@ __device__ void accumulate_rhob_dev(vpb_field_t *__restrict__ f, float dx, float
 struct FaceInfo {
   int64_t rbase[6];    // range[] of the rank across each face (0 if not shared remotely)
   int64_t rangem;      // range[nproc]
+  int nb;              // grid->nb: custom particle-boundary handlers of the deck (neighbor code -3-k, k < nb)
+  int handled;         // != 0: the caller has already run those handlers on the host for this round's movers
 };
 
 // boundary_p.c:203-316: which face did mover k end on, and what happens there.
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(256) classify_kernel(const PView p, const vpb_
   const int vi = __float_as_int(r0.w);
   const float pos[3] = {r0.x, r0.y, r0.z}, u[3] = {r1.x, r1.y, r1.z};
   int c = -1;
-  bool unknown = true;
+  bool unknown = true, handler = false;
 #pragma unroll
   for (int face = 0; face < 6 && c < 0; face++) {
     const int ax = face % 3;
@@ -197,10 +199,16 @@ __global__ void __launch_bounds__(256) classify_kernel(const PView p, const vpb_
     const int64_t nn = g.nbr64[6 * (size_t)vi + face];
     if (nn == vpb_absorb_particles) { c = 6; unknown = false; }
     else if ((nn >= 0 && nn < g.rangel) || (nn > g.rangeh && nn <= fi.rangem)) { c = face; unknown = false; }
-    // custom handlers (nn <= -3) are host callbacks in the reference: not available here -> falls through
+    else if (nn <= -3 && -nn - 3 < (int64_t)fi.nb) {
+      // boundary_p.c:271-277: the deck's handler -nn-3, a HOST callback.  The reference-named boundary_p() has run it
+      // for this mover before coming here (vpb_dropin.cu); what is left is to destroy the particle ("Particle is
+      // destroyed after it is handled"), without the rhob deposit of an absorption.  Anyone else must not get here.
+      c = 6; unknown = false; handler = true;
+      if (!fi.handled) atomicAdd(n_unknown + 5, 1);
+    }
   }
   if (c < 0) c = 6;
-  if (c == 6) {
+  if (c == 6 && !handler) {
     accumulate_rhob_dev(f, r0.x, r0.y, r0.z, vi, r1.w, g);
     if (unknown) atomicAdd(n_unknown, 1);
   }
@@ -408,11 +416,13 @@ struct BoundaryBuffers {
   size_t cap[6] = {};          // records (injectors + the fused header)
   float4 *xrecv = nullptr;     // second messages of over-full faces (fused protocol)
   size_t xcap = 0;
+  float4 *local = nullptr;     // injectors made by the deck's custom handlers on the host
+  size_t lcap = 0;
   float4 **d_send_table = nullptr;
   // [0..6] send bins (faces 0..5, 6 = absorbed), [8..13] counts received, [14] injectors in the arrival list,
   // [16..22] arrivals per species, [24..30] new movers per species, [32] nh, [33] unknown interactions,
   // [34] mover-order violations, [35] arrivals beyond max_np, [36] new movers beyond max_nm, [37] bad headers,
-  // [40..47] tail bins
+  // [38] movers on a custom-handler face whose handler nobody ran, [40..47] tail bins
   int *d_counts = nullptr;
 };
 static BoundaryBuffers g_bb;
@@ -437,6 +447,12 @@ static const int kFaceBound[6] = {VPB_BOUNDARY(-1, 0, 0), VPB_BOUNDARY(0, -1, 0)
                                   VPB_BOUNDARY(1, 0, 0),  VPB_BOUNDARY(0, 1, 0),  VPB_BOUNDARY(0, 0, 1)};
 static const int kRecvOrder[6] = {3, 4, 5, 0, 1, 2};   // the reference's receive loop: what arrived from +x first
 
+// Injectors the deck's custom boundary handlers made on the host for this round (boundary_p.c's cmlist): set by the
+// reference-named boundary_p() around its call, injected after the received buffers (boundary_p.c:457-461, face 6)
+static const vpb_particle_injector_t *g_local_inj = nullptr;
+static int g_local_inj_n = 0;
+static bool g_local_inj_set = false;
+
 struct Faces {
   bool remote[6], any_remote = false;
   int peer[6];
@@ -456,6 +472,8 @@ static Faces faces_of(const vpb_domain_t *dom) {
     if (F.remote[f]) F.mask |= 1u << f;
   }
   F.fi.rangem = dom->range[g.nproc];
+  F.fi.nb = dom->host_grid ? dom->host_grid->nb : 0;
+  F.fi.handled = g_local_inj_set ? 1 : 0;
   return F;
 }
 
@@ -512,6 +530,10 @@ static void pack_and_remove(vpb_domain_t *dom, vpb_species_state_t *sp, int n_sp
 }
 
 static void check_mover_flags(const int *h, int rank) {
+  if (h[38])
+    VPB_ERROR("boundary_p: %d movers ended on cell faces bound to the deck's custom particle-boundary handlers.  Those are host "
+              "callbacks (boundary_p.c:271-277): only the reference-named boundary_p(), which runs them on the host first, "
+              "can process such a grid", h[38]);
   if (h[33]) VPB_WARNING("Unknown boundary interaction ... using absorption (%d particles, rank=%d)", h[33], rank);
   if (h[34])
     VPB_ERROR("boundary_p: a mover list is not in ascending particle order (%d inversions); removing its particles would "
@@ -535,12 +557,12 @@ static void *g_grow_user = nullptr;
 // Injection with counts the host knows (boundary_p.c:388-497): nr[f] injectors in rbuf[f].  Two read-backs: arrivals
 // per species (the arrays may have to grow first), new movers per species.
 static void inject_known(vpb_domain_t *dom, vpb_species_state_t *sp, int n_sp, vpb_accumulator_t *d_a, const float4 *const rbuf[6],
-                         const int nr[6], bool append_movers) {
+                         const int nr[6], bool append_movers, const float4 *local = nullptr, int n_local = 0) {
   Context &c = ctx();
   cudaStream_t st = c.stream;
   const DomainDev &g = dom->d;
   int *dc = g_bb.d_counts;
-  long n_in = 0;
+  long n_in = n_local;
   for (int f = 0; f < 6; f++) n_in += nr[f];
   if (n_in == 0) { VPB_CUDA(cudaStreamSynchronize(st)); return; }
   if (!d_a) VPB_ERROR("Bad accumulator");
@@ -557,6 +579,11 @@ static void inject_known(vpb_domain_t *dom, vpb_species_state_t *sp, int n_sp, v
     gather_injectors_kernel<<<blocks(3L * nr[f], 256), 256, 0, st>>>(list, rbuf[f], nr[f], off);
     count_launch();
     off += nr[f];
+  }
+  if (n_local) {   // the handlers' own injectors come last (face 6 of boundary_p.c:457-461), back to front like the others
+    gather_injectors_kernel<<<blocks(3L * n_local, 256), 256, 0, st>>>(list, local, n_local, off);
+    count_launch();
+    off += n_local;
   }
   SpeciesTable T = species_table(dom, sp, n_sp);
   const int n = (int)n_in;
@@ -689,7 +716,18 @@ static void boundary_round_exact(vpb_domain_t *dom, vpb_species_state_t *sp, int
     }
     if (nx) comm_exchange(x, nx);
   }
-  inject_known(dom, sp, n_sp, d_a, g_bb.recv, nr, false);
+  const float4 *local = nullptr;
+  if (g_local_inj_n > 0) {
+    if ((size_t)g_local_inj_n > g_bb.lcap) {
+      VPB_CUDA(cudaStreamSynchronize(st));
+      if (g_bb.local) cudaFree(g_bb.local);
+      g_bb.lcap = (size_t)g_local_inj_n + (size_t)g_local_inj_n / 4 + 1024;
+      VPB_CUDA(cudaMalloc(&g_bb.local, g_bb.lcap * 48));
+    }
+    VPB_CUDA(cudaMemcpyAsync(g_bb.local, g_local_inj, (size_t)g_local_inj_n * 48, cudaMemcpyHostToDevice, st));
+    local = g_bb.local;
+  }
+  inject_known(dom, sp, n_sp, d_a, g_bb.recv, nr, false, local, g_local_inj_n);
 }
 
 // capacity both sides of a face derive from the counts they both know
@@ -858,7 +896,7 @@ void vpb_boundary_p_round(vpb_domain_t *dom, vpb_species_state_t *sp, int n_sp, 
     const int b = dom->d.bc[kFaceBound[f]];
     any_remote |= b >= 0 && b < dom->d.nproc && b != dom->d.rank;
   }
-  if (round < 0 || mode == 0 || !any_remote) { boundary_round_exact(dom, sp, n_sp, d_f, d_a, nullptr, nullptr); return; }
+  if (round < 0 || mode == 0 || !any_remote || g_local_inj_set) { boundary_round_exact(dom, sp, n_sp, d_f, d_a, nullptr, nullptr); return; }
   const int slot = round < 3 ? round : 2;
   if (!dom->mig_cap_valid[slot]) {
     int ns[6], nr[6];
@@ -877,6 +915,14 @@ void vpb_boundary_p(vpb_domain_t *dom, vpb_species_state_t *sp, int n_sp, vpb_fi
   static long calls = 0;
   const int round = tuning("boundary.fused", 0) == 2 ? (int)(calls++ % 3) : -1;
   vpb_boundary_p_round(dom, sp, n_sp, d_f, d_a, round);
+}
+
+// The reference-named boundary_p() brackets its call with these: `inj[0..n)` are the injectors the deck's custom
+// handlers made on the host for this round's movers (n may be 0); NULL/-1 ends the bracket.
+void vpb_boundary_set_local_injectors(const vpb_particle_injector_t *inj, int n) {
+  g_local_inj = n > 0 ? inj : nullptr;
+  g_local_inj_n = n > 0 ? n : 0;
+  g_local_inj_set = n >= 0;
 }
 
 void vpb_boundary_set_grow_hook(vpb_grow_hook_t hook, void *user) {

@@ -134,6 +134,7 @@ struct vpb_domain {
   float *face_send[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   float *face_recv[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t face_cap[6] = {0, 0, 0, 0, 0, 0};
+  size_t n_handler_faces = 0;   // cell faces bound to the deck's custom particle-boundary handlers (host callbacks)
   // particle migration (vpb_boundary.cu): injectors a fused message of round 0, 1, 2+ may carry through each face;
   // both sides of a face derive the same number from the counts of earlier rounds
   int mig_cap[3][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};

@@ -319,16 +319,16 @@ vpb_domain_t *vpb_domain_create(const vpb_grid_t *g, int rank, int nproc) {
       else if (n == vpb_absorb_particles) nb[k] = -2;
       else if (n < 0) {
         // boundary_p.c:271-277: -3-k selects the deck's k-th custom particle-boundary handler, a HOST callback with user
-        // parameters and the host RNG.  The device cannot run it, and absorbing such particles instead (with a rhob
-        // deposit the handler would not have made) silently changes the physics: refuse the grid.
+        // parameters and the host RNG.  The device cannot run it: move_p leaves such a particle as a mover, and the
+        // reference-named boundary_p() calls the handler on the host before the device removes the particle
+        // (vpb_dropin.cu).  Callers without that step (layer B, the device-resident driver) are refused when they get
+        // there -- absorbing the particle instead would add a rhob deposit the handler never makes.
         if (-n - 3 < (int64_t)g->nb) n_handler++;
         nb[k] = (n > -0x40000000L) ? (int32_t)n : -3;               // any other code: "unknown boundary interaction"
       }
       else nb[k] = INT32_MIN;                                        // owned by another rank
     }
-    if (n_handler)
-      VPB_ERROR("grid has %zu cell faces bound to custom particle-boundary handlers (grid->nb = %d): host callbacks are not "
-                "supported by libvpic_b200 (no CPU fallback); use reflect_particles / absorb_particles faces", n_handler, g->nb);
+    dom->n_handler_faces = n_handler;
     VPB_CUDA(cudaMalloc(&dom->nbr, nb.size() * sizeof(int32_t)));
     VPB_CUDA(cudaMemcpyAsync(dom->nbr, nb.data(), nb.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c.stream));
     VPB_CUDA(cudaMalloc(&dom->nbr64, nb.size() * sizeof(int64_t)));

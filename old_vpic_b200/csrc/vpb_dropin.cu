@@ -555,17 +555,56 @@ static int grow_species(void *user, int index, int need_np, int need_nm, vpb_spe
   return 1;
 }
 
-// boundary_p.c:77-505: one round over the species list.  rng is only used by custom boundary
-// handlers in the reference (host callbacks), which the device path does not run.
+// boundary_p.c:77-505: one round over the species list.  rng belongs to the deck's custom boundary
+// handlers (host callbacks), which are called from here (below).
 void boundary_p(vpb_species_t *sp_list, vpb_field_t *f0, vpb_accumulator_t *a0, const vpb_grid_t *g, void *rng) {
   TraceScope _ts("boundary_p");
-  (void)rng;
   if (!g) VPB_ERROR("Bad grid");
   vpb_domain_t *dom = domain_of(g);
   Residency r;
   std::vector<vpb_species_t *> list;
   for (vpb_species_t *sp = sp_list; sp; sp = sp->next) list.push_back(sp);
   if (list.size() > 7) VPB_ERROR("boundary_p handles at most 7 species per call");
+  // boundary_p.c:271-277: movers that ended on a face bound to one of the deck's custom handlers (neighbor code -3-k,
+  // k < grid->nb).  The handlers are the host program's code (parameters, host RNG, calls back into accumulate_rhob ...):
+  // they run HERE, on the host, in the order the reference visits the movers -- species in list order, each species'
+  // movers from the last to the first, faces tested in the order of the reference's TEST_FACE sequence -- so that the
+  // handlers' random-number draws and their injector list (cmlist) come out the same.  The device then destroys those
+  // particles without the rhob deposit of an absorption and injects the list after the received buffers.
+  const bool with_handlers = g->nb > 0 && g->boundary != nullptr && dom->n_handler_faces > 0;
+  std::vector<vpb_particle_injector_t> cm;
+  int ncm = 0;
+  if (with_handlers) {
+    if (!g->neighbor) VPB_ERROR("Bad grid");
+    VPB_CUDA(cudaStreamSynchronize(ctx().stream));
+    size_t total = 0;
+    for (vpb_species_t *sp : list) total += (size_t)(sp->nm > 0 ? sp->nm : 0);
+    cm.resize(total + 1);
+    vpb_particle_injector_t *cmp = cm.data();
+    const vpb_boundary_t *bt = (const vpb_boundary_t *)g->boundary;
+    const int64_t rangem = dom->range[dom->d.nproc];
+    for (vpb_species_t *sp : list) {
+      for (int k = sp->nm - 1; k >= 0; k--) {
+        vpb_particle_t *pr = sp->p + sp->pm[k].i;
+        const float pos[3] = {pr->dx, pr->dy, pr->dz}, u[3] = {pr->ux, pr->uy, pr->uz};
+        for (int face = 0; face < 6; face++) {
+          const int ax = face % 3;
+          const bool hit = face < 3 ? (pos[ax] == -1.f && u[ax] < 0) : (pos[ax] == 1.f && u[ax] > 0);
+          if (!hit) continue;
+          const int64_t nn = g->neighbor[6 * (size_t)pr->i + face];
+          if (nn == vpb_absorb_particles) break;                                                    // :207-212
+          if ((nn >= 0 && nn < g->rangel) || (nn > g->rangeh && nn <= rangem)) break;               // :218-267
+          const int64_t h = -nn - 3;
+          if (h >= 0 && h < (int64_t)g->nb) {                                                       // :272-277
+            bt[h].handler(const_cast<char *>(bt[h].params), pr, sp->pm + k, f0, a0, g, sp, &cmp, rng, face);
+            break;
+          }
+        }
+      }
+    }
+    ncm = (int)(cmp - cm.data());
+    if ((size_t)ncm > total) VPB_ERROR("custom boundary handlers made %d injectors for %zu movers", ncm, total);
+  }
   std::vector<vpb_species_state_t> st(list.size());
   for (size_t s = 0; s < list.size(); s++) {
     vpb_species_t *sp = list[s];
@@ -577,7 +616,9 @@ void boundary_p(vpb_species_t *sp_list, vpb_field_t *f0, vpb_accumulator_t *a0, 
   vpb_field_t *df = f0 ? (vpb_field_t *)r.get_field(dom, f0, nvox(g) * sizeof(*f0), RW) : nullptr;
   vpb_accumulator_t *da = a0 ? (vpb_accumulator_t *)r.get(a0, nvox(g) * sizeof(*a0), RW) : nullptr;
   vpb_boundary_set_grow_hook(grow_species, &list);
+  if (with_handlers) vpb_boundary_set_local_injectors(cm.data(), ncm);
   vpb_boundary_p(dom, st.data(), (int)st.size(), df, da);
+  if (with_handlers) vpb_boundary_set_local_injectors(nullptr, -1);
   vpb_boundary_set_grow_hook(nullptr, nullptr);
   for (size_t s = 0; s < list.size(); s++) { list[s]->np = st[s].np; list[s]->nm = st[s].nm; }
   r.finish();

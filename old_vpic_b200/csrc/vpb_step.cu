@@ -289,6 +289,10 @@ vpb_sim_t *vpb_sim_create(const vpb_grid_t *g, int rank, int nproc, int n_mat, i
   s->g = g; s->rank = rank; s->nproc = nproc; s->n_mat = n_mat; s->vacuum = vacuum != 0;
   s->particle_planes = particle_planes != 0;
   s->dom = vpb_domain_create(g, rank, nproc);
+  if (s->dom->n_handler_faces)
+    VPB_ERROR("grid has %zu cell faces bound to custom particle-boundary handlers (grid->nb = %d): those are host callbacks "
+              "(boundary_p.c:271-277) which only the reference-named boundary_p() can run; the device-resident driver has none -- "
+              "use reflect_particles / absorb_particles faces", s->dom->n_handler_faces, g->nb);
   s->nv = vpb_domain_nvoxel(s->dom);
   s->field_only = g->neighbor == nullptr;
   vpb_domain_set_field_layout(s->dom, field_planar ? 1 : 0);

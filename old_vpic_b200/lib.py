@@ -98,6 +98,7 @@ SIGNATURES = {
     "vpb_comm_init": (None, [_i, _i, _vp]),
     "vpb_comm_autoboot": (_i, [_vp]),
     "vpb_boundary_set_grow_hook": (None, [_vp, _vp]),
+    "vpb_boundary_set_local_injectors": (None, [_vp, _i]),
     "vpb_sim_set_callbacks": (None, [_vp, _vp]),
     "vpb_comm_finalize": (None, []),
     "vpb_comm_rank": (_i, []),
