@@ -10,15 +10,9 @@
 
 namespace vpb {
 
-// One thread per interior voxel (1..nx, 1..ny, 1..nz).  The first 32 bytes of a
-// field_t are {ex,ey,ez,div_e_err | cbx,cby,cbz,div_b_err}: two 128-bit loads.
-__global__ void __launch_bounds__(256) load_interpolator_kernel(vpb_interpolator_t *__restrict__ fi,
-                                                                const vpb_field_t *__restrict__ f, const DomainDev g) {
-  const int x = 1 + blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = 1 + blockIdx.y;
-  const int z = 1 + blockIdx.z;
-  if (x > g.nx) return;
-  const size_t v = (size_t)x + (size_t)g.sx * ((size_t)y + (size_t)g.sy * z);
+// The 18 coefficients of one voxel (load_interpolator.cxx:45-120) as the six quads of the 96-byte device record
+// (bytes 72..95 belong to nobody and are written as zeros).
+__device__ __forceinline__ void interpolator_of_voxel(const vpb_field_t *__restrict__ f, const DomainDev &g, size_t v, float4 (&o)[6]) {
   const size_t sX = 1, sY = (size_t)g.sx, sZ = (size_t)g.sxy;
   const float4 e0 = __ldg(CFQ(f, g, v, 0)), b0 = __ldg(CFQ(f, g, v, 1));
   const float4 ex_ = __ldg(CFQ(f, g, v + sX, 0)), bx_ = __ldg(CFQ(f, g, v + sX, 1));
@@ -29,41 +23,75 @@ __global__ void __launch_bounds__(256) load_interpolator_kernel(vpb_interpolator
   const float4 exy = __ldg(CFQ(f, g, v + sX + sY, 0));
   const float fourth = 0.25f, half = 0.5f;
   float w0, w1, w2, w3;
-  float4 o0, o1, o2, o3;
-  float2 o4;
-  // ex: w0=f0 w1=fy w2=fz w3=fyz
   w0 = e0.x; w1 = ey_.x; w2 = ez_.x; w3 = eyz.x;
-  o0.x = fourth * ((w3 + w0) + (w1 + w2));
-  o0.y = fourth * ((w3 - w0) + (w1 - w2));
-  o0.z = fourth * ((w3 - w0) - (w1 - w2));
-  o0.w = fourth * ((w3 + w0) - (w1 + w2));
-  // ey: w0=f0 w1=fz w2=fx w3=fzx
+  o[0].x = fourth * ((w3 + w0) + (w1 + w2));
+  o[0].y = fourth * ((w3 - w0) + (w1 - w2));
+  o[0].z = fourth * ((w3 - w0) - (w1 - w2));
+  o[0].w = fourth * ((w3 + w0) - (w1 + w2));
   w0 = e0.y; w1 = ez_.y; w2 = ex_.y; w3 = ezx.y;
-  o1.x = fourth * ((w3 + w0) + (w1 + w2));
-  o1.y = fourth * ((w3 - w0) + (w1 - w2));
-  o1.z = fourth * ((w3 - w0) - (w1 - w2));
-  o1.w = fourth * ((w3 + w0) - (w1 + w2));
-  // ez: w0=f0 w1=fx w2=fy w3=fxy
+  o[1].x = fourth * ((w3 + w0) + (w1 + w2));
+  o[1].y = fourth * ((w3 - w0) + (w1 - w2));
+  o[1].z = fourth * ((w3 - w0) - (w1 - w2));
+  o[1].w = fourth * ((w3 + w0) - (w1 + w2));
   w0 = e0.z; w1 = ex_.z; w2 = ey_.z; w3 = exy.z;
-  o2.x = fourth * ((w3 + w0) + (w1 + w2));
-  o2.y = fourth * ((w3 - w0) + (w1 - w2));
-  o2.z = fourth * ((w3 - w0) - (w1 - w2));
-  o2.w = fourth * ((w3 + w0) - (w1 + w2));
+  o[2].x = fourth * ((w3 + w0) + (w1 + w2));
+  o[2].y = fourth * ((w3 - w0) + (w1 - w2));
+  o[2].z = fourth * ((w3 - w0) - (w1 - w2));
+  o[2].w = fourth * ((w3 + w0) - (w1 + w2));
   w0 = b0.x; w1 = bx_.x;
-  o3.x = half * (w1 + w0); o3.y = half * (w1 - w0);
+  o[3].x = half * (w1 + w0); o[3].y = half * (w1 - w0);
   w0 = b0.y; w1 = by_.y;
-  o3.z = half * (w1 + w0); o3.w = half * (w1 - w0);
+  o[3].z = half * (w1 + w0); o[3].w = half * (w1 - w0);
   w0 = b0.z; w1 = bz_.z;
-  o4.x = half * (w1 + w0); o4.y = half * (w1 - w0);
+  o[4] = make_float4(half * (w1 + w0), half * (w1 - w0), 0.f, 0.f);
+  o[5] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// One thread per interior voxel (1..nx, 1..ny, 1..nz).  The first 32 bytes of a
+// field_t are {ex,ey,ez,div_e_err | cbx,cby,cbz,div_b_err}: two 128-bit loads.
+// STAGE (96-byte device records only): a lane's six quads sit 96 bytes from its neighbour's, so each of the six store
+// instructions of a warp touches 24 lines; instead the warp's 3072 contiguous output bytes go through shared memory
+// (rows of seven quads: conflict-free) and leave as six stores of 512 contiguous bytes.
+template <int STAGE>
+__global__ void __launch_bounds__(256) load_interpolator_kernel(vpb_interpolator_t *__restrict__ fi,
+                                                                const vpb_field_t *__restrict__ f, const DomainDev g) {
+  const int x = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = 1 + blockIdx.y;
+  const int z = 1 + blockIdx.z;
+  if (STAGE) {
+    __shared__ float4 stage[8][32 * 7];
+    const int lane = threadIdx.x & 31, x0 = x - lane;
+    float4 *sw = stage[threadIdx.x >> 5];
+    const size_t v0 = (size_t)x0 + (size_t)g.sx * ((size_t)y + (size_t)g.sy * z);
+    if (x <= g.nx) {
+      float4 o[6];
+      interpolator_of_voxel(f, g, v0 + lane, o);
+#pragma unroll
+      for (int k = 0; k < 6; k++) sw[lane * 7 + k] = o[k];
+    }
+    __syncwarp();
+    const int nq = 6 * min(32, g.nx - x0 + 1);            // quads this warp owes (<= 0: the whole warp is past the row)
+    float4 *ob = reinterpret_cast<float4 *>(reinterpret_cast<char *>(fi) + v0 * 96);
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+      const int q = lane + 32 * j;
+      if (q < nq) ob[q] = sw[(q / 6) * 7 + q % 6];
+    }
+    return;
+  }
+  if (x > g.nx) return;
+  const size_t v = (size_t)x + (size_t)g.sx * ((size_t)y + (size_t)g.sy * z);
+  float4 q[6];
+  interpolator_of_voxel(f, g, v, q);
   float4 *o = reinterpret_cast<float4 *>(reinterpret_cast<char *>(fi) + v * (size_t)g.fi_bytes);
-  o[0] = o0; o[1] = o1; o[2] = o2; o[3] = o3;
+  o[0] = q[0]; o[1] = q[1]; o[2] = q[2]; o[3] = q[3];
   if (g.fi_bytes == 96) {
     // the padded device record: its last sector is written whole (a lone 8-byte store would make DRAM read the other
     // 24 bytes first); bytes 72..95 belong to nobody
-    o[4] = make_float4(o4.x, o4.y, 0.f, 0.f);
-    o[5] = make_float4(0.f, 0.f, 0.f, 0.f);
+    o[4] = q[4];
+    o[5] = q[5];
   } else {
-    *reinterpret_cast<float2 *>(o + 4) = o4;   // _pad[2] is left untouched, like the reference
+    *reinterpret_cast<float2 *>(o + 4) = make_float2(q[4].x, q[4].y);   // _pad[2] is left untouched, like the reference
   }
 }
 
@@ -116,7 +144,10 @@ void vpb_load_interpolator(vpb_domain_t *dom, vpb_interpolator_t *d_fi, const vp
   const int tb = g.nx >= 256 ? 256 : (g.nx >= 128 ? 128 : (g.nx >= 64 ? 64 : 32));
   dim3 grid((g.nx + tb - 1) / tb, g.ny, g.nz);
   ProfScope prof(4);
-  load_interpolator_kernel<<<grid, tb, 0, ctx().stream>>>(d_fi, d_f, g);
+  // sf.stage_store (tuning): the 96-byte records leave through shared memory as whole lines (1, default) or straight
+  // from the registers (0)
+  if (g.fi_bytes == 96 && tuning("sf.stage_store", 1)) load_interpolator_kernel<1><<<grid, tb, 0, ctx().stream>>>(d_fi, d_f, g);
+  else load_interpolator_kernel<0><<<grid, tb, 0, ctx().stream>>>(d_fi, d_f, g);
   count_launch();
   VPB_CUDA(cudaGetLastError());
 }

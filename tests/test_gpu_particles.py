@@ -642,3 +642,39 @@ def test_sort_p_planes_grouped(vpb, n, np_, L, vth, variant):
     for arr in (d_p, d_out, d_part):
         arr.free()
     vpb.vpb_domain_destroy(dom)
+
+
+@pytest.mark.parametrize("n", [(70, 3, 2), (32, 2, 2), (33, 1, 3), (5, 4, 3)])
+@pytest.mark.parametrize("stage", [1, 0])
+def test_wide_interpolator_store_paths(vpb, orc, n, stage):
+    """load_interpolator into the 96-byte device records: through shared memory as whole lines (sf.stage_store = 1, the
+    default) or straight from the registers (0) -- the 18 coefficients bit-identical to the oracle's, the six pad floats of
+    interior records zero, ghost records untouched."""
+    from old_vpic_b200.sim import DevArray, FieldArray
+    from helpers import random_fields
+    g = host_grid(n)
+    f = random_fields(np.random.default_rng(77), g)
+    fi_o = abi.aligned_zeros(g.nv, abi.interpolator_dtype)
+    orc.orc_load_interpolator(ptr(fi_o), ptr(f), g.ref())
+    dom = vpb.vpb_domain_create(g.ref(), 0, 1)
+    vpb.vpb_domain_set_field_layout(dom, 1)
+    vpb.vpb_domain_set_interpolator_layout(dom, 1)
+    d_f = FieldArray(vpb, dom, g.nv)
+    d_f.upload(f)
+    d_fi = DevArray(vpb, 96 * g.nv, np.uint8)
+    d_fi.upload(np.full(96 * g.nv, 0x5a, np.uint8))
+    vpb.vpb_set_tuning(b"sf.stage_store", stage)
+    try:
+        vpb.vpb_load_interpolator(dom, d_fi.ptr, d_f.ptr)
+    finally:
+        vpb.vpb_set_tuning(b"sf.stage_store", 1)
+    got = d_fi.download().view(np.float32).reshape(g.nv, 24)
+    sz, sy, sx = g.shape
+    iz, iy, ix = np.meshgrid(np.arange(sz), np.arange(sy), np.arange(sx), indexing="ij")
+    interior = ((ix >= 1) & (ix <= n[0]) & (iy >= 1) & (iy <= n[1]) & (iz >= 1) & (iz <= n[2])).reshape(-1)
+    want = fi_o.view(np.float32).reshape(g.nv, 20)[:, :18]
+    assert_bits_equal(got[interior, :18].copy(), want[interior].copy(), "coefficients")
+    assert not np.any(got[interior, 18:].view(np.uint32))
+    assert np.all(got[~interior].view(np.uint8) == 0x5a)
+    d_f.free(); d_fi.free()
+    vpb.vpb_domain_destroy(dom)
