@@ -123,8 +123,6 @@ def test_boundary_p_runs_the_decks_handlers_on_the_host(vpb, orc, ref_scalar):
     tolerance."""
     from helpers import RefGrid
     R = ref_scalar
-    for name in ("new_mt_rng", "mt_urand_fill"):
-        pass
     R.new_mt_rng.restype, R.new_mt_rng.argtypes = C.c_void_p, [C.c_uint]
     R.mt_urand_fill.restype, R.mt_urand_fill.argtypes = None, [C.c_void_p, C.c_void_p, C.c_size_t]
     n = (6, 5, 4)

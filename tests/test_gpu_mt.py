@@ -161,3 +161,54 @@ def test_device_run_from_the_seed_alone_reproduces_the_reference_deck(vpb):
     # the kinetic energies of the freshly loaded plasma are sums over the very same particles: tighter
     assert np.all(rel[0, 6:] < 1e-6), rel[0]
     sim.free()
+
+
+def test_device_against_the_committed_reference_fixtures(vpb):
+    """The device stream and the device load against what the REFERENCE ITSELF produced (tests/golden/ref_mt_stream.npz,
+    ref_thermal_c1_load.npz, written by tests/golden/make_mt_golden.py from oracle/_ref): words, mt_drand, mt_drandn, the
+    tail-layer deviates among the first 250000 normals, and both particle arrays of the deck's load loop."""
+    import os
+    from old_vpic_b200.sim import ParticleArray
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    G = np.load(os.path.join(gold, "ref_mt_stream.npz"))
+    for seed in (0, 7, 0xfffffffe):
+        rng = vpb.vpb_mt_create(seed)
+        w, u, n = dev(vpb, 2000, np.uint32), dev(vpb, 500, np.float64), dev(vpb, 4000, np.float64)
+        vpb.vpb_mt_words(rng, w.ptr, 2000)
+        vpb.vpb_mt_draw(rng, b"U", 500, u.ptr)
+        vpb.vpb_mt_draw(rng, b"N", 4000, n.ptr)
+        assert np.array_equal(w.download(), G["words_%d" % seed])
+        assert np.array_equal(u.download().view(np.uint64), G["drand_%d" % seed].view(np.uint64))
+        assert np.array_equal(n.download().view(np.uint64), G["drandn_%d" % seed].view(np.uint64))
+        for a in (w, u, n):
+            a.free()
+        vpb.vpb_mt_destroy(rng)
+    rng = vpb.vpb_mt_create(7)
+    big = dev(vpb, 250000, np.float64)
+    vpb.vpb_mt_draw(rng, b"N", 250000, big.ptr)
+    got = big.download()
+    where = np.flatnonzero(np.abs(got) > 3.6554204190269413)
+    assert np.array_equal(where, G["tail_where_7"])
+    assert np.array_equal(got[where].view(np.uint64), G["tail_value_7"].view(np.uint64))
+    big.free()
+    vpb.vpb_mt_destroy(rng)
+    D = np.load(os.path.join(gold, "ref_thermal_c1_load.npz"))
+    cells, ppc = int(D["cells"]), int(D["ppc"])
+    n = cells ** 3 * ppc
+    import old_vpic_b200.grid as G2
+    g = host_grid((cells,) * 3, "periodic", L=(float(cells),) * 3, dt=0.95 * G2.courant_dt(1.0, 1.0, 1.0, frac=1.0))
+    dom = vpb.vpb_domain_create(g.ref(), 0, 1)
+    d_e, d_i = ParticleArray(vpb, dom, n), ParticleArray(vpb, dom, n)
+    rng = vpb.vpb_mt_create(int(D["seed"]))
+    np2 = (C.c_int * 2)(0, 0)
+    lo, hi = np.zeros(3), np.full(3, float(cells))
+    q = float(cells) ** 3 / n
+    assert vpb.vpb_load_pairs_mt(dom, rng, n, ptr(lo), ptr(hi), float(D["vth"]), float(D["vth"]), -q, q, d_e.ptr, n, d_i.ptr, n, np2, 1) == n
+    pe, pi = d_e.download(n), d_i.download(n)
+    for name in ("dx", "dy", "dz", "i", "ux", "uy", "uz", "q"):
+        assert np.array_equal(pe[name].view(np.uint32), D["electron"][name].view(np.uint32)), ("electron", name)
+        assert np.array_equal(pi[name].view(np.uint32), D["ion"][name].view(np.uint32)), ("ion", name)
+    for a in (d_e, d_i):
+        a.free()
+    vpb.vpb_mt_destroy(rng)
+    vpb.vpb_domain_destroy(dom)

@@ -149,3 +149,41 @@ def test_library_builds_the_same_layer_table():
     O.orc_mt_zig_table(*[ptr(v) for v in b])
     for u, v in zip(a, b):
         assert np.array_equal(u.view(np.uint64), v.view(np.uint64))
+
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_oracle_against_the_committed_reference_fixtures():
+    """tests/golden/ref_mt_stream.npz and ref_thermal_c1_load.npz were written by the reference itself
+    (tests/golden/make_mt_golden.py); they travel to the GPU box, where /root/reference does not exist."""
+    O = oracle_mt()
+    G = np.load(os.path.join(GOLDEN, "ref_mt_stream.npz"))
+    for seed in (0, 7, 0xfffffffe):
+        rng = new_rng(O, seed)
+        w, u, n = np.zeros(2000, np.uint32), np.zeros(500), np.zeros(4000)
+        O.orc_mt_fill_u32(ptr(rng), ptr(w), len(w))
+        O.orc_mt_fill_drand(ptr(rng), ptr(u), len(u))
+        O.orc_mt_fill_drandn(ptr(rng), ptr(n), len(n))
+        assert np.array_equal(w, G["words_%d" % seed])
+        assert np.array_equal(u.view(np.uint64), G["drand_%d" % seed].view(np.uint64))
+        assert np.array_equal(n.view(np.uint64), G["drandn_%d" % seed].view(np.uint64))
+    rng = new_rng(O, 7)
+    big = np.zeros(250000)
+    O.orc_mt_fill_drandn(ptr(rng), ptr(big), len(big))
+    assert np.array_equal(big[G["tail_where_7"]].view(np.uint64), G["tail_value_7"].view(np.uint64))
+    D = np.load(os.path.join(GOLDEN, "ref_thermal_c1_load.npz"))
+    cells, ppc = int(D["cells"]), int(D["ppc"])
+    n = cells ** 3 * ppc
+    import old_vpic_b200.grid as G2
+    g = host_grid((cells,) * 3, "periodic", L=(float(cells),) * 3, dt=0.95 * G2.courant_dt(1.0, 1.0, 1.0, frac=1.0))
+    rng = new_rng(O, int(D["seed"]))
+    pe, pi = abi.aligned_zeros(n, abi.particle_dtype), abi.aligned_zeros(n, abi.particle_dtype)
+    npe, npi = C.c_int(0), C.c_int(0)
+    lo, hi = np.zeros(3), np.full(3, float(cells))
+    q = float(cells) ** 3 / n
+    assert O.orc_load_thermal_pairs(ptr(rng), n, ptr(lo), ptr(hi), float(D["vth"]), float(D["vth"]), q, ptr(pe), C.byref(npe), n, ptr(pi),
+                                    C.byref(npi), n, g.ref()) == n
+    for name in ("dx", "dy", "dz", "i", "ux", "uy", "uz", "q"):
+        assert np.array_equal(pe[name].view(np.uint32), D["electron"][name].view(np.uint32)), ("electron", name)
+        assert np.array_equal(pi[name].view(np.uint32), D["ion"][name].view(np.uint32)), ("ion", name)
