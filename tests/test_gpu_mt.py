@@ -212,3 +212,47 @@ def test_device_against_the_committed_reference_fixtures(vpb):
         a.free()
     vpb.vpb_mt_destroy(rng)
     vpb.vpb_domain_destroy(dom)
+
+
+def test_draws_and_load_across_internal_batches(vpb):
+    """vpb_mt_draw parses at most 2^24 records at a time and vpb_load_pairs_mt loads 2^23 iterations at a time: streams and
+    loads longer than that continue seamlessly (16.8 M normal deviates; 8 392 704 load iterations on 16^3 cells)."""
+    from old_vpic_b200.sim import ParticleArray
+    O = oracle_mt()
+    n = (1 << 24) + 12345
+    rng_o = new_rng(O, 3)
+    want = np.zeros(n, np.float64)
+    O.orc_mt_fill_drandn(ptr(rng_o), ptr(want), n)
+    rng = vpb.vpb_mt_create(3)
+    d = dev(vpb, n, np.float64)
+    vpb.vpb_mt_draw(rng, b"N", n, d.ptr)
+    got = d.download()
+    bad = np.flatnonzero(got.view(np.uint64) != want.view(np.uint64))
+    assert len(bad) == 0, (len(bad), bad[:5])
+    d.free()
+    vpb.vpb_mt_destroy(rng)
+    del want, got
+    cells, ppc = 16, 2049
+    g = host_grid((cells,) * 3, "periodic")
+    pairs = cells ** 3 * ppc
+    assert pairs > (1 << 23)
+    lo, hi = np.zeros(3), np.full(3, float(cells))
+    q = float(cells) ** 3 / pairs
+    rng_o = new_rng(O, 11)
+    pe, pi = abi.aligned_zeros(pairs, abi.particle_dtype), abi.aligned_zeros(pairs, abi.particle_dtype)
+    npe, npi = C.c_int(0), C.c_int(0)
+    assert O.orc_load_thermal_pairs(ptr(rng_o), pairs, ptr(lo), ptr(hi), 0.1, 0.1, q, ptr(pe), C.byref(npe), pairs, ptr(pi), C.byref(npi), pairs,
+                                    g.ref()) == pairs
+    dom = vpb.vpb_domain_create(g.ref(), 0, 1)
+    vpb.vpb_domain_set_particle_layout(dom, (pairs + 63) // 64 * 64)
+    d_e, d_i = ParticleArray(vpb, dom, pairs), ParticleArray(vpb, dom, pairs)
+    rng = vpb.vpb_mt_create(11)
+    np2 = (C.c_int * 2)(0, 0)
+    assert vpb.vpb_load_pairs_mt(dom, rng, pairs, ptr(lo), ptr(hi), 0.1, 0.1, -q, q, d_e.ptr, pairs, d_i.ptr, pairs, np2, 1) == pairs
+    assert (np2[0], np2[1]) == (pairs, pairs)
+    assert_bits_equal(d_e.download(pairs), pe, "electrons")
+    assert_bits_equal(d_i.download(pairs), pi, "ions")
+    for a in (d_e, d_i):
+        a.free()
+    vpb.vpb_mt_destroy(rng)
+    vpb.vpb_domain_destroy(dom)
