@@ -238,7 +238,10 @@ void vpb_mt_ziggurat_table(double *x, double *y, double *r);
  * d_table[n*stride]: x = lo[0]*(1-t[col[0]]) + hi[0]*t[col[0]] (uniform_rand), y, z alike from col[1], col[2];
  * ux = dev[0]*t[col[3]] (maxwellian_rand), uy, uz from col[4], col[5].  Particles the reference would not inject on this
  * rank (outside the local box, or on a far wall shared with a neighbour; misc.cxx:37-39) are skipped, the others appended
- * at d_p[np...] in order (d_p in the domain's particle layout).  Returns the new np; more than max_np is an error. */
+ * at d_p[np...] in order (d_p in the domain's particle layout).  Returns the new np; more than max_np is an error.
+ * With lo = 0, hi = 1 and dev = 1 the mapping is exact (0*(1-t) + 1*t = t, 1*t = t): the table then holds x, y, z, ux, uy, uz
+ * themselves and the call is the batched inject_particle for momenta a deck computed its own way (drifting or
+ * relativistic loads such as decks/trecon-part/turbulence.cxx:535-541). */
 int vpb_inject_from_draws(vpb_domain_t *dom, vpb_particle_t *d_p, int np, int max_np, const double *d_table, int stride, long n,
                           const int col[6], const double lo[3], const double hi[3], const double dev[3], double q, long tag);
 /* The load loop of a thermal deck (BASELINE configs[0]/[3] recipe): n iterations of one position from three
