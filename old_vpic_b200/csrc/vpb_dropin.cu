@@ -565,6 +565,21 @@ void boundary_p(vpb_species_t *sp_list, vpb_field_t *f0, vpb_accumulator_t *a0, 
   std::vector<vpb_species_t *> list;
   for (vpb_species_t *sp = sp_list; sp; sp = sp->next) list.push_back(sp);
   if (list.size() > 7) VPB_ERROR("boundary_p handles at most 7 species per call");
+  {
+    // nothing pending anywhere and no face shared with another rank: the reference's loops all run zero times
+    // (a one-rank periodic deck calls this three times a step)
+    long pending = 0;
+    for (vpb_species_t *sp : list) pending += sp->nm;
+    bool remote = false;
+    static const int fb[6] = {VPB_BOUNDARY(-1, 0, 0), VPB_BOUNDARY(0, -1, 0), VPB_BOUNDARY(0, 0, -1),
+                              VPB_BOUNDARY(1, 0, 0),  VPB_BOUNDARY(0, 1, 0),  VPB_BOUNDARY(0, 0, 1)};
+    for (int f = 0; f < 6; f++) remote |= g->bc[fb[f]] >= 0 && g->bc[fb[f]] < dom->d.nproc && g->bc[fb[f]] != dom->d.rank;
+    if (pending == 0 && !remote) {
+      for (vpb_species_t *sp : list)
+        if (sp->id < 0 || sp->id >= 64) VPB_ERROR("Invalid sp->id");   // boundary_p.c:396
+      return;
+    }
+  }
   // boundary_p.c:271-277: movers that ended on a face bound to one of the deck's custom handlers (neighbor code -3-k,
   // k < grid->nb).  The handlers are the host program's code (parameters, host RNG, calls back into accumulate_rhob ...):
   // they run HERE, on the host, in the order the reference visits the movers -- species in list order, each species'
