@@ -126,3 +126,29 @@ def test_reference_named_prototypes_match_the_reference_headers():
         assert ret == r_ret, (name, ret, r_ret)
         checked += 1
     assert checked >= 27
+
+
+def test_product_does_not_use_the_oracle():
+    """oracle/ is test infrastructure: nothing under old_vpic_b200/ imports, links or executes it (comments may name its
+    files), the library does not depend on an oracle shared object, and bench.py reaches for it only inside its
+    cpu_baseline / --impl reference legs."""
+    import re
+    import subprocess
+    pkg = os.path.join(ROOT, "old_vpic_b200")
+    for base, _, files in os.walk(pkg):
+        if "_obj" in base:
+            continue
+        for name in files:
+            if not name.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
+                continue
+            for ln in open(os.path.join(base, name), errors="replace"):
+                code = ln.split("//")[0].split("#")[0] if not name.endswith(".py") else ln.split("#")[0]
+                assert not re.search(r"(import|from)\s+oracle|libvpic_oracle|orc_[a-z_]+\s*\(|oracle/_ref", code), (name, ln)
+    so = os.path.join(pkg, "libvpic_b200.so")
+    if os.path.exists(so):
+        needed = subprocess.run(["objdump", "-p", so], capture_output=True, text=True).stdout
+        assert "oracle" not in needed and "vpic_ref" not in needed
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    for m in re.finditer(r"^(\s*)from oracle import|^(\s*)import oracle", src, re.M):
+        indent = len(m.group(1) or m.group(2) or "")
+        assert indent >= 4, "bench.py imports the oracle at module level"
