@@ -565,7 +565,10 @@ def run_b200(args):
     if world == 1 and args.workload == "thermal" and not args.no_e2e:
         line["small_step"] = small_step_measure(L)
     if world == 1 and args.workload == "thermal" and not args.no_e2e:
-        line["load_mt"] = load_mt_measure(L, not args.no_cpu_baseline)
+        try:
+            line["load_mt"] = load_mt_measure(L, not args.no_cpu_baseline)
+        except Exception as exc:              # a side measurement must not cost the bench line
+            line["load_mt"] = {"failed": repr(exc)}
     if harris and args.trecon_deck:
         hyb = os.path.join(ROOT, "oracle", "_ref", "hybrid")
         line["trecon_deck"] = trecon_deck(os.path.join(hyb, "turbulence_c2.b200.op"), 2048 * 1024, 60, 1,
@@ -616,8 +619,9 @@ def load_mt_measure(L, with_cpu, n=64, ppc=32):
     i = sim.define_species("ion", 1.0, pairs + 1024, sort_interval=20)
     q = float(n) ** 3 / pairs
     out = {"workload": "BASELINE configs[0] load: %d iterations of {3 uniform_rand, 6 maxwellian_rand, 2 inject_particle}, seed 7" % pairs}
-    for rep in range(2):                      # the second call is the timed one (buffers allocated, kernels loaded)
-        if rep == 1:
+    times = []
+    for rep in range(4):                      # the first call is untimed (buffers allocated, kernels loaded)
+        if rep:
             sim.free()
             sim = NativeSimulation(g, L=L)
             e = sim.define_species("electron", -1.0, pairs + 1024, sort_interval=20)
@@ -626,8 +630,12 @@ def load_mt_measure(L, with_cpu, n=64, ppc=32):
         t0 = time.perf_counter()
         sim.load_pairs_mt(e, i, pairs, [0, 0, 0], [n, n, n], 0.1, 0.1, -q, q, seed=7)
         L.vpb_sync()
-        dt = time.perf_counter() - t0
-    out["device"] = {"seconds": dt, "pairs_per_s": pairs / dt, "particles": 2 * pairs}
+        if rep:
+            times.append(time.perf_counter() - t0)
+    # the call allocates and frees ~1.2 GB of device buffers (word stream, deviate table); now and then one of those
+    # cudaMalloc/cudaFree calls takes half a second on its own, so: the median of three calls, all three listed
+    dt = sorted(times)[1]
+    out["device"] = {"seconds": dt, "pairs_per_s": pairs / dt, "particles": 2 * pairs, "seconds_each_call": [round(t, 4) for t in times]}
     sim.free()
     if with_cpu:
         from oracle import loader

@@ -243,13 +243,15 @@ void vpb_mt_ziggurat_table(double *x, double *y, double *r);
  * themselves and the call is the batched inject_particle for momenta a deck computed its own way (drifting or
  * relativistic loads such as decks/trecon-part/turbulence.cxx:535-541). */
 int vpb_inject_from_draws(vpb_domain_t *dom, vpb_particle_t *d_p, int np, int max_np, const double *d_table, int stride, long n,
-                          const int col[6], const double lo[3], const double hi[3], const double dev[3], double q, long tag);
+                          const int col[6], const double lo[3], const double hi[3], const double dev[3], double q, long tag, long tag_step);
 /* The load loop of a thermal deck (BASELINE configs[0]/[3] recipe): n iterations of one position from three
  * uniform_rand(lo, hi) and two co-located particles (charges q_a, q_b) with three maxwellian_rand(vth) each, the deviates
  * written as arguments of inject_particle -- evaluated right to left by g++ (args_right_to_left = 1: the first deviate
- * is uz) or left to right (0).  np[2]: particle counts of the two arrays, in and out. */
+ * is uz) or left to right (0).  np[2]: particle counts of the two arrays, in and out.  Iteration k tags its particles
+ * tag0 + k*tag_step (oracle/decks/thermal_c1.cxx passes 0, thermal_small.cxx the loop counter). */
 long vpb_load_pairs_mt(vpb_domain_t *dom, vpb_mt_t *rng, long n, const double lo[3], const double hi[3], double vth_a, double vth_b, double q_a,
-                       double q_b, vpb_particle_t *d_a, int max_a, vpb_particle_t *d_b, int max_b, int np[2], int args_right_to_left);
+                       double q_b, vpb_particle_t *d_a, int max_a, vpb_particle_t *d_b, int max_b, int np[2], int args_right_to_left,
+                       long tag0, long tag_step);
 /* Device field layout.  A domain starts out with the reference's 80-byte AoS field_t (what every layer-A entry
  * point uses).  A caller that keeps the field array resident on the device can switch the domain to the PLANAR
  * layout: five planes (e|div_e, cb|div_b, tca|rhob, jf|rhof, material ids) of one 16-byte quad per voxel, so a
@@ -414,7 +416,7 @@ int vpb_sim_define_species(vpb_sim_t *s, const char *name, float q_m, long max_n
 void vpb_sim_load_thermal(vpb_sim_t *s, int species, int ppc, float vth, float q, unsigned long long seed, long tag0);
 /* vpb_load_pairs_mt (the deck's load loop from the reference's random-number stream) into two species of the run */
 long vpb_sim_load_pairs_mt(vpb_sim_t *s, vpb_mt_t *rng, int species_a, int species_b, long n, const double lo[3], const double hi[3],
-                           double vth_a, double vth_b, double q_a, double q_b, int args_right_to_left);
+                           double vth_a, double vth_b, double q_a, double q_b, int args_right_to_left, long tag0, long tag_step);
 void vpb_sim_set_particles(vpb_sim_t *s, int species, const vpb_particle_t *host, long np);
 long vpb_sim_get_particles(vpb_sim_t *s, int species, vpb_particle_t *host, long max);
 void vpb_sim_set_fields(vpb_sim_t *s, const vpb_field_t *host);       /* field_t[nvoxel], reference layout */

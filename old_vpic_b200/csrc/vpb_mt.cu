@@ -306,7 +306,7 @@ __device__ __forceinline__ bool place(double &x, int &ix, double x0, double x1, 
 template <int PASS>
 __global__ void __launch_bounds__(256) inject_table_kernel(const double *__restrict__ tab, int stride, long n, const LoadMap M, const GridBox G,
                                                            int *__restrict__ keep, const int *__restrict__ slot, const PView p, int np0, int max_np,
-                                                           float q, long tag, int *__restrict__ overflow) {
+                                                           float q, long tag, long tag_step, int *__restrict__ overflow) {
   for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long)gridDim.x * blockDim.x) {
     const double *row = tab + k * (long)stride;
     double d = row[M.col[0]];
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(256) inject_table_kernel(const double *__restr
     const double ux = M.dev[0] * row[M.col[3]], uy = M.dev[1] * row[M.col[4]], uz = M.dev[2] * row[M.col[5]];
     p.set_pos(pos, make_float4((float)x, (float)y, (float)z, __int_as_float(ix + (G.nx + 2) * (iy + (G.ny + 2) * iz))));
     p.set_mom(pos, make_float4((float)ux, (float)uy, (float)uz, q));
-    const longlong2 tags = make_longlong2(tag, 0);
+    const longlong2 tags = make_longlong2(tag + k * tag_step, 0);
     p.set_tag(pos, *reinterpret_cast<const float4 *>(&tags));
   }
 }
@@ -603,9 +603,10 @@ void vpb_mt_draw(vpb_mt_t *m, const char *prog, long n, double *d_out) {
 // n calls of inject_particle(sp, x, y, z, ux, uy, uz, q, tag, 0, 0) (misc.cxx:16-105) in order, the arguments taken from
 // row k of a table of deviates: x = lo*(1-t[col0]) + hi*t[col0] ..., ux = dev0 * t[col3] ...  Particles outside the
 // local domain (or on a far wall shared with a neighbour) are skipped as the reference skips them; the others are
-// appended in order.  Returns the new particle count.  d_p is in the domain's particle layout.
+// appended in order; row k carries the tag `tag + k*tag_step`.  Returns the new particle count.  d_p is in the domain's
+// particle layout.
 int vpb_inject_from_draws(vpb_domain_t *dom, vpb_particle_t *d_p, int np, int max_np, const double *d_table, int stride, long n,
-                          const int col[6], const double lo[3], const double hi[3], const double dev[3], double q, long tag) {
+                          const int col[6], const double lo[3], const double hi[3], const double dev[3], double q, long tag, long tag_step) {
   if (!dom || !dom->host_grid) VPB_ERROR("Bad grid");
   if (!d_p || !d_table || n < 0 || np < 0 || np > max_np) VPB_ERROR("Bad args");
   if (n == 0) return np;
@@ -633,9 +634,9 @@ int vpb_inject_from_draws(vpb_domain_t *dom, vpb_particle_t *d_p, int np, int ma
   const PView pv(d_p, dom->d.p_plane);
   VPB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
   VPB_CUDA(cudaMemsetAsync(keep + n, 0, sizeof(int), st));
-  inject_table_kernel<0><<<c.sm_count * 8, 256, 0, st>>>(d_table, stride, n, M, G, keep, nullptr, pv, np, max_np, (float)q, tag, flag);
+  inject_table_kernel<0><<<c.sm_count * 8, 256, 0, st>>>(d_table, stride, n, M, G, keep, nullptr, pv, np, max_np, (float)q, tag, tag_step, flag);
   exclusive_scan_i32(keep, slot, (int)(n + 1), s + o_scan, st);
-  inject_table_kernel<1><<<c.sm_count * 8, 256, 0, st>>>(d_table, stride, n, M, G, nullptr, slot, pv, np, max_np, (float)q, tag, flag);
+  inject_table_kernel<1><<<c.sm_count * 8, 256, 0, st>>>(d_table, stride, n, M, G, nullptr, slot, pv, np, max_np, (float)q, tag, tag_step, flag);
   count_launch(2 + scan_launches(n + 1));
   int h[2];
   VPB_CUDA(cudaMemcpyAsync(&h[0], slot + n, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -650,9 +651,11 @@ int vpb_inject_from_draws(vpb_domain_t *dom, vpb_particle_t *d_p, int np, int ma
 // position from three uniform_rand(lo, hi) and two co-located particles, each with three maxwellian_rand.  A deck
 // writes the three deviates as ARGUMENTS of inject_particle, whose evaluation order is the compiler's: g++ on x86-64
 // goes right to left, so the first deviate drawn is uz (args_right_to_left = 1); 0 = ux first.
-// np[2] (in/out): particle counts of the two arrays.  Returns the number of iterations.
+// np[2] (in/out): particle counts of the two arrays.  Iteration k tags both its particles tag0 + k*tag_step (decks pass 0 or
+// the loop counter).  Returns the number of iterations.
 long vpb_load_pairs_mt(vpb_domain_t *dom, vpb_mt_t *rng, long n, const double lo[3], const double hi[3], double vth_a, double vth_b, double q_a,
-                       double q_b, vpb_particle_t *d_a, int max_a, vpb_particle_t *d_b, int max_b, int np[2], int args_right_to_left) {
+                       double q_b, vpb_particle_t *d_a, int max_a, vpb_particle_t *d_b, int max_b, int np[2], int args_right_to_left,
+                       long tag0, long tag_step) {
   if (!dom || !rng || n < 0 || !np) VPB_ERROR("Bad args");
   const long kBatch = 1L << 23;
   const int o = args_right_to_left ? 1 : 0;
@@ -664,8 +667,8 @@ long vpb_load_pairs_mt(vpb_domain_t *dom, vpb_mt_t *rng, long n, const double lo
   for (long done = 0; done < n;) {
     const long nb = n - done < kBatch ? n - done : kBatch;
     vpb_mt_draw(rng, "UUUNNNNNN", nb, tab);
-    np[0] = vpb_inject_from_draws(dom, d_a, np[0], max_a, tab, 9, nb, col_a, lo, hi, dev_a, q_a, 0);
-    np[1] = vpb_inject_from_draws(dom, d_b, np[1], max_b, tab, 9, nb, col_b, lo, hi, dev_b, q_b, 0);
+    np[0] = vpb_inject_from_draws(dom, d_a, np[0], max_a, tab, 9, nb, col_a, lo, hi, dev_a, q_a, tag0 + done * tag_step, tag_step);
+    np[1] = vpb_inject_from_draws(dom, d_b, np[1], max_b, tab, 9, nb, col_b, lo, hi, dev_b, q_b, tag0 + done * tag_step, tag_step);
     done += nb;
   }
   if (tab) { VPB_CUDA(cudaStreamSynchronize(ctx().stream)); cudaFree(tab); }

@@ -387,10 +387,10 @@ void vpb_sim_load_thermal(vpb_sim_t *s, int id, int ppc, float vth, float q, uns
 
 // The thermal deck's load loop from the reference's random-number stream (vpb_mt.cu), appended to two species of the run
 long vpb_sim_load_pairs_mt(vpb_sim_t *s, vpb_mt_t *rng, int id_a, int id_b, long n, const double lo[3], const double hi[3], double vth_a,
-                           double vth_b, double q_a, double q_b, int args_right_to_left) {
+                           double vth_b, double q_a, double q_b, int args_right_to_left, long tag0, long tag_step) {
   Species &a = species_of(s, id_a), &b = species_of(s, id_b);
   int np[2] = {a.np, b.np};
-  const long done = vpb_load_pairs_mt(s->dom, rng, n, lo, hi, vth_a, vth_b, q_a, q_b, a.p, a.max_np, b.p, b.max_np, np, args_right_to_left);
+  const long done = vpb_load_pairs_mt(s->dom, rng, n, lo, hi, vth_a, vth_b, q_a, q_b, a.p, a.max_np, b.p, b.max_np, np, args_right_to_left, tag0, tag_step);
   a.np = np[0];
   b.np = np[1];
   return done;

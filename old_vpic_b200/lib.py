@@ -81,8 +81,8 @@ SIGNATURES = {
     "vpb_mt_words": (None, [_vp, _vp, _l]),
     "vpb_mt_draw": (None, [_vp, C.c_char_p, _l, _vp]),
     "vpb_mt_ziggurat_table": (None, [_vp, _vp, _vp]),
-    "vpb_inject_from_draws": (_i, [_vp, _vp, _i, _i, _vp, _i, _l, _vp, _vp, _vp, _vp, C.c_double, _l]),
-    "vpb_load_pairs_mt": (_l, [_vp, _vp, _l, _vp, _vp, C.c_double, C.c_double, C.c_double, C.c_double, _vp, _i, _vp, _i, _vp, _i]),
+    "vpb_inject_from_draws": (_i, [_vp, _vp, _i, _i, _vp, _i, _l, _vp, _vp, _vp, _vp, C.c_double, _l, _l]),
+    "vpb_load_pairs_mt": (_l, [_vp, _vp, _l, _vp, _vp, C.c_double, C.c_double, C.c_double, C.c_double, _vp, _i, _vp, _i, _vp, _i, _l, _l]),
     "vpb_load_plane_wave": (None, [_vp, _vp, _i, _f]),
     "vpb_domain_set_particle_layout": (None, [_vp, _l]),
     "vpb_domain_particle_layout": (_l, [_vp]),
@@ -167,7 +167,7 @@ SIGNATURES = {
     "vpb_sim_define_species": (_i, [_vp, C.c_char_p, _f, _l, _l, _i]),
     "vpb_sim_load_thermal": (None, [_vp, _i, _i, _f, _f, C.c_ulonglong, _l]),
     "vpb_sim_initialize": (None, [_vp, _vp]),
-    "vpb_sim_load_pairs_mt": (_l, [_vp, _vp, _i, _i, _l, _vp, _vp, C.c_double, C.c_double, C.c_double, C.c_double, _i]),
+    "vpb_sim_load_pairs_mt": (_l, [_vp, _vp, _i, _i, _l, _vp, _vp, C.c_double, C.c_double, C.c_double, C.c_double, _i, _l, _l]),
     "vpb_sim_set_particles": (None, [_vp, _i, _vp, _l]),
     "vpb_sim_get_particles": (_l, [_vp, _i, _vp, _l]),
     "vpb_sim_set_fields": (None, [_vp, _vp]),

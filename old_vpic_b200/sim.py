@@ -157,7 +157,7 @@ class NativeSimulation:
     def load_thermal(self, sp, ppc, vth, q, seed, tag0=0):
         self.L.vpb_sim_load_thermal(self.h, sp.id, ppc, vth, q, seed, tag0)
 
-    def load_pairs_mt(self, sp_a, sp_b, n, lo, hi, vth_a, vth_b, q_a, q_b, seed=None, rng=None, args_right_to_left=1):
+    def load_pairs_mt(self, sp_a, sp_b, n, lo, hi, vth_a, vth_b, q_a, q_b, seed=None, rng=None, args_right_to_left=1, tag0=0, tag_step=0):
         """The thermal deck's load loop (seed_rand(seed); n x {3 uniform_rand, 2 x 3 maxwellian_rand -> inject_particle})
         from the reference's own random-number stream, on the device (include/vpic_b200.h vpb_load_pairs_mt)."""
         own = rng is None
@@ -165,7 +165,7 @@ class NativeSimulation:
             rng = self.L.vpb_mt_create(int(seed))
         lo, hi = np.ascontiguousarray(lo, np.float64), np.ascontiguousarray(hi, np.float64)
         done = self.L.vpb_sim_load_pairs_mt(self.h, rng, sp_a.id, sp_b.id, int(n), lo.ctypes.data, hi.ctypes.data, vth_a, vth_b, q_a, q_b,
-                                            int(args_right_to_left))
+                                            int(args_right_to_left), int(tag0), int(tag_step))
         if own:
             self.L.vpb_mt_destroy(rng)
         return done

@@ -190,8 +190,18 @@ int orc_inject_particle(vpb_particle_t *p0, int *np, int max_np, double x, doubl
 /* The load loop of oracle/decks/thermal_c1.cxx (SURVEY.md 8d, C1/C4 recipe): per iteration one position from three
  * uniform_rand(lo, hi), then an electron and a co-located ion with three maxwellian_rand(vth) each.  Returns the
  * number of iterations done (stops when an array is full). */
+long orc_load_thermal_pairs_tagged(orc_mt_t *rng, long n, const double lo[3], const double hi[3], double vth_e, double vth_i, double q,
+                                   vpb_particle_t *pe, int *npe, int max_e, vpb_particle_t *pi, int *npi, int max_i, const vpb_grid_t *g,
+                                   long tag0, long tag_step);
 long orc_load_thermal_pairs(orc_mt_t *rng, long n, const double lo[3], const double hi[3], double vth_e, double vth_i, double q,
                             vpb_particle_t *pe, int *npe, int max_e, vpb_particle_t *pi, int *npi, int max_i, const vpb_grid_t *g) {
+  return orc_load_thermal_pairs_tagged(rng, n, lo, hi, vth_e, vth_i, q, pe, npe, max_e, pi, npi, max_i, g, 0, 0);
+}
+
+/* the same with inject_particle's tag argument = tag0 + k*tag_step (oracle/decks/thermal_small.cxx passes the loop counter) */
+long orc_load_thermal_pairs_tagged(orc_mt_t *rng, long n, const double lo[3], const double hi[3], double vth_e, double vth_i, double q,
+                                   vpb_particle_t *pe, int *npe, int max_e, vpb_particle_t *pi, int *npi, int max_i, const vpb_grid_t *g,
+                                   long tag0, long tag_step) {
   for (long k = 0; k < n; k++) {
     double d = orc_mt_drand(rng);
     const double x = lo[0] * (1 - d) + hi[0] * d;
@@ -203,9 +213,9 @@ long orc_load_thermal_pairs(orc_mt_t *rng, long n, const double lo[3], const dou
      * order in which a call's arguments are evaluated is the compiler's choice, and g++ on x86-64 (what builds the
      * reference here and on the Cray the deck was written for) goes right to left -- the FIRST deviate is uz */
     const double ez = vth_e * orc_mt_drandn(rng), ey = vth_e * orc_mt_drandn(rng), ex = vth_e * orc_mt_drandn(rng);
-    if (orc_inject_particle(pe, npe, max_e, x, y, z, ex, ey, ez, -q, 0, g) < 0) return k;
+    if (orc_inject_particle(pe, npe, max_e, x, y, z, ex, ey, ez, -q, tag0 + k * tag_step, g) < 0) return k;
     const double jz = vth_i * orc_mt_drandn(rng), jy = vth_i * orc_mt_drandn(rng), jx = vth_i * orc_mt_drandn(rng);
-    if (orc_inject_particle(pi, npi, max_i, x, y, z, jx, jy, jz, q, 0, g) < 0) return k;
+    if (orc_inject_particle(pi, npi, max_i, x, y, z, jx, jy, jz, q, tag0 + k * tag_step, g) < 0) return k;
   }
   return n;
 }

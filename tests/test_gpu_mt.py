@@ -102,7 +102,8 @@ def test_thermal_load_matches_the_serial_loop(vpb, n_cells, ppc, topo, rank, pla
     rng_o = new_rng(O, 7)
     pe, pi = abi.aligned_zeros(cap, abi.particle_dtype), abi.aligned_zeros(cap, abi.particle_dtype)
     npe, npi = C.c_int(0), C.c_int(0)
-    assert O.orc_load_thermal_pairs(ptr(rng_o), n, ptr(lo), ptr(hi), 0.1, 0.25, q, ptr(pe), C.byref(npe), cap, ptr(pi), C.byref(npi), cap, g.ref()) == n
+    assert O.orc_load_thermal_pairs_tagged(ptr(rng_o), n, ptr(lo), ptr(hi), 0.1, 0.25, q, ptr(pe), C.byref(npe), cap, ptr(pi), C.byref(npi), cap,
+                                           g.ref(), 100, 3) == n        # tag = 100 + 3k, k the loop counter (skipped iterations count)
     if topo == (1, 1, 1):
         assert npe.value == n
     else:
@@ -113,7 +114,7 @@ def test_thermal_load_matches_the_serial_loop(vpb, n_cells, ppc, topo, rank, pla
     d_e, d_i = ParticleArray(vpb, dom, cap), ParticleArray(vpb, dom, cap)
     rng = vpb.vpb_mt_create(7)
     np2 = (C.c_int * 2)(0, 0)
-    assert vpb.vpb_load_pairs_mt(dom, rng, n, ptr(lo), ptr(hi), 0.1, 0.25, -q, q, d_e.ptr, cap, d_i.ptr, cap, np2, 1) == n
+    assert vpb.vpb_load_pairs_mt(dom, rng, n, ptr(lo), ptr(hi), 0.1, 0.25, -q, q, d_e.ptr, cap, d_i.ptr, cap, np2, 1, 100, 3) == n
     assert (np2[0], np2[1]) == (npe.value, npi.value)
     assert_bits_equal(d_e.download(np2[0]), pe[:np2[0]], "electrons")
     assert_bits_equal(d_i.download(np2[1]), pi[:np2[1]], "ions")
@@ -145,7 +146,7 @@ def test_device_run_from_the_seed_alone_reproduces_the_reference_deck(vpb):
     i = sim.define_species("ion", 1.0, int(1.5 * ne), sort_interval=5)
     e = sim.define_species("electron", -1.0, int(1.5 * ne), sort_interval=5)
     q = float(n) ** 3 / ne
-    assert sim.load_pairs_mt(e, i, ne, [0, 0, 0], [n, n, n], 0.1, 0.1, -q, q, seed=7) == ne
+    assert sim.load_pairs_mt(e, i, ne, [0, 0, 0], [n, n, n], 0.1, 0.1, -q, q, seed=7, tag_step=1) == ne     # the deck's tag = k
     assert (e.np, i.np) == (ne, ne)
     sim.set_fields(abi.aligned_zeros(g.nv, abi.field_dtype))
     errs = sim.initialize()
@@ -203,7 +204,7 @@ def test_device_against_the_committed_reference_fixtures(vpb):
     np2 = (C.c_int * 2)(0, 0)
     lo, hi = np.zeros(3), np.full(3, float(cells))
     q = float(cells) ** 3 / n
-    assert vpb.vpb_load_pairs_mt(dom, rng, n, ptr(lo), ptr(hi), float(D["vth"]), float(D["vth"]), -q, q, d_e.ptr, n, d_i.ptr, n, np2, 1) == n
+    assert vpb.vpb_load_pairs_mt(dom, rng, n, ptr(lo), ptr(hi), float(D["vth"]), float(D["vth"]), -q, q, d_e.ptr, n, d_i.ptr, n, np2, 1, 0, 0) == n
     pe, pi = d_e.download(n), d_i.download(n)
     for name in ("dx", "dy", "dz", "i", "ux", "uy", "uz", "q"):
         assert np.array_equal(pe[name].view(np.uint32), D["electron"][name].view(np.uint32)), ("electron", name)
@@ -241,14 +242,14 @@ def test_draws_and_load_across_internal_batches(vpb):
     rng_o = new_rng(O, 11)
     pe, pi = abi.aligned_zeros(pairs, abi.particle_dtype), abi.aligned_zeros(pairs, abi.particle_dtype)
     npe, npi = C.c_int(0), C.c_int(0)
-    assert O.orc_load_thermal_pairs(ptr(rng_o), pairs, ptr(lo), ptr(hi), 0.1, 0.1, q, ptr(pe), C.byref(npe), pairs, ptr(pi), C.byref(npi), pairs,
-                                    g.ref()) == pairs
+    assert O.orc_load_thermal_pairs_tagged(ptr(rng_o), pairs, ptr(lo), ptr(hi), 0.1, 0.1, q, ptr(pe), C.byref(npe), pairs, ptr(pi), C.byref(npi), pairs,
+                                           g.ref(), 5, 1) == pairs
     dom = vpb.vpb_domain_create(g.ref(), 0, 1)
     vpb.vpb_domain_set_particle_layout(dom, (pairs + 63) // 64 * 64)
     d_e, d_i = ParticleArray(vpb, dom, pairs), ParticleArray(vpb, dom, pairs)
     rng = vpb.vpb_mt_create(11)
     np2 = (C.c_int * 2)(0, 0)
-    assert vpb.vpb_load_pairs_mt(dom, rng, pairs, ptr(lo), ptr(hi), 0.1, 0.1, -q, q, d_e.ptr, pairs, d_i.ptr, pairs, np2, 1) == pairs
+    assert vpb.vpb_load_pairs_mt(dom, rng, pairs, ptr(lo), ptr(hi), 0.1, 0.1, -q, q, d_e.ptr, pairs, d_i.ptr, pairs, np2, 1, 5, 1) == pairs
     assert (np2[0], np2[1]) == (pairs, pairs)
     assert_bits_equal(d_e.download(pairs), pe, "electrons")
     assert_bits_equal(d_i.download(pairs), pi, "ions")

@@ -20,7 +20,8 @@ def oracle_mt():
                             ("orc_mt_fill_u32", None, [_vp, _vp, _l]), ("orc_mt_fill_drand", None, [_vp, _vp, _l]),
                             ("orc_mt_fill_drandn", None, [_vp, _vp, _l]), ("orc_mt_draw", None, [_vp, C.c_char_p, _l, _vp]),
                             ("orc_mt_zig_table", None, [_vp, _vp, _vp]),
-                            ("orc_load_thermal_pairs", _l, [_vp, _l, _vp, _vp, _d, _d, _d, _vp, _vp, _i, _vp, _vp, _i, _vp])):
+                            ("orc_load_thermal_pairs", _l, [_vp, _l, _vp, _vp, _d, _d, _d, _vp, _vp, _i, _vp, _vp, _i, _vp]),
+                            ("orc_load_thermal_pairs_tagged", _l, [_vp, _l, _vp, _vp, _d, _d, _d, _vp, _vp, _i, _vp, _vp, _i, _vp, _l, _l])):
         fn = getattr(O, name)
         fn.restype, fn.argtypes = res, args
     return O
