@@ -342,6 +342,8 @@ struct vpb_mt {
   double *d_zig = nullptr;         // zig_x[257] | zig_y[257]
   double zig_r = 0;
   uint32_t h_state[kMtN];          // host copy of the seed / imported state until the first block is generated
+  double *d_table = nullptr;       // deviate table of the load loops (grow-only, freed with the generator)
+  size_t table_cap = 0;
 };
 
 // make_zig.c:9-62.  The inverse density goes through a double sqrt there, which is part of what the table is.
@@ -449,6 +451,7 @@ void vpb_mt_destroy(vpb_mt_t *m) {
   cudaFree(m->d_state);
   cudaFree(m->d_words);
   cudaFree(m->d_zig);
+  cudaFree(m->d_table);
   delete m;
 }
 
@@ -661,9 +664,14 @@ long vpb_load_pairs_mt(vpb_domain_t *dom, vpb_mt_t *rng, long n, const double lo
   const int o = args_right_to_left ? 1 : 0;
   const int col_a[6] = {0, 1, 2, o ? 5 : 3, 4, o ? 3 : 5}, col_b[6] = {0, 1, 2, o ? 8 : 6, 7, o ? 6 : 8};
   const double dev_a[3] = {vth_a, vth_a, vth_a}, dev_b[3] = {vth_b, vth_b, vth_b};
-  double *tab = nullptr;
   const long nb_max = n < kBatch ? n : kBatch;
-  if (nb_max) VPB_CUDA(cudaMalloc(&tab, (size_t)nb_max * 9 * sizeof(double)));
+  if ((size_t)nb_max * 9 > rng->table_cap) {
+    VPB_CUDA(cudaStreamSynchronize(ctx().stream));
+    cudaFree(rng->d_table);
+    rng->table_cap = (size_t)nb_max * 9;
+    VPB_CUDA(cudaMalloc(&rng->d_table, rng->table_cap * sizeof(double)));
+  }
+  double *tab = rng->d_table;
   for (long done = 0; done < n;) {
     const long nb = n - done < kBatch ? n - done : kBatch;
     vpb_mt_draw(rng, "UUUNNNNNN", nb, tab);
@@ -671,7 +679,6 @@ long vpb_load_pairs_mt(vpb_domain_t *dom, vpb_mt_t *rng, long n, const double lo
     np[1] = vpb_inject_from_draws(dom, d_b, np[1], max_b, tab, 9, nb, col_b, lo, hi, dev_b, q_b, tag0 + done * tag_step, tag_step);
     done += nb;
   }
-  if (tab) { VPB_CUDA(cudaStreamSynchronize(ctx().stream)); cudaFree(tab); }
   return n;
 }
 
