@@ -47,9 +47,16 @@ def test_reference_deck_with_walls_sheet_and_hydro_dump(tmp_path):
     w = z["hydro"]
     hs = np.abs(w[:, :14]).max(axis=0)
     hrel = np.abs(h[:, :14] - w[:, :14]) / hs
-    assert hrel[:, 3].max() < 1e-3 and hrel[:, 7].max() < 1e-3         # rho, ke: large means
-    # the zero-mean moments of a node move by a fraction of ONE particle's contribution when that particle's
-    # in-cell test falls the other way in the two runs; such nodes are isolated
+    # Twenty steps of history separate the two dumps.  Now and then ONE particle's in-cell test (advance_p.cxx:124-125)
+    # falls the other way in the two runs -- the float sums of the deposits are ordered differently -- and that particle
+    # sits in the neighbouring cell at the dump: the eight nodes of two cells then differ by a fraction of one
+    # particle's contribution (a node collects ~64 particles here: up to 1.5e-2 of its rho or ke; seen: 2.4e-3 in one run
+    # of ten), every other node agrees to rounding, and the totals do not notice.
+    big = hrel[:, [3, 7]]                                               # rho, ke: large means
+    assert big.max() < 5e-2 and int((big > 1e-3).sum()) <= 32, (big.max(), int((big > 1e-3).sum()))
+    tot_g, tot_w = h[:, [3, 7]].astype(np.float64).sum(axis=0), w[:, [3, 7]].astype(np.float64).sum(axis=0)
+    assert np.all(np.abs(tot_g - tot_w) <= 1e-4 * np.abs(tot_w)), (tot_g, tot_w)
+    # the zero-mean moments of such nodes move by the same particle's contribution; the nodes are isolated
     assert hrel.max() < 5e-2 and np.mean(hrel > 2e-3) < 2e-3, (hrel.max(), float(np.mean(hrel > 2e-3)))
 
 
