@@ -73,7 +73,7 @@ def test_reference_deck_with_absorbing_walls(tmp_path):
     got_counts = dict(line.split() for line in open(tmp_path / "counts"))
     assert set(got_counts) == set(want_counts)
     for name in want_counts:
-        assert abs(int(got_counts[name]) - int(want_counts[name])) <= 2, (got_counts, want_counts)
+        assert abs(int(got_counts[name]) - int(want_counts[name])) <= 4, (got_counts, want_counts)   # the energy bound below = 4 particles
         assert int(want_counts[name]) < 12 * 10 * 8 * 16 * 0.6           # the walls did absorb
     got, want = read_energies(tmp_path / "energies"), read_energies(GOLD.replace("thermal_small", "absorb_small"))
     assert got.shape == want.shape == (21, 9)
@@ -190,7 +190,7 @@ def test_reference_wall_decks_on_two_ranks(deck, tmp_path):
                 tot[k] = tot.get(k, 0) + int(v)
         want_counts = dict(line.split() for line in open(GOLD.replace("thermal_small_energies", "absorb_small_counts")))
         for name in want_counts:
-            assert abs(tot[name] - int(want_counts[name])) <= 2, (tot, want_counts)
+            assert abs(tot[name] - int(want_counts[name])) <= 4, (tot, want_counts)
 
 
 def test_trecon_part_deck_as_shipped(tmp_path):
